@@ -1,0 +1,235 @@
+/*
+ * mb200.h -- C-ABI of the B200-native tree-likelihood engine for MrBayes.
+ *
+ * Plain C, plain pointers and sizes, no torch / CUDA types.  The library
+ * (libmb200.so) owns every floating-point buffer of a data division on one
+ * GPU; the caller owns all integer bookkeeping and addresses the buffers by
+ * the same integer indices MrBayes keeps in ModelInfo (condLikeIndex,
+ * tiProbsIndex, nodeScalerIndex, siteScalerIndex, cijkIndex and their
+ * *ScratchIndex twins, reference src/bayes.h:1374-1385).  Accept / reject is
+ * therefore a pure host-side index swap (ResetFlips, src/mcmc.c:15695-15765)
+ * that the engine never sees.
+ *
+ * What each entry point replaces in the reference (file:line under
+ * /root/reference):
+ *
+ *   mb200_create_instance        createBeagleInstance / InitBeagleInstance
+ *                                (src/mbbeagle.c:60-395) and the buffer
+ *                                allocation of InitChainCondLikes
+ *                                (src/mcmc.c:5703-6508)
+ *   mb200_set_tip_states         tip partial fill from parsSets
+ *                                (src/mcmc.c:6302-6413), beagleSetTipStates /
+ *                                beagleSetTipPartials (src/mbbeagle.c:123-166)
+ *   mb200_set_pattern_weights    numSitesOfPat rows (src/mcmc.c:4188,
+ *                                src/likelihood.c:5830)
+ *   mb200_set_cijk               the cijk block written by UpDateCijk /
+ *                                CalcCijk (src/likelihood.c:10476,
+ *                                src/utils.c:9734)
+ *   mb200_set_eigen_decomposition  beagleSetEigenDecomposition
+ *                                (src/likelihood.c:10652)
+ *   mb200_update_transition_matrices  TiProbs_Gen (src/likelihood.c:9424) /
+ *                                TreeTiProbs_Beagle (src/mbbeagle.c:1368)
+ *   mb200_update_partials        CondLikeDown_* / CondLikeRoot_* /
+ *                                CondLikeScaler_* / RemoveNodeScalers
+ *                                (src/likelihood.c:204-5610, 7981) and
+ *                                TreeCondLikes_Beagle_Always_Rescale
+ *                                (src/mbbeagle.c:995)
+ *   mb200_root_log_likelihood    Likelihood_NUC4* / Likelihood_Gen*
+ *                                (src/likelihood.c:5764-6960) /
+ *                                TreeLikelihood_Beagle (src/mbbeagle.c:1117)
+ *   mb200_evaluate               one whole LaunchLogLikeForDivision
+ *                                (src/likelihood.c:7851-7973) per element,
+ *                                any number of chains per call, ONE fused
+ *                                launch (the chain-batched generation of
+ *                                SURVEY.md section 8f-1)
+ *
+ * Every function returns MB200_SUCCESS (0) or a negative MB200_ERROR_* code;
+ * there is no CPU fallback: without a usable sm_100 device
+ * mb200_create_instance fails with MB200_ERROR_NO_DEVICE.
+ */
+#ifndef MB200_H_
+#define MB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_ABI_VERSION 1
+
+/* return codes */
+#define MB200_SUCCESS                 0
+#define MB200_ERROR_GENERAL          -1
+#define MB200_ERROR_OUT_OF_MEMORY    -2
+#define MB200_ERROR_OUT_OF_RANGE     -3
+#define MB200_ERROR_NO_DEVICE        -4
+#define MB200_ERROR_UNSUPPORTED      -5
+#define MB200_ERROR_BAD_INSTANCE     -6
+#define MB200_ERROR_CUDA             -7
+
+/* per-evaluation status written by mb200_evaluate / mb200_root_log_likelihood */
+#define MB200_EVAL_OK                 0
+/* some pattern had like < LIKE_EPSILON (1e-300): lnL = -DBL_MAX and the caller
+ * must set abortMove = YES (src/likelihood.c:44, 5852-5860) */
+#define MB200_EVAL_UNDERFLOW          1
+
+#define MB200_MAX_STATES             64   /* numModelStates; 61-state codon fits   */
+#define MB200_MAX_CATEGORIES         20   /* MAX_RATE_CATS (src/bayes.h:316)       */
+#define MB200_NONE                  (-1)  /* "no buffer" sentinel, like BEAGLE_OP_NONE */
+
+/* evaluation flags */
+/* Root integration follows Likelihood_NUC4_{SSE,AVX,FMA}: when the site scaler is
+ * below -200 and likeI > 1e-70 the pattern contributes (lnScaler + log(likeI))
+ * (src/likelihood.c:6590-6617); without the flag it follows Likelihood_Gen*
+ * and contributes log(likeI) alone (src/likelihood.c:5881-5888). */
+#define MB200_FLAG_NUC4_PINVAR_QUIRK  1
+
+typedef struct mb200_instance_config
+{
+    int tip_count;        /* numLocalTaxa; partials buffers 0..tip_count-1 are tips       */
+    int partials_count;   /* m->numCondLikes: tips + (chains+1)*nIntNodes                 */
+    int state_count;      /* m->numModelStates (2..64)                                    */
+    int pattern_count;    /* m->numChars, unique site patterns                            */
+    int category_count;   /* m->numRateCats (Gamma) or numOmegaCats; 1..20                */
+    int matrix_count;     /* m->numTiProbs: (chains+1)*nNodes                             */
+    int scaler_count;     /* m->numScalers: (chains+1)*(nIntNodes+1), node + site scalers */
+    int eigen_count;      /* cijk slots: chains+1                                         */
+    int weight_rows;      /* rows of numSitesOfPat (1, or numChains when reweighting)     */
+    int device;           /* CUDA device ordinal                                          */
+    int max_evaluations;  /* largest `count` ever passed to mb200_evaluate (>=1)          */
+    int flags;            /* reserved, 0                                                  */
+} mb200_instance_config;
+
+/* One interior-node update: what CondLikeDown / CondLikeRoot + RemoveNodeScalers +
+ * CondLikeScaler do for one node of LaunchLogLikeForDivision's post-order loop
+ * (src/likelihood.c:7892-7967).  Seven-int BeagleOperation (src/mbbeagle.c:817-843)
+ * widened by the third neighbour of the unrooted interior root. */
+typedef struct mb200_operation
+{
+    int dest;          /* partials buffer written                                          */
+    int child1;        /* left child partials buffer (index < tip_count => tip)            */
+    int matrix1;       /* transition-matrix buffer of the left branch                      */
+    int child2;        /* right child                                                      */
+    int matrix2;
+    int child3;        /* MB200_NONE, or p->anc of the interior root (CondLikeRoot_*)      */
+    int matrix3;       /* MB200_NONE, or the interior root's own branch matrix             */
+    int scale_write;   /* node-scaler buffer to write after rescaling, MB200_NONE = keep   */
+    int scale_remove;  /* node-scaler buffer subtracted from the site scaler first
+                          (RemoveNodeScalers), MB200_NONE = nothing to remove              */
+} mb200_operation;
+
+/* One branch whose P(t) must be rebuilt (TiProbs_*).  `length` is the branch
+ * length after relaxed-clock substitution (src/likelihood.c:9471-9496). */
+typedef struct mb200_matrix_update
+{
+    int    matrix;     /* transition-matrix buffer written                                 */
+    int    eigen;      /* cijk slot read                                                   */
+    double length;
+} mb200_matrix_update;
+
+/* One LaunchLogLikeForDivision call. */
+typedef struct mb200_evaluation
+{
+    int                         matrix_update_count;
+    const mb200_matrix_update  *matrix_updates;
+    int                         operation_count;
+    const mb200_operation      *operations;      /* post-order (intDownPass)               */
+    int                         site_scaler_dst; /* m->siteScalerIndex[chain] after flip    */
+    int                         site_scaler_src; /* previous site scaler (CopySiteScalers),
+                                                    MB200_NONE = ResetSiteScalers           */
+    int                         root_buffer;     /* partials of tree->root->left            */
+    int                         weights_row;     /* chainId % numChains                     */
+    int                         flags;           /* MB200_FLAG_*                            */
+    double                      p_invar;         /* 0 when the model has no pInvar          */
+    int                         has_p_invar;     /* m->pInvar != NULL                       */
+    /* r_k = GetRate(d,chain) / (1-pInvar) * catRate[k] * correctionFactor
+       (src/likelihood.c:9438-9464, 9501) */
+    double                      category_rates[MB200_MAX_CATEGORIES];
+    /* mixture weights w_k: (1-pInvar)/K for Gamma models (src/likelihood.c:5821-5824),
+       omega-category frequencies for NY98 (src/likelihood.c:7000) */
+    double                      category_weights[MB200_MAX_CATEGORIES];
+    /* stationary frequencies of the model states (covarion-adjusted by the caller,
+       src/likelihood.c:5797-5818) */
+    double                      state_freqs[MB200_MAX_STATES];
+} mb200_evaluation;
+
+/* ---- library ---------------------------------------------------------------------- */
+int         mb200_abi_version (void);
+const char *mb200_version_string (void);
+const char *mb200_error_string (int code);
+int         mb200_device_count (void);     /* sm_100-class devices visible; 0 = none       */
+
+/* ---- instance ---------------------------------------------------------------------- */
+int mb200_create_instance   (const mb200_instance_config *config, int *instance);
+int mb200_finalize_instance (int instance);
+
+/* ---- static data ------------------------------------------------------------------- */
+/* state_masks[c] bit s set <=> model state s is compatible with the observation at
+ * pattern c (missing/gap: all state_count bits set).  Hidden covarion states are
+ * replicated by the caller exactly as src/mcmc.c:6402-6411 does. */
+int mb200_set_tip_states      (int instance, int tip, const uint64_t *state_masks);
+int mb200_set_pattern_weights (int instance, int row, const float *weights);
+
+/* ---- eigen systems ----------------------------------------------------------------- */
+/* block = [lambda_re(S), lambda_im(S), c_ijk(S*S*S)] exactly as m->cijks[idx] holds it
+ * (src/likelihood.c:9467-9468; src/utils.c:9734-9746) */
+int mb200_set_cijk (int instance, int eigen, const double *block);
+/* row-major V and V^-1 and real eigenvalues; c_ijk = V[i][k]*Vinv[k][j] is formed on
+ * the device */
+int mb200_set_eigen_decomposition (int instance, int eigen, const double *eigvecs,
+                                   const double *inverse_eigvecs, const double *eigvals);
+
+/* ---- node-granular verbs (the function-pointer / BEAGLE-verb level) ---------------- */
+int mb200_update_transition_matrices (int instance, const mb200_matrix_update *updates,
+                                      int count, const double *category_rates,
+                                      const double *state_freqs);
+/* site_scaler = cumulative scale buffer that node scalers are removed from / added to
+ * (MB200_NONE: leave site scalers alone) */
+int mb200_update_partials (int instance, const mb200_operation *operations, int count,
+                           int site_scaler);
+int mb200_reset_scalers   (int instance, int scaler);                 /* ResetSiteScalers */
+int mb200_copy_scalers    (int instance, int dst, int src);           /* CopySiteScalers  */
+int mb200_root_log_likelihood (int instance, int root_buffer, int site_scaler,
+                               int weights_row, const double *state_freqs,
+                               const double *category_weights, int has_p_invar,
+                               double p_invar, int flags, double *lnL, int *status);
+
+/* ---- fused, chain-batched evaluation (the hot path) -------------------------------- */
+/* count evaluations (normally one per MC^3 chain) in ONE pass: P(t) build, pruning over
+ * each evaluation's operation list with the rescaler fused, root integration and the
+ * weighted log-sum.  lnL[i] and status[i] are written for every evaluation.
+ * The evaluations of one call must not write the same buffers. */
+int mb200_evaluate (int instance, const mb200_evaluation *evaluations, int count,
+                    double *lnL, int *status);
+
+/* ---- read-back / seeding (parity tests, debugging) --------------------------------- */
+/* host layout of partials: [k][c][s] floats, the reference's scalar layout
+ * (src/mcmc.c:5756, 6397-6413) */
+int mb200_get_partials          (int instance, int buffer, float *out);
+int mb200_set_partials          (int instance, int buffer, const float *in);
+int mb200_get_transition_matrix (int instance, int matrix, float *out);  /* [k][i][j]     */
+int mb200_set_transition_matrix (int instance, int matrix, const float *in);
+int mb200_get_scalers           (int instance, int scaler, float *out);  /* [c]           */
+int mb200_set_scalers           (int instance, int scaler, const float *in);
+
+/* ---- device-resident replay (benchmark "value" leg; inputs already in HBM) --------- */
+/* Pack evaluations into the engine's device job format and keep them resident; returns a
+ * handle.  mb200_replay launches the fused pass for a packed batch without any
+ * host<->device copy; results stay on the device until mb200_replay_results. */
+int mb200_pack_evaluations (int instance, const mb200_evaluation *evaluations, int count,
+                            int *batch);
+int mb200_replay           (int instance, int batch);
+int mb200_replay_results   (int instance, int batch, double *lnL, int *status);
+int mb200_free_batch       (int instance, int batch);
+int mb200_synchronize      (int instance);
+/* the CUDA stream (cudaStream_t as void*) all work of the instance is issued on, so a
+ * caller can bracket it with its own events */
+int mb200_get_stream       (int instance, void **stream);
+/* kernels launched by the instance since creation (bench.py's gpu_launches) */
+int mb200_get_launch_count (int instance, long long *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MB200_H_ */

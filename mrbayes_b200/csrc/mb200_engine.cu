@@ -1,0 +1,820 @@
+// mb200_engine.cu -- host runtime + C-ABI (include/mb200.h) of the B200 tree-likelihood
+// engine.  Everything a data division needs lives in HBM for the life of the instance; a
+// likelihood evaluation moves a few hundred bytes of indices host->device and 12 bytes per
+// chain (lnL + status) device->host.  There is no CPU fallback in this file: without an
+// sm_100 device every entry point that needs the GPU fails.
+#include "mb200.h"
+#include "mb200_device.cuh"
+#include "mb200_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+
+namespace {
+
+struct Batch                       // packed evaluations (device job format)
+{
+    char   *hBlob  = nullptr;      // pinned host copy
+    char   *dBlob  = nullptr;      // device copy
+    size_t  cap    = 0;            // bytes allocated
+    size_t  bytes  = 0;            // bytes used
+    int     nEval = 0, nMat = 0, nOp = 0;
+    size_t  offEval = 0, offMat = 0, offOp = 0;
+    double *dLnL   = nullptr;      // [capEval]
+    int    *dStatus = nullptr;
+    double *hLnL   = nullptr;      // pinned
+    int    *hStatus = nullptr;
+    int     capEval = 0;
+    bool    used = false;
+};
+
+struct Instance
+{
+    mb200_instance_config cfg;
+    DevCtx        ctx;
+    cudaStream_t  stream = nullptr;
+    uint8_t      *dTip8 = nullptr;
+    uint64_t     *dTip64 = nullptr;
+    float        *dPartials = nullptr, *dMatrices = nullptr, *dScalers = nullptr, *dWeights = nullptr;
+    double       *dEigen = nullptr;
+    uint64_t     *dInvMask = nullptr;
+    double       *dTilePartial = nullptr;
+    int          *dTileAbort = nullptr;
+    unsigned int *dTicket = nullptr;
+    bool          invMaskValid = false;
+    int           maxEval = 1, maxTiles = 1, numSMs = 148;
+    size_t        eigenStride = 0;     // doubles per eigen slot
+    size_t        smemGen = 0;         // dynamic smem of eval_gen_kernel
+    long long     launches = 0;
+    Batch         scratch;             // used by the synchronous entry points
+    std::vector<Batch *> batches;      // resident batches (mb200_pack_evaluations)
+    void         *hostStage = nullptr; // pinned staging for set/get calls
+    size_t        hostStageBytes = 0;
+};
+
+std::mutex               gLock;
+std::vector<Instance *>  gInstances;
+
+const int NT_SMALL = 32, NT_LARGE = 128, NT_GEN = 256;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fprintf (stderr, "mb200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorName (e_), __FILE__, __LINE__, cudaGetErrorString (e_)); \
+    return MB200_ERROR_CUDA; } } while (0)
+
+Instance *get (int id)
+{
+    std::lock_guard<std::mutex> g (gLock);
+    if (id < 0 || id >= (int) gInstances.size ())
+        return nullptr;
+    return gInstances[id];
+}
+
+int use (Instance *I)
+{
+    CK (cudaSetDevice (I->cfg.device));
+    return MB200_SUCCESS;
+}
+
+int ensureStage (Instance *I, size_t bytes)
+{
+    if (bytes <= I->hostStageBytes)
+        return MB200_SUCCESS;
+    if (I->hostStage) cudaFreeHost (I->hostStage);
+    I->hostStage = nullptr; I->hostStageBytes = 0;
+    CK (cudaMallocHost (&I->hostStage, bytes));
+    I->hostStageBytes = bytes;
+    return MB200_SUCCESS;
+}
+
+void freeBatch (Batch &b)
+{
+    if (b.hBlob)   cudaFreeHost (b.hBlob);
+    if (b.dBlob)   cudaFree (b.dBlob);
+    if (b.dLnL)    cudaFree (b.dLnL);
+    if (b.dStatus) cudaFree (b.dStatus);
+    if (b.hLnL)    cudaFreeHost (b.hLnL);
+    if (b.hStatus) cudaFreeHost (b.hStatus);
+    b = Batch ();
+}
+
+int reserveBatch (Batch &b, size_t bytes, int nEval)
+{
+    if (bytes > b.cap)
+        {
+        size_t cap = bytes + bytes / 2 + 4096;
+        if (b.hBlob) cudaFreeHost (b.hBlob);
+        if (b.dBlob) cudaFree (b.dBlob);
+        b.hBlob = nullptr; b.dBlob = nullptr; b.cap = 0;
+        CK (cudaMallocHost ((void **)&b.hBlob, cap));
+        CK (cudaMalloc ((void **)&b.dBlob, cap));
+        b.cap = cap;
+        }
+    if (nEval > b.capEval)
+        {
+        int cap = nEval + 8;
+        if (b.dLnL) cudaFree (b.dLnL);
+        if (b.dStatus) cudaFree (b.dStatus);
+        if (b.hLnL) cudaFreeHost (b.hLnL);
+        if (b.hStatus) cudaFreeHost (b.hStatus);
+        b.capEval = 0;
+        CK (cudaMalloc ((void **)&b.dLnL, sizeof(double) * cap));
+        CK (cudaMalloc ((void **)&b.dStatus, sizeof(int) * cap));
+        CK (cudaMallocHost ((void **)&b.hLnL, sizeof(double) * cap));
+        CK (cudaMallocHost ((void **)&b.hStatus, sizeof(int) * cap));
+        b.capEval = cap;
+        }
+    return MB200_SUCCESS;
+}
+
+bool okPartials (const Instance *I, int b, bool allowTip)
+{
+    return b >= (allowTip ? 0 : I->cfg.tip_count) && b < I->cfg.partials_count;
+}
+
+// validate + flatten host evaluations into the device job format
+int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
+{
+    const mb200_instance_config &c = I->cfg;
+    if (count < 1 || count > I->maxEval)
+        return MB200_ERROR_OUT_OF_RANGE;
+    int nMat = 0, nOp = 0;
+    for (int e = 0; e < count; e++)
+        {
+        if (evs[e].matrix_update_count < 0 || evs[e].operation_count < 0)
+            return MB200_ERROR_OUT_OF_RANGE;
+        nMat += evs[e].matrix_update_count;
+        nOp  += evs[e].operation_count;
+        }
+    size_t offEval = mb200_align16 (sizeof(DevBatchHeader));
+    size_t offMat  = mb200_align16 (offEval + sizeof(DevEval) * (size_t)count);
+    size_t offOp   = mb200_align16 (offMat + sizeof(DevMat) * (size_t)nMat);
+    size_t bytes   = mb200_align16 (offOp + sizeof(DevOp) * (size_t)nOp);
+    int rc = reserveBatch (b, bytes, count);
+    if (rc != MB200_SUCCESS)
+        return rc;
+    memset (b.hBlob, 0, bytes);
+    DevBatchHeader *h = (DevBatchHeader *) b.hBlob;
+    h->nEval = count; h->nMat = nMat; h->nOp = nOp;
+    DevEval *de = (DevEval *)(b.hBlob + offEval);
+    DevMat  *dm = (DevMat  *)(b.hBlob + offMat);
+    DevOp   *dops = (DevOp   *)(b.hBlob + offOp);
+    int mOff = 0, oOff = 0;
+    for (int e = 0; e < count; e++)
+        {
+        const mb200_evaluation &ev = evs[e];
+        DevEval &d = de[e];
+        d.nMat = ev.matrix_update_count; d.matOff = mOff;
+        d.nOp  = ev.operation_count;     d.opOff  = oOff;
+        d.siteDst = ev.site_scaler_dst;  d.siteSrc = ev.site_scaler_src;
+        d.root = ev.root_buffer;         d.weightsRow = ev.weights_row;
+        d.flags = ev.flags;              d.hasPInvar = ev.has_p_invar ? 1 : 0;
+        d.pInvar = ev.p_invar;
+        if (d.siteDst < -1 || d.siteDst >= c.scaler_count || d.siteSrc < -1 || d.siteSrc >= c.scaler_count)
+            return MB200_ERROR_OUT_OF_RANGE;
+        if (d.root != MB200_NONE)
+            {
+            if (!okPartials (I, d.root, false) || d.weightsRow < 0 || d.weightsRow >= c.weight_rows)
+                return MB200_ERROR_OUT_OF_RANGE;
+            }
+        bool eq = true;
+        for (int k = 0; k < c.category_count; k++)
+            {
+            d.rates[k] = ev.category_rates[k];
+            d.catW[k]  = ev.category_weights[k];
+            if (ev.category_weights[k] != ev.category_weights[0]) eq = false;
+            }
+        d.equalWeights = eq ? 1 : 0;
+        for (int s = 0; s < c.state_count; s++)
+            d.freqs[s] = ev.state_freqs[s];
+        for (int i = 0; i < ev.matrix_update_count; i++)
+            {
+            const mb200_matrix_update &u = ev.matrix_updates[i];
+            if (u.matrix < 0 || u.matrix >= c.matrix_count || u.eigen < 0 || u.eigen >= c.eigen_count)
+                return MB200_ERROR_OUT_OF_RANGE;
+            DevMat &m = dm[mOff + i];
+            m.matrix = u.matrix; m.eigen = u.eigen; m.length = u.length; m.eval = e;
+            }
+        for (int i = 0; i < ev.operation_count; i++)
+            {
+            const mb200_operation &op = ev.operations[i];
+            if (!okPartials (I, op.dest, false) || !okPartials (I, op.child1, true) || !okPartials (I, op.child2, true))
+                return MB200_ERROR_OUT_OF_RANGE;
+            if (op.matrix1 < 0 || op.matrix1 >= c.matrix_count || op.matrix2 < 0 || op.matrix2 >= c.matrix_count)
+                return MB200_ERROR_OUT_OF_RANGE;
+            if (op.child3 != MB200_NONE && (!okPartials (I, op.child3, true) || op.matrix3 < 0 || op.matrix3 >= c.matrix_count))
+                return MB200_ERROR_OUT_OF_RANGE;
+            if (op.scale_write < -1 || op.scale_write >= c.scaler_count || op.scale_remove < -1 || op.scale_remove >= c.scaler_count)
+                return MB200_ERROR_OUT_OF_RANGE;
+            DevOp &o = dops[oOff + i];
+            o.dest = op.dest; o.c1 = op.child1; o.m1 = op.matrix1; o.c2 = op.child2; o.m2 = op.matrix2;
+            o.c3 = op.child3; o.m3 = (op.child3 == MB200_NONE) ? MB200_NONE : op.matrix3;
+            o.sw = op.scale_write; o.sr = op.scale_remove;
+            }
+        mOff += ev.matrix_update_count;
+        oOff += ev.operation_count;
+        }
+    b.bytes = bytes; b.nEval = count; b.nMat = nMat; b.nOp = nOp;
+    b.offEval = offEval; b.offMat = offMat; b.offOp = offOp;
+    return MB200_SUCCESS;
+}
+
+int ensureInvMask (Instance *I)
+{
+    if (I->invMaskValid)
+        return MB200_SUCCESS;
+    int C = I->cfg.pattern_count;
+    invmask_kernel<<<(C + 255) / 256, 256, 0, I->stream>>> (I->dInvMask, I->dTip64, I->cfg.tip_count, C);
+    CK (cudaGetLastError ());
+    I->launches++;
+    I->invMaskValid = true;
+    return MB200_SUCCESS;
+}
+
+template <int NT>
+int launchNuc4 (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const DevOp *dops, double *lnL, int *st)
+{
+    switch (ctx.K)
+        {
+#define MB200_CASE(KK) case KK: eval_nuc4_kernel<KK, NT><<<grid, NT, 0, I->stream>>> (ctx, de, dops, lnL, st); break;
+        MB200_CASE(1) MB200_CASE(2) MB200_CASE(3) MB200_CASE(4) MB200_CASE(5) MB200_CASE(6) MB200_CASE(7) MB200_CASE(8)
+#undef MB200_CASE
+        default: return MB200_ERROR_UNSUPPORTED;
+        }
+    return MB200_SUCCESS;
+}
+
+// launch the fused pass for a packed batch already resident on the device
+int launch (Instance *I, Batch &b)
+{
+    const DevEval *de = (const DevEval *)(b.dBlob + b.offEval);
+    const DevMat  *dm = (const DevMat  *)(b.dBlob + b.offMat);
+    const DevOp   *dops = (const DevOp   *)(b.dBlob + b.offOp);
+    DevCtx ctx = I->ctx;
+
+    bool needInv = false;
+    {
+    const DevEval *he = (const DevEval *)(b.hBlob + b.offEval);
+    for (int e = 0; e < b.nEval; e++) if (he[e].hasPInvar && he[e].root >= 0) needInv = true;
+    }
+    if (needInv)
+        {
+        int rc = ensureInvMask (I);
+        if (rc != MB200_SUCCESS) return rc;
+        }
+    if (b.nMat > 0)
+        {
+        dim3 grid (b.nMat, ctx.K);
+        tiprobs_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, dm);
+        CK (cudaGetLastError ());
+        I->launches++;
+        }
+    if (ctx.S == 4 && ctx.K <= 8)
+        {
+        // small problems: one warp per CTA spreads the latency-bound work over more SMs
+        long tilesLarge = (long)((ctx.C + NT_LARGE - 1) / NT_LARGE) * b.nEval;
+        int  rc;
+        if (tilesLarge < 2L * I->numSMs)
+            {
+            ctx.tilePatterns = NT_SMALL;
+            ctx.numTiles = (ctx.C + NT_SMALL - 1) / NT_SMALL;
+            rc = launchNuc4<NT_SMALL> (I, ctx, dim3 (ctx.numTiles, b.nEval), de, dops, b.dLnL, b.dStatus);
+            }
+        else
+            {
+            ctx.tilePatterns = NT_LARGE;
+            ctx.numTiles = (ctx.C + NT_LARGE - 1) / NT_LARGE;
+            rc = launchNuc4<NT_LARGE> (I, ctx, dim3 (ctx.numTiles, b.nEval), de, dops, b.dLnL, b.dStatus);
+            }
+        if (rc != MB200_SUCCESS) return rc;
+        }
+    else
+        {
+        eval_gen_kernel<NT_GEN><<<dim3 (ctx.numTiles, b.nEval), NT_GEN, I->smemGen, I->stream>>> (ctx, de, dops, b.dLnL, b.dStatus);
+        }
+    CK (cudaGetLastError ());
+    I->launches++;
+    return MB200_SUCCESS;
+}
+
+int runSync (Instance *I, const mb200_evaluation *evs, int count, double *lnL, int *status)
+{
+    Batch &b = I->scratch;
+    int rc = pack (I, b, evs, count);
+    if (rc != MB200_SUCCESS) return rc;
+    CK (cudaMemcpyAsync (b.dBlob, b.hBlob, b.bytes, cudaMemcpyHostToDevice, I->stream));
+    rc = launch (I, b);
+    if (rc != MB200_SUCCESS) return rc;
+    bool wantRoot = false;
+    for (int e = 0; e < count; e++) if (evs[e].root_buffer != MB200_NONE) wantRoot = true;
+    if (wantRoot)
+        {
+        CK (cudaMemcpyAsync (b.hLnL, b.dLnL, sizeof(double) * count, cudaMemcpyDeviceToHost, I->stream));
+        CK (cudaMemcpyAsync (b.hStatus, b.dStatus, sizeof(int) * count, cudaMemcpyDeviceToHost, I->stream));
+        }
+    CK (cudaStreamSynchronize (I->stream));
+    for (int e = 0; e < count; e++)
+        {
+        if (evs[e].root_buffer != MB200_NONE)
+            {
+            if (lnL)    lnL[e] = b.hLnL[e];
+            if (status) status[e] = b.hStatus[e];
+            }
+        else
+            {
+            if (lnL)    lnL[e] = 0.0;
+            if (status) status[e] = MB200_EVAL_OK;
+            }
+        }
+    return MB200_SUCCESS;
+}
+
+void destroy (Instance *I)
+{
+    if (!I) return;
+    cudaSetDevice (I->cfg.device);
+    if (I->stream) cudaStreamSynchronize (I->stream);
+    freeBatch (I->scratch);
+    for (Batch *b : I->batches) if (b) { freeBatch (*b); delete b; }
+    cudaFree (I->dTip8); cudaFree (I->dTip64); cudaFree (I->dPartials); cudaFree (I->dMatrices);
+    cudaFree (I->dScalers); cudaFree (I->dWeights); cudaFree (I->dEigen); cudaFree (I->dInvMask);
+    cudaFree (I->dTilePartial); cudaFree (I->dTileAbort); cudaFree (I->dTicket);
+    if (I->hostStage) cudaFreeHost (I->hostStage);
+    if (I->stream) cudaStreamDestroy (I->stream);
+    delete I;
+}
+
+} // namespace
+
+extern "C" {
+
+int mb200_abi_version (void) { return MB200_ABI_VERSION; }
+
+const char *mb200_version_string (void) { return "mb200 0.1 (sm_100a)"; }
+
+const char *mb200_error_string (int code)
+{
+    switch (code)
+        {
+        case MB200_SUCCESS:             return "success";
+        case MB200_ERROR_GENERAL:       return "general error";
+        case MB200_ERROR_OUT_OF_MEMORY: return "out of device memory";
+        case MB200_ERROR_OUT_OF_RANGE:  return "index or size out of range";
+        case MB200_ERROR_NO_DEVICE:     return "no sm_100 (B200) device available; the engine has no CPU fallback";
+        case MB200_ERROR_UNSUPPORTED:   return "unsupported configuration";
+        case MB200_ERROR_BAD_INSTANCE:  return "bad instance handle";
+        case MB200_ERROR_CUDA:          return "CUDA runtime error";
+        default:                        return "unknown error";
+        }
+}
+
+int mb200_device_count (void)
+{
+    int n = 0, ok = 0;
+    if (cudaGetDeviceCount (&n) != cudaSuccess)
+        { cudaGetLastError (); return 0; }
+    for (int d = 0; d < n; d++)
+        {
+        int major = 0;
+        if (cudaDeviceGetAttribute (&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10)
+            ok++;
+        }
+    return ok;
+}
+
+int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
+{
+    if (!cfg || !instance)
+        return MB200_ERROR_GENERAL;
+    *instance = -1;
+    if (cfg->state_count < 2 || cfg->state_count > MB200_MAX_STATES ||
+        cfg->category_count < 1 || cfg->category_count > MB200_MAX_CATEGORIES ||
+        cfg->pattern_count < 1 || cfg->tip_count < 2 || cfg->partials_count <= cfg->tip_count ||
+        cfg->matrix_count < 1 || cfg->scaler_count < 1 || cfg->eigen_count < 1 || cfg->weight_rows < 1)
+        return MB200_ERROR_OUT_OF_RANGE;
+
+    int n = 0;
+    if (cudaGetDeviceCount (&n) != cudaSuccess || n < 1)
+        { cudaGetLastError (); return MB200_ERROR_NO_DEVICE; }
+    if (cfg->device < 0 || cfg->device >= n)
+        return MB200_ERROR_NO_DEVICE;
+    int major = 0, sms = 0;
+    if (cudaDeviceGetAttribute (&major, cudaDevAttrComputeCapabilityMajor, cfg->device) != cudaSuccess || major != 10)
+        return MB200_ERROR_NO_DEVICE;        // kernels exist for sm_100a only
+    CK (cudaSetDevice (cfg->device));
+    cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+
+    Instance *I = new Instance ();
+    I->cfg = *cfg;
+    I->numSMs = sms > 0 ? sms : 148;
+    I->maxEval = cfg->max_evaluations > 0 ? cfg->max_evaluations : 1;
+    const int S = cfg->state_count, K = cfg->category_count, C = cfg->pattern_count;
+    const int Sp = (S + 3) & ~3;
+    const size_t nInt = (size_t)(cfg->partials_count - cfg->tip_count);
+    I->eigenStride = 2*(size_t)S + (size_t)S*S*S;
+
+    // tile geometry of the generic kernel: keep P + child tile + product under ~96 KB
+    int TP = 32;
+    auto smemFor = [&] (int tp) { return sizeof(float) * ((size_t)S*S + (size_t)tp*(Sp+1) + (size_t)K*tp*S + 2*(size_t)tp); };
+    while (TP > 1 && smemFor (TP) > 96*1024) TP >>= 1;
+    I->smemGen = smemFor (TP);
+    const bool nuc4 = (S == 4 && K <= 8);
+    I->maxTiles = nuc4 ? (C + NT_SMALL - 1) / NT_SMALL : (C + TP - 1) / TP;
+
+#define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc ((void **)&(ptr), (bytes)); if (e_ != cudaSuccess) { \
+        cudaGetLastError (); destroy (I); return (e_ == cudaErrorMemoryAllocation) ? MB200_ERROR_OUT_OF_MEMORY : MB200_ERROR_CUDA; } } while (0)
+    if (cudaStreamCreateWithFlags (&I->stream, cudaStreamNonBlocking) != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
+    ALLOC (I->dTip8,     (size_t)cfg->tip_count * C);
+    ALLOC (I->dTip64,    (size_t)cfg->tip_count * C * sizeof(uint64_t));
+    ALLOC (I->dPartials, nInt * K * C * Sp * sizeof(float));
+    ALLOC (I->dMatrices, (size_t)cfg->matrix_count * K * S * S * sizeof(float));
+    ALLOC (I->dScalers,  (size_t)cfg->scaler_count * C * sizeof(float));
+    ALLOC (I->dWeights,  (size_t)cfg->weight_rows * C * sizeof(float));
+    ALLOC (I->dEigen,    (size_t)cfg->eigen_count * I->eigenStride * sizeof(double));
+    ALLOC (I->dInvMask,  (size_t)C * sizeof(uint64_t));
+    ALLOC (I->dTilePartial, (size_t)I->maxEval * I->maxTiles * sizeof(double));
+    ALLOC (I->dTileAbort,   (size_t)I->maxEval * I->maxTiles * sizeof(int));
+    ALLOC (I->dTicket,      (size_t)I->maxEval * sizeof(unsigned int));
+#undef ALLOC
+    cudaMemsetAsync (I->dTip8, 0, (size_t)cfg->tip_count * C, I->stream);
+    cudaMemsetAsync (I->dTip64, 0, (size_t)cfg->tip_count * C * sizeof(uint64_t), I->stream);
+    cudaMemsetAsync (I->dPartials, 0, nInt * K * C * Sp * sizeof(float), I->stream);
+    cudaMemsetAsync (I->dMatrices, 0, (size_t)cfg->matrix_count * K * S * S * sizeof(float), I->stream);
+    cudaMemsetAsync (I->dScalers, 0, (size_t)cfg->scaler_count * C * sizeof(float), I->stream);
+    cudaMemsetAsync (I->dWeights, 0, (size_t)cfg->weight_rows * C * sizeof(float), I->stream);
+    cudaMemsetAsync (I->dEigen, 0, (size_t)cfg->eigen_count * I->eigenStride * sizeof(double), I->stream);
+    cudaMemsetAsync (I->dTicket, 0, (size_t)I->maxEval * sizeof(unsigned int), I->stream);
+
+    if (I->smemGen > 48*1024)
+        {
+        if (cudaFuncSetAttribute (eval_gen_kernel<NT_GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) I->smemGen) != cudaSuccess)
+            { destroy (I); return MB200_ERROR_CUDA; }
+        }
+
+    DevCtx &x = I->ctx;
+    memset (&x, 0, sizeof(x));
+    x.S = S; x.Sp = Sp; x.K = K; x.C = C;
+    x.tipCount = cfg->tip_count; x.partialsCount = cfg->partials_count; x.matrixCount = cfg->matrix_count;
+    x.scalerCount = cfg->scaler_count; x.eigenCount = cfg->eigen_count; x.weightRows = cfg->weight_rows;
+    x.tilePatterns = nuc4 ? NT_SMALL : TP;
+    x.numTiles = I->maxTiles;
+    x.tip8 = I->dTip8; x.tip64 = I->dTip64; x.partials = I->dPartials; x.matrices = I->dMatrices;
+    x.scalers = I->dScalers; x.eigen = I->dEigen; x.weights = I->dWeights; x.invMask = I->dInvMask;
+    x.tilePartial = I->dTilePartial; x.tileAbort = I->dTileAbort; x.ticket = I->dTicket;
+
+    if (cudaStreamSynchronize (I->stream) != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
+
+    std::lock_guard<std::mutex> g (gLock);
+    for (size_t i = 0; i < gInstances.size (); i++)
+        if (gInstances[i] == nullptr) { gInstances[i] = I; *instance = (int) i; return MB200_SUCCESS; }
+    gInstances.push_back (I);
+    *instance = (int) gInstances.size () - 1;
+    return MB200_SUCCESS;
+}
+
+int mb200_finalize_instance (int instance)
+{
+    Instance *I;
+    {
+    std::lock_guard<std::mutex> g (gLock);
+    if (instance < 0 || instance >= (int) gInstances.size () || !gInstances[instance])
+        return MB200_ERROR_BAD_INSTANCE;
+    I = gInstances[instance];
+    gInstances[instance] = nullptr;
+    }
+    destroy (I);
+    return MB200_SUCCESS;
+}
+
+int mb200_set_tip_states (int instance, int tip, const uint64_t *masks)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (tip < 0 || tip >= I->cfg.tip_count || !masks) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    const int C = I->cfg.pattern_count;
+    rc = ensureStage (I, (size_t)C * 9); if (rc) return rc;
+    uint64_t *h64 = (uint64_t *) I->hostStage;
+    uint8_t  *h8  = (uint8_t *)(h64 + C);
+    const uint64_t full = (I->cfg.state_count == 64) ? ~(uint64_t)0 : (((uint64_t)1 << I->cfg.state_count) - 1);
+    for (int c = 0; c < C; c++)
+        {
+        h64[c] = masks[c] & full;
+        h8[c]  = (uint8_t)(h64[c] & 0xff);
+        }
+    CK (cudaMemcpyAsync (I->dTip64 + (size_t)tip * C, h64, (size_t)C * 8, cudaMemcpyHostToDevice, I->stream));
+    CK (cudaMemcpyAsync (I->dTip8 + (size_t)tip * C, h8, (size_t)C, cudaMemcpyHostToDevice, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    I->invMaskValid = false;
+    return MB200_SUCCESS;
+}
+
+int mb200_set_pattern_weights (int instance, int row, const float *w)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (row < 0 || row >= I->cfg.weight_rows || !w) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    const int C = I->cfg.pattern_count;
+    CK (cudaMemcpyAsync (I->dWeights + (size_t)row * C, w, (size_t)C * sizeof(float), cudaMemcpyHostToDevice, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    return MB200_SUCCESS;
+}
+
+int mb200_set_cijk (int instance, int eigen, const double *block)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (eigen < 0 || eigen >= I->cfg.eigen_count || !block) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    CK (cudaMemcpyAsync (I->dEigen + (size_t)eigen * I->eigenStride, block, I->eigenStride * sizeof(double),
+                         cudaMemcpyHostToDevice, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    return MB200_SUCCESS;
+}
+
+int mb200_set_eigen_decomposition (int instance, int eigen, const double *V, const double *Vinv, const double *lambda)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (eigen < 0 || eigen >= I->cfg.eigen_count || !V || !Vinv || !lambda) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    const int S = I->cfg.state_count;
+    const size_t n2 = (size_t)S * S;
+    double *tmp = nullptr;
+    CK (cudaMalloc ((void **)&tmp, (2*n2 + S) * sizeof(double)));
+    cudaMemcpyAsync (tmp, V, n2 * sizeof(double), cudaMemcpyHostToDevice, I->stream);
+    cudaMemcpyAsync (tmp + n2, Vinv, n2 * sizeof(double), cudaMemcpyHostToDevice, I->stream);
+    cudaMemcpyAsync (tmp + 2*n2, lambda, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, I->stream);
+    size_t n3 = n2 * S;
+    int blocks = (int)((n3 + 255) / 256); if (blocks > 1024) blocks = 1024;
+    cijk_kernel<<<blocks, 256, 0, I->stream>>> (I->dEigen + (size_t)eigen * I->eigenStride, tmp, tmp + n2, tmp + 2*n2, S);
+    I->launches++;
+    cudaError_t e = cudaStreamSynchronize (I->stream);
+    cudaFree (tmp);
+    CK (e);
+    return MB200_SUCCESS;
+}
+
+int mb200_update_transition_matrices (int instance, const mb200_matrix_update *updates, int count,
+                                      const double *category_rates, const double *state_freqs)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (count < 0 || (count > 0 && !updates) || !category_rates) return MB200_ERROR_OUT_OF_RANGE;
+    if (count == 0) return MB200_SUCCESS;
+    int rc = use (I); if (rc) return rc;
+    mb200_evaluation ev;
+    memset (&ev, 0, sizeof(ev));
+    ev.matrix_update_count = count; ev.matrix_updates = updates;
+    ev.site_scaler_dst = MB200_NONE; ev.site_scaler_src = MB200_NONE; ev.root_buffer = MB200_NONE;
+    for (int k = 0; k < I->cfg.category_count; k++) { ev.category_rates[k] = category_rates[k]; ev.category_weights[k] = 1.0; }
+    if (state_freqs)
+        for (int s = 0; s < I->cfg.state_count; s++) ev.state_freqs[s] = state_freqs[s];
+    return runSync (I, &ev, 1, nullptr, nullptr);
+}
+
+int mb200_update_partials (int instance, const mb200_operation *operations, int count, int site_scaler)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (count < 0 || (count > 0 && !operations)) return MB200_ERROR_OUT_OF_RANGE;
+    if (count == 0) return MB200_SUCCESS;
+    int rc = use (I); if (rc) return rc;
+    mb200_evaluation ev;
+    memset (&ev, 0, sizeof(ev));
+    ev.operation_count = count; ev.operations = operations;
+    ev.site_scaler_dst = site_scaler; ev.site_scaler_src = site_scaler; ev.root_buffer = MB200_NONE;
+    for (int k = 0; k < I->cfg.category_count; k++) ev.category_weights[k] = 1.0;
+    return runSync (I, &ev, 1, nullptr, nullptr);
+}
+
+int mb200_reset_scalers (int instance, int scaler)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (scaler < 0 || scaler >= I->cfg.scaler_count) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    const int C = I->cfg.pattern_count;
+    CK (cudaMemsetAsync (I->dScalers + (size_t)scaler * C, 0, (size_t)C * sizeof(float), I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    return MB200_SUCCESS;
+}
+
+int mb200_copy_scalers (int instance, int dst, int src)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (dst < 0 || dst >= I->cfg.scaler_count || src < 0 || src >= I->cfg.scaler_count) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    const int C = I->cfg.pattern_count;
+    CK (cudaMemcpyAsync (I->dScalers + (size_t)dst * C, I->dScalers + (size_t)src * C, (size_t)C * sizeof(float),
+                         cudaMemcpyDeviceToDevice, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    return MB200_SUCCESS;
+}
+
+int mb200_root_log_likelihood (int instance, int root_buffer, int site_scaler, int weights_row,
+                               const double *state_freqs, const double *category_weights, int has_p_invar,
+                               double p_invar, int flags, double *lnL, int *status)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (!state_freqs || !category_weights || !lnL) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    mb200_evaluation ev;
+    memset (&ev, 0, sizeof(ev));
+    ev.site_scaler_dst = MB200_NONE; ev.site_scaler_src = site_scaler; ev.root_buffer = root_buffer;
+    ev.weights_row = weights_row; ev.flags = flags; ev.has_p_invar = has_p_invar; ev.p_invar = p_invar;
+    for (int k = 0; k < I->cfg.category_count; k++) ev.category_weights[k] = category_weights[k];
+    for (int s = 0; s < I->cfg.state_count; s++) ev.state_freqs[s] = state_freqs[s];
+    int st = 0;
+    rc = runSync (I, &ev, 1, lnL, &st);
+    if (status) *status = st;
+    return rc;
+}
+
+int mb200_evaluate (int instance, const mb200_evaluation *evaluations, int count, double *lnL, int *status)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (!evaluations || !lnL || !status) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    return runSync (I, evaluations, count, lnL, status);
+}
+
+// ---- read-back / seeding ---------------------------------------------------------------
+int mb200_get_partials (int instance, int buffer, float *out)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (!okPartials (I, buffer, false) || !out) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    const int S = I->cfg.state_count, K = I->cfg.category_count, C = I->cfg.pattern_count, Sp = I->ctx.Sp;
+    const size_t n = (size_t)K * C * Sp;
+    std::vector<float> tmp (n);
+    CK (cudaMemcpyAsync (tmp.data (), I->dPartials + (size_t)(buffer - I->cfg.tip_count) * n, n * sizeof(float),
+                         cudaMemcpyDeviceToHost, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    for (size_t r = 0; r < (size_t)K * C; r++)
+        for (int s = 0; s < S; s++)
+            out[r * S + s] = tmp[r * Sp + s];
+    return MB200_SUCCESS;
+}
+
+int mb200_set_partials (int instance, int buffer, const float *in)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (!okPartials (I, buffer, false) || !in) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    const int S = I->cfg.state_count, K = I->cfg.category_count, C = I->cfg.pattern_count, Sp = I->ctx.Sp;
+    const size_t n = (size_t)K * C * Sp;
+    std::vector<float> tmp (n, 0.0f);
+    for (size_t r = 0; r < (size_t)K * C; r++)
+        for (int s = 0; s < S; s++)
+            tmp[r * Sp + s] = in[r * S + s];
+    CK (cudaMemcpyAsync (I->dPartials + (size_t)(buffer - I->cfg.tip_count) * n, tmp.data (), n * sizeof(float),
+                         cudaMemcpyHostToDevice, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    return MB200_SUCCESS;
+}
+
+int mb200_get_transition_matrix (int instance, int matrix, float *out)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (matrix < 0 || matrix >= I->cfg.matrix_count || !out) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    const size_t n = (size_t)I->cfg.category_count * I->cfg.state_count * I->cfg.state_count;
+    CK (cudaMemcpyAsync (out, I->dMatrices + (size_t)matrix * n, n * sizeof(float), cudaMemcpyDeviceToHost, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    return MB200_SUCCESS;
+}
+
+int mb200_set_transition_matrix (int instance, int matrix, const float *in)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (matrix < 0 || matrix >= I->cfg.matrix_count || !in) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    const size_t n = (size_t)I->cfg.category_count * I->cfg.state_count * I->cfg.state_count;
+    CK (cudaMemcpyAsync (I->dMatrices + (size_t)matrix * n, in, n * sizeof(float), cudaMemcpyHostToDevice, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    return MB200_SUCCESS;
+}
+
+int mb200_get_scalers (int instance, int scaler, float *out)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (scaler < 0 || scaler >= I->cfg.scaler_count || !out) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    const int C = I->cfg.pattern_count;
+    CK (cudaMemcpyAsync (out, I->dScalers + (size_t)scaler * C, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    return MB200_SUCCESS;
+}
+
+int mb200_set_scalers (int instance, int scaler, const float *in)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (scaler < 0 || scaler >= I->cfg.scaler_count || !in) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    const int C = I->cfg.pattern_count;
+    CK (cudaMemcpyAsync (I->dScalers + (size_t)scaler * C, in, (size_t)C * sizeof(float), cudaMemcpyHostToDevice, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    return MB200_SUCCESS;
+}
+
+// ---- device-resident replay ---------------------------------------------------------------
+int mb200_pack_evaluations (int instance, const mb200_evaluation *evaluations, int count, int *batch)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (!evaluations || !batch) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    Batch *b = new Batch ();
+    rc = pack (I, *b, evaluations, count);
+    if (rc != MB200_SUCCESS) { freeBatch (*b); delete b; return rc; }
+    if (cudaMemcpyAsync (b->dBlob, b->hBlob, b->bytes, cudaMemcpyHostToDevice, I->stream) != cudaSuccess ||
+        cudaStreamSynchronize (I->stream) != cudaSuccess)
+        { freeBatch (*b); delete b; return MB200_ERROR_CUDA; }
+    b->used = true;
+    for (size_t i = 0; i < I->batches.size (); i++)
+        if (I->batches[i] == nullptr) { I->batches[i] = b; *batch = (int) i; return MB200_SUCCESS; }
+    I->batches.push_back (b);
+    *batch = (int) I->batches.size () - 1;
+    return MB200_SUCCESS;
+}
+
+int mb200_replay (int instance, int batch)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (batch < 0 || batch >= (int) I->batches.size () || !I->batches[batch]) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    return launch (I, *I->batches[batch]);
+}
+
+int mb200_replay_results (int instance, int batch, double *lnL, int *status)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (batch < 0 || batch >= (int) I->batches.size () || !I->batches[batch]) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    Batch &b = *I->batches[batch];
+    CK (cudaMemcpyAsync (b.hLnL, b.dLnL, sizeof(double) * b.nEval, cudaMemcpyDeviceToHost, I->stream));
+    CK (cudaMemcpyAsync (b.hStatus, b.dStatus, sizeof(int) * b.nEval, cudaMemcpyDeviceToHost, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    for (int e = 0; e < b.nEval; e++)
+        {
+        if (lnL) lnL[e] = b.hLnL[e];
+        if (status) status[e] = b.hStatus[e];
+        }
+    return MB200_SUCCESS;
+}
+
+int mb200_free_batch (int instance, int batch)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (batch < 0 || batch >= (int) I->batches.size () || !I->batches[batch]) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    CK (cudaStreamSynchronize (I->stream));
+    freeBatch (*I->batches[batch]);
+    delete I->batches[batch];
+    I->batches[batch] = nullptr;
+    return MB200_SUCCESS;
+}
+
+int mb200_synchronize (int instance)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    int rc = use (I); if (rc) return rc;
+    CK (cudaStreamSynchronize (I->stream));
+    return MB200_SUCCESS;
+}
+
+int mb200_get_stream (int instance, void **stream)
+{
+    Instance *I = get (instance);
+    if (!I || !stream) return MB200_ERROR_BAD_INSTANCE;
+    *stream = (void *) I->stream;
+    return MB200_SUCCESS;
+}
+
+int mb200_get_launch_count (int instance, long long *launches)
+{
+    Instance *I = get (instance);
+    if (!I || !launches) return MB200_ERROR_BAD_INSTANCE;
+    *launches = I->launches;
+    return MB200_SUCCESS;
+}
+
+} // extern "C"

@@ -1,0 +1,39 @@
+/*
+ * mb200_seam.h -- what the seam adds on top of the reference's src/mbbeagle.h.
+ *
+ * The seam TU (mb200_seam.c) defines the mbbeagle.h entry points
+ * (InitBeagleInstance, LaunchBEAGLELogLikeForDivision, TreeTiProbs_Beagle,
+ * TreeCondLikes_Beagle_*, TreeLikelihood_Beagle) against the B200 engine; this
+ * header declares only the few extra symbols a caller needs.
+ */
+#ifndef MB200_SEAM_H_
+#define MB200_SEAM_H_
+
+#include "mb200.h"
+
+/* Replacement for LaunchLogLikeForDivision (src/likelihood.c:7851): returns YES (1)
+ * when the engine evaluated the division (lnL / abortMove set like the reference),
+ * NO (0) when the division's model is outside the engine's coverage and the caller
+ * must use the reference's own function-pointer path. */
+int       MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL);
+int       MB200SeamDivisionSupported (ModelInfo *m);
+void      MB200SeamFinalize (void);
+long long MB200SeamUpdateCount (int division);   /* node*pattern*rate CL updates issued  */
+int       MB200SeamInstance (int division);      /* engine instance of a division, or -1 */
+
+/* Every engine call the seam makes goes through this table, so a test harness can
+ * record the calls (golden vectors), shadow them, or both. */
+typedef struct
+    {
+    int (*create_instance)     (const mb200_instance_config *config, int *instance);
+    int (*finalize_instance)   (int instance);
+    int (*set_tip_states)      (int instance, int tip, const uint64_t *state_masks);
+    int (*set_pattern_weights) (int instance, int row, const float *weights);
+    int (*set_cijk)            (int instance, int eigen, const double *block);
+    int (*evaluate)            (int instance, const mb200_evaluation *evaluations, int count,
+                                double *lnL, int *status);
+    } MB200SeamBackend;
+
+void      MB200SeamSetBackend (const MB200SeamBackend *backend);   /* NULL = the engine  */
+
+#endif /* MB200_SEAM_H_ */

@@ -1,0 +1,475 @@
+/*
+ * ref_harness.c -- TEST INFRASTRUCTURE (oracle side), not product code.
+ *
+ * Linked with the UNMODIFIED reference objects (compiled from /root/reference/src by
+ * oracle/Makefile) using GNU ld's --wrap on the single cross-TU call site of the
+ * hot path, LogLike -> LaunchLogLikeForDivision (src/mcmc.c:7437 ->
+ * src/likelihood.c:7851), and on CalcCijk (src/utils.c:9734) to see V and V^-1.
+ *
+ * MB200_MODE selects what the wrapper does for every likelihood evaluation:
+ *   cpu     reference path only; time it and count CL updates (CPU baseline)
+ *   dump    reference path drives the chain; the seam's engine calls are RECORDED
+ *           (not executed) together with the reference lnL -> golden vectors
+ *   shadow  reference path drives the chain; the same calls also run on the GPU
+ *           engine and |lnL_gpu - lnL_cpu| / |lnL_cpu| is checked per evaluation
+ *   gpu     the GPU engine alone drives the chain (the drop-in), timed
+ * Other environment variables:
+ *   MB200_DUMP_FILE   output of dump mode (default mb200_golden.bin)
+ *   MB200_DUMP_MAX    stop recording after this many evaluations (default: all)
+ *   MB200_TOL         shadow-mode relative tolerance (default 1e-6)
+ *   MB200_REPORT      file the JSON summary is appended to (default: stderr)
+ *
+ * Golden file: "MB200GLD" u32 version=1, then chunks {u32 tag, u32 bytes, payload}:
+ *   'INST' i32 division, 12 x i32 mb200_instance_config
+ *   'TIPS' i32 division, i32 tip, i32 C, C x u64
+ *   'WGHT' i32 division, i32 row, i32 C, C x f32
+ *   'EIGN' i32 division, i32 eigen, i32 S, f64 lambda[S], V[S*S], Vinv[S*S]
+ *   'CIJK' i32 division, i32 eigen, i32 S, f64 block[2S+S^3]   (when V/Vinv unavailable)
+ *   'EVAL' i32 division, i32 chain, i32 nMat, i32 nOp, i32 siteDst, i32 siteSrc,
+ *          i32 root, i32 weightsRow, i32 flags, i32 hasPInvar, i32 K, i32 S,
+ *          f64 pInvar, f64 rates[K], f64 weights[K], f64 freqs[S],
+ *          nMat x {i32 matrix, i32 eigen, f64 length}, nOp x 9 x i32,
+ *          f64 lnL_reference, i32 abort, i32 pad
+ */
+#include "bayes.h"
+#include "likelihood.h"
+#include "mcmc.h"
+#include "model.h"
+#include "utils.h"
+#include "mb200.h"
+#include "mb200_seam.h"
+
+#include <time.h>
+
+void __real_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL);
+void __real_CalcCijk (int dim, MrBFlt *c_ijk, MrBFlt **u, MrBFlt **v);
+
+enum { MODE_CPU, MODE_DUMP, MODE_SHADOW, MODE_GPU };
+
+static int        hMode = -1;
+static FILE      *hDump = NULL;
+static long       hDumpMax = -1, hDumped = 0;
+static double     hTol = 1e-6;
+static double     hSecCpu = 0.0, hSecGpu = 0.0;
+static long long  hCalls = 0, hUpdates = 0, hNodeUpdates = 0, hAborts = 0, hUnsupported = 0;
+static double     hMaxRel = 0.0, hSumRel = 0.0;
+static long long  hCompared = 0, hFailed = 0;
+
+/* last eigensystem seen by CalcCijk */
+static int        hEigDim = 0;
+static double    *hEigU = NULL, *hEigV = NULL;
+
+/* evaluation stashed by the recorder until the reference value is known */
+static struct
+    {
+    int                  valid, instance;
+    mb200_evaluation     ev;
+    mb200_operation     *ops;
+    mb200_matrix_update *mats;
+    int                  capOps, capMats;
+    double               lnLGpu;
+    int                  statusGpu;
+    } hLast;
+
+static int hInstDivision[4096];     /* recorder instance id -> division */
+static int hInstReal[4096];         /* recorder instance id -> engine instance (shadow) */
+static mb200_instance_config hInstCfg[4096];
+static int hNumInst = 0;
+
+static double Now (void)
+{
+    struct timespec ts;
+    clock_gettime (CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static void Chunk (const char *tag, const void *hdr, size_t hdrBytes, const void *body, size_t bodyBytes)
+{
+    unsigned int n = (unsigned int)(hdrBytes + bodyBytes);
+    if (!hDump)
+        return;
+    fwrite (tag, 1, 4, hDump);
+    fwrite (&n, 4, 1, hDump);
+    if (hdrBytes)  fwrite (hdr, 1, hdrBytes, hDump);
+    if (bodyBytes) fwrite (body, 1, bodyBytes, hDump);
+}
+
+/* ---- recording backend ------------------------------------------------------------- */
+static int rec_create (const mb200_instance_config *c, int *inst)
+{
+    int hdr[13], id = hNumInst++;
+    /* division is found by matching the seam's bookkeeping after the call; the seam
+       creates instances one division at a time, in LogLike order */
+    hInstCfg[id] = *c;
+    hInstReal[id] = -1;
+    *inst = id;
+    if (hMode == MODE_SHADOW)
+        {
+        int rc = mb200_create_instance (c, &hInstReal[id]);
+        if (rc != MB200_SUCCESS)
+            return rc;
+        }
+    hdr[0] = -1;   /* patched by the caller through hInstDivision once known */
+    memcpy (hdr + 1, c, 12 * sizeof(int));
+    (void) hdr;
+    return MB200_SUCCESS;
+}
+
+static int rec_finalize (int inst)
+{
+    if (hMode == MODE_SHADOW && hInstReal[inst] >= 0)
+        return mb200_finalize_instance (hInstReal[inst]);
+    return MB200_SUCCESS;
+}
+
+static int rec_tips (int inst, int tip, const uint64_t *masks)
+{
+    int hdr[3];
+    hdr[0] = hInstDivision[inst]; hdr[1] = tip; hdr[2] = hInstCfg[inst].pattern_count;
+    Chunk ("TIPS", hdr, sizeof(hdr), masks, (size_t)hdr[2] * sizeof(uint64_t));
+    if (hMode == MODE_SHADOW)
+        return mb200_set_tip_states (hInstReal[inst], tip, masks);
+    return MB200_SUCCESS;
+}
+
+static int rec_weights (int inst, int row, const float *w)
+{
+    int hdr[3];
+    hdr[0] = hInstDivision[inst]; hdr[1] = row; hdr[2] = hInstCfg[inst].pattern_count;
+    Chunk ("WGHT", hdr, sizeof(hdr), w, (size_t)hdr[2] * sizeof(float));
+    if (hMode == MODE_SHADOW)
+        return mb200_set_pattern_weights (hInstReal[inst], row, w);
+    return MB200_SUCCESS;
+}
+
+static int rec_cijk (int inst, int eigen, const double *block)
+{
+    int     hdr[3], S = hInstCfg[inst].state_count, i, j, k, same = 0;
+    size_t  n3 = (size_t)S * S * S;
+
+    hdr[0] = hInstDivision[inst]; hdr[1] = eigen; hdr[2] = S;
+    if (hDump)
+        {
+        /* prefer the compact (lambda, V, V^-1) form when it reproduces the block exactly */
+        if (hEigDim == S && hEigU != NULL)
+            {
+            const double *c = block + 2*S;
+            same = 1;
+            for (i=0; i<S && same; i++)
+                for (j=0; j<S && same; j++)
+                    for (k=0; k<S; k++)
+                        if (c[((size_t)i*S + j)*S + k] != hEigU[i*S+k] * hEigV[k*S+j])
+                            { same = 0; break; }
+            }
+        if (same)
+            {
+            double *buf = (double *) malloc ((size_t)(S + 2*S*S) * sizeof(double));
+            memcpy (buf, block, (size_t)S * sizeof(double));
+            memcpy (buf + S, hEigU, (size_t)S*S * sizeof(double));
+            memcpy (buf + S + S*S, hEigV, (size_t)S*S * sizeof(double));
+            Chunk ("EIGN", hdr, sizeof(hdr), buf, (size_t)(S + 2*S*S) * sizeof(double));
+            free (buf);
+            }
+        else
+            Chunk ("CIJK", hdr, sizeof(hdr), block, (2*(size_t)S + n3) * sizeof(double));
+        }
+    if (hMode == MODE_SHADOW)
+        return mb200_set_cijk (hInstReal[inst], eigen, block);
+    return MB200_SUCCESS;
+}
+
+static int rec_eval (int inst, const mb200_evaluation *e, int n, double *lnL, int *status)
+{
+    int i;
+    if (n != 1)
+        return MB200_ERROR_UNSUPPORTED;
+    if (e->operation_count > hLast.capOps)
+        {
+        hLast.capOps = e->operation_count + 64;
+        hLast.ops = (mb200_operation *) realloc (hLast.ops, (size_t)hLast.capOps * sizeof(mb200_operation));
+        }
+    if (e->matrix_update_count > hLast.capMats)
+        {
+        hLast.capMats = e->matrix_update_count + 64;
+        hLast.mats = (mb200_matrix_update *) realloc (hLast.mats, (size_t)hLast.capMats * sizeof(mb200_matrix_update));
+        }
+    hLast.ev = *e;
+    for (i=0; i<e->operation_count; i++)      hLast.ops[i]  = e->operations[i];
+    for (i=0; i<e->matrix_update_count; i++)  hLast.mats[i] = e->matrix_updates[i];
+    hLast.ev.operations = hLast.ops;
+    hLast.ev.matrix_updates = hLast.mats;
+    hLast.instance = inst;
+    hLast.valid = 1;
+    lnL[0] = 0.0;
+    status[0] = MB200_EVAL_OK;
+    if (hMode == MODE_SHADOW)
+        {
+        double t0 = Now ();
+        int rc = mb200_evaluate (hInstReal[inst], e, 1, lnL, status);
+        hSecGpu += Now () - t0;
+        hLast.lnLGpu = lnL[0];
+        hLast.statusGpu = status[0];
+        return rc;
+        }
+    return MB200_SUCCESS;
+}
+
+static void WriteEval (int division, int chain, double lnLRef, int aborted)
+{
+    int         hdr[12], tail[2], i;
+    size_t      nb;
+    char       *buf, *q;
+    const mb200_evaluation *e = &hLast.ev;
+    int         K = hInstCfg[hLast.instance].category_count, S = hInstCfg[hLast.instance].state_count;
+
+    if (!hDump || !hLast.valid)
+        return;
+    hdr[0] = division; hdr[1] = chain; hdr[2] = e->matrix_update_count; hdr[3] = e->operation_count;
+    hdr[4] = e->site_scaler_dst; hdr[5] = e->site_scaler_src; hdr[6] = e->root_buffer; hdr[7] = e->weights_row;
+    hdr[8] = e->flags; hdr[9] = e->has_p_invar; hdr[10] = K; hdr[11] = S;
+    nb = sizeof(double) * (size_t)(1 + 2*K + S) + (size_t)e->matrix_update_count * 16 + (size_t)e->operation_count * 36 + 16;
+    buf = q = (char *) malloc (nb);
+    memcpy (q, &e->p_invar, 8); q += 8;
+    memcpy (q, e->category_rates, 8*(size_t)K); q += 8*(size_t)K;
+    memcpy (q, e->category_weights, 8*(size_t)K); q += 8*(size_t)K;
+    memcpy (q, e->state_freqs, 8*(size_t)S); q += 8*(size_t)S;
+    for (i=0; i<e->matrix_update_count; i++)
+        {
+        memcpy (q, &e->matrix_updates[i].matrix, 4); q += 4;
+        memcpy (q, &e->matrix_updates[i].eigen, 4); q += 4;
+        memcpy (q, &e->matrix_updates[i].length, 8); q += 8;
+        }
+    for (i=0; i<e->operation_count; i++)
+        {
+        memcpy (q, &e->operations[i], 36); q += 36;
+        }
+    memcpy (q, &lnLRef, 8); q += 8;
+    tail[0] = aborted; tail[1] = 0;
+    memcpy (q, tail, 8); q += 8;
+    Chunk ("EVAL", hdr, sizeof(hdr), buf, (size_t)(q - buf));
+    free (buf);
+    hDumped++;
+}
+
+/* ---- summary ----------------------------------------------------------------------- */
+static void Report (void)
+{
+    const char *path = getenv ("MB200_REPORT");
+    const char *names[] = { "cpu", "dump", "shadow", "gpu" };
+    FILE *f = path ? fopen (path, "a") : stderr;
+    if (!f) f = stderr;
+    fprintf (f, "{\"mb200_harness\": \"%s\", \"calls\": %lld, \"node_updates\": %lld, \"cl_updates\": %lld, "
+                "\"sec_cpu\": %.6f, \"sec_gpu\": %.6f, \"aborts\": %lld, \"unsupported_calls\": %lld, "
+                "\"compared\": %lld, \"failed\": %lld, \"max_rel\": %.3e, \"mean_rel\": %.3e, \"tol\": %.1e, \"dumped\": %ld}\n",
+             names[hMode], hCalls, hNodeUpdates, hUpdates, hSecCpu, hSecGpu, hAborts, hUnsupported,
+             hCompared, hFailed, hMaxRel, hCompared ? hSumRel / hCompared : 0.0, hTol, hDumped);
+    if (f != stderr) fclose (f);
+    if (hDump) { fclose (hDump); hDump = NULL; }
+    if (hMode == MODE_SHADOW || hMode == MODE_GPU)
+        MB200SeamFinalize ();
+}
+
+static void Setup (void)
+{
+    const char *s = getenv ("MB200_MODE");
+    hMode = MODE_CPU;
+    if (s && !strcmp (s, "dump"))   hMode = MODE_DUMP;
+    if (s && !strcmp (s, "shadow")) hMode = MODE_SHADOW;
+    if (s && !strcmp (s, "gpu"))    hMode = MODE_GPU;
+    if ((s = getenv ("MB200_TOL")) != NULL)      hTol = atof (s);
+    if ((s = getenv ("MB200_DUMP_MAX")) != NULL) hDumpMax = atol (s);
+    memset (&hLast, 0, sizeof(hLast));
+    if (hMode == MODE_DUMP)
+        {
+        unsigned int ver = 1;
+        s = getenv ("MB200_DUMP_FILE");
+        hDump = fopen (s ? s : "mb200_golden.bin", "wb");
+        if (!hDump) { perror ("MB200_DUMP_FILE"); exit (2); }
+        fwrite ("MB200GLD", 1, 8, hDump);
+        fwrite (&ver, 4, 1, hDump);
+        }
+    if (hMode == MODE_DUMP || hMode == MODE_SHADOW)
+        {
+        MB200SeamBackend be = { rec_create, rec_finalize, rec_tips, rec_weights, rec_cijk, rec_eval };
+        MB200SeamSetBackend (&be);
+        }
+    atexit (Report);
+}
+
+void __wrap_CalcCijk (int dim, MrBFlt *c_ijk, MrBFlt **u, MrBFlt **v)
+{
+    int i, j;
+    if (hMode == MODE_DUMP)
+        {
+        if (dim != hEigDim)
+            {
+            free (hEigU); free (hEigV);
+            hEigU = (double *) malloc ((size_t)dim*dim*sizeof(double));
+            hEigV = (double *) malloc ((size_t)dim*dim*sizeof(double));
+            hEigDim = dim;
+            }
+        for (i=0; i<dim; i++)
+            for (j=0; j<dim; j++)
+                {
+                hEigU[i*dim+j] = u[i][j];
+                hEigV[i*dim+j] = v[i][j];
+                }
+        }
+    __real_CalcCijk (dim, c_ijk, u, v);
+}
+
+/* ---- index-table snapshot (so the reference can redo the same flips) ---------------- */
+typedef struct
+    {
+    int  nNodes, *cl, *clS, *ti, *tiS, *ns, *nsS, *un, *unS, site, siteS;
+    } Snap;
+
+static void SnapTake (Snap *s, ModelInfo *m, int chain, int nNodes)
+{
+    size_t nb = (size_t)nNodes * sizeof(int);
+    s->nNodes = nNodes;
+    s->cl  = (int *) malloc (8*nb);
+    s->clS = s->cl + nNodes;  s->ti  = s->clS + nNodes; s->tiS = s->ti + nNodes;
+    s->ns  = s->tiS + nNodes; s->nsS = s->ns + nNodes;  s->un  = s->nsS + nNodes; s->unS = s->un + nNodes;
+    memcpy (s->cl,  m->condLikeIndex[chain], nb);    memcpy (s->clS, m->condLikeScratchIndex, nb);
+    memcpy (s->ti,  m->tiProbsIndex[chain], nb);     memcpy (s->tiS, m->tiProbsScratchIndex, nb);
+    memcpy (s->ns,  m->nodeScalerIndex[chain], nb);  memcpy (s->nsS, m->nodeScalerScratchIndex, nb);
+    memcpy (s->un,  m->unscaledNodes[chain], nb);    memcpy (s->unS, m->unscaledNodesScratch, nb);
+    s->site = m->siteScalerIndex[chain]; s->siteS = m->siteScalerScratchIndex;
+}
+
+static void SnapRestore (Snap *s, ModelInfo *m, int chain)
+{
+    size_t nb = (size_t)s->nNodes * sizeof(int);
+    memcpy (m->condLikeIndex[chain], s->cl, nb);     memcpy (m->condLikeScratchIndex, s->clS, nb);
+    memcpy (m->tiProbsIndex[chain], s->ti, nb);      memcpy (m->tiProbsScratchIndex, s->tiS, nb);
+    memcpy (m->nodeScalerIndex[chain], s->ns, nb);   memcpy (m->nodeScalerScratchIndex, s->nsS, nb);
+    memcpy (m->unscaledNodes[chain], s->un, nb);     memcpy (m->unscaledNodesScratch, s->unS, nb);
+    m->siteScalerIndex[chain] = s->site; m->siteScalerScratchIndex = s->siteS;
+    free (s->cl);
+}
+
+static long long CountDirty (Tree *t)
+{
+    int i; long long n = 0;
+    for (i=0; i<t->nIntNodes; i++)
+        if (t->intDownPass[i]->upDateCl == YES)
+            n++;
+    return n;
+}
+
+void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
+{
+    ModelInfo  *m = &modelSettings[d];
+    Tree       *tree;
+    long long   dirty;
+    double      t0;
+
+    if (hMode < 0)
+        Setup ();
+
+    tree  = GetTree (m->brlens, chain, state[chain]);
+    dirty = CountDirty (tree);
+    hCalls++;
+    hNodeUpdates += dirty;
+    hUpdates += dirty * m->numChars * m->numRateCats;
+
+    if (hMode == MODE_CPU || (hMode == MODE_DUMP && hDumpMax >= 0 && hDumped >= hDumpMax))
+        {
+        t0 = Now ();
+        __real_LaunchLogLikeForDivision (chain, d, lnL);
+        hSecCpu += Now () - t0;
+        return;
+        }
+
+    if (hMode == MODE_GPU)
+        {
+        t0 = Now ();
+        if (MB200LaunchLogLikeForDivision (chain, d, lnL) == NO)
+            {
+            hUnsupported++;
+            __real_LaunchLogLikeForDivision (chain, d, lnL);
+            }
+        hSecGpu += Now () - t0;
+        if (abortMove == YES) hAborts++;
+        return;
+        }
+
+    /* dump / shadow: engine calls first on a snapshot of the index tables, then the
+       reference does the very same flips for real */
+    {
+    Snap    snap;
+    int     hadCijk = m->upDateCijk, handled, nInstBefore = hNumInst, savedAbort = abortMove;
+    MrBFlt  lnLSeam = 0.0, lnLRef = 0.0;
+
+    if (MB200SeamDivisionSupported (m) == NO)
+        {
+        hUnsupported++;
+        t0 = Now ();
+        __real_LaunchLogLikeForDivision (chain, d, lnL);
+        hSecCpu += Now () - t0;
+        return;
+        }
+    if (MB200SeamInstance (d) < 0)
+        {
+        /* the instance about to be created belongs to this division */
+        int hdr[13];
+        hInstDivision[hNumInst] = d;
+        hdr[0] = d;
+        {
+        mb200_instance_config c;
+        memset (&c, 0, sizeof(c));
+        c.tip_count = numLocalTaxa; c.partials_count = m->numCondLikes; c.state_count = m->numModelStates;
+        c.pattern_count = m->numChars; c.category_count = m->numRateCats; c.matrix_count = m->numTiProbs;
+        c.scaler_count = m->numScalers;
+        {
+        extern int numLocalChains;
+        c.eigen_count = numLocalChains + 1;
+        }
+        c.weight_rows = chainParams.numChains; c.device = 0; c.max_evaluations = 1; c.flags = 0;
+        memcpy (hdr + 1, &c, 12 * sizeof(int));
+        }
+        Chunk ("INST", hdr, sizeof(hdr), NULL, 0);
+        }
+    (void) nInstBefore;
+
+    SnapTake (&snap, m, chain, tree->nNodes);
+    hLast.valid = 0;
+    handled = MB200LaunchLogLikeForDivision (chain, d, &lnLSeam);   /* runs UpDateCijk for real */
+    SnapRestore (&snap, m, chain);
+    abortMove = savedAbort;
+
+    if (hadCijk == YES)
+        m->upDateCijk = NO;              /* already done by the seam call above */
+    t0 = Now ();
+    __real_LaunchLogLikeForDivision (chain, d, &lnLRef);
+    hSecCpu += Now () - t0;
+    m->upDateCijk = hadCijk;
+    *lnL = lnLRef;
+    if (abortMove == YES) hAborts++;
+
+    if (handled == YES && hLast.valid)
+        {
+        if (hMode == MODE_DUMP)
+            WriteEval (d, chain, lnLRef, lnLRef == MRBFLT_NEG_MAX);
+        else
+            {
+            double rel;
+            if (lnLRef == MRBFLT_NEG_MAX || hLast.statusGpu != MB200_EVAL_OK)
+                rel = (lnLRef == MRBFLT_NEG_MAX && hLast.statusGpu != MB200_EVAL_OK) ? 0.0 : 1.0;
+            else
+                rel = fabs (hLast.lnLGpu - lnLRef) / fabs (lnLRef);
+            hCompared++;
+            hSumRel += rel;
+            if (rel > hMaxRel) hMaxRel = rel;
+            if (!(rel <= hTol))
+                {
+                hFailed++;
+                if (hFailed <= 20)
+                    fprintf (stderr, "MB200 SHADOW MISMATCH call %lld chain %d div %d: gpu %.17g cpu %.17g rel %.3e\n",
+                             hCalls, chain, d, hLast.lnLGpu, lnLRef, rel);
+                }
+            }
+        }
+    }
+}
