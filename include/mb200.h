@@ -84,6 +84,12 @@ extern "C" {
  * (src/likelihood.c:6590-6617); without the flag it follows Likelihood_Gen*
  * and contributes log(likeI) alone (src/likelihood.c:5881-5888). */
 #define MB200_FLAG_NUC4_PINVAR_QUIRK  1
+/* Terminal-branch shortcut of the scalar and *_Gen_SSE kernels (preLikeL/R/A,
+ * src/likelihood.c:236-260, 2441-2520): on a tip WITHOUT partially ambiguous patterns a
+ * missing/gap observation contributes exactly 1.0 to every ancestral state instead of
+ * sum_j P[i][j] (which is 1 only up to rounding).  The 4-state SSE/AVX/FMA kernels treat
+ * tips as dense vectors and do not take the shortcut (src/likelihood.c:1121-1250). */
+#define MB200_FLAG_TIP_SHORTCUTS      2
 
 typedef struct mb200_instance_config
 {

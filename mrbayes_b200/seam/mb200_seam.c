@@ -414,8 +414,12 @@ int TreeLikelihood_Beagle (Tree *t, int division, int chain, MrBFlt *lnL, int wh
         sd->ev.has_p_invar = YES;
         }
     sd->ev.p_invar = pInvar;
+    /* which reference kernel family this division would run (SetLikeFunctions,
+       src/mcmc.c:17995-18010 vs 18109-18243) decides two rounding-level details */
     if (m->numModelStates == 4 && (m->dataType == DNA || m->dataType == RNA))
         sd->ev.flags |= MB200_FLAG_NUC4_PINVAR_QUIRK;   /* Likelihood_NUC4_* family */
+    else
+        sd->ev.flags |= MB200_FLAG_TIP_SHORTCUTS;       /* *_Gen_SSE family */
 
     /* category weights (src/likelihood.c:5821-5824) */
     if (m->pInvar == NULL)

@@ -1,0 +1,563 @@
+/*
+ * pruning_oracle.c -- TEST INFRASTRUCTURE (see pruning_oracle.h): plain-C restatement of the
+ * reference's tree-likelihood path.  Each function cites the reference code it follows.
+ * Compiled with -ffp-contract=off so that every float multiply/add rounds exactly where the
+ * reference's intrinsics round; fused operations are written explicitly with fmaf().
+ *
+ * Layouts are the reference's scalar ones: CL [k][c][s] (src/mcmc.c:5756, 6397-6413),
+ * P [k][i][j] (src/likelihood.c:300-309), scalers [c], cijk block [lambda_re, lambda_im, c_ijk]
+ * (src/likelihood.c:9467-9468).  Tips are kept as state-set masks and expanded to the 0/1
+ * vectors the reference stores (src/mcmc.c:6350-6413).
+ */
+#include "pruning_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_MAX_INST 256
+#define ORC_TIME_MIN ((double)1.0E-11f)   /* src/bayes.h:321 (float literal) */
+#define ORC_TIME_MAX ((double)100.0f)     /* src/bayes.h:322                 */
+#define ORC_LIKE_EPSILON 1.0e-300         /* src/likelihood.c:44             */
+
+typedef struct
+    {
+    mb200_instance_config cfg;
+    int         arith;
+    uint64_t   *tips;        /* [tip][C]                                             */
+    int        *tipPartAmbig;/* [tip]: some pattern neither single state nor missing  */
+    float      *partials;    /* [interior buffer][K][C][S]                           */
+    float      *matrices;    /* [matrix][K][S][S]                                    */
+    float      *scalers;     /* [scaler][C]                                          */
+    double     *eigen;       /* [slot][2S+S^3]                                       */
+    float      *weights;     /* [row][C]                                             */
+    float      *tmp[3];      /* per-child matvec results [K][C][S]                   */
+    long long   updates;
+    } OrcInst;
+
+static OrcInst *orcTab[ORC_MAX_INST];
+
+static OrcInst *Get (int id)
+{
+    if (id < 0 || id >= ORC_MAX_INST)
+        return NULL;
+    return orcTab[id];
+}
+
+int orc_create_instance (const mb200_instance_config *c, int *instance)
+{
+    int     id, i;
+    size_t  S, K, C, nInt;
+    OrcInst *o;
+
+    if (!c || !instance)
+        return MB200_ERROR_GENERAL;
+    if (c->state_count < 2 || c->state_count > MB200_MAX_STATES || c->category_count < 1 ||
+        c->category_count > MB200_MAX_CATEGORIES || c->pattern_count < 1 || c->tip_count < 2 ||
+        c->partials_count <= c->tip_count)
+        return MB200_ERROR_OUT_OF_RANGE;
+    for (id=0; id<ORC_MAX_INST; id++)
+        if (orcTab[id] == NULL)
+            break;
+    if (id == ORC_MAX_INST)
+        return MB200_ERROR_OUT_OF_MEMORY;
+    o = (OrcInst *) calloc (1, sizeof(OrcInst));
+    o->cfg = *c;
+    o->arith = ORC_ARITH_FMA;
+    S = (size_t)c->state_count; K = (size_t)c->category_count; C = (size_t)c->pattern_count;
+    nInt = (size_t)(c->partials_count - c->tip_count);
+    o->tips         = (uint64_t *) calloc ((size_t)c->tip_count * C, sizeof(uint64_t));
+    o->tipPartAmbig = (int *)      calloc ((size_t)c->tip_count, sizeof(int));
+    o->partials     = (float *)    calloc (nInt * K * C * S, sizeof(float));
+    o->matrices     = (float *)    calloc ((size_t)c->matrix_count * K * S * S, sizeof(float));
+    o->scalers      = (float *)    calloc ((size_t)c->scaler_count * C, sizeof(float));
+    o->eigen        = (double *)   calloc ((size_t)c->eigen_count * (2*S + S*S*S), sizeof(double));
+    o->weights      = (float *)    calloc ((size_t)c->weight_rows * C, sizeof(float));
+    for (i=0; i<3; i++)
+        o->tmp[i]   = (float *)    calloc (K * C * S, sizeof(float));
+    orcTab[id] = o;
+    *instance = id;
+    return MB200_SUCCESS;
+}
+
+int orc_finalize_instance (int instance)
+{
+    int i;
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    free (o->tips); free (o->tipPartAmbig); free (o->partials); free (o->matrices);
+    free (o->scalers); free (o->eigen); free (o->weights);
+    for (i=0; i<3; i++) free (o->tmp[i]);
+    free (o);
+    orcTab[instance] = NULL;
+    return MB200_SUCCESS;
+}
+
+int orc_set_arith (int instance, int arith)
+{
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    o->arith = arith;
+    return MB200_SUCCESS;
+}
+
+long long orc_cl_updates (int instance)
+{
+    OrcInst *o = Get (instance);
+    return o ? o->updates : 0;
+}
+
+/* tip codes; isPartAmbig as SetUpTermState decides it (src/mcmc.c:18631-18651) */
+int orc_set_tip_states (int instance, int tip, const uint64_t *masks)
+{
+    int c, C, S;
+    uint64_t full, m;
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    if (tip < 0 || tip >= o->cfg.tip_count || !masks) return MB200_ERROR_OUT_OF_RANGE;
+    C = o->cfg.pattern_count; S = o->cfg.state_count;
+    full = (S == 64) ? ~(uint64_t)0 : (((uint64_t)1 << S) - 1);
+    o->tipPartAmbig[tip] = 0;
+    for (c=0; c<C; c++)
+        {
+        m = masks[c] & full;
+        o->tips[(size_t)tip*C + c] = m;
+        if (m != full && (m == 0 || (m & (m - 1)) != 0))
+            o->tipPartAmbig[tip] = 1;
+        }
+    return MB200_SUCCESS;
+}
+
+int orc_set_pattern_weights (int instance, int row, const float *w)
+{
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    if (row < 0 || row >= o->cfg.weight_rows || !w) return MB200_ERROR_OUT_OF_RANGE;
+    memcpy (o->weights + (size_t)row * o->cfg.pattern_count, w, (size_t)o->cfg.pattern_count * sizeof(float));
+    return MB200_SUCCESS;
+}
+
+int orc_set_cijk (int instance, int eigen, const double *block)
+{
+    size_t S, n;
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    if (eigen < 0 || eigen >= o->cfg.eigen_count || !block) return MB200_ERROR_OUT_OF_RANGE;
+    S = (size_t)o->cfg.state_count; n = 2*S + S*S*S;
+    memcpy (o->eigen + (size_t)eigen * n, block, n * sizeof(double));
+    return MB200_SUCCESS;
+}
+
+/* CalcCijk (src/utils.c:9734-9746): c[i][j][k] = u[i][k] * v[k][j] */
+int orc_set_eigen_decomposition (int instance, int eigen, const double *u, const double *v, const double *lam)
+{
+    size_t S, n, i, j, k;
+    double *b, *pc;
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    if (eigen < 0 || eigen >= o->cfg.eigen_count || !u || !v || !lam) return MB200_ERROR_OUT_OF_RANGE;
+    S = (size_t)o->cfg.state_count; n = 2*S + S*S*S;
+    b = o->eigen + (size_t)eigen * n;
+    for (i=0; i<S; i++) { b[i] = lam[i]; b[S+i] = 0.0; }
+    pc = b + 2*S;
+    for (i=0; i<S; i++)
+        for (j=0; j<S; j++)
+            for (k=0; k<S; k++)
+                *pc++ = u[i*S+k] * v[k*S+j];
+    return MB200_SUCCESS;
+}
+
+/* TiProbs_Gen (src/likelihood.c:9499-9542) for one branch */
+static void TiProbs (OrcInst *o, const mb200_matrix_update *mu, const mb200_evaluation *ev)
+{
+    int     S = o->cfg.state_count, K = o->cfg.category_count, i, j, k, s, index;
+    double  t, sum, e[MB200_MAX_STATES];
+    const double *lam = o->eigen + (size_t)mu->eigen * (2*(size_t)S + (size_t)S*S*S);
+    const double *ptr;
+    float  *tiP = o->matrices + (size_t)mu->matrix * K * S * S;
+
+    for (k=index=0; k<K; k++)
+        {
+        t = mu->length * ev->category_rates[k];
+        if (t < ORC_TIME_MIN)
+            {
+            for (i=0; i<S; i++)
+                for (j=0; j<S; j++)
+                    tiP[index++] = (i == j) ? 1.0f : 0.0f;
+            }
+        else if (t > ORC_TIME_MAX)
+            {
+            for (i=0; i<S; i++)
+                for (j=0; j<S; j++)
+                    tiP[index++] = (float) ev->state_freqs[j];
+            }
+        else
+            {
+            for (s=0; s<S; s++)
+                e[s] = exp (lam[s] * t);
+            ptr = lam + 2*S;
+            for (i=0; i<S; i++)
+                for (j=0; j<S; j++)
+                    {
+                    sum = 0.0;
+                    for (s=0; s<S; s++)
+                        sum += (*ptr++) * e[s];
+                    tiP[index++] = (float) ((sum < 0.0) ? 0.0 : sum);
+                    }
+            }
+        }
+}
+
+/* one child's contribution q[k][c][i] = sum_j P_k[i][j] * cl[k][c][j]
+ * interior / dense tips: CondLikeDown_Gen case 0 (src/likelihood.c:298-318) and
+ *   CondLikeDown_NUC4_FMA (src/likelihood.c:1147-1169) for the fused variant;
+ * tips without partial ambiguity when shortcuts apply: the preLike tables
+ *   (src/likelihood.c:236-260): a single observed state copies the P column, a missing
+ *   observation contributes exactly 1.0 */
+static void ChildTerm (OrcInst *o, int child, int matrix, int shortcuts, float *out)
+{
+    int     S = o->cfg.state_count, K = o->cfg.category_count, C = o->cfg.pattern_count, c, i, j, k;
+    const float *P, *cl;
+    float   x[MB200_MAX_STATES], acc;
+    uint64_t full = (S == 64) ? ~(uint64_t)0 : (((uint64_t)1 << S) - 1), m;
+    int     isTip = child < o->cfg.tip_count;
+    int     useShort = isTip && shortcuts && !o->tipPartAmbig[child];
+
+    for (k=0; k<K; k++)
+        {
+        P = o->matrices + ((size_t)matrix * K + k) * S * S;
+        for (c=0; c<C; c++)
+            {
+            float *dst = out + ((size_t)k*C + c)*S;
+            if (isTip)
+                {
+                m = o->tips[(size_t)child*C + c];
+                if (useShort && m == full)
+                    {
+                    for (i=0; i<S; i++) dst[i] = 1.0f;
+                    continue;
+                    }
+                for (j=0; j<S; j++) x[j] = ((m >> j) & 1) ? 1.0f : 0.0f;
+                cl = x;
+                }
+            else
+                cl = o->partials + ((size_t)(child - o->cfg.tip_count)*K + k)*C*S + (size_t)c*S;
+            for (i=0; i<S; i++)
+                {
+                const float *row = P + (size_t)i*S;
+                if (o->arith == ORC_ARITH_FMA && S == 4)
+                    {
+                    acc = row[0] * cl[0];
+                    acc = fmaf (row[1], cl[1], acc);
+                    acc = fmaf (row[2], cl[2], acc);
+                    acc = fmaf (row[3], cl[3], acc);
+                    }
+                else if (S == 4)
+                    {
+                    /* CondLikeDown_NUC4_SSE / _AVX: first product, then mul + add */
+                    acc = row[0] * cl[0];
+                    acc = row[1] * cl[1] + acc;
+                    acc = row[2] * cl[2] + acc;
+                    acc = row[3] * cl[3] + acc;
+                    }
+                else
+                    {
+                    acc = 0.0f;
+                    for (j=0; j<S; j++)
+                        acc = row[j] * cl[j] + acc;
+                    }
+                dst[i] = acc;
+                }
+            }
+        }
+}
+
+/* one interior node: CondLikeDown / CondLikeRoot, RemoveNodeScalers, CondLikeScaler
+ * (src/likelihood.c:7920-7965) */
+static void Operation (OrcInst *o, const mb200_operation *op, const mb200_evaluation *ev, float *lnScaler)
+{
+    int     S = o->cfg.state_count, K = o->cfg.category_count, C = o->cfg.pattern_count, c, k, s;
+    size_t  n = (size_t)K * C * S, idx;
+    int     shortcuts = (ev->flags & MB200_FLAG_TIP_SHORTCUTS) != 0;
+    float  *dst = o->partials + (size_t)(op->dest - o->cfg.tip_count) * n;
+    float   scaler, *scP;
+
+    ChildTerm (o, op->child1, op->matrix1, shortcuts, o->tmp[0]);
+    ChildTerm (o, op->child2, op->matrix2, shortcuts, o->tmp[1]);
+    if (op->child3 != MB200_NONE)
+        {
+        ChildTerm (o, op->child3, op->matrix3, shortcuts, o->tmp[2]);
+        for (idx=0; idx<n; idx++)
+            dst[idx] = o->tmp[0][idx] * o->tmp[1][idx] * o->tmp[2][idx];
+        }
+    else
+        {
+        for (idx=0; idx<n; idx++)
+            dst[idx] = o->tmp[0][idx] * o->tmp[1][idx];
+        }
+    o->updates += (long long) K * C;
+
+    /* RemoveNodeScalers (src/likelihood.c:7981-8002) */
+    if (op->scale_remove != MB200_NONE && lnScaler)
+        {
+        scP = o->scalers + (size_t)op->scale_remove * C;
+        for (c=0; c<C; c++)
+            lnScaler[c] -= scP[c];
+        }
+    /* CondLikeScaler_* (src/likelihood.c:4939-4990, 5202-5262) */
+    if (op->scale_write != MB200_NONE)
+        {
+        scP = o->scalers + (size_t)op->scale_write * C;
+        for (c=0; c<C; c++)
+            {
+            scaler = 0.0f;
+            for (k=0; k<K; k++)
+                for (s=0; s<S; s++)
+                    if (dst[((size_t)k*C + c)*S + s] > scaler)
+                        scaler = dst[((size_t)k*C + c)*S + s];
+            for (k=0; k<K; k++)
+                for (s=0; s<S; s++)
+                    dst[((size_t)k*C + c)*S + s] /= scaler;
+            if (o->arith == ORC_ARITH_FMA && S == 4)
+                scP[c] = logf (scaler);              /* CondLikeScaler_NUC4_AVX :5257 */
+            else
+                scP[c] = (float) log (scaler);       /* _Gen_SSE :5055, _NUC4_SSE :5328 */
+            if (lnScaler)
+                lnScaler[c] += scP[c];
+            }
+        }
+}
+
+/* Likelihood_NUC4_{FMA,SSE} (src/likelihood.c:6468-6625, 6804-6960) and
+ * Likelihood_Gen_SSE / Likelihood_Gen (src/likelihood.c:5926-6090, 5764-5916) */
+static int RootLikelihood (OrcInst *o, const mb200_evaluation *ev, const float *lnScaler, double *lnL)
+{
+    int     S = o->cfg.state_count, K = o->cfg.category_count, C = o->cfg.pattern_count, c, k, s, t, equal = 1;
+    size_t  n = (size_t)K * C * S;
+    const float *cl = o->partials + (size_t)(ev->root_buffer - o->cfg.tip_count) * n;
+    const float *w = o->weights + (size_t)ev->weights_row * C;
+    float   bs[MB200_MAX_STATES], likeF, catLike, likeIF;
+    double  like, likeI, lnLike, sum = 0.0;
+    uint64_t inv;
+    int     quirk = (ev->flags & MB200_FLAG_NUC4_PINVAR_QUIRK) != 0;
+
+    for (s=0; s<S; s++) bs[s] = (float) ev->state_freqs[s];
+    for (k=1; k<K; k++) if (ev->category_weights[k] != ev->category_weights[0]) equal = 0;
+
+    for (c=0; c<C; c++)
+        {
+        if (S == 4 && equal)
+            {
+            likeF = 0.0f;
+            for (k=0; k<K; k++)
+                for (s=0; s<4; s++)
+                    {
+                    if (o->arith == ORC_ARITH_FMA)
+                        likeF = fmaf (cl[((size_t)k*C + c)*4 + s], bs[s], likeF);
+                    else
+                        likeF = cl[((size_t)k*C + c)*4 + s] * bs[s] + likeF;
+                    }
+            likeF = likeF * (float) ev->category_weights[0];
+            }
+        else
+            {
+            likeF = 0.0f;
+            for (k=0; k<K; k++)
+                {
+                catLike = 0.0f;
+                for (s=0; s<S; s++)
+                    catLike = catLike + cl[((size_t)k*C + c)*S + s] * bs[s];
+                likeF = likeF + catLike * (float) ev->category_weights[k];
+                }
+            }
+        like = (double) likeF;
+        likeI = 0.0;
+        if (ev->has_p_invar)
+            {
+            /* invariable-site CL = AND of the tip sets (InitInvCondLikes, src/mcmc.c:6712-6790) */
+            inv = ~(uint64_t)0;
+            for (t=0; t<o->cfg.tip_count; t++)
+                inv &= o->tips[(size_t)t*C + c];
+            if (S == 4)
+                {
+                likeIF = ((inv & 1) ? 1.0f : 0.0f) * bs[0];
+                for (s=1; s<4; s++)
+                    {
+                    if (o->arith == ORC_ARITH_FMA)
+                        likeIF = fmaf (((inv >> s) & 1) ? 1.0f : 0.0f, bs[s], likeIF);
+                    else
+                        likeIF = (((inv >> s) & 1) ? 1.0f : 0.0f) * bs[s] + likeIF;
+                    }
+                likeIF = likeIF * (float) ev->p_invar;
+                likeI = (double) likeIF;
+                }
+            else
+                {
+                for (s=0; s<S; s++)
+                    if ((inv >> s) & 1)
+                        likeI += ev->state_freqs[s] * ev->p_invar;
+                }
+            }
+
+        if (!ev->has_p_invar)
+            {
+            if (like < ORC_LIKE_EPSILON)
+                { *lnL = -DBL_MAX; return MB200_EVAL_UNDERFLOW; }
+            lnLike = lnScaler[c] + log (like);
+            }
+        else if (quirk)
+            {
+            if (lnScaler[c] < -200)
+                {
+                if (likeI > 1E-70)
+                    like = likeI;
+                }
+            else
+                like = like + (likeI / exp (lnScaler[c]));
+            if (like < ORC_LIKE_EPSILON)
+                { *lnL = -DBL_MAX; return MB200_EVAL_UNDERFLOW; }
+            lnLike = lnScaler[c] + log (like);
+            }
+        else
+            {
+            if (lnScaler[c] < -200.0)
+                {
+                if (likeI > 1E-70)
+                    lnLike = log (likeI);
+                else
+                    lnLike = log (like) + lnScaler[c];
+                }
+            else
+                lnLike = log (like + (likeI / exp (lnScaler[c]))) + lnScaler[c];
+            if (like < ORC_LIKE_EPSILON)
+                { *lnL = -DBL_MAX; return MB200_EVAL_UNDERFLOW; }
+            }
+        sum += lnLike * w[c];
+        }
+    *lnL = sum;
+    return MB200_EVAL_OK;
+}
+
+/* LaunchLogLikeForDivision (src/likelihood.c:7851-7973), one call per evaluation */
+int orc_evaluate (int instance, const mb200_evaluation *evs, int count, double *lnL, int *status)
+{
+    int     e, i, C;
+    float  *lnScaler, *zero = NULL;
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    C = o->cfg.pattern_count;
+    for (e=0; e<count; e++)
+        {
+        const mb200_evaluation *ev = &evs[e];
+        for (i=0; i<ev->matrix_update_count; i++)
+            TiProbs (o, &ev->matrix_updates[i], ev);
+        /* FlipSiteScalerSpace + ResetSiteScalers | CopySiteScalers (src/likelihood.c:7885-7889) */
+        if (ev->site_scaler_dst != MB200_NONE)
+            {
+            lnScaler = o->scalers + (size_t)ev->site_scaler_dst * C;
+            if (ev->site_scaler_src == MB200_NONE)
+                memset (lnScaler, 0, (size_t)C * sizeof(float));
+            else if (ev->site_scaler_src != ev->site_scaler_dst)
+                memcpy (lnScaler, o->scalers + (size_t)ev->site_scaler_src * C, (size_t)C * sizeof(float));
+            }
+        else
+            {
+            zero = (float *) calloc ((size_t)C, sizeof(float));
+            if (ev->site_scaler_src != MB200_NONE)
+                memcpy (zero, o->scalers + (size_t)ev->site_scaler_src * C, (size_t)C * sizeof(float));
+            lnScaler = zero;
+            }
+        for (i=0; i<ev->operation_count; i++)
+            Operation (o, &ev->operations[i], ev, lnScaler);
+        if (ev->root_buffer != MB200_NONE)
+            {
+            int st = RootLikelihood (o, ev, lnScaler, &lnL[e]);
+            if (status) status[e] = st;
+            }
+        else
+            {
+            if (lnL) lnL[e] = 0.0;
+            if (status) status[e] = MB200_EVAL_OK;
+            }
+        free (zero); zero = NULL;
+        }
+    return MB200_SUCCESS;
+}
+
+int orc_get_partials (int instance, int buffer, float *out)
+{
+    size_t n;
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    if (buffer < o->cfg.tip_count || buffer >= o->cfg.partials_count) return MB200_ERROR_OUT_OF_RANGE;
+    n = (size_t)o->cfg.category_count * o->cfg.pattern_count * o->cfg.state_count;
+    memcpy (out, o->partials + (size_t)(buffer - o->cfg.tip_count) * n, n * sizeof(float));
+    return MB200_SUCCESS;
+}
+
+int orc_set_partials (int instance, int buffer, const float *in)
+{
+    size_t n;
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    if (buffer < o->cfg.tip_count || buffer >= o->cfg.partials_count) return MB200_ERROR_OUT_OF_RANGE;
+    n = (size_t)o->cfg.category_count * o->cfg.pattern_count * o->cfg.state_count;
+    memcpy (o->partials + (size_t)(buffer - o->cfg.tip_count) * n, in, n * sizeof(float));
+    return MB200_SUCCESS;
+}
+
+int orc_get_transition_matrix (int instance, int matrix, float *out)
+{
+    size_t n;
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    if (matrix < 0 || matrix >= o->cfg.matrix_count) return MB200_ERROR_OUT_OF_RANGE;
+    n = (size_t)o->cfg.category_count * o->cfg.state_count * o->cfg.state_count;
+    memcpy (out, o->matrices + (size_t)matrix * n, n * sizeof(float));
+    return MB200_SUCCESS;
+}
+
+int orc_get_scalers (int instance, int scaler, float *out)
+{
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    if (scaler < 0 || scaler >= o->cfg.scaler_count) return MB200_ERROR_OUT_OF_RANGE;
+    memcpy (out, o->scalers + (size_t)scaler * o->cfg.pattern_count, (size_t)o->cfg.pattern_count * sizeof(float));
+    return MB200_SUCCESS;
+}
+
+/* CompressData's uniqueness scan (src/model.c:2618-2686): a column joins the FIRST earlier
+ * column that is identical over all taxa, otherwise it becomes a new pattern; weights are
+ * integer site counts (tempSitesOfPat). */
+int orc_compress_patterns (const uint64_t *matrix, int n_taxa, int n_sites,
+                           int *pattern_of_site, int *first_site_of_pattern, int *weights)
+{
+    int site, p, t, nPat = 0, same;
+    for (site=0; site<n_sites; site++)
+        {
+        same = 0;
+        for (p=0; p<nPat; p++)
+            {
+            same = 1;
+            for (t=0; t<n_taxa; t++)
+                if (matrix[(size_t)t*n_sites + site] != matrix[(size_t)t*n_sites + first_site_of_pattern[p]])
+                    { same = 0; break; }
+            if (same)
+                break;
+            }
+        if (same)
+            {
+            weights[p]++;
+            pattern_of_site[site] = p;
+            }
+        else
+            {
+            first_site_of_pattern[nPat] = site;
+            weights[nPat] = 1;
+            pattern_of_site[site] = nPat;
+            nPat++;
+            }
+        }
+    return nPat;
+}
