@@ -234,6 +234,12 @@ int mb200_synchronize      (int instance);
 int mb200_get_stream       (int instance, void **stream);
 /* kernels launched by the instance since creation (bench.py's gpu_launches) */
 int mb200_get_launch_count (int instance, long long *launches);
+/* Device-side timing of the dominant (fused pruning) kernel: when enabled, every launch of
+ * it is bracketed by CUDA events on the instance's stream.  mb200_get_kernel_time
+ * synchronises, returns the summed duration (ms) and the number of launches measured since
+ * the last call, and clears the measurements (at most the 2048 most recent launches are kept). */
+int mb200_set_kernel_timing (int instance, int enabled);
+int mb200_get_kernel_time   (int instance, double *milliseconds, int *launches);
 
 #ifdef __cplusplus
 }

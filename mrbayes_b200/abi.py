@@ -130,6 +130,8 @@ class Library:
             "synchronize": [I],
             "get_stream": [I, P(C.c_void_p)],
             "get_launch_count": [I, P(C.c_longlong)],
+            "set_kernel_timing": [I, I],
+            "get_kernel_time": [I, P(D), P(I)],
             "device_count": [],
             "abi_version": [],
             # oracle only
@@ -326,6 +328,16 @@ class Instance:
         n = C.c_longlong(0)
         self._call("get_launch_count", C.byref(n))
         return n.value
+
+    def set_kernel_timing(self, on: bool):
+        self._call("set_kernel_timing", 1 if on else 0)
+
+    def kernel_time(self):
+        """-> (summed ms, launches) of the fused pruning kernel since the last call."""
+        ms = C.c_double(0.0)
+        n = C.c_int(0)
+        self._call("get_kernel_time", C.byref(ms), C.byref(n))
+        return ms.value, n.value
 
     # -- node-granular verbs --------------------------------------------------------------
     def update_transition_matrices(self, mats, rates, freqs=None):

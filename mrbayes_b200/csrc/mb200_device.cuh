@@ -64,6 +64,7 @@ struct DevCtx                       // instance geometry + buffer bases, passed 
     int numTiles;
     const uint8_t  *tip8;
     const uint64_t *tip64;
+    const int      *tipPartAmbig;   // [tip] 1: some pattern is partially ambiguous (isPartAmbig)
     float          *partials;
     float          *matrices;
     float          *scalers;

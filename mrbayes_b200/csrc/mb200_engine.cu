@@ -39,6 +39,7 @@ struct Instance
     cudaStream_t  stream = nullptr;
     uint8_t      *dTip8 = nullptr;
     uint64_t     *dTip64 = nullptr;
+    int          *dTipPartAmbig = nullptr;
     float        *dPartials = nullptr, *dMatrices = nullptr, *dScalers = nullptr, *dWeights = nullptr;
     double       *dEigen = nullptr;
     uint64_t     *dInvMask = nullptr;
@@ -54,12 +55,16 @@ struct Instance
     std::vector<Batch *> batches;      // resident batches (mb200_pack_evaluations)
     void         *hostStage = nullptr; // pinned staging for set/get calls
     size_t        hostStageBytes = 0;
+    bool          timing = false;      // bracket the fused kernel with events
+    std::vector<cudaEvent_t> evA, evB; // ring of event pairs
+    long long     evCount = 0;         // pairs recorded since the last read
 };
 
 std::mutex               gLock;
 std::vector<Instance *>  gInstances;
 
 const int NT_SMALL = 32, NT_LARGE = 128, NT_GEN = 256;
+const int EV_RING = 2048;
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     fprintf (stderr, "mb200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorName (e_), __FILE__, __LINE__, cudaGetErrorString (e_)); \
@@ -272,6 +277,9 @@ int launch (Instance *I, Batch &b)
         CK (cudaGetLastError ());
         I->launches++;
         }
+    const int evSlot = (int)(I->evCount % EV_RING);
+    if (I->timing)
+        CK (cudaEventRecord (I->evA[evSlot], I->stream));
     if (ctx.S == 4 && ctx.K <= 8)
         {
         // small problems: one warp per CTA spreads the latency-bound work over more SMs
@@ -297,6 +305,11 @@ int launch (Instance *I, Batch &b)
         }
     CK (cudaGetLastError ());
     I->launches++;
+    if (I->timing)
+        {
+        CK (cudaEventRecord (I->evB[evSlot], I->stream));
+        I->evCount++;
+        }
     return MB200_SUCCESS;
 }
 
@@ -339,10 +352,12 @@ void destroy (Instance *I)
     if (I->stream) cudaStreamSynchronize (I->stream);
     freeBatch (I->scratch);
     for (Batch *b : I->batches) if (b) { freeBatch (*b); delete b; }
-    cudaFree (I->dTip8); cudaFree (I->dTip64); cudaFree (I->dPartials); cudaFree (I->dMatrices);
+    cudaFree (I->dTip8); cudaFree (I->dTip64); cudaFree (I->dTipPartAmbig); cudaFree (I->dPartials); cudaFree (I->dMatrices);
     cudaFree (I->dScalers); cudaFree (I->dWeights); cudaFree (I->dEigen); cudaFree (I->dInvMask);
     cudaFree (I->dTilePartial); cudaFree (I->dTileAbort); cudaFree (I->dTicket);
     if (I->hostStage) cudaFreeHost (I->hostStage);
+    for (cudaEvent_t e : I->evA) cudaEventDestroy (e);
+    for (cudaEvent_t e : I->evB) cudaEventDestroy (e);
     if (I->stream) cudaStreamDestroy (I->stream);
     delete I;
 }
@@ -418,7 +433,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
 
     // tile geometry of the generic kernel: keep P + child tile + product under ~96 KB
     int TP = 32;
-    auto smemFor = [&] (int tp) { return sizeof(float) * ((size_t)S*S + (size_t)tp*(Sp+1) + (size_t)K*tp*S + 2*(size_t)tp); };
+    auto smemFor = [&] (int tp) { return sizeof(float) * ((size_t)S*S + (size_t)tp*(Sp+1) + (size_t)K*tp*S + 3*(size_t)tp); };
     while (TP > 1 && smemFor (TP) > 96*1024) TP >>= 1;
     I->smemGen = smemFor (TP);
     const bool nuc4 = (S == 4 && K <= 8);
@@ -429,6 +444,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     if (cudaStreamCreateWithFlags (&I->stream, cudaStreamNonBlocking) != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
     ALLOC (I->dTip8,     (size_t)cfg->tip_count * C);
     ALLOC (I->dTip64,    (size_t)cfg->tip_count * C * sizeof(uint64_t));
+    ALLOC (I->dTipPartAmbig, (size_t)cfg->tip_count * sizeof(int));
     ALLOC (I->dPartials, nInt * K * C * Sp * sizeof(float));
     ALLOC (I->dMatrices, (size_t)cfg->matrix_count * K * S * S * sizeof(float));
     ALLOC (I->dScalers,  (size_t)cfg->scaler_count * C * sizeof(float));
@@ -441,6 +457,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
 #undef ALLOC
     cudaMemsetAsync (I->dTip8, 0, (size_t)cfg->tip_count * C, I->stream);
     cudaMemsetAsync (I->dTip64, 0, (size_t)cfg->tip_count * C * sizeof(uint64_t), I->stream);
+    cudaMemsetAsync (I->dTipPartAmbig, 0, (size_t)cfg->tip_count * sizeof(int), I->stream);
     cudaMemsetAsync (I->dPartials, 0, nInt * K * C * Sp * sizeof(float), I->stream);
     cudaMemsetAsync (I->dMatrices, 0, (size_t)cfg->matrix_count * K * S * S * sizeof(float), I->stream);
     cudaMemsetAsync (I->dScalers, 0, (size_t)cfg->scaler_count * C * sizeof(float), I->stream);
@@ -461,7 +478,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     x.scalerCount = cfg->scaler_count; x.eigenCount = cfg->eigen_count; x.weightRows = cfg->weight_rows;
     x.tilePatterns = nuc4 ? NT_SMALL : TP;
     x.numTiles = I->maxTiles;
-    x.tip8 = I->dTip8; x.tip64 = I->dTip64; x.partials = I->dPartials; x.matrices = I->dMatrices;
+    x.tip8 = I->dTip8; x.tip64 = I->dTip64; x.tipPartAmbig = I->dTipPartAmbig; x.partials = I->dPartials; x.matrices = I->dMatrices;
     x.scalers = I->dScalers; x.eigen = I->dEigen; x.weights = I->dWeights; x.invMask = I->dInvMask;
     x.tilePartial = I->dTilePartial; x.tileAbort = I->dTileAbort; x.ticket = I->dTicket;
 
@@ -500,11 +517,15 @@ int mb200_set_tip_states (int instance, int tip, const uint64_t *masks)
     uint64_t *h64 = (uint64_t *) I->hostStage;
     uint8_t  *h8  = (uint8_t *)(h64 + C);
     const uint64_t full = (I->cfg.state_count == 64) ? ~(uint64_t)0 : (((uint64_t)1 << I->cfg.state_count) - 1);
+    int partAmbig = 0;      // isPartAmbig of SetUpTermState (src/mcmc.c:18631-18651)
     for (int c = 0; c < C; c++)
         {
         h64[c] = masks[c] & full;
         h8[c]  = (uint8_t)(h64[c] & 0xff);
+        if (h64[c] != full && (h64[c] == 0 || (h64[c] & (h64[c] - 1)) != 0))
+            partAmbig = 1;
         }
+    CK (cudaMemcpyAsync (I->dTipPartAmbig + tip, &partAmbig, sizeof(int), cudaMemcpyHostToDevice, I->stream));
     CK (cudaMemcpyAsync (I->dTip64 + (size_t)tip * C, h64, (size_t)C * 8, cudaMemcpyHostToDevice, I->stream));
     CK (cudaMemcpyAsync (I->dTip8 + (size_t)tip * C, h8, (size_t)C, cudaMemcpyHostToDevice, I->stream));
     CK (cudaStreamSynchronize (I->stream));
@@ -814,6 +835,46 @@ int mb200_get_launch_count (int instance, long long *launches)
     Instance *I = get (instance);
     if (!I || !launches) return MB200_ERROR_BAD_INSTANCE;
     *launches = I->launches;
+    return MB200_SUCCESS;
+}
+
+int mb200_set_kernel_timing (int instance, int enabled)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    int rc = use (I); if (rc) return rc;
+    CK (cudaStreamSynchronize (I->stream));
+    if (enabled && I->evA.empty ())
+        {
+        I->evA.resize (EV_RING); I->evB.resize (EV_RING);
+        for (int i = 0; i < EV_RING; i++)
+            {
+            CK (cudaEventCreate (&I->evA[i]));
+            CK (cudaEventCreate (&I->evB[i]));
+            }
+        }
+    I->timing = enabled != 0;
+    I->evCount = 0;
+    return MB200_SUCCESS;
+}
+
+int mb200_get_kernel_time (int instance, double *milliseconds, int *launches)
+{
+    Instance *I = get (instance);
+    if (!I || !milliseconds || !launches) return MB200_ERROR_BAD_INSTANCE;
+    int rc = use (I); if (rc) return rc;
+    CK (cudaStreamSynchronize (I->stream));
+    long long n = I->evCount < EV_RING ? I->evCount : EV_RING;
+    double tot = 0.0;
+    for (long long i = 0; i < n; i++)
+        {
+        float ms = 0.0f;
+        CK (cudaEventElapsedTime (&ms, I->evA[i], I->evB[i]));
+        tot += ms;
+        }
+    *milliseconds = tot;
+    *launches = (int) n;
+    I->evCount = 0;
     return MB200_SUCCESS;
 }
 

@@ -26,6 +26,7 @@
 #define MB200_TIME_MAX ((double)100.0f)     /* TIME_MAX, src/bayes.h:322                    */
 #define MB200_LIKE_EPSILON 1.0e-300         /* src/likelihood.c:44                           */
 #define MB200_QUIRK_FLAG 1
+#define MB200_SHORTCUT_FLAG 2                /* MB200_FLAG_TIP_SHORTCUTS */
 
 // ---------------------------------------------------------------------------------------
 // K1: transition matrices.  grid = (matrix updates, K), block = 128.
@@ -254,6 +255,9 @@ eval_nuc4_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const DevOp *__
             const float4 *P4 = reinterpret_cast<const float4 *>(ctx.matrices + (size_t)mat * K * 16);
             if (child < ctx.tipCount)
                 {
+                // scalar-kernel shortcut: a missing observation on a tip without partial
+                // ambiguity is exactly 1.0 (preLike tables, src/likelihood.c:816-832)
+                const bool shortcut = (ev->flags & MB200_SHORTCUT_FLAG) && !ctx.tipPartAmbig[child];
                 for (int e = threadIdx.x; e < K*64; e += NT)
                     {
                     const int i = e & 3, mask = (e >> 2) & 15, k = e >> 6;
@@ -262,6 +266,7 @@ eval_nuc4_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const DevOp *__
                     if (mask & 2) r += row.y;                     // selected columns == dense
                     if (mask & 4) r += row.z;                     // 0/1 matvec, bit for bit
                     if (mask & 8) r += row.w;
+                    if (shortcut && mask == 15) r = 1.0f;
                     reinterpret_cast<float *>(&sLut[pb][ch][k][mask])[i] = r;
                     }
                 }
@@ -458,6 +463,8 @@ eval_gen_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const DevOp *__r
     float *sProd = sCh + TP*ldc;                  // [K][TP][S]
     float *sMax  = sProd + (size_t)K*TP*S;        // [TP]
     float *sSite = sMax + TP;                     // [TP]
+    int   *sFull = reinterpret_cast<int *>(sSite + TP);   // [TP] tip shortcut: pattern is missing
+    const uint64_t fullMask = (S == 64) ? ~(uint64_t)0 : ((((uint64_t)1) << S) - 1);
 
     const DevEval *ev = evals + blockIdx.y;
     const int   c0 = blockIdx.x * TP;
@@ -482,13 +489,17 @@ eval_gen_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const DevOp *__r
                 const float *P = ctx.matrices + ((size_t)mat * K + k) * S * S;
                 for (int idx = threadIdx.x; idx < S*S; idx += NT)
                     sPm[idx] = P[idx];
-                if (child < ctx.tipCount)
+                const bool isTip = child < ctx.tipCount;
+                const bool shortcut = isTip && (ev->flags & MB200_SHORTCUT_FLAG) && !ctx.tipPartAmbig[child];
+                if (isTip)
                     {
                     for (int idx = threadIdx.x; idx < np*S; idx += NT)
                         {
                         const int p = idx / S, j = idx % S;
                         const uint64_t m = ctx.tip64[(size_t)child * C + c0 + p];
                         sCh[p*ldc + j] = ((m >> j) & 1) ? 1.0f : 0.0f;
+                        if (j == 0)
+                            sFull[p] = (shortcut && m == fullMask) ? 1 : 0;
                         }
                     }
                 else
@@ -511,6 +522,8 @@ eval_gen_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const DevOp *__r
                     float acc = 0.0f;
                     for (int j = 0; j < S; j++)
                         acc = fmaf (prow[j], crow[j], acc);
+                    if (isTip && sFull[p])
+                        acc = 1.0f;                 // preLike shortcut (src/likelihood.c:257-258)
                     float *dst = sProd + ((size_t)k*TP + p)*S + i;
                     *dst = (ch == 0) ? acc : (*dst) * acc;
                     }
