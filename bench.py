@@ -443,7 +443,7 @@ def bench_engine(args):
             "gpu_launches": all_launches,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": (ach / peaks["hbm_gbs"]) if ach else None, "traffic": None,
-                         "kernel": "eval_nuc4_kernel<4,32>", "avg_kernel_us": k_avg_s * 1e6, "launches_timed": kt_n,
+                         "kernel": "eval_nuc4_kernel<4,128,64>", "avg_kernel_us": k_avg_s * 1e6, "launches_timed": kt_n,
                          "bytes_per_update": BYTES_PER_UPDATE[4], "peak_source": peaks["which"],
                          "note": "latency-bound by construction: 2.7 MB working set, ~42 dirty nodes x 413 patterns per launch"},
             "clocks": clocks,
@@ -466,8 +466,8 @@ class pack_bytes:
         a16 = lambda x: (x + 15) & ~15
         n_mat = sum(len(s.mats) for s in specs)
         n_op = sum(len(s.ops) for s in specs)
-        dev_eval = 56 + 8 * (20 + 20 + 64)
-        self.bytes = a16(a16(a16(16 + 0) + dev_eval * len(specs)) + 32 * n_mat) + 48 * n_op
+        n_dbl = sum(len(s.rates) + len(s.cat_weights) + len(s.freqs) for s in specs)
+        self.bytes = a16(a16(a16(a16(16) + 80 * len(specs)) + 8 * n_dbl) + 16 * n_mat) + 48 * n_op
 
 
 def main():

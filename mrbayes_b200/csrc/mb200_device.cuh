@@ -22,38 +22,53 @@
 #define MB200_DEV_MAX_CATS   20
 #define MB200_DEV_MAX_STATES 64
 
-struct DevEval                      // one LaunchLogLikeForDivision
+struct DevEval                      // one LaunchLogLikeForDivision (80 bytes)
 {
     int    nMat, matOff;            // matrix updates [matOff, matOff+nMat) of the batch
     int    nOp,  opOff;             // operations     [opOff,  opOff+nOp)
     int    siteDst, siteSrc;        // -1: do not store / start from zero
     int    root, weightsRow;        // root -1: no root integration
     int    flags, hasPInvar;
-    int    equalWeights, pad0;
+    int    equalWeights;
+    int    dOff;                    // doubles [dOff ...): rates[K], catW[K], freqs[S]
     double pInvar;
-    double rates  [MB200_DEV_MAX_CATS];
-    double catW   [MB200_DEV_MAX_CATS];
-    double freqs  [MB200_DEV_MAX_STATES];
-};
-
-struct DevMat                       // one P(t) rebuild
-{
-    int    matrix, eigen;
-    double length;
-    int    eval;                    // which DevEval supplies rates / freqs
+    int    fuseP;                   // 1: the pruning kernel rebuilds this evaluation's P(t) itself
+    int    nClean;                  // fused only: clean matrices listed after the nMat dirty ones
+                                    // (copied to shared memory so every node finds its P(t) in a slot)
+    int    eigen0;                  // eigen slot of the first matrix update (normally of all of them)
     int    pad[3];
 };
 
-struct DevOp                        // one interior-node update
+struct DevMat                       // one P(t) rebuild (16 bytes)
+{
+    int    matrix, eigen;
+    double length;
+};
+
+struct DevOp                        // one interior-node update (48 bytes)
 {
     int dest, c1, m1, c2, m2, c3, m3, sw, sr;
-    int pad[3];
+    int s1, s2, s3;                 // fused launches: shared-memory slot of m1/m2/m3 (index into the
+                                    // evaluation's matrix list, dirty first, then clean); else -1
 };
+
+struct DevResult                    // 16 bytes per evaluation
+{
+    double lnL;
+    int    status;
+    int    seq;                     // launch sequence number, written LAST: a host polling the
+                                    // (mapped, pinned) result sees lnL/status complete once seq matches
+};
+
+// Job descriptors handed over as a kernel parameter (constant bank) instead of a host->device
+// copy: removes one stream operation from the latency path of small evaluations.
+template <int CAP> struct ParamBlob { char bytes[CAP]; };
+struct BlobOffsets { int eval, dbl, mat, op; };
 
 struct DevBatchHeader
 {
-    int nEval, nMat, nOp, pad;
-    // followed by DevEval[nEval], DevMat[nMat], DevOp[nOp] (each 16-byte aligned)
+    int nEval, nMat, nOp, nDbl;
+    // followed by DevEval[nEval], double[nDbl], DevMat[nMat], DevOp[nOp] (each 16-byte aligned)
 };
 
 struct DevCtx                       // instance geometry + buffer bases, passed by value
@@ -64,6 +79,8 @@ struct DevCtx                       // instance geometry + buffer bases, passed 
     int numTiles;
     const uint8_t  *tip8;
     const uint64_t *tip64;
+    const float4   *tipDense4;      // [tip][C] 0/1 state vectors (S = 4 only): dense tips for the
+                                    // latency-bound kernel (uniform child handling, no mask branches)
     const int      *tipPartAmbig;   // [tip] 1: some pattern is partially ambiguous (isPartAmbig)
     float          *partials;
     float          *matrices;
@@ -74,6 +91,7 @@ struct DevCtx                       // instance geometry + buffer bases, passed 
     double         *tilePartial;    // [maxEval][numTiles] per-tile lnL partial sums
     int            *tileAbort;      // [maxEval][numTiles]
     unsigned int   *ticket;         // [maxEval]
+    unsigned long long *dbg;        // [maxEval][64] phase timestamps (MB200_PHASE_TIMING builds only)
 };
 
 static inline size_t mb200_align16 (size_t x) { return (x + 15) & ~(size_t)15; }

@@ -22,13 +22,16 @@ struct Batch                       // packed evaluations (device job format)
     char   *dBlob  = nullptr;      // device copy
     size_t  cap    = 0;            // bytes allocated
     size_t  bytes  = 0;            // bytes used
-    int     nEval = 0, nMat = 0, nOp = 0;
-    size_t  offEval = 0, offMat = 0, offOp = 0;
-    double *dLnL   = nullptr;      // [capEval]
-    int    *dStatus = nullptr;
-    double *hLnL   = nullptr;      // pinned
-    int    *hStatus = nullptr;
+    int     nEval = 0, nMat = 0, nOp = 0, nDbl = 0;
+    size_t  offEval = 0, offDbl = 0, offMat = 0, offOp = 0;
+    DevResult *dRes = nullptr;     // [capEval] results in HBM (device-resident replay)
+    DevResult *hRes = nullptr;     // [capEval] pinned + mapped: kernels of the host-call path write
+                                   // results straight into host memory, the caller polls `seq`
+    DevResult *hResDev = nullptr;  // device alias of hRes
     int     capEval = 0;
+    int     nDirty = 0;            // P(t) rebuilds in the batch
+    bool    fused = false;         // 4-state latency path: P(t) rebuilt inside the pruning kernel
+    bool    needInv = false;
     bool    used = false;
 };
 
@@ -40,12 +43,15 @@ struct Instance
     uint8_t      *dTip8 = nullptr;
     uint64_t     *dTip64 = nullptr;
     int          *dTipPartAmbig = nullptr;
+    float4       *dTipDense = nullptr;   // S = 4 only
+    int           seq = 0;               // launch sequence number stamped into results
     float        *dPartials = nullptr, *dMatrices = nullptr, *dScalers = nullptr, *dWeights = nullptr;
     double       *dEigen = nullptr;
     uint64_t     *dInvMask = nullptr;
     double       *dTilePartial = nullptr;
     int          *dTileAbort = nullptr;
     unsigned int *dTicket = nullptr;
+    unsigned long long *dDbg = nullptr;
     bool          invMaskValid = false;
     int           maxEval = 1, maxTiles = 1, numSMs = 148;
     size_t        eigenStride = 0;     // doubles per eigen slot
@@ -55,6 +61,8 @@ struct Instance
     std::vector<Batch *> batches;      // resident batches (mb200_pack_evaluations)
     void         *hostStage = nullptr; // pinned staging for set/get calls
     size_t        hostStageBytes = 0;
+    std::vector<int> slotOf;           // scratch: matrix index -> shared-memory slot in the current evaluation
+    std::vector<int> slotTmp, cleanTmp, nCleanTmp;
     bool          timing = false;      // bracket the fused kernel with events
     std::vector<cudaEvent_t> evA, evB; // ring of event pairs
     long long     evCount = 0;         // pairs recorded since the last read
@@ -63,12 +71,23 @@ struct Instance
 std::mutex               gLock;
 std::vector<Instance *>  gInstances;
 
-const int NT_SMALL = 32, NT_LARGE = 128, NT_GEN = 256;
+const int NT_NUC4 = 128, NT_GEN = 256;
+#ifndef MB200_NT_SMALL
+#define MB200_NT_SMALL 256
+#endif
+const int NT_SMALL = MB200_NT_SMALL;   // threads per CTA of the 4-state latency kernel
 const int EV_RING = 2048;
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     fprintf (stderr, "mb200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorName (e_), __FILE__, __LINE__, cudaGetErrorString (e_)); \
     return MB200_ERROR_CUDA; } } while (0)
+
+// patterns one CTA of a 4-state kernel owns: NT threads / lanes-per-pattern (pow2ceil(K))
+int nuc4PatternsPerBlock (int K, bool small)
+{
+    int L = (K <= 1) ? 1 : (K <= 2) ? 2 : (K <= 4) ? 4 : 8;
+    return (small ? NT_SMALL : NT_NUC4) / L;
+}
 
 Instance *get (int id)
 {
@@ -99,10 +118,8 @@ void freeBatch (Batch &b)
 {
     if (b.hBlob)   cudaFreeHost (b.hBlob);
     if (b.dBlob)   cudaFree (b.dBlob);
-    if (b.dLnL)    cudaFree (b.dLnL);
-    if (b.dStatus) cudaFree (b.dStatus);
-    if (b.hLnL)    cudaFreeHost (b.hLnL);
-    if (b.hStatus) cudaFreeHost (b.hStatus);
+    if (b.dRes)    cudaFree (b.dRes);
+    if (b.hRes)    cudaFreeHost (b.hRes);
     b = Batch ();
 }
 
@@ -110,7 +127,7 @@ int reserveBatch (Batch &b, size_t bytes, int nEval)
 {
     if (bytes > b.cap)
         {
-        size_t cap = bytes + bytes / 2 + 4096;
+        size_t cap = bytes + bytes / 2 + 32768;      // never smaller than the largest parameter blob
         if (b.hBlob) cudaFreeHost (b.hBlob);
         if (b.dBlob) cudaFree (b.dBlob);
         b.hBlob = nullptr; b.dBlob = nullptr; b.cap = 0;
@@ -121,15 +138,13 @@ int reserveBatch (Batch &b, size_t bytes, int nEval)
     if (nEval > b.capEval)
         {
         int cap = nEval + 8;
-        if (b.dLnL) cudaFree (b.dLnL);
-        if (b.dStatus) cudaFree (b.dStatus);
-        if (b.hLnL) cudaFreeHost (b.hLnL);
-        if (b.hStatus) cudaFreeHost (b.hStatus);
+        if (b.dRes) cudaFree (b.dRes);
+        if (b.hRes) cudaFreeHost (b.hRes);
         b.capEval = 0;
-        CK (cudaMalloc ((void **)&b.dLnL, sizeof(double) * cap));
-        CK (cudaMalloc ((void **)&b.dStatus, sizeof(int) * cap));
-        CK (cudaMallocHost ((void **)&b.hLnL, sizeof(double) * cap));
-        CK (cudaMallocHost ((void **)&b.hStatus, sizeof(int) * cap));
+        CK (cudaMalloc ((void **)&b.dRes, sizeof(DevResult) * cap));
+        CK (cudaHostAlloc ((void **)&b.hRes, sizeof(DevResult) * cap, cudaHostAllocMapped));
+        CK (cudaHostGetDevicePointer ((void **)&b.hResDev, b.hRes, 0));
+        memset (b.hRes, 0, sizeof(DevResult) * cap);
         b.capEval = cap;
         }
     return MB200_SUCCESS;
@@ -144,30 +159,106 @@ bool okPartials (const Instance *I, int b, bool allowTip)
 int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
 {
     const mb200_instance_config &c = I->cfg;
+    const int K = c.category_count, S = c.state_count;
     if (count < 1 || count > I->maxEval)
         return MB200_ERROR_OUT_OF_RANGE;
-    int nMat = 0, nOp = 0;
-    for (int e = 0; e < count; e++)
+
+    // ---- pass 1: validate; for the 4-state latency path give every matrix an evaluation touches a
+    //      shared-memory slot (dirty ones first, then the clean ones) ----
+    const bool nuc4 = (S == 4 && K <= 8);
+    const int  ppb  = nuc4 ? nuc4PatternsPerBlock (K, true) : 1;
+    const long ctas = (long)((c.pattern_count + ppb - 1) / ppb) * count;
+    bool fused = nuc4 && ctas <= 4L * I->numSMs;       // small launch: latency-bound regime
+    const int maxSlots = (256 / K > 128) ? 128 : 256 / K;      // Nuc4Geom<K>::MAXS
+    if ((int) I->slotOf.size () < c.matrix_count)
+        I->slotOf.assign (c.matrix_count, -1);
+    std::vector<int> &slots = I->slotTmp;              // 3 per operation, all evaluations
+    std::vector<int> &clean = I->cleanTmp;             // clean matrices, all evaluations
+    std::vector<int> &nCleanOf = I->nCleanTmp;
+    slots.clear (); clean.clear (); nCleanOf.assign (count, 0);
+    int nMat = 0, nOp = 0, rcv = MB200_SUCCESS;
+    for (int e = 0; e < count && rcv == MB200_SUCCESS; e++)
         {
-        if (evs[e].matrix_update_count < 0 || evs[e].operation_count < 0)
+        const mb200_evaluation &ev = evs[e];
+        if (ev.matrix_update_count < 0 || ev.operation_count < 0 ||
+            (ev.matrix_update_count > 0 && !ev.matrix_updates) || (ev.operation_count > 0 && !ev.operations))
             return MB200_ERROR_OUT_OF_RANGE;
-        nMat += evs[e].matrix_update_count;
-        nOp  += evs[e].operation_count;
+        if (ev.site_scaler_dst < -1 || ev.site_scaler_dst >= c.scaler_count || ev.site_scaler_src < -1 || ev.site_scaler_src >= c.scaler_count)
+            return MB200_ERROR_OUT_OF_RANGE;
+        if (ev.root_buffer != MB200_NONE &&
+            (!okPartials (I, ev.root_buffer, false) || ev.weights_row < 0 || ev.weights_row >= c.weight_rows))
+            return MB200_ERROR_OUT_OF_RANGE;
+        int nSlot = 0;
+        const size_t cleanStart = clean.size ();
+        for (int i = 0; i < ev.matrix_update_count; i++)
+            {
+            const mb200_matrix_update &u = ev.matrix_updates[i];
+            if (u.matrix < 0 || u.matrix >= c.matrix_count || u.eigen < 0 || u.eigen >= c.eigen_count)
+                { rcv = MB200_ERROR_OUT_OF_RANGE; break; }
+            I->slotOf[u.matrix] = nSlot++;
+            }
+        for (int i = 0; i < ev.operation_count && rcv == MB200_SUCCESS; i++)
+            {
+            const mb200_operation &op = ev.operations[i];
+            if (!okPartials (I, op.dest, false) || !okPartials (I, op.child1, true) || !okPartials (I, op.child2, true) ||
+                op.matrix1 < 0 || op.matrix1 >= c.matrix_count || op.matrix2 < 0 || op.matrix2 >= c.matrix_count ||
+                (op.child3 != MB200_NONE && (!okPartials (I, op.child3, true) || op.matrix3 < 0 || op.matrix3 >= c.matrix_count)) ||
+                op.scale_write < -1 || op.scale_write >= c.scaler_count || op.scale_remove < -1 || op.scale_remove >= c.scaler_count)
+                { rcv = MB200_ERROR_OUT_OF_RANGE; break; }
+            const int m3 = (op.child3 == MB200_NONE) ? -1 : op.matrix3;
+            const int mm[3] = { op.matrix1, op.matrix2, m3 };
+            for (int q = 0; q < 3; q++)
+                {
+                int sl = -1;
+                if (mm[q] >= 0)
+                    {
+                    if (I->slotOf[mm[q]] < 0)
+                        {
+                        I->slotOf[mm[q]] = nSlot++;
+                        clean.push_back (mm[q]);
+                        }
+                    sl = I->slotOf[mm[q]];
+                    }
+                slots.push_back (sl);
+                }
+            }
+        // reset the scratch map
+        for (int i = 0; i < ev.matrix_update_count; i++)
+            if (ev.matrix_updates[i].matrix >= 0 && ev.matrix_updates[i].matrix < c.matrix_count)
+                I->slotOf[ev.matrix_updates[i].matrix] = -1;
+        for (size_t q = cleanStart; q < clean.size (); q++)
+            I->slotOf[clean[q]] = -1;
+        nCleanOf[e] = (int)(clean.size () - cleanStart);
+        if (nSlot > maxSlots)
+            fused = false;
+        nMat += ev.matrix_update_count;
+        nOp  += ev.operation_count;
         }
+    if (rcv != MB200_SUCCESS)
+        return rcv;
+
+    // ---- pass 2: lay the blob out ----
+    const int nMatEntries = nMat + (fused ? (int) clean.size () : 0);
+    const int perEvalDbl = 2*K + S;
+    const int nDbl = perEvalDbl * count;
     size_t offEval = mb200_align16 (sizeof(DevBatchHeader));
-    size_t offMat  = mb200_align16 (offEval + sizeof(DevEval) * (size_t)count);
-    size_t offOp   = mb200_align16 (offMat + sizeof(DevMat) * (size_t)nMat);
+    size_t offDbl  = mb200_align16 (offEval + sizeof(DevEval) * (size_t)count);
+    size_t offMat  = mb200_align16 (offDbl + sizeof(double) * (size_t)nDbl);
+    size_t offOp   = mb200_align16 (offMat + sizeof(DevMat) * (size_t)nMatEntries);
     size_t bytes   = mb200_align16 (offOp + sizeof(DevOp) * (size_t)nOp);
     int rc = reserveBatch (b, bytes, count);
     if (rc != MB200_SUCCESS)
         return rc;
-    memset (b.hBlob, 0, bytes);
     DevBatchHeader *h = (DevBatchHeader *) b.hBlob;
-    h->nEval = count; h->nMat = nMat; h->nOp = nOp;
+    h->nEval = count; h->nMat = nMatEntries; h->nOp = nOp; h->nDbl = nDbl;
     DevEval *de = (DevEval *)(b.hBlob + offEval);
+    double  *dd = (double  *)(b.hBlob + offDbl);
     DevMat  *dm = (DevMat  *)(b.hBlob + offMat);
-    DevOp   *dops = (DevOp   *)(b.hBlob + offOp);
+    DevOp   *dops = (DevOp *)(b.hBlob + offOp);
+
     int mOff = 0, oOff = 0;
+    size_t cleanPos = 0, slotPos = 0;
+    b.needInv = false;
     for (int e = 0; e < count; e++)
         {
         const mb200_evaluation &ev = evs[e];
@@ -178,52 +269,52 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         d.root = ev.root_buffer;         d.weightsRow = ev.weights_row;
         d.flags = ev.flags;              d.hasPInvar = ev.has_p_invar ? 1 : 0;
         d.pInvar = ev.p_invar;
-        if (d.siteDst < -1 || d.siteDst >= c.scaler_count || d.siteSrc < -1 || d.siteSrc >= c.scaler_count)
-            return MB200_ERROR_OUT_OF_RANGE;
-        if (d.root != MB200_NONE)
-            {
-            if (!okPartials (I, d.root, false) || d.weightsRow < 0 || d.weightsRow >= c.weight_rows)
-                return MB200_ERROR_OUT_OF_RANGE;
-            }
+        d.dOff = e * perEvalDbl;
+        d.fuseP = fused ? 1 : 0;
+        d.nClean = fused ? nCleanOf[e] : 0;
+        d.eigen0 = (ev.matrix_update_count > 0) ? ev.matrix_updates[0].eigen : 0;
+        d.pad[0] = d.pad[1] = d.pad[2] = 0;
+        if (d.root != MB200_NONE && d.hasPInvar) b.needInv = true;
+        double *dv = dd + d.dOff;
         bool eq = true;
-        for (int k = 0; k < c.category_count; k++)
+        for (int k = 0; k < K; k++)
             {
-            d.rates[k] = ev.category_rates[k];
-            d.catW[k]  = ev.category_weights[k];
+            dv[k]     = ev.category_rates[k];
+            dv[K + k] = ev.category_weights[k];
             if (ev.category_weights[k] != ev.category_weights[0]) eq = false;
             }
         d.equalWeights = eq ? 1 : 0;
-        for (int s = 0; s < c.state_count; s++)
-            d.freqs[s] = ev.state_freqs[s];
+        for (int s = 0; s < S; s++)
+            dv[2*K + s] = ev.state_freqs[s];
         for (int i = 0; i < ev.matrix_update_count; i++)
             {
             const mb200_matrix_update &u = ev.matrix_updates[i];
-            if (u.matrix < 0 || u.matrix >= c.matrix_count || u.eigen < 0 || u.eigen >= c.eigen_count)
-                return MB200_ERROR_OUT_OF_RANGE;
             DevMat &m = dm[mOff + i];
-            m.matrix = u.matrix; m.eigen = u.eigen; m.length = u.length; m.eval = e;
+            m.matrix = u.matrix; m.eigen = u.eigen; m.length = u.length;
             }
+        if (fused)
+            for (int i = 0; i < nCleanOf[e]; i++)
+                {
+                DevMat &m = dm[mOff + ev.matrix_update_count + i];
+                m.matrix = clean[cleanPos + i]; m.eigen = 0; m.length = 0.0;
+                }
+        cleanPos += nCleanOf[e];
         for (int i = 0; i < ev.operation_count; i++)
             {
             const mb200_operation &op = ev.operations[i];
-            if (!okPartials (I, op.dest, false) || !okPartials (I, op.child1, true) || !okPartials (I, op.child2, true))
-                return MB200_ERROR_OUT_OF_RANGE;
-            if (op.matrix1 < 0 || op.matrix1 >= c.matrix_count || op.matrix2 < 0 || op.matrix2 >= c.matrix_count)
-                return MB200_ERROR_OUT_OF_RANGE;
-            if (op.child3 != MB200_NONE && (!okPartials (I, op.child3, true) || op.matrix3 < 0 || op.matrix3 >= c.matrix_count))
-                return MB200_ERROR_OUT_OF_RANGE;
-            if (op.scale_write < -1 || op.scale_write >= c.scaler_count || op.scale_remove < -1 || op.scale_remove >= c.scaler_count)
-                return MB200_ERROR_OUT_OF_RANGE;
             DevOp &o = dops[oOff + i];
             o.dest = op.dest; o.c1 = op.child1; o.m1 = op.matrix1; o.c2 = op.child2; o.m2 = op.matrix2;
             o.c3 = op.child3; o.m3 = (op.child3 == MB200_NONE) ? MB200_NONE : op.matrix3;
             o.sw = op.scale_write; o.sr = op.scale_remove;
+            o.s1 = fused ? slots[slotPos] : -1; o.s2 = fused ? slots[slotPos + 1] : -1; o.s3 = fused ? slots[slotPos + 2] : -1;
+            slotPos += 3;
             }
-        mOff += ev.matrix_update_count;
+        mOff += ev.matrix_update_count + d.nClean;
         oOff += ev.operation_count;
         }
-    b.bytes = bytes; b.nEval = count; b.nMat = nMat; b.nOp = nOp;
-    b.offEval = offEval; b.offMat = offMat; b.offOp = offOp;
+    b.bytes = bytes; b.nEval = count; b.nMat = nMatEntries; b.nOp = nOp; b.nDbl = nDbl;
+    b.nDirty = nMat; b.fused = fused;
+    b.offEval = offEval; b.offDbl = offDbl; b.offMat = offMat; b.offOp = offOp;
     return MB200_SUCCESS;
 }
 
@@ -239,12 +330,13 @@ int ensureInvMask (Instance *I)
     return MB200_SUCCESS;
 }
 
-template <int NT>
-int launchNuc4 (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const DevOp *dops, double *lnL, int *st)
+int launchNuc4 (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const double *dd, const DevMat *dm,
+                const DevOp *dops, DevResult *res, int seq, bool fused)
 {
     switch (ctx.K)
         {
-#define MB200_CASE(KK) case KK: eval_nuc4_kernel<KK, NT><<<grid, NT, 0, I->stream>>> (ctx, de, dops, lnL, st); break;
+#define MB200_CASE(KK) case KK: if (fused) eval_nuc4_small_kernel<KK, NT_SMALL><<<grid, NT_SMALL, 0, I->stream>>> (ctx, de, dd, dm, dops, res, seq); \
+                                 else eval_nuc4_stream_kernel<KK, NT_NUC4><<<grid, NT_NUC4, 0, I->stream>>> (ctx, de, dd, dm, dops, res, seq); break;
         MB200_CASE(1) MB200_CASE(2) MB200_CASE(3) MB200_CASE(4) MB200_CASE(5) MB200_CASE(6) MB200_CASE(7) MB200_CASE(8)
 #undef MB200_CASE
         default: return MB200_ERROR_UNSUPPORTED;
@@ -252,28 +344,49 @@ int launchNuc4 (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, co
     return MB200_SUCCESS;
 }
 
-// launch the fused pass for a packed batch already resident on the device
-int launch (Instance *I, Batch &b)
+// the same kernel with the job descriptors riding in the parameter block (no H2D copy)
+template <int CAP>
+int launchNuc4Param (Instance *I, const DevCtx &ctx, dim3 grid, const Batch &b, DevResult *res, int seq)
+{
+    const ParamBlob<CAP> &blob = *reinterpret_cast<const ParamBlob<CAP> *>(b.hBlob);
+    BlobOffsets off = { (int) b.offEval, (int) b.offDbl, (int) b.offMat, (int) b.offOp };
+    switch (ctx.K)
+        {
+#define MB200_CASE(KK) case KK: eval_nuc4_small_pkernel<KK, NT_SMALL, CAP><<<grid, NT_SMALL, 0, I->stream>>> (ctx, blob, off, res, seq); break;
+        MB200_CASE(1) MB200_CASE(2) MB200_CASE(3) MB200_CASE(4) MB200_CASE(5) MB200_CASE(6) MB200_CASE(7) MB200_CASE(8)
+#undef MB200_CASE
+        default: return MB200_ERROR_UNSUPPORTED;
+        }
+    return MB200_SUCCESS;
+}
+
+const int PARAM_SMALL = 2048, PARAM_MID = 8192, PARAM_BIG = 30720;
+
+bool paramEligible (const Instance *I, const Batch &b)
+{
+    return b.fused && b.bytes <= (size_t) PARAM_BIG;
+}
+
+// launch the fused pass for a packed batch; fromHost: the job lives in b.hBlob only and is
+// delivered through the parameter block when it fits (otherwise the caller has copied it to dBlob)
+int launch (Instance *I, Batch &b, DevResult *res, bool viaParams)
 {
     const DevEval *de = (const DevEval *)(b.dBlob + b.offEval);
+    const double  *dd = (const double  *)(b.dBlob + b.offDbl);
     const DevMat  *dm = (const DevMat  *)(b.dBlob + b.offMat);
-    const DevOp   *dops = (const DevOp   *)(b.dBlob + b.offOp);
+    const DevOp   *dops = (const DevOp *)(b.dBlob + b.offOp);
     DevCtx ctx = I->ctx;
+    const int seq = ++I->seq;
 
-    bool needInv = false;
-    {
-    const DevEval *he = (const DevEval *)(b.hBlob + b.offEval);
-    for (int e = 0; e < b.nEval; e++) if (he[e].hasPInvar && he[e].root >= 0) needInv = true;
-    }
-    if (needInv)
+    if (b.needInv)
         {
         int rc = ensureInvMask (I);
         if (rc != MB200_SUCCESS) return rc;
         }
-    if (b.nMat > 0)
+    if (b.nDirty > 0 && !b.fused)
         {
         dim3 grid (b.nMat, ctx.K);
-        tiprobs_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, dm);
+        tiprobs_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, b.nEval, dd, dm);
         CK (cudaGetLastError ());
         I->launches++;
         }
@@ -282,26 +395,23 @@ int launch (Instance *I, Batch &b)
         CK (cudaEventRecord (I->evA[evSlot], I->stream));
     if (ctx.S == 4 && ctx.K <= 8)
         {
-        // small problems: one warp per CTA spreads the latency-bound work over more SMs
-        long tilesLarge = (long)((ctx.C + NT_LARGE - 1) / NT_LARGE) * b.nEval;
-        int  rc;
-        if (tilesLarge < 2L * I->numSMs)
+        ctx.tilePatterns = nuc4PatternsPerBlock (ctx.K, b.fused);
+        ctx.numTiles = (ctx.C + ctx.tilePatterns - 1) / ctx.tilePatterns;
+        dim3 grid (ctx.numTiles, b.nEval);
+        int rc;
+        if (viaParams)
             {
-            ctx.tilePatterns = NT_SMALL;
-            ctx.numTiles = (ctx.C + NT_SMALL - 1) / NT_SMALL;
-            rc = launchNuc4<NT_SMALL> (I, ctx, dim3 (ctx.numTiles, b.nEval), de, dops, b.dLnL, b.dStatus);
+            if (b.bytes <= (size_t) PARAM_SMALL)    rc = launchNuc4Param<PARAM_SMALL> (I, ctx, grid, b, res, seq);
+            else if (b.bytes <= (size_t) PARAM_MID) rc = launchNuc4Param<PARAM_MID> (I, ctx, grid, b, res, seq);
+            else                                    rc = launchNuc4Param<PARAM_BIG> (I, ctx, grid, b, res, seq);
             }
         else
-            {
-            ctx.tilePatterns = NT_LARGE;
-            ctx.numTiles = (ctx.C + NT_LARGE - 1) / NT_LARGE;
-            rc = launchNuc4<NT_LARGE> (I, ctx, dim3 (ctx.numTiles, b.nEval), de, dops, b.dLnL, b.dStatus);
-            }
+            rc = launchNuc4 (I, ctx, grid, de, dd, dm, dops, res, seq, b.fused);
         if (rc != MB200_SUCCESS) return rc;
         }
     else
         {
-        eval_gen_kernel<NT_GEN><<<dim3 (ctx.numTiles, b.nEval), NT_GEN, I->smemGen, I->stream>>> (ctx, de, dops, b.dLnL, b.dStatus);
+        eval_gen_kernel<NT_GEN><<<dim3 (ctx.numTiles, b.nEval), NT_GEN, I->smemGen, I->stream>>> (ctx, de, dd, dops, res, seq);
         }
     CK (cudaGetLastError ());
     I->launches++;
@@ -313,28 +423,64 @@ int launch (Instance *I, Batch &b)
     return MB200_SUCCESS;
 }
 
+// wait until the kernel has written every result of the batch into the mapped host buffer
+int waitResults (Instance *I, Batch &b, int count)
+{
+    const int seq = I->seq;
+    volatile DevResult *r = b.hRes;
+    unsigned long long spins = 0;
+    for (int e = 0; e < count; e++)
+        {
+        while (r[e].seq != seq)
+            {
+#if defined(__x86_64__)
+            __builtin_ia32_pause ();
+#endif
+            if ((++spins & 0xfffff) == 0)
+                {
+                cudaError_t q = cudaStreamQuery (I->stream);
+                if (q == cudaSuccess)
+                    {
+                    if (r[e].seq == seq) break;
+                    // stream idle but no result: treat as failure rather than spin forever
+                    if (spins > (1ull << 26)) return MB200_ERROR_GENERAL;
+                    }
+                else if (q != cudaErrorNotReady)
+                    {
+                    fprintf (stderr, "mb200: CUDA error %s while waiting for results\n", cudaGetErrorName (q));
+                    return MB200_ERROR_CUDA;
+                    }
+                }
+            }
+        }
+    return MB200_SUCCESS;
+}
+
 int runSync (Instance *I, const mb200_evaluation *evs, int count, double *lnL, int *status)
 {
     Batch &b = I->scratch;
     int rc = pack (I, b, evs, count);
     if (rc != MB200_SUCCESS) return rc;
-    CK (cudaMemcpyAsync (b.dBlob, b.hBlob, b.bytes, cudaMemcpyHostToDevice, I->stream));
-    rc = launch (I, b);
+    const bool viaParams = paramEligible (I, b);
+    if (!viaParams)
+        CK (cudaMemcpyAsync (b.dBlob, b.hBlob, b.bytes, cudaMemcpyHostToDevice, I->stream));
+    rc = launch (I, b, b.hResDev, viaParams);
     if (rc != MB200_SUCCESS) return rc;
-    bool wantRoot = false;
-    for (int e = 0; e < count; e++) if (evs[e].root_buffer != MB200_NONE) wantRoot = true;
-    if (wantRoot)
+    bool allRoot = true;
+    for (int e = 0; e < count; e++) if (evs[e].root_buffer == MB200_NONE) allRoot = false;
+    if (allRoot)
         {
-        CK (cudaMemcpyAsync (b.hLnL, b.dLnL, sizeof(double) * count, cudaMemcpyDeviceToHost, I->stream));
-        CK (cudaMemcpyAsync (b.hStatus, b.dStatus, sizeof(int) * count, cudaMemcpyDeviceToHost, I->stream));
+        rc = waitResults (I, b, count);           // results land in pinned host memory; no D2H copy
+        if (rc != MB200_SUCCESS) return rc;
         }
-    CK (cudaStreamSynchronize (I->stream));
+    else
+        CK (cudaStreamSynchronize (I->stream));
     for (int e = 0; e < count; e++)
         {
         if (evs[e].root_buffer != MB200_NONE)
             {
-            if (lnL)    lnL[e] = b.hLnL[e];
-            if (status) status[e] = b.hStatus[e];
+            if (lnL)    lnL[e] = b.hRes[e].lnL;
+            if (status) status[e] = b.hRes[e].status;
             }
         else
             {
@@ -352,9 +498,9 @@ void destroy (Instance *I)
     if (I->stream) cudaStreamSynchronize (I->stream);
     freeBatch (I->scratch);
     for (Batch *b : I->batches) if (b) { freeBatch (*b); delete b; }
-    cudaFree (I->dTip8); cudaFree (I->dTip64); cudaFree (I->dTipPartAmbig); cudaFree (I->dPartials); cudaFree (I->dMatrices);
+    cudaFree (I->dTip8); cudaFree (I->dTip64); cudaFree (I->dTipPartAmbig); cudaFree (I->dTipDense); cudaFree (I->dPartials); cudaFree (I->dMatrices);
     cudaFree (I->dScalers); cudaFree (I->dWeights); cudaFree (I->dEigen); cudaFree (I->dInvMask);
-    cudaFree (I->dTilePartial); cudaFree (I->dTileAbort); cudaFree (I->dTicket);
+    cudaFree (I->dTilePartial); cudaFree (I->dTileAbort); cudaFree (I->dTicket); cudaFree (I->dDbg);
     if (I->hostStage) cudaFreeHost (I->hostStage);
     for (cudaEvent_t e : I->evA) cudaEventDestroy (e);
     for (cudaEvent_t e : I->evB) cudaEventDestroy (e);
@@ -437,7 +583,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     while (TP > 1 && smemFor (TP) > 96*1024) TP >>= 1;
     I->smemGen = smemFor (TP);
     const bool nuc4 = (S == 4 && K <= 8);
-    I->maxTiles = nuc4 ? (C + NT_SMALL - 1) / NT_SMALL : (C + TP - 1) / TP;
+    I->maxTiles = nuc4 ? (C + nuc4PatternsPerBlock (K, false) - 1) / nuc4PatternsPerBlock (K, false) : (C + TP - 1) / TP;
 
 #define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc ((void **)&(ptr), (bytes)); if (e_ != cudaSuccess) { \
         cudaGetLastError (); destroy (I); return (e_ == cudaErrorMemoryAllocation) ? MB200_ERROR_OUT_OF_MEMORY : MB200_ERROR_CUDA; } } while (0)
@@ -445,6 +591,8 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     ALLOC (I->dTip8,     (size_t)cfg->tip_count * C);
     ALLOC (I->dTip64,    (size_t)cfg->tip_count * C * sizeof(uint64_t));
     ALLOC (I->dTipPartAmbig, (size_t)cfg->tip_count * sizeof(int));
+    if (S == 4)
+        ALLOC (I->dTipDense, (size_t)cfg->tip_count * C * sizeof(float4));
     ALLOC (I->dPartials, nInt * K * C * Sp * sizeof(float));
     ALLOC (I->dMatrices, (size_t)cfg->matrix_count * K * S * S * sizeof(float));
     ALLOC (I->dScalers,  (size_t)cfg->scaler_count * C * sizeof(float));
@@ -454,6 +602,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     ALLOC (I->dTilePartial, (size_t)I->maxEval * I->maxTiles * sizeof(double));
     ALLOC (I->dTileAbort,   (size_t)I->maxEval * I->maxTiles * sizeof(int));
     ALLOC (I->dTicket,      (size_t)I->maxEval * sizeof(unsigned int));
+    ALLOC (I->dDbg,         (size_t)I->maxEval * 64 * sizeof(unsigned long long));
 #undef ALLOC
     cudaMemsetAsync (I->dTip8, 0, (size_t)cfg->tip_count * C, I->stream);
     cudaMemsetAsync (I->dTip64, 0, (size_t)cfg->tip_count * C * sizeof(uint64_t), I->stream);
@@ -476,11 +625,11 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     x.S = S; x.Sp = Sp; x.K = K; x.C = C;
     x.tipCount = cfg->tip_count; x.partialsCount = cfg->partials_count; x.matrixCount = cfg->matrix_count;
     x.scalerCount = cfg->scaler_count; x.eigenCount = cfg->eigen_count; x.weightRows = cfg->weight_rows;
-    x.tilePatterns = nuc4 ? NT_SMALL : TP;
+    x.tilePatterns = nuc4 ? nuc4PatternsPerBlock (K, false) : TP;
     x.numTiles = I->maxTiles;
-    x.tip8 = I->dTip8; x.tip64 = I->dTip64; x.tipPartAmbig = I->dTipPartAmbig; x.partials = I->dPartials; x.matrices = I->dMatrices;
+    x.tip8 = I->dTip8; x.tip64 = I->dTip64; x.tipPartAmbig = I->dTipPartAmbig; x.tipDense4 = I->dTipDense; x.partials = I->dPartials; x.matrices = I->dMatrices;
     x.scalers = I->dScalers; x.eigen = I->dEigen; x.weights = I->dWeights; x.invMask = I->dInvMask;
-    x.tilePartial = I->dTilePartial; x.tileAbort = I->dTileAbort; x.ticket = I->dTicket;
+    x.tilePartial = I->dTilePartial; x.tileAbort = I->dTileAbort; x.ticket = I->dTicket; x.dbg = I->dDbg;
 
     if (cudaStreamSynchronize (I->stream) != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
 
@@ -513,21 +662,25 @@ int mb200_set_tip_states (int instance, int tip, const uint64_t *masks)
     if (tip < 0 || tip >= I->cfg.tip_count || !masks) return MB200_ERROR_OUT_OF_RANGE;
     int rc = use (I); if (rc) return rc;
     const int C = I->cfg.pattern_count;
-    rc = ensureStage (I, (size_t)C * 9); if (rc) return rc;
+    rc = ensureStage (I, (size_t)C * 32); if (rc) return rc;
     uint64_t *h64 = (uint64_t *) I->hostStage;
-    uint8_t  *h8  = (uint8_t *)(h64 + C);
+    float4   *hd  = (float4 *)(h64 + C);
+    uint8_t  *h8  = (uint8_t *)(hd + C);
     const uint64_t full = (I->cfg.state_count == 64) ? ~(uint64_t)0 : (((uint64_t)1 << I->cfg.state_count) - 1);
     int partAmbig = 0;      // isPartAmbig of SetUpTermState (src/mcmc.c:18631-18651)
     for (int c = 0; c < C; c++)
         {
         h64[c] = masks[c] & full;
         h8[c]  = (uint8_t)(h64[c] & 0xff);
+        hd[c]  = make_float4 ((h64[c] & 1) ? 1.f : 0.f, (h64[c] & 2) ? 1.f : 0.f, (h64[c] & 4) ? 1.f : 0.f, (h64[c] & 8) ? 1.f : 0.f);
         if (h64[c] != full && (h64[c] == 0 || (h64[c] & (h64[c] - 1)) != 0))
             partAmbig = 1;
         }
     CK (cudaMemcpyAsync (I->dTipPartAmbig + tip, &partAmbig, sizeof(int), cudaMemcpyHostToDevice, I->stream));
     CK (cudaMemcpyAsync (I->dTip64 + (size_t)tip * C, h64, (size_t)C * 8, cudaMemcpyHostToDevice, I->stream));
     CK (cudaMemcpyAsync (I->dTip8 + (size_t)tip * C, h8, (size_t)C, cudaMemcpyHostToDevice, I->stream));
+    if (I->dTipDense)
+        CK (cudaMemcpyAsync (I->dTipDense + (size_t)tip * C, hd, (size_t)C * sizeof(float4), cudaMemcpyHostToDevice, I->stream));
     CK (cudaStreamSynchronize (I->stream));
     I->invMaskValid = false;
     return MB200_SUCCESS;
@@ -779,7 +932,8 @@ int mb200_replay (int instance, int batch)
     if (!I) return MB200_ERROR_BAD_INSTANCE;
     if (batch < 0 || batch >= (int) I->batches.size () || !I->batches[batch]) return MB200_ERROR_OUT_OF_RANGE;
     int rc = use (I); if (rc) return rc;
-    return launch (I, *I->batches[batch]);
+    Batch &rb = *I->batches[batch];
+    return launch (I, rb, rb.dRes, false);
 }
 
 int mb200_replay_results (int instance, int batch, double *lnL, int *status)
@@ -789,13 +943,12 @@ int mb200_replay_results (int instance, int batch, double *lnL, int *status)
     if (batch < 0 || batch >= (int) I->batches.size () || !I->batches[batch]) return MB200_ERROR_OUT_OF_RANGE;
     int rc = use (I); if (rc) return rc;
     Batch &b = *I->batches[batch];
-    CK (cudaMemcpyAsync (b.hLnL, b.dLnL, sizeof(double) * b.nEval, cudaMemcpyDeviceToHost, I->stream));
-    CK (cudaMemcpyAsync (b.hStatus, b.dStatus, sizeof(int) * b.nEval, cudaMemcpyDeviceToHost, I->stream));
     CK (cudaStreamSynchronize (I->stream));
+    CK (cudaMemcpy (b.hRes, b.dRes, sizeof(DevResult) * b.nEval, cudaMemcpyDeviceToHost));
     for (int e = 0; e < b.nEval; e++)
         {
-        if (lnL) lnL[e] = b.hLnL[e];
-        if (status) status[e] = b.hStatus[e];
+        if (lnL) lnL[e] = b.hRes[e].lnL;
+        if (status) status[e] = b.hRes[e].status;
         }
     return MB200_SUCCESS;
 }
@@ -835,6 +988,19 @@ int mb200_get_launch_count (int instance, long long *launches)
     Instance *I = get (instance);
     if (!I || !launches) return MB200_ERROR_BAD_INSTANCE;
     *launches = I->launches;
+    return MB200_SUCCESS;
+}
+
+// phase timestamps of the last launch (debug builds compiled with -DMB200_PHASE_TIMING only)
+int mb200_debug_read_stamps (int instance, unsigned long long *out, int evaluations)
+{
+    Instance *I = get (instance);
+    if (!I || !out) return MB200_ERROR_BAD_INSTANCE;
+    if (evaluations < 1 || evaluations > I->maxEval) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    CK (cudaStreamSynchronize (I->stream));
+    CK (cudaMemcpy (out, I->dDbg, (size_t)evaluations * 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK (cudaMemset (I->dDbg, 0, (size_t)I->maxEval * 64 * sizeof(unsigned long long)));
     return MB200_SUCCESS;
 }
 

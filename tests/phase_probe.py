@@ -1,0 +1,25 @@
+import sys, ctypes as C, numpy as np
+sys.path.insert(0,'/root/repo')
+from mrbayes_b200 import abi
+import bench
+lib = abi.Library('/root/repo/mrbayes_b200/lib/libmb200_%s.so' % (sys.argv[1] if len(sys.argv)>1 else 'dbg'),'mb200_')
+lib.fn('debug_read_stamps').argtypes=[C.c_int, C.POINTER(C.c_ulonglong), C.c_int]
+pr = bench.primates_problem(8, 1)
+inst = pr.create(lib, max_evaluations=8)
+steps = bench.make_cycle(pr, inst, 16, 3)
+import torch
+flush = torch.empty(256<<20, dtype=torch.uint8, device='cuda')
+for rep in range(2):
+  for si in [15, 3]:
+    specs = steps[si]
+    if rep==1: flush.zero_(); torch.cuda.synchronize()
+    inst.evaluate(specs)
+    buf=(C.c_ulonglong*(8*64))()
+    lib.fn('debug_read_stamps')(inst.handle, buf, 8)
+    a=np.array(buf[:],dtype=np.uint64).reshape(8,64).astype(np.int64)
+    t0=a[:,0].min()
+    print("rep",rep,"step",si)
+    for e in range(8):
+        nop=len(specs[e].ops); nm=len(specs[e].mats)
+        r=a[e]; ops=[int(r[8+o]-r[3]) if o==0 else int(r[8+o]-r[8+o-1]) for o in range(nop)]
+        print(f" eval{e} nOp={nop:2d} nMat={nm:2d} start+{r[0]-t0:6d} hdr={r[1]-r[0]:5d} sD={r[2]-r[1]:5d} P={r[3]-r[2]:6d} ops={ops} tail={r[5]-r[4]:5d} fin={r[6]-r[5]:5d} total={r[6]-r[0]:6d} | op3: sync={r[41]-r[40]} loads+mv={r[42]-r[41]} scale={r[43]-r[42]} rest={r[8+3]-r[43]} pre={r[40]-r[8+2]}" if nop>3 else "")
