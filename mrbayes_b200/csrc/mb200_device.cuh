@@ -22,9 +22,16 @@
 #define MB200_DEV_MAX_CATS   20
 #define MB200_DEV_MAX_STATES 64
 
-struct DevEval                      // one LaunchLogLikeForDivision (80 bytes)
+struct DevChunk                     // a run of nodes whose branches fit the shared-memory P(t) slots
 {
-    int    nMat, matOff;            // matrix updates [matOff, matOff+nMat) of the batch
+    int opOff, nOp;                 // nodes    [opOff, opOff+nOp)   of the batch's operation array
+    int matOff, nMat;               // branches [matOff, matOff+nMat) of the batch's chunk-matrix array
+};
+
+struct DevEval                      // one LaunchLogLikeForDivision (96 bytes)
+{
+    int    nMat, matOff;            // P(t) rebuilds [matOff, matOff+nMat) of the update-matrix array
+                                    // (consumed by tiprobs_kernel; empty for fused batches)
     int    nOp,  opOff;             // operations     [opOff,  opOff+nOp)
     int    siteDst, siteSrc;        // -1: do not store / start from zero
     int    root, weightsRow;        // root -1: no root integration
@@ -33,15 +40,18 @@ struct DevEval                      // one LaunchLogLikeForDivision (80 bytes)
     int    dOff;                    // doubles [dOff ...): rates[K], catW[K], freqs[S]
     double pInvar;
     int    fuseP;                   // 1: the pruning kernel rebuilds this evaluation's P(t) itself
-    int    nClean;                  // fused only: clean matrices listed after the nMat dirty ones
-                                    // (copied to shared memory so every node finds its P(t) in a slot)
+    int    nChunk;                  // 4-state path: chunk0 below + (nChunk-1) entries at chunkOff
     int    eigen0;                  // eigen slot of the first matrix update (normally of all of them)
-    int    pad[3];
+    int    chunkOff;
+    DevChunk chunk0;
+    int    pad[2];
 };
 
-struct DevMat                       // one P(t) rebuild (16 bytes)
+struct DevMat                       // one branch (16 bytes)
 {
-    int    matrix, eigen;
+    int    matrix;                  // transition-matrix buffer
+    int    eigen;                   // eigen slot to rebuild P(t) from; -1 in a chunk list: clean
+                                    // branch, copy the rows from the matrix buffer
     double length;
 };
 
@@ -63,12 +73,13 @@ struct DevResult                    // 16 bytes per evaluation
 // Job descriptors handed over as a kernel parameter (constant bank) instead of a host->device
 // copy: removes one stream operation from the latency path of small evaluations.
 template <int CAP> struct ParamBlob { char bytes[CAP]; };
-struct BlobOffsets { int eval, dbl, mat, op; };
+struct BlobOffsets { int eval, dbl, upd, chunk, cmat, op; };
 
 struct DevBatchHeader
 {
     int nEval, nMat, nOp, nDbl;
-    // followed by DevEval[nEval], double[nDbl], DevMat[nMat], DevOp[nOp] (each 16-byte aligned)
+    // followed by DevEval[nEval], double[nDbl], DevMat upd[nMat], DevChunk[], DevMat cmat[], DevOp[nOp]
+    // (each section 16-byte aligned)
 };
 
 struct DevCtx                       // instance geometry + buffer bases, passed by value
@@ -79,8 +90,6 @@ struct DevCtx                       // instance geometry + buffer bases, passed 
     int numTiles;
     const uint8_t  *tip8;
     const uint64_t *tip64;
-    const float4   *tipDense4;      // [tip][C] 0/1 state vectors (S = 4 only): dense tips for the
-                                    // latency-bound kernel (uniform child handling, no mask branches)
     const int      *tipPartAmbig;   // [tip] 1: some pattern is partially ambiguous (isPartAmbig)
     float          *partials;
     float          *matrices;

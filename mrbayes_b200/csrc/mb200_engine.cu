@@ -23,7 +23,7 @@ struct Batch                       // packed evaluations (device job format)
     size_t  cap    = 0;            // bytes allocated
     size_t  bytes  = 0;            // bytes used
     int     nEval = 0, nMat = 0, nOp = 0, nDbl = 0;
-    size_t  offEval = 0, offDbl = 0, offMat = 0, offOp = 0;
+    size_t  offEval = 0, offDbl = 0, offUpd = 0, offChunk = 0, offCmat = 0, offOp = 0;
     DevResult *dRes = nullptr;     // [capEval] results in HBM (device-resident replay)
     DevResult *hRes = nullptr;     // [capEval] pinned + mapped: kernels of the host-call path write
                                    // results straight into host memory, the caller polls `seq`
@@ -43,7 +43,6 @@ struct Instance
     uint8_t      *dTip8 = nullptr;
     uint64_t     *dTip64 = nullptr;
     int          *dTipPartAmbig = nullptr;
-    float4       *dTipDense = nullptr;   // S = 4 only
     int           seq = 0;               // launch sequence number stamped into results
     float        *dPartials = nullptr, *dMatrices = nullptr, *dScalers = nullptr, *dWeights = nullptr;
     double       *dEigen = nullptr;
@@ -62,7 +61,9 @@ struct Instance
     void         *hostStage = nullptr; // pinned staging for set/get calls
     size_t        hostStageBytes = 0;
     std::vector<int> slotOf;           // scratch: matrix index -> shared-memory slot in the current evaluation
-    std::vector<int> slotTmp, cleanTmp, nCleanTmp;
+    std::vector<int> touched;          // scratch: matrices whose slotOf entry is set
+    std::vector<int> dirtyOf;          // scratch: matrix index -> index in the evaluation's update list
+    std::vector<DevChunk> chunkTmp; std::vector<DevMat> cmatTmp; std::vector<int> slotTmp, nChunkTmp;
     bool          timing = false;      // bracket the fused kernel with events
     std::vector<cudaEvent_t> evA, evB; // ring of event pairs
     long long     evCount = 0;         // pairs recorded since the last read
@@ -71,11 +72,17 @@ struct Instance
 std::mutex               gLock;
 std::vector<Instance *>  gInstances;
 
-const int NT_NUC4 = 128, NT_GEN = 256;
-#ifndef MB200_NT_SMALL
-#define MB200_NT_SMALL 256
-#endif
-const int NT_SMALL = MB200_NT_SMALL;   // threads per CTA of the 4-state latency kernel
+const int NT_GEN = 256;
+// threads per CTA of the 4-state kernels: latency regime (FUSE) and bandwidth regime; both sizes are
+// compiled, MB200_NT_SMALL / MB200_NT_STREAM (128 or 256) pick at run time for tuning
+int ntFromEnv (const char *name, int dflt)
+{
+    const char *v = getenv (name);
+    int n = v ? atoi (v) : dflt;
+    return (n == 128 || n == 256) ? n : dflt;
+}
+const int NT_SMALL = ntFromEnv ("MB200_NT_SMALL", 256);
+const int NT_STREAM = ntFromEnv ("MB200_NT_STREAM", 256);
 const int EV_RING = 2048;
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -86,7 +93,7 @@ const int EV_RING = 2048;
 int nuc4PatternsPerBlock (int K, bool small)
 {
     int L = (K <= 1) ? 1 : (K <= 2) ? 2 : (K <= 4) ? 4 : 8;
-    return (small ? NT_SMALL : NT_NUC4) / L;
+    return (small ? NT_SMALL : NT_STREAM) / L;
 }
 
 Instance *get (int id)
@@ -163,19 +170,23 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     if (count < 1 || count > I->maxEval)
         return MB200_ERROR_OUT_OF_RANGE;
 
-    // ---- pass 1: validate; for the 4-state latency path give every matrix an evaluation touches a
-    //      shared-memory slot (dirty ones first, then the clean ones) ----
     const bool nuc4 = (S == 4 && K <= 8);
-    const int  ppb  = nuc4 ? nuc4PatternsPerBlock (K, true) : 1;
-    const long ctas = (long)((c.pattern_count + ppb - 1) / ppb) * count;
-    bool fused = nuc4 && ctas <= 4L * I->numSMs;       // small launch: latency-bound regime
-    const int maxSlots = (256 / K > 128) ? 128 : 256 / K;      // Nuc4Geom<K>::MAXS
+    const int  ppbS = nuc4 ? nuc4PatternsPerBlock (K, true) : 1;
+    const long ctas = (long)((c.pattern_count + ppbS - 1) / ppbS) * count;
+    const bool fused = nuc4 && ctas <= 4L * I->numSMs;          // small launch: latency-bound regime
+    const int  ppb  = nuc4 ? nuc4PatternsPerBlock (K, fused) : 1;
+    const int  maxSlots = (256 / K > 96) ? 96 : 256 / K;        // Nuc4Geom<K>::MAXS
+    const int  opc = (2048 / ppb > 32) ? 32 : (2048 / ppb < 8 ? 8 : 2048 / ppb);   // nodes per chunk, as in the kernel
     if ((int) I->slotOf.size () < c.matrix_count)
-        I->slotOf.assign (c.matrix_count, -1);
-    std::vector<int> &slots = I->slotTmp;              // 3 per operation, all evaluations
-    std::vector<int> &clean = I->cleanTmp;             // clean matrices, all evaluations
-    std::vector<int> &nCleanOf = I->nCleanTmp;
-    slots.clear (); clean.clear (); nCleanOf.assign (count, 0);
+        { I->slotOf.assign (c.matrix_count, -1); I->dirtyOf.assign (c.matrix_count, -1); }
+    std::vector<DevChunk> &chunks = I->chunkTmp;   // all evaluations, chunk0 of each included
+    std::vector<DevMat>   &cmats  = I->cmatTmp;
+    std::vector<int>      &slots  = I->slotTmp;    // 3 per operation
+    std::vector<int>      &nChunkOf = I->nChunkTmp;
+    chunks.clear (); cmats.clear (); slots.clear (); nChunkOf.assign (count, 0);
+
+    // ---- pass 1: validate; 4-state path: cut every operation list into chunks whose branches fit
+    //      the kernel's shared-memory P(t) slots ----
     int nMat = 0, nOp = 0, rcv = MB200_SUCCESS;
     for (int e = 0; e < count && rcv == MB200_SUCCESS; e++)
         {
@@ -188,15 +199,41 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         if (ev.root_buffer != MB200_NONE &&
             (!okPartials (I, ev.root_buffer, false) || ev.weights_row < 0 || ev.weights_row >= c.weight_rows))
             return MB200_ERROR_OUT_OF_RANGE;
-        int nSlot = 0;
-        const size_t cleanStart = clean.size ();
         for (int i = 0; i < ev.matrix_update_count; i++)
             {
             const mb200_matrix_update &u = ev.matrix_updates[i];
             if (u.matrix < 0 || u.matrix >= c.matrix_count || u.eigen < 0 || u.eigen >= c.eigen_count)
                 { rcv = MB200_ERROR_OUT_OF_RANGE; break; }
-            I->slotOf[u.matrix] = nSlot++;
+            I->dirtyOf[u.matrix] = i;
             }
+        // chunking
+        DevChunk cur = { nOp, 0, (int) cmats.size (), 0 };
+        std::vector<int> &touched = I->touched;
+        touched.clear ();
+        auto closeChunk = [&] ()
+            {
+            for (int m : touched) I->slotOf[m] = -1;
+            touched.clear ();
+            chunks.push_back (cur);
+            nChunkOf[e]++;
+            cur.opOff += cur.nOp; cur.nOp = 0; cur.matOff = (int) cmats.size (); cur.nMat = 0;
+            };
+        auto slotFor = [&] (int m) -> int
+            {
+            if (I->slotOf[m] < 0)
+                {
+                I->slotOf[m] = cur.nMat++;
+                touched.push_back (m);
+                DevMat dm; dm.matrix = m;
+                int di = I->dirtyOf[m];
+                if (di <= -2) di = -2 - di;       // already rebuilt in an earlier chunk: rebuild again (other
+                                                  // tiles must not wait for tile 0's copy in the matrix buffer)
+                if (fused && di >= 0) { dm.eigen = ev.matrix_updates[di].eigen; dm.length = ev.matrix_updates[di].length; I->dirtyOf[m] = -2 - di; }
+                else                  { dm.eigen = -1; dm.length = 0.0; }
+                cmats.push_back (dm);
+                }
+            return I->slotOf[m];
+            };
         for (int i = 0; i < ev.operation_count && rcv == MB200_SUCCESS; i++)
             {
             const mb200_operation &op = ev.operations[i];
@@ -205,65 +242,84 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
                 (op.child3 != MB200_NONE && (!okPartials (I, op.child3, true) || op.matrix3 < 0 || op.matrix3 >= c.matrix_count)) ||
                 op.scale_write < -1 || op.scale_write >= c.scaler_count || op.scale_remove < -1 || op.scale_remove >= c.scaler_count)
                 { rcv = MB200_ERROR_OUT_OF_RANGE; break; }
+            if (!nuc4)
+                { slots.push_back (-1); slots.push_back (-1); slots.push_back (-1); continue; }
             const int m3 = (op.child3 == MB200_NONE) ? -1 : op.matrix3;
-            const int mm[3] = { op.matrix1, op.matrix2, m3 };
-            for (int q = 0; q < 3; q++)
-                {
-                int sl = -1;
-                if (mm[q] >= 0)
-                    {
-                    if (I->slotOf[mm[q]] < 0)
-                        {
-                        I->slotOf[mm[q]] = nSlot++;
-                        clean.push_back (mm[q]);
-                        }
-                    sl = I->slotOf[mm[q]];
-                    }
-                slots.push_back (sl);
-                }
+            int need = 0;
+            if (I->slotOf[op.matrix1] < 0) need++;
+            if (I->slotOf[op.matrix2] < 0 && op.matrix2 != op.matrix1) need++;
+            if (m3 >= 0 && I->slotOf[m3] < 0 && m3 != op.matrix1 && m3 != op.matrix2) need++;
+            if (cur.nOp >= opc || cur.nMat + need > maxSlots)
+                closeChunk ();
+            slots.push_back (slotFor (op.matrix1));
+            slots.push_back (slotFor (op.matrix2));
+            slots.push_back (m3 >= 0 ? slotFor (m3) : -1);
+            cur.nOp++;
             }
-        // reset the scratch map
+        if (nuc4 && rcv == MB200_SUCCESS)
+            {
+            // fused: dirty branches no node of this evaluation reads still have to be rebuilt
+            if (fused)
+                for (int i = 0; i < ev.matrix_update_count; i++)
+                    if (I->dirtyOf[ev.matrix_updates[i].matrix] == i)
+                        {
+                        if (cur.nMat >= maxSlots) closeChunk ();
+                        slotFor (ev.matrix_updates[i].matrix);
+                        }
+            if (cur.nOp > 0 || cur.nMat > 0 || nChunkOf[e] == 0)
+                closeChunk ();
+            for (int m : touched) I->slotOf[m] = -1;
+            touched.clear ();
+            }
         for (int i = 0; i < ev.matrix_update_count; i++)
             if (ev.matrix_updates[i].matrix >= 0 && ev.matrix_updates[i].matrix < c.matrix_count)
-                I->slotOf[ev.matrix_updates[i].matrix] = -1;
-        for (size_t q = cleanStart; q < clean.size (); q++)
-            I->slotOf[clean[q]] = -1;
-        nCleanOf[e] = (int)(clean.size () - cleanStart);
-        if (nSlot > maxSlots)
-            fused = false;
+                I->dirtyOf[ev.matrix_updates[i].matrix] = -1;
         nMat += ev.matrix_update_count;
         nOp  += ev.operation_count;
         }
     if (rcv != MB200_SUCCESS)
+        {
+        for (int m : I->touched) I->slotOf[m] = -1;
+        I->touched.clear ();
         return rcv;
+        }
 
     // ---- pass 2: lay the blob out ----
-    const int nMatEntries = nMat + (fused ? (int) clean.size () : 0);
+    const int nUpd = fused ? 0 : nMat;                 // update list only feeds the stand-alone P(t) kernel
+    int nExtraChunks = 0;
+    for (int e = 0; e < count; e++) nExtraChunks += (nChunkOf[e] > 1) ? nChunkOf[e] - 1 : 0;
     const int perEvalDbl = 2*K + S;
     const int nDbl = perEvalDbl * count;
-    size_t offEval = mb200_align16 (sizeof(DevBatchHeader));
-    size_t offDbl  = mb200_align16 (offEval + sizeof(DevEval) * (size_t)count);
-    size_t offMat  = mb200_align16 (offDbl + sizeof(double) * (size_t)nDbl);
-    size_t offOp   = mb200_align16 (offMat + sizeof(DevMat) * (size_t)nMatEntries);
-    size_t bytes   = mb200_align16 (offOp + sizeof(DevOp) * (size_t)nOp);
+    size_t offEval  = mb200_align16 (sizeof(DevBatchHeader));
+    size_t offDbl   = mb200_align16 (offEval + sizeof(DevEval) * (size_t)count);
+    size_t offUpd   = mb200_align16 (offDbl + sizeof(double) * (size_t)nDbl);
+    size_t offChunk = mb200_align16 (offUpd + sizeof(DevMat) * (size_t)nUpd);
+    size_t offCmat  = mb200_align16 (offChunk + sizeof(DevChunk) * (size_t)nExtraChunks);
+    size_t offOp    = mb200_align16 (offCmat + sizeof(DevMat) * cmats.size ());
+    size_t bytes    = mb200_align16 (offOp + sizeof(DevOp) * (size_t)nOp);
     int rc = reserveBatch (b, bytes, count);
     if (rc != MB200_SUCCESS)
         return rc;
     DevBatchHeader *h = (DevBatchHeader *) b.hBlob;
-    h->nEval = count; h->nMat = nMatEntries; h->nOp = nOp; h->nDbl = nDbl;
-    DevEval *de = (DevEval *)(b.hBlob + offEval);
-    double  *dd = (double  *)(b.hBlob + offDbl);
-    DevMat  *dm = (DevMat  *)(b.hBlob + offMat);
-    DevOp   *dops = (DevOp *)(b.hBlob + offOp);
+    h->nEval = count; h->nMat = nUpd; h->nOp = nOp; h->nDbl = nDbl;
+    DevEval  *de = (DevEval  *)(b.hBlob + offEval);
+    double   *dd = (double   *)(b.hBlob + offDbl);
+    DevMat   *du = (DevMat   *)(b.hBlob + offUpd);
+    DevChunk *dc = (DevChunk *)(b.hBlob + offChunk);
+    DevMat   *dm = (DevMat   *)(b.hBlob + offCmat);
+    DevOp    *dops = (DevOp  *)(b.hBlob + offOp);
+    if (!cmats.empty ())
+        memcpy (dm, cmats.data (), sizeof(DevMat) * cmats.size ());
 
-    int mOff = 0, oOff = 0;
-    size_t cleanPos = 0, slotPos = 0;
+    int mOff = 0, oOff = 0, chunkPos = 0, extraPos = 0;
+    size_t slotPos = 0;
     b.needInv = false;
     for (int e = 0; e < count; e++)
         {
         const mb200_evaluation &ev = evs[e];
         DevEval &d = de[e];
-        d.nMat = ev.matrix_update_count; d.matOff = mOff;
+        memset (&d, 0, sizeof(d));
+        d.nMat = fused ? 0 : ev.matrix_update_count; d.matOff = mOff;
         d.nOp  = ev.operation_count;     d.opOff  = oOff;
         d.siteDst = ev.site_scaler_dst;  d.siteSrc = ev.site_scaler_src;
         d.root = ev.root_buffer;         d.weightsRow = ev.weights_row;
@@ -271,9 +327,16 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         d.pInvar = ev.p_invar;
         d.dOff = e * perEvalDbl;
         d.fuseP = fused ? 1 : 0;
-        d.nClean = fused ? nCleanOf[e] : 0;
         d.eigen0 = (ev.matrix_update_count > 0) ? ev.matrix_updates[0].eigen : 0;
-        d.pad[0] = d.pad[1] = d.pad[2] = 0;
+        d.nChunk = nChunkOf[e];
+        d.chunkOff = extraPos;
+        if (nChunkOf[e] > 0)
+            {
+            d.chunk0 = chunks[chunkPos];
+            for (int q = 1; q < nChunkOf[e]; q++)
+                dc[extraPos++] = chunks[chunkPos + q];
+            chunkPos += nChunkOf[e];
+            }
         if (d.root != MB200_NONE && d.hasPInvar) b.needInv = true;
         double *dv = dd + d.dOff;
         bool eq = true;
@@ -286,19 +349,13 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         d.equalWeights = eq ? 1 : 0;
         for (int s = 0; s < S; s++)
             dv[2*K + s] = ev.state_freqs[s];
-        for (int i = 0; i < ev.matrix_update_count; i++)
-            {
-            const mb200_matrix_update &u = ev.matrix_updates[i];
-            DevMat &m = dm[mOff + i];
-            m.matrix = u.matrix; m.eigen = u.eigen; m.length = u.length;
-            }
-        if (fused)
-            for (int i = 0; i < nCleanOf[e]; i++)
+        if (!fused)
+            for (int i = 0; i < ev.matrix_update_count; i++)
                 {
-                DevMat &m = dm[mOff + ev.matrix_update_count + i];
-                m.matrix = clean[cleanPos + i]; m.eigen = 0; m.length = 0.0;
+                const mb200_matrix_update &u = ev.matrix_updates[i];
+                DevMat &m = du[mOff + i];
+                m.matrix = u.matrix; m.eigen = u.eigen; m.length = u.length;
                 }
-        cleanPos += nCleanOf[e];
         for (int i = 0; i < ev.operation_count; i++)
             {
             const mb200_operation &op = ev.operations[i];
@@ -306,15 +363,15 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
             o.dest = op.dest; o.c1 = op.child1; o.m1 = op.matrix1; o.c2 = op.child2; o.m2 = op.matrix2;
             o.c3 = op.child3; o.m3 = (op.child3 == MB200_NONE) ? MB200_NONE : op.matrix3;
             o.sw = op.scale_write; o.sr = op.scale_remove;
-            o.s1 = fused ? slots[slotPos] : -1; o.s2 = fused ? slots[slotPos + 1] : -1; o.s3 = fused ? slots[slotPos + 2] : -1;
+            o.s1 = slots[slotPos]; o.s2 = slots[slotPos + 1]; o.s3 = slots[slotPos + 2];
             slotPos += 3;
             }
-        mOff += ev.matrix_update_count + d.nClean;
+        mOff += fused ? 0 : ev.matrix_update_count;
         oOff += ev.operation_count;
         }
-    b.bytes = bytes; b.nEval = count; b.nMat = nMatEntries; b.nOp = nOp; b.nDbl = nDbl;
+    b.bytes = bytes; b.nEval = count; b.nMat = nUpd; b.nOp = nOp; b.nDbl = nDbl;
     b.nDirty = nMat; b.fused = fused;
-    b.offEval = offEval; b.offDbl = offDbl; b.offMat = offMat; b.offOp = offOp;
+    b.offEval = offEval; b.offDbl = offDbl; b.offUpd = offUpd; b.offChunk = offChunk; b.offCmat = offCmat; b.offOp = offOp;
     return MB200_SUCCESS;
 }
 
@@ -330,29 +387,38 @@ int ensureInvMask (Instance *I)
     return MB200_SUCCESS;
 }
 
-int launchNuc4 (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const double *dd, const DevMat *dm,
-                const DevOp *dops, DevResult *res, int seq, bool fused)
+template <int NT>
+int launchNuc4T (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const double *dd, const DevChunk *dc,
+                 const DevMat *dm, const DevOp *dops, DevResult *res, int seq, bool fused)
 {
     switch (ctx.K)
         {
-#define MB200_CASE(KK) case KK: if (fused) eval_nuc4_small_kernel<KK, NT_SMALL><<<grid, NT_SMALL, 0, I->stream>>> (ctx, de, dd, dm, dops, res, seq); \
-                                 else eval_nuc4_stream_kernel<KK, NT_NUC4><<<grid, NT_NUC4, 0, I->stream>>> (ctx, de, dd, dm, dops, res, seq); break;
+#define MB200_CASE(KK) case KK: if (fused) eval_nuc4_kernel<KK, NT, true><<<grid, NT, 0, I->stream>>> (ctx, de, dd, dc, dm, dops, res, seq); \
+                                 else eval_nuc4_kernel<KK, NT, false><<<grid, NT, 0, I->stream>>> (ctx, de, dd, dc, dm, dops, res, seq); break;
         MB200_CASE(1) MB200_CASE(2) MB200_CASE(3) MB200_CASE(4) MB200_CASE(5) MB200_CASE(6) MB200_CASE(7) MB200_CASE(8)
 #undef MB200_CASE
         default: return MB200_ERROR_UNSUPPORTED;
         }
     return MB200_SUCCESS;
+}
+
+int launchNuc4 (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const double *dd, const DevChunk *dc,
+                const DevMat *dm, const DevOp *dops, DevResult *res, int seq, bool fused)
+{
+    const int nt = fused ? NT_SMALL : NT_STREAM;
+    return (nt == 256) ? launchNuc4T<256> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, fused)
+                       : launchNuc4T<128> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, fused);
 }
 
 // the same kernel with the job descriptors riding in the parameter block (no H2D copy)
-template <int CAP>
-int launchNuc4Param (Instance *I, const DevCtx &ctx, dim3 grid, const Batch &b, DevResult *res, int seq)
+template <int CAP, int NT>
+int launchNuc4ParamT (Instance *I, const DevCtx &ctx, dim3 grid, const Batch &b, DevResult *res, int seq)
 {
     const ParamBlob<CAP> &blob = *reinterpret_cast<const ParamBlob<CAP> *>(b.hBlob);
-    BlobOffsets off = { (int) b.offEval, (int) b.offDbl, (int) b.offMat, (int) b.offOp };
+    BlobOffsets off = { (int) b.offEval, (int) b.offDbl, (int) b.offUpd, (int) b.offChunk, (int) b.offCmat, (int) b.offOp };
     switch (ctx.K)
         {
-#define MB200_CASE(KK) case KK: eval_nuc4_small_pkernel<KK, NT_SMALL, CAP><<<grid, NT_SMALL, 0, I->stream>>> (ctx, blob, off, res, seq); break;
+#define MB200_CASE(KK) case KK: eval_nuc4_pkernel<KK, NT, CAP><<<grid, NT, 0, I->stream>>> (ctx, blob, off, res, seq); break;
         MB200_CASE(1) MB200_CASE(2) MB200_CASE(3) MB200_CASE(4) MB200_CASE(5) MB200_CASE(6) MB200_CASE(7) MB200_CASE(8)
 #undef MB200_CASE
         default: return MB200_ERROR_UNSUPPORTED;
@@ -360,7 +426,14 @@ int launchNuc4Param (Instance *I, const DevCtx &ctx, dim3 grid, const Batch &b, 
     return MB200_SUCCESS;
 }
 
-const int PARAM_SMALL = 2048, PARAM_MID = 8192, PARAM_BIG = 30720;
+template <int CAP>
+int launchNuc4Param (Instance *I, const DevCtx &ctx, dim3 grid, const Batch &b, DevResult *res, int seq)
+{
+    return (NT_SMALL == 256) ? launchNuc4ParamT<CAP, 256> (I, ctx, grid, b, res, seq)
+                             : launchNuc4ParamT<CAP, 128> (I, ctx, grid, b, res, seq);
+}
+
+const int PARAM_SMALL = 4096, PARAM_BIG = 30720;
 
 bool paramEligible (const Instance *I, const Batch &b)
 {
@@ -371,10 +444,12 @@ bool paramEligible (const Instance *I, const Batch &b)
 // delivered through the parameter block when it fits (otherwise the caller has copied it to dBlob)
 int launch (Instance *I, Batch &b, DevResult *res, bool viaParams)
 {
-    const DevEval *de = (const DevEval *)(b.dBlob + b.offEval);
-    const double  *dd = (const double  *)(b.dBlob + b.offDbl);
-    const DevMat  *dm = (const DevMat  *)(b.dBlob + b.offMat);
-    const DevOp   *dops = (const DevOp *)(b.dBlob + b.offOp);
+    const DevEval  *de = (const DevEval  *)(b.dBlob + b.offEval);
+    const double   *dd = (const double   *)(b.dBlob + b.offDbl);
+    const DevMat   *du = (const DevMat   *)(b.dBlob + b.offUpd);
+    const DevChunk *dc = (const DevChunk *)(b.dBlob + b.offChunk);
+    const DevMat   *dm = (const DevMat   *)(b.dBlob + b.offCmat);
+    const DevOp    *dops = (const DevOp  *)(b.dBlob + b.offOp);
     DevCtx ctx = I->ctx;
     const int seq = ++I->seq;
 
@@ -386,7 +461,7 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams)
     if (b.nDirty > 0 && !b.fused)
         {
         dim3 grid (b.nMat, ctx.K);
-        tiprobs_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, b.nEval, dd, dm);
+        tiprobs_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, b.nEval, dd, du);
         CK (cudaGetLastError ());
         I->launches++;
         }
@@ -401,12 +476,11 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams)
         int rc;
         if (viaParams)
             {
-            if (b.bytes <= (size_t) PARAM_SMALL)    rc = launchNuc4Param<PARAM_SMALL> (I, ctx, grid, b, res, seq);
-            else if (b.bytes <= (size_t) PARAM_MID) rc = launchNuc4Param<PARAM_MID> (I, ctx, grid, b, res, seq);
-            else                                    rc = launchNuc4Param<PARAM_BIG> (I, ctx, grid, b, res, seq);
+            if (b.bytes <= (size_t) PARAM_SMALL) rc = launchNuc4Param<PARAM_SMALL> (I, ctx, grid, b, res, seq);
+            else                                 rc = launchNuc4Param<PARAM_BIG> (I, ctx, grid, b, res, seq);
             }
         else
-            rc = launchNuc4 (I, ctx, grid, de, dd, dm, dops, res, seq, b.fused);
+            rc = launchNuc4 (I, ctx, grid, de, dd, dc, dm, dops, res, seq, b.fused);
         if (rc != MB200_SUCCESS) return rc;
         }
     else
@@ -498,7 +572,7 @@ void destroy (Instance *I)
     if (I->stream) cudaStreamSynchronize (I->stream);
     freeBatch (I->scratch);
     for (Batch *b : I->batches) if (b) { freeBatch (*b); delete b; }
-    cudaFree (I->dTip8); cudaFree (I->dTip64); cudaFree (I->dTipPartAmbig); cudaFree (I->dTipDense); cudaFree (I->dPartials); cudaFree (I->dMatrices);
+    cudaFree (I->dTip8); cudaFree (I->dTip64); cudaFree (I->dTipPartAmbig); cudaFree (I->dPartials); cudaFree (I->dMatrices);
     cudaFree (I->dScalers); cudaFree (I->dWeights); cudaFree (I->dEigen); cudaFree (I->dInvMask);
     cudaFree (I->dTilePartial); cudaFree (I->dTileAbort); cudaFree (I->dTicket); cudaFree (I->dDbg);
     if (I->hostStage) cudaFreeHost (I->hostStage);
@@ -591,8 +665,6 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     ALLOC (I->dTip8,     (size_t)cfg->tip_count * C);
     ALLOC (I->dTip64,    (size_t)cfg->tip_count * C * sizeof(uint64_t));
     ALLOC (I->dTipPartAmbig, (size_t)cfg->tip_count * sizeof(int));
-    if (S == 4)
-        ALLOC (I->dTipDense, (size_t)cfg->tip_count * C * sizeof(float4));
     ALLOC (I->dPartials, nInt * K * C * Sp * sizeof(float));
     ALLOC (I->dMatrices, (size_t)cfg->matrix_count * K * S * S * sizeof(float));
     ALLOC (I->dScalers,  (size_t)cfg->scaler_count * C * sizeof(float));
@@ -627,7 +699,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     x.scalerCount = cfg->scaler_count; x.eigenCount = cfg->eigen_count; x.weightRows = cfg->weight_rows;
     x.tilePatterns = nuc4 ? nuc4PatternsPerBlock (K, false) : TP;
     x.numTiles = I->maxTiles;
-    x.tip8 = I->dTip8; x.tip64 = I->dTip64; x.tipPartAmbig = I->dTipPartAmbig; x.tipDense4 = I->dTipDense; x.partials = I->dPartials; x.matrices = I->dMatrices;
+    x.tip8 = I->dTip8; x.tip64 = I->dTip64; x.tipPartAmbig = I->dTipPartAmbig; x.partials = I->dPartials; x.matrices = I->dMatrices;
     x.scalers = I->dScalers; x.eigen = I->dEigen; x.weights = I->dWeights; x.invMask = I->dInvMask;
     x.tilePartial = I->dTilePartial; x.tileAbort = I->dTileAbort; x.ticket = I->dTicket; x.dbg = I->dDbg;
 
@@ -662,25 +734,21 @@ int mb200_set_tip_states (int instance, int tip, const uint64_t *masks)
     if (tip < 0 || tip >= I->cfg.tip_count || !masks) return MB200_ERROR_OUT_OF_RANGE;
     int rc = use (I); if (rc) return rc;
     const int C = I->cfg.pattern_count;
-    rc = ensureStage (I, (size_t)C * 32); if (rc) return rc;
+    rc = ensureStage (I, (size_t)C * 9); if (rc) return rc;
     uint64_t *h64 = (uint64_t *) I->hostStage;
-    float4   *hd  = (float4 *)(h64 + C);
-    uint8_t  *h8  = (uint8_t *)(hd + C);
+    uint8_t  *h8  = (uint8_t *)(h64 + C);
     const uint64_t full = (I->cfg.state_count == 64) ? ~(uint64_t)0 : (((uint64_t)1 << I->cfg.state_count) - 1);
     int partAmbig = 0;      // isPartAmbig of SetUpTermState (src/mcmc.c:18631-18651)
     for (int c = 0; c < C; c++)
         {
         h64[c] = masks[c] & full;
         h8[c]  = (uint8_t)(h64[c] & 0xff);
-        hd[c]  = make_float4 ((h64[c] & 1) ? 1.f : 0.f, (h64[c] & 2) ? 1.f : 0.f, (h64[c] & 4) ? 1.f : 0.f, (h64[c] & 8) ? 1.f : 0.f);
         if (h64[c] != full && (h64[c] == 0 || (h64[c] & (h64[c] - 1)) != 0))
             partAmbig = 1;
         }
     CK (cudaMemcpyAsync (I->dTipPartAmbig + tip, &partAmbig, sizeof(int), cudaMemcpyHostToDevice, I->stream));
     CK (cudaMemcpyAsync (I->dTip64 + (size_t)tip * C, h64, (size_t)C * 8, cudaMemcpyHostToDevice, I->stream));
     CK (cudaMemcpyAsync (I->dTip8 + (size_t)tip * C, h8, (size_t)C, cudaMemcpyHostToDevice, I->stream));
-    if (I->dTipDense)
-        CK (cudaMemcpyAsync (I->dTipDense + (size_t)tip * C, hd, (size_t)C * sizeof(float4), cudaMemcpyHostToDevice, I->stream));
     CK (cudaStreamSynchronize (I->stream));
     I->invMaskValid = false;
     return MB200_SUCCESS;

@@ -54,14 +54,14 @@ tiprobs_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, const 
         int e = 0;                                // the evaluation whose update list holds this matrix
         while (e + 1 < nEval && (int) blockIdx.x >= evals[e + 1].matOff)
             e++;
-        while (e > 0 && evals[e].nMat + evals[e].nClean == 0)   // matOff is non-decreasing; skip empty lists
+        while (e > 0 && evals[e].nMat == 0)       // matOff is non-decreasing; skip empty lists
             e--;
         sEvalIdx = e;
         }
     __syncthreads ();
     const DevEval *ev = evals + sEvalIdx;
-    if (ev->fuseP || (int) blockIdx.x >= ev->matOff + ev->nMat)
-        return;                                   // rebuilt inside the pruning kernel / clean entry
+    if (ev->fuseP)
+        return;                                   // rebuilt inside the pruning kernel
     const double  *rates = dvals + ev->dOff;
     const double  *freqs = rates + 2*ctx.K;
     const double   t  = mu.length * rates[k];
@@ -259,51 +259,61 @@ __device__ __forceinline__ float tip_dot4 (const float4 p, int mask)
     return r;
 }
 
-// One site pattern is spread over L = pow2ceil(K) adjacent lanes, one rate category each: a
-// lane owns one float4 (4 states) per conditional-likelihood vector.  The rescaler's max over
-// categories is a log2(L)-step xor-shuffle; everything else is lane-local.
+// ---------------------------------------------------------------------------------------
+// S = 4: fused evaluation (K2 + K3 + K4 + K5, and K1 when FUSE).
+//
+// Thread mapping.  One site pattern is spread over L = pow2ceil(K) adjacent lanes, one rate
+// category each: a lane owns one float4 (the 4 states) per conditional-likelihood vector.  The
+// rescaler's max over categories is a log2(L)-step xor-shuffle; everything else is lane-local.
+//
+// The operation list of an evaluation is cut (on the host) into chunks of <= OPC nodes that touch
+// <= MAXS distinct branches.  Per chunk the CTA
+//   1. stages the chunk's node list and branch list into shared memory;
+//   2. fills one shared-memory slot per branch with the K x 4 rows of P(t): rebuilt in double
+//      precision from the eigensystem when the branch is dirty and FUSE is on (TiProbs_Gen; the CTA
+//      of tile 0 also publishes it to the matrix buffer), copied from the matrix buffer otherwise;
+//   3. walks the nodes WITHOUT any barrier -- a thread only ever touches its own pattern: child
+//      loads are prefetched one node ahead, the child that is the previous node's result stays in
+//      registers, tips are 1-byte state masks expanded to 0/1 vectors in registers, so every child
+//      takes the same matvec path; the scaler maxima go to shared memory;
+//   4. takes the logarithms of the chunk's scalers in one batched pass (full ILP instead of a
+//      ~50-instruction dependent chain per node), writes the node scalers, reads the old ones, and
+//      replays the site-scaler additions in the reference's order (... - old(o) + new(o) ...), so
+//      the float rounding sequence is the reference's.
+// Root integration, the weighted log-sum and the ticketed cross-tile reduction close the kernel.
+//
+// FUSE = true : small launches (latency-bound: one warp per scheduler, the dependent instruction
+//               chain per node is what counts).  No separate P(t) kernel, no launch gap.
+// FUSE = false: large grids (issue/bandwidth-bound).  P(t) comes from tiprobs_kernel once instead
+//               of once per CTA; no double-precision exp code, so more CTAs fit per SM.
+// ---------------------------------------------------------------------------------------
 template <int K> struct Nuc4Geom
 {
     static constexpr int L = (K <= 1) ? 1 : (K <= 2) ? 2 : (K <= 4) ? 4 : 8;   // lanes per pattern
-    static constexpr int MAXS = (256 / K > 128) ? 128 : 256 / K;               // P(t) slots in shared memory
-
+    static constexpr int MAXS = (256 / K > 96) ? 96 : 256 / K;                 // P(t) slots per chunk
 };
 
-// ---------------------------------------------------------------------------------------
-// S = 4, latency-bound regime (small alignments: one warp per scheduler, nothing to hide
-// latency with, so the dependent instruction chain per node is what counts).
-//   * the job (header, rates/weights/freqs, matrix list, operation list) arrives in the kernel
-//     parameter block or in global memory and is staged to shared memory in one round;
-//   * K1 fused: the CTA rebuilds the evaluation's dirty P(t) itself (double precision, TiProbs_Gen)
-//     and copies the clean P(t) its nodes touch, so every node finds its matrices in a shared-
-//     memory slot and the node loop needs NO barrier and no staging code;
-//   * tips are dense 0/1 vectors: every child takes the same load + matvec path;
-//   * child loads are prefetched one node ahead; the child that is the previous node's result
-//     stays in registers;
-//   * the node-scaler logarithms (double precision, ~25 % of a node's dependent chain) are taken
-//     out of the node loop: the maxima go to shared memory and a batched pass at the end of each
-//     chunk takes the logs with full ILP, then replays the site-scaler additions in the
-//     reference's order (... - old(o) + new(o) ...), so the float rounding sequence is unchanged.
-// ---------------------------------------------------------------------------------------
-template <int K, int NT>
+template <int K, int NT, bool FUSE>
 __device__ __forceinline__ void
-nuc4_small_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
-                 const DevMat *__restrict__ mats, const DevOp *__restrict__ ops, DevResult *out, int seq)
+nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
+           const DevChunk *__restrict__ chunks, const DevMat *__restrict__ cmats,
+           const DevOp *__restrict__ ops, DevResult *out, int seq)
 {
     constexpr int L    = Nuc4Geom<K>::L;
     constexpr int MAXS = Nuc4Geom<K>::MAXS;
     constexpr int PPB  = NT / L;                 // patterns per CTA
-    constexpr int OPC  = (2048 / PPB > 32) ? 32 : (2048 / PPB < 8 ? 8 : 2048 / PPB);   // nodes per chunk (scaler staging)
+    constexpr int OPC  = (2048 / PPB > 32) ? 32 : (2048 / PPB < 8 ? 8 : 2048 / PPB);   // nodes per chunk
     constexpr int LDR  = 5;                      // float4 per (slot,k): 4 rows + 1 pad (bank spread)
-    __shared__ float4 sP[MAXS][K][LDR];          // P(t) rows of every branch this evaluation touches
-    __shared__ double sExp[MAXS][K][4];          // exp(lambda_s t) of the dirty branches
+    __shared__ float4 sP[MAXS][K][LDR];          // P(t) rows of every branch the chunk touches
+    __shared__ double sExp[FUSE ? MAXS : 1][K][4];   // exp(lambda_s t) of the dirty branches
     __shared__ __align__(16) DevMat sMat[MAXS];
     __shared__ __align__(16) DevOp  sOps[OPC];
     __shared__ float  sNew[OPC][PPB];            // per node: scaler maximum, later its logarithm
     __shared__ float  sOld[OPC][PPB];            // per node: the old node scaler to remove
     __shared__ __align__(16) DevEval sEv;
+    __shared__ __align__(16) DevChunk sCh;
     __shared__ __align__(16) double sD[2*K + 4]; // rates[K], catW[K], freqs[4]
-    __shared__ double sEig[72];                  // lambda_re[4], lambda_im[4], c_ijk[64] of slot eigen0
+    __shared__ double sEig[FUSE ? 72 : 1];       // lambda_re[4], lambda_im[4], c_ijk[64] of slot eigen0
 
     MB200_STAMP (0);
     if (threadIdx.x < (int)(sizeof(DevEval) / 4))
@@ -320,76 +330,22 @@ nuc4_small_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const dou
     const int   cc     = (c < C) ? c : C - 1;
     const size_t bufStride = (size_t)K * C;                 // float4 per partials buffer
     float4 *partials4 = reinterpret_cast<float4 *>(ctx.partials);
-    const int   nOp = sEv.nOp, nMat = sEv.nMat, nClean = sEv.nClean;
     const bool  shortcutFlag = (sEv.flags & MB200_SHORTCUT_FLAG) != 0;
     const unsigned groupBase = (threadIdx.x & 31) & ~(L - 1);
+    const int   eig0 = sEv.eigen0;
+    const int   nChunk = sEv.nChunk;
 
-    // the whole job in ONE round of independent loads
+    // evaluation-wide inputs, one round of independent loads (together with chunk 0's lists below)
     if (threadIdx.x < 2*K + 4)
         sD[threadIdx.x] = dvals[sEv.dOff + threadIdx.x];
-    for (int e = threadIdx.x; e < (nMat + nClean) * 4; e += NT)
-        reinterpret_cast<int *>(sMat)[e] = reinterpret_cast<const int *>(mats + sEv.matOff)[e];
-    {
-    const int nFirst = min (OPC, nOp);
-    for (int e = threadIdx.x; e < nFirst * (int)(sizeof(DevOp)/4); e += NT)
-        reinterpret_cast<int *>(sOps)[e] = reinterpret_cast<const int *>(ops + sEv.opOff)[e];
-    }
-    // the eigensystem the evaluation's branches share (lambda + c_ijk = 72 doubles), from HBM/L2
-    // in the same round; a branch that names another slot reads it from global memory instead
-    const int eig0 = sEv.eigen0;
-    if (nMat > 0 && threadIdx.x < 72)
+    if (FUSE && threadIdx.x < 72)
         sEig[threadIdx.x] = ctx.eigen[(size_t)eig0 * 72 + threadIdx.x];
     float  lnScaler = (sEv.siteSrc >= 0) ? ctx.scalers[(size_t)sEv.siteSrc * C + cc] : 0.0f;
-    __syncthreads ();
-    MB200_STAMP (2);
-
-    // ---- K1 fused (TiProbs_Gen, src/likelihood.c:9499-9542) + copy of the clean matrices ----
-    for (int r = threadIdx.x; r < nMat * K * 4; r += NT)
-        {
-        const int s = r & 3, k = (r >> 2) % K, m = r / (4*K);
-        const double lam = (sMat[m].eigen == eig0) ? sEig[s] : ctx.eigen[(size_t)sMat[m].eigen * 72 + s];
-        sExp[m][k][s] = exp (lam * (sMat[m].length * sD[k]));
-        }
-    for (int r = threadIdx.x; r < nClean * K * 4; r += NT)
-        {
-        const int i = r & 3, k = (r >> 2) % K, m = nMat + r / (4*K);
-        sP[m][k][i] = reinterpret_cast<const float4 *>(ctx.matrices + (size_t)sMat[m].matrix * K * 16)[k*4 + i];
-        }
-    __syncthreads ();
-    for (int r = threadIdx.x; r < nMat * K * 4; r += NT)
-        {
-        const int i = r & 3, k = (r >> 2) % K, m = r / (4*K);
-        const double t = sMat[m].length * sD[k];
-        float4 row;
-        if (t < MB200_TIME_MIN)
-            row = make_float4 (i == 0 ? 1.f : 0.f, i == 1 ? 1.f : 0.f, i == 2 ? 1.f : 0.f, i == 3 ? 1.f : 0.f);
-        else if (t > MB200_TIME_MAX)
-            row = make_float4 ((float) sD[2*K], (float) sD[2*K+1], (float) sD[2*K+2], (float) sD[2*K+3]);
-        else
-            {
-            const double *cij = (sMat[m].eigen == eig0) ? (sEig + 8 + i*16) : (ctx.eigen + (size_t)sMat[m].eigen * 72 + 8 + i*16);
-            const double e0 = sExp[m][k][0], e1 = sExp[m][k][1], e2 = sExp[m][k][2], e3 = sExp[m][k][3];
-            float v[4];
-            #pragma unroll
-            for (int j = 0; j < 4; j++)
-                {
-                double sum = 0.0;
-                sum += cij[j*4+0] * e0; sum += cij[j*4+1] * e1; sum += cij[j*4+2] * e2; sum += cij[j*4+3] * e3;
-                v[j] = (float) ((sum < 0.0) ? 0.0 : sum);
-                }
-            row = make_float4 (v[0], v[1], v[2], v[3]);
-            }
-        sP[m][k][i] = row;
-        if (blockIdx.x == 0)                      // tile 0 publishes the rebuilt matrices
-            reinterpret_cast<float4 *>(ctx.matrices + (size_t)sMat[m].matrix * K * 16)[k*4 + i] = row;
-        }
-    __syncthreads ();
-    MB200_STAMP (3);
 
     float4 cur = make_float4 (0.f, 0.f, 0.f, 0.f);
     int    curBuf = -2;
     float4 xn[3];                                 // prefetched child vectors of the next node
-    int    tn[3];                                 // -1: vector in xn, -2: take `cur`, 0..15 tip mask, 16: shortcut
+    int    tn[3];                                 // -1: vector in xn, -2: take `cur`, 16: tip shortcut (all ones)
 
     auto issue = [&] (const DevOp &op, int prevDest)
         {
@@ -403,16 +359,14 @@ nuc4_small_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const dou
                 continue;
             if (child < ctx.tipCount)
                 {
-                if (!shortcutFlag)
-                    xn[ch] = ctx.tipDense4[(size_t)child * C + cc];           // dense 0/1 vector
-                else
-                    {
-                    tn[ch] = ctx.tip8[(size_t)child * C + cc] & 15;
-                    // scalar-kernel shortcut: a missing observation on a tip without partial
-                    // ambiguity is exactly 1.0 (preLike tables, src/likelihood.c:816-832)
-                    if (tn[ch] == 15 && !ctx.tipPartAmbig[child])
-                        tn[ch] = 16;
-                    }
+                // tip: 1-byte state mask -> 0/1 vector; the dense matvec then equals the reference's
+                // 0/1 matvec bit for bit (products by 0 and 1 are exact)
+                const int mask = ctx.tip8[(size_t)child * C + cc];
+                xn[ch] = make_float4 ((mask & 1) ? 1.f : 0.f, (mask & 2) ? 1.f : 0.f, (mask & 4) ? 1.f : 0.f, (mask & 8) ? 1.f : 0.f);
+                // scalar-kernel shortcut: a missing observation on a tip without partial ambiguity
+                // contributes exactly 1.0 (preLike tables, src/likelihood.c:816-832)
+                if (shortcutFlag && (mask & 15) == 15 && !ctx.tipPartAmbig[child])
+                    tn[ch] = 16;
                 }
             else if (child == prevDest)
                 tn[ch] = -2;
@@ -421,58 +375,106 @@ nuc4_small_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const dou
             }
         };
 
-    for (int base = 0; base < nOp; base += OPC)
+    for (int ci = 0; ci < nChunk; ci++)
         {
-        const int nChunk = min (OPC, nOp - base);
-        if (base > 0)
+        // ---- 1. chunk descriptor, node list, branch list ----
+        if (ci == 0)
             {
-            for (int e = threadIdx.x; e < nChunk * (int)(sizeof(DevOp)/4); e += NT)
-                reinterpret_cast<int *>(sOps)[e] = reinterpret_cast<const int *>(ops + sEv.opOff + base)[e];
+            ;
+            }
+        else
+            {
+            __syncthreads ();                     // previous chunk completely done: shared arrays free
+            if (threadIdx.x < 4)
+                reinterpret_cast<int *>(&sCh)[threadIdx.x] = reinterpret_cast<const int *>(chunks + sEv.chunkOff + ci - 1)[threadIdx.x];
             __syncthreads ();
             }
-        issue (sOps[0], curBuf);
+        const DevChunk ch = (ci == 0) ? sEv.chunk0 : sCh;
+        for (int e = threadIdx.x; e < ch.nMat * 4; e += NT)
+            reinterpret_cast<int *>(sMat)[e] = reinterpret_cast<const int *>(cmats + ch.matOff)[e];
+        for (int e = threadIdx.x; e < ch.nOp * (int)(sizeof(DevOp)/4); e += NT)
+            reinterpret_cast<int *>(sOps)[e] = reinterpret_cast<const int *>(ops + ch.opOff)[e];
+        __syncthreads ();
+        if (ci == 0) MB200_STAMP (2);
 
-        // ---- node loop: no barrier, a thread only ever touches its own pattern ----
-        for (int oo = 0; oo < nChunk; oo++)
+        // ---- 2. P(t) slots (K1 fused: TiProbs_Gen, src/likelihood.c:9499-9542) ----
+        for (int r = threadIdx.x; r < ch.nMat * K * 4; r += NT)
+            {
+            const int s = r & 3, k = (r >> 2) % K, m = r / (4*K);
+            const int eg = sMat[m].eigen;
+            if (FUSE && eg >= 0)
+                {
+                const double lam = (eg == eig0) ? sEig[s] : ctx.eigen[(size_t)eg * 72 + s];
+                sExp[m][k][s] = exp (lam * (sMat[m].length * sD[k]));
+                }
+            else                                  // clean branch (or P(t) prepared by tiprobs_kernel): copy row s
+                sP[m][k][s] = reinterpret_cast<const float4 *>(ctx.matrices + (size_t)sMat[m].matrix * K * 16)[k*4 + s];
+            }
+        if (FUSE)
+            {
+            __syncthreads ();
+            for (int r = threadIdx.x; r < ch.nMat * K * 4; r += NT)
+                {
+                const int i = r & 3, k = (r >> 2) % K, m = r / (4*K);
+                const int eg = sMat[m].eigen;
+                if (eg < 0)
+                    continue;
+                const double t = sMat[m].length * sD[k];
+                float4 row;
+                if (t < MB200_TIME_MIN)
+                    row = make_float4 (i == 0 ? 1.f : 0.f, i == 1 ? 1.f : 0.f, i == 2 ? 1.f : 0.f, i == 3 ? 1.f : 0.f);
+                else if (t > MB200_TIME_MAX)
+                    row = make_float4 ((float) sD[2*K], (float) sD[2*K+1], (float) sD[2*K+2], (float) sD[2*K+3]);
+                else
+                    {
+                    const double *cij = (eg == eig0) ? (sEig + 8 + i*16) : (ctx.eigen + (size_t)eg * 72 + 8 + i*16);
+                    const double e0 = sExp[m][k][0], e1 = sExp[m][k][1], e2 = sExp[m][k][2], e3 = sExp[m][k][3];
+                    float v[4];
+                    #pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        {
+                        double sum = 0.0;
+                        sum += cij[j*4+0] * e0; sum += cij[j*4+1] * e1; sum += cij[j*4+2] * e2; sum += cij[j*4+3] * e3;
+                        v[j] = (float) ((sum < 0.0) ? 0.0 : sum);
+                        }
+                    row = make_float4 (v[0], v[1], v[2], v[3]);
+                    }
+                sP[m][k][i] = row;
+                if (blockIdx.x == 0)              // tile 0 publishes the rebuilt matrices
+                    reinterpret_cast<float4 *>(ctx.matrices + (size_t)sMat[m].matrix * K * 16)[k*4 + i] = row;
+                }
+            }
+        __syncthreads ();
+        if (ci == 0) MB200_STAMP (3);
+
+        // ---- 3. node loop: no barrier, a thread only ever touches its own pattern ----
+        const int nOp = ch.nOp;
+        if (nOp > 0)
+            issue (sOps[0], curBuf);
+        for (int oo = 0; oo < nOp; oo++)
             {
             const DevOp op = sOps[oo];
-            float4 x[3];
-            int    tmask[3];
-            #pragma unroll
-            for (int ch = 0; ch < 3; ch++)
-                {
-                x[ch] = (tn[ch] == -2) ? cur : xn[ch];
-                tmask[ch] = (tn[ch] == -2) ? -1 : tn[ch];
-                }
-            if (oo + 1 < nChunk)
+            float4 x0 = (tn[0] == -2) ? cur : xn[0];
+            float4 x1 = (tn[1] == -2) ? cur : xn[1];
+            float4 x2 = (tn[2] == -2) ? cur : xn[2];
+            const int t0 = tn[0], t1 = tn[1], t2 = tn[2];
+            if (oo + 1 < nOp)
                 issue (sOps[oo + 1], op.dest);    // next node's loads in flight
 
-            float4 res = matvec4 (sP[op.s1][kk], x[0]);
-            float4 v   = matvec4 (sP[op.s2][kk], x[1]);
+            float4 res = matvec4 (sP[op.s1][kk], x0);
+            float4 v   = matvec4 (sP[op.s2][kk], x1);
             if (shortcutFlag)
                 {
-                if (tmask[0] >= 0)
-                    res = (tmask[0] == 16) ? make_float4 (1.f, 1.f, 1.f, 1.f)
-                        : make_float4 (tip_dot4 (sP[op.s1][kk][0], tmask[0]), tip_dot4 (sP[op.s1][kk][1], tmask[0]),
-                                       tip_dot4 (sP[op.s1][kk][2], tmask[0]), tip_dot4 (sP[op.s1][kk][3], tmask[0]));
-                if (tmask[1] >= 0)
-                    v = (tmask[1] == 16) ? make_float4 (1.f, 1.f, 1.f, 1.f)
-                      : make_float4 (tip_dot4 (sP[op.s2][kk][0], tmask[1]), tip_dot4 (sP[op.s2][kk][1], tmask[1]),
-                                     tip_dot4 (sP[op.s2][kk][2], tmask[1]), tip_dot4 (sP[op.s2][kk][3], tmask[1]));
+                if (t0 == 16) res = make_float4 (1.f, 1.f, 1.f, 1.f);
+                if (t1 == 16) v   = make_float4 (1.f, 1.f, 1.f, 1.f);
                 }
             res.x *= v.x; res.y *= v.y; res.z *= v.z; res.w *= v.w;
             if (op.c3 >= 0)                       // unrooted interior root: third neighbour
                 {
-                v = matvec4 (sP[op.s3][kk], x[2]);
-                if (shortcutFlag && tmask[2] >= 0)
-                    v = (tmask[2] == 16) ? make_float4 (1.f, 1.f, 1.f, 1.f)
-                      : make_float4 (tip_dot4 (sP[op.s3][kk][0], tmask[2]), tip_dot4 (sP[op.s3][kk][1], tmask[2]),
-                                     tip_dot4 (sP[op.s3][kk][2], tmask[2]), tip_dot4 (sP[op.s3][kk][3], tmask[2]));
+                v = matvec4 (sP[op.s3][kk], x2);
+                if (shortcutFlag && t2 == 16) v = make_float4 (1.f, 1.f, 1.f, 1.f);
                 res.x *= v.x; res.y *= v.y; res.z *= v.z; res.w *= v.w;
                 }
-#ifdef MB200_PHASE_TIMING
-            if (base + oo == 3 && blockIdx.x == 0 && threadIdx.x == 0 && res.x > -1e30f) MB200_STAMP (42);
-#endif
             float m = 0.0f;                       // 0 marks "node not rescaled"
             if (op.sw >= 0)
                 {
@@ -489,12 +491,12 @@ nuc4_small_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const dou
                 partials4[(size_t)(op.dest - ctx.tipCount) * bufStride + (size_t)kk * C + c] = res;
             cur = res;
             curBuf = op.dest;
-            MB200_STAMP (8 + base + oo);
+            if (ci == 0) MB200_STAMP (8 + oo);
             }
 
-        // ---- batched scaler pass: logs with full ILP, node scalers out, old scalers in ----
+        // ---- 4. batched scaler pass: logs with full ILP, node scalers out, old scalers in ----
         __syncthreads ();
-        for (int e = threadIdx.x; e < nChunk * PPB; e += NT)
+        for (int e = threadIdx.x; e < nOp * PPB; e += NT)
             {
             const int oo = e / PPB, p = e % PPB;
             const int cp = c0 + p;
@@ -507,11 +509,7 @@ nuc4_small_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const dou
                     // (float) log (double): CondLikeScaler_NUC4 / _SSE (src/likelihood.c:5183, 5328);
                     // the correctly rounded value, which the AVX variant's logf returns too in all
                     // but rare last-bit cases
-#ifdef MB200_SCALER_LOGF
-                    sc = logf (sNew[oo][p]);
-#else
                     sc = (float) log ((double) sNew[oo][p]);
-#endif
                     ctx.scalers[(size_t)sw * C + cp] = sc;
                     }
                 if (sr >= 0)
@@ -524,304 +522,13 @@ nuc4_small_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const dou
         // site scaler: the reference's sequence  ... - old(o) + new(o) ...  (RemoveNodeScalers then
         // CondLikeScaler per node, src/likelihood.c:7938-7965), replayed per pattern
         if (lk == 0)
-            for (int oo = 0; oo < nChunk; oo++)
+            for (int oo = 0; oo < nOp; oo++)
                 {
                 lnScaler -= sOld[oo][pl];
                 if (sOps[oo].sw >= 0)
                     lnScaler += sNew[oo][pl];
                 }
-        if (base + OPC < nOp)
-            __syncthreads ();                     // before sOps / sNew are overwritten
         }
-
-    MB200_STAMP (4);
-    if (sEv.siteDst >= 0 && active && lk == 0)
-        ctx.scalers[(size_t)sEv.siteDst * C + c] = lnScaler;
-
-    if (sEv.root < 0)
-        return;
-
-    // ---- root integration (Likelihood_NUC4_FMA, src/likelihood.c:6468-6625) ----
-    if (sEv.root != curBuf)
-        cur = partials4[(size_t)(sEv.root - ctx.tipCount) * bufStride + (size_t)kk * C + cc];
-    const double *freqs = sD + 2*K, *catW = sD + K;
-    const float fA = (float) freqs[0], fC = (float) freqs[1], fG = (float) freqs[2], fT = (float) freqs[3];
-    // the reference accumulates one fused chain over k = 0..K-1 and the four states; the chain
-    // hops from lane to lane so that the rounding sequence is the same
-    float likeF = 0.0f;
-    if (sEv.equalWeights)
-        {
-        #pragma unroll
-        for (int k = 0; k < K; k++)
-            {
-            float mine = fmaf (cur.x, fA, likeF);
-            mine = fmaf (cur.y, fC, mine);
-            mine = fmaf (cur.z, fG, mine);
-            mine = fmaf (cur.w, fT, mine);
-            likeF = __shfl_sync (0xffffffffu, mine, groupBase + k);
-            }
-        likeF *= (float) catW[0];
-        }
-    else
-        {
-        float s = cur.x * fA;
-        s = fmaf (cur.y, fC, s);
-        s = fmaf (cur.z, fG, s);
-        s = fmaf (cur.w, fT, s);
-        #pragma unroll
-        for (int k = 0; k < K; k++)
-            {
-            const float mine = fmaf (s, (float) catW[kk], likeF);
-            likeF = __shfl_sync (0xffffffffu, mine, groupBase + k);
-            }
-        }
-    double likeI = 0.0;
-    if (sEv.hasPInvar)
-        {
-        const unsigned int im = (unsigned int) ctx.invMask[cc];
-        float li = (im & 1) ? fA : 0.0f;
-        li = fmaf ((im & 2) ? 1.0f : 0.0f, fC, li);
-        li = fmaf ((im & 4) ? 1.0f : 0.0f, fG, li);
-        li = fmaf ((im & 8) ? 1.0f : 0.0f, fT, li);
-        li *= (float) sEv.pInvar;
-        likeI = (double) li;
-        }
-    int    abortFlag = 0;
-    double term = 0.0;
-    if (active && lk == 0)
-        term = site_term ((double) likeF, likeI, sEv.hasPInvar, sEv.flags & MB200_QUIRK_FLAG, lnScaler,
-                          ctx.weights[(size_t)sEv.weightsRow * C + c], abortFlag);
-    MB200_STAMP (5);
-    finish_lnl<NT> (ctx, blockIdx.y, term, abortFlag, out, seq);
-    MB200_STAMP (6);
-}
-
-// ---------------------------------------------------------------------------------------
-// S = 4, bandwidth-bound regime (large grids): P(t) comes from tiprobs_kernel, tips are 1-byte
-// state masks (16x less traffic than a dense vector), P rows of each node are staged through a
-// double-buffered shared-memory slot one node ahead, child loads are prefetched one node ahead.
-// No double-precision exp code and no P(t) cache, so 12 CTAs of 128 threads fit per SM.
-// ---------------------------------------------------------------------------------------
-template <int K, int NT>
-__device__ __forceinline__ void
-nuc4_stream_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
-           const DevMat *__restrict__ mats, const DevOp *__restrict__ ops, DevResult *out, int seq)
-{
-    constexpr int L    = Nuc4Geom<K>::L;
-    constexpr int OPC  = 32;                     // operations staged per chunk
-    constexpr int LDR  = 5;                      // float4 per (slot,k): 4 rows + 1 pad (bank spread)
-    __shared__ float4 sStage[2][3][K][LDR];      // P(t) of clean branches, double-buffered by op parity
-    __shared__ DevOp  sOps[OPC];
-    __shared__ DevEval sEv;
-    __shared__ double sD[2*K + 4];               // rates[K], catW[K], freqs[4]
-
-    MB200_STAMP (0);
-    // header: 16 ints of DevEval, one per lane
-    if (threadIdx.x < (int)(sizeof(DevEval) / 4))
-        reinterpret_cast<int *>(&sEv)[threadIdx.x] = reinterpret_cast<const int *>(evals + blockIdx.y)[threadIdx.x];
-    __syncthreads ();
-    MB200_STAMP (1);
-    const int   C      = ctx.C;
-    const int   lk     = threadIdx.x % L;                   // this lane's rate category
-    const int   kk     = (lk < K) ? lk : K - 1;
-    const int   c      = blockIdx.x * (NT / L) + threadIdx.x / L;
-    const bool  active = (c < C) && (lk < K);
-    const int   cc     = (c < C) ? c : C - 1;
-    const size_t bufStride = (size_t)K * C;                 // float4 per partials buffer
-    float4 *partials4 = reinterpret_cast<float4 *>(ctx.partials);
-    const int   nOp = sEv.nOp;
-    const bool  shortcutFlag = (sEv.flags & MB200_SHORTCUT_FLAG) != 0;
-    const unsigned groupBase = (threadIdx.x & 31) & ~(L - 1);
-
-    // everything the evaluation needs from the job, fetched in ONE round of independent loads
-    if (threadIdx.x < 2*K + 4)
-        sD[threadIdx.x] = dvals[sEv.dOff + threadIdx.x];
-    {
-    const int nFirst = min (OPC, nOp);
-    for (int e = threadIdx.x; e < nFirst * (int)(sizeof(DevOp)/4); e += NT)
-        reinterpret_cast<int *>(sOps)[e] = reinterpret_cast<const int *>(ops + sEv.opOff)[e];
-    }
-    float  lnScaler = (sEv.siteSrc >= 0) ? ctx.scalers[(size_t)sEv.siteSrc * C + cc] : 0.0f;
-    __syncthreads ();
-    MB200_STAMP (2);
-
-    MB200_STAMP (3);
-
-    float4 cur = make_float4 (0.f, 0.f, 0.f, 0.f);
-    int    curBuf = -2;
-
-    // stage the P rows of operation o's CLEAN branches into buffer o & 1 (dirty ones are in sDirty)
-    auto stage = [&] (const DevOp &op, int pb)
-        {
-        #pragma unroll
-        for (int ch = 0; ch < 3; ch++)
-            {
-            const int child = (ch == 0) ? op.c1 : (ch == 1) ? op.c2 : op.c3;
-            const int mat   = (ch == 0) ? op.m1 : (ch == 1) ? op.m2 : op.m3;
-            if (child < 0)
-                continue;
-            const float4 *P4 = reinterpret_cast<const float4 *>(ctx.matrices + (size_t)mat * K * 16);
-            for (int e = threadIdx.x; e < K*4; e += NT)
-                sStage[pb][ch][e >> 2][e & 3] = P4[e];
-            }
-        };
-
-    // Software pipeline over the operation list.  While node o is being computed, the loads of
-    // node o+1 that do not depend on node o (sibling subtree, tips, the old node scaler, the clean
-    // P(t) rows) are already in flight, and the logarithm of node o-1's scaler -- which nothing
-    // but the site-scaler sum waits for -- is evaluated in the shadow of those loads.  The child
-    // that IS node o's result never leaves registers (`cur`).
-    float4 xn[3];                                 // prefetched child vectors of the next node
-    int    tn[3];                                 // -1: vector in xn, -2: take `cur`, 0..15 tip mask, 16: shortcut
-    float  osn = 0.0f;                            // prefetched old node scaler
-    float  pendM = 1.0f;                          // scaler of the previous node, log still owed
-    int    pendSw = -1;
-
-    auto issue = [&] (const DevOp &op, int prevDest)
-        {
-        #pragma unroll
-        for (int ch = 0; ch < 3; ch++)
-            {
-            tn[ch] = -1;
-            xn[ch] = make_float4 (0.f, 0.f, 0.f, 0.f);
-            const int child = (ch == 0) ? op.c1 : (ch == 1) ? op.c2 : op.c3;
-            if (child < 0)
-                continue;
-            if (child < ctx.tipCount)
-                {
-                tn[ch] = ctx.tip8[(size_t)child * C + cc] & 15;   // 1-byte state mask
-                // scalar-kernel shortcut: a missing observation on a tip without partial
-                // ambiguity is exactly 1.0 (preLike tables, src/likelihood.c:816-832)
-                if (shortcutFlag && tn[ch] == 15 && !ctx.tipPartAmbig[child])
-                    tn[ch] = 16;
-                }
-            else if (child == prevDest)
-                tn[ch] = -2;
-            else
-                xn[ch] = partials4[(size_t)(child - ctx.tipCount) * bufStride + (size_t)kk * C + cc];
-            }
-        osn = (op.sr >= 0) ? ctx.scalers[(size_t)op.sr * C + cc] : 0.0f;
-        };
-
-    auto settle = [&] ()                          // the owed logarithm: node scaler out, site scaler up
-        {
-        if (pendSw >= 0)
-            {
-            // (float) log (double): what CondLikeScaler_NUC4 / _SSE compute (src/likelihood.c:5183,
-            // 5328) -- the correctly rounded value, which the AVX variant's logf also returns in all
-            // but rare last-bit cases
-#ifdef MB200_SCALER_LOGF
-            const float sc = logf (pendM);
-#else
-            const float sc = (float) log ((double) pendM);
-#endif
-            if (active && lk == 0)
-                ctx.scalers[(size_t)pendSw * C + c] = sc;
-            lnScaler += sc;
-            pendSw = -1;
-            }
-        };
-
-    for (int base = 0; base < nOp; base += OPC)
-        {
-        const int nChunk = min (OPC, nOp - base);
-        if (base > 0)
-            {
-            __syncthreads ();                     // everyone is done with the previous chunk's sOps
-            for (int e = threadIdx.x; e < nChunk * (int)(sizeof(DevOp)/4); e += NT)
-                reinterpret_cast<int *>(sOps)[e] = reinterpret_cast<const int *>(ops + sEv.opOff + base)[e];
-            __syncthreads ();
-            }
-        stage (sOps[0], base & 1);
-        issue (sOps[0], curBuf);
-
-        for (int oo = 0; oo < nChunk; oo++)
-            {
-            const int   o  = base + oo;
-            const DevOp op = sOps[oo];
-            const int   pb = o & 1;
-            const int   nChild = (op.c3 >= 0) ? 3 : 2;
-
-            // staged rows (and, first time round, sDirty) visible; every thread is past op o-1,
-            // so stage buffer (o+1)&1 is free
-            MB200_SUBSTAMP (o, 0);
-            __syncthreads ();
-            MB200_SUBSTAMP (o, 1);
-
-            // this node's operands: prefetched one node ago, or the previous result
-            float4 x[3];
-            int    tmask[3];
-            #pragma unroll
-            for (int ch = 0; ch < 3; ch++)
-                {
-                tmask[ch] = tn[ch];
-                x[ch] = (tn[ch] == -2) ? cur : xn[ch];
-                if (tn[ch] == -2) tmask[ch] = -1;
-                }
-            const float oldScaler = osn;
-
-            // next node: stage its clean matrices, put its loads in flight
-            if (oo + 1 < nChunk)
-                {
-                stage (sOps[oo + 1], (o + 1) & 1);
-                issue (sOps[oo + 1], op.dest);
-                }
-
-            // the previous node's logarithm, in the shadow of those loads
-            settle ();
-
-            // ---- two (three at the unrooted interior root) matvecs and their product ----
-            float4 res = make_float4 (1.f, 1.f, 1.f, 1.f);
-            #pragma unroll
-            for (int ch = 0; ch < 3; ch++)
-                {
-                if (ch == 2 && nChild == 2)
-                    break;
-                const float4 *rows = sStage[pb][ch][kk];
-                float4 v;
-                if (tmask[ch] == 16)
-                    v = make_float4 (1.f, 1.f, 1.f, 1.f);
-                else if (tmask[ch] >= 0)
-                    v = make_float4 (tip_dot4 (rows[0], tmask[ch]), tip_dot4 (rows[1], tmask[ch]),
-                                     tip_dot4 (rows[2], tmask[ch]), tip_dot4 (rows[3], tmask[ch]));
-                else
-                    v = matvec4 (rows, x[ch]);
-                if (ch == 0)
-                    res = v;
-                else
-                    {
-                    res.x *= v.x; res.y *= v.y; res.z *= v.z; res.w *= v.w;
-                    }
-                }
-#ifdef MB200_PHASE_TIMING
-            if (o == 3 && blockIdx.x == 0 && threadIdx.x == 0 && res.x + oldScaler > -1e30f) MB200_STAMP (42);
-#endif
-            // ---- scaler bookkeeping: remove the node's old scaler, rescale; the new scaler's
-            //      logarithm is settled one node later (same order of float additions as the
-            //      reference: ... + new(o-1) - old(o) + new(o) ...) ----
-            lnScaler -= oldScaler;
-            if (op.sw >= 0)
-                {
-                float m = (lk < K) ? fmaxf (fmaxf (res.x, res.y), fmaxf (res.z, res.w)) : 0.0f;
-                m = fmaxf (m, 0.0f);
-                #pragma unroll
-                for (int off = 1; off < L; off <<= 1)
-                    m = fmaxf (m, __shfl_xor_sync (0xffffffffu, m, off));
-                res.x /= m; res.y /= m; res.z /= m; res.w /= m;
-                pendM = m;
-                pendSw = op.sw;
-#ifdef MB200_PHASE_TIMING
-                if (o == 3 && blockIdx.x == 0 && threadIdx.x == 0 && res.x > -1e30f) MB200_STAMP (43);
-#endif
-                }
-            if (active)
-                partials4[(size_t)(op.dest - ctx.tipCount) * bufStride + (size_t)kk * C + c] = res;
-            cur = res;
-            curBuf = op.dest;
-            MB200_STAMP (8 + o);
-            }
-        }
-    settle ();
 
     MB200_STAMP (4);
     if (sEv.siteDst >= 0 && active && lk == 0)
@@ -886,33 +593,26 @@ nuc4_stream_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const do
 }
 
 // ---- kernel entry points of the 4-state path ----
-// latency path, job descriptors in global memory (device-resident batches)
-template <int K, int NT>
-__global__ void __launch_bounds__(NT, 1)
-eval_nuc4_small_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
-                        const DevMat *__restrict__ mats, const DevOp *__restrict__ ops, DevResult *out, int seq)
+// job descriptors in global memory (device-resident batches, large jobs)
+template <int K, int NT, bool FUSE>
+__global__ void __launch_bounds__(NT, FUSE ? 1 : 1024 / NT)
+eval_nuc4_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
+                  const DevChunk *__restrict__ chunks, const DevMat *__restrict__ cmats,
+                  const DevOp *__restrict__ ops, DevResult *out, int seq)
 {
-    nuc4_small_body<K, NT> (ctx, evals, dvals, mats, ops, out, seq);
+    nuc4_body<K, NT, FUSE> (ctx, evals, dvals, chunks, cmats, ops, out, seq);
 }
 
-// latency path, job descriptors delivered in the kernel parameter block (host call path):
+// job descriptors delivered in the kernel parameter block (host call path of small evaluations):
 // no host->device copy on the way in
 template <int K, int NT, int CAP>
 __global__ void __launch_bounds__(NT, 1)
-eval_nuc4_small_pkernel (DevCtx ctx, const __grid_constant__ ParamBlob<CAP> blob, BlobOffsets off, DevResult *out, int seq)
+eval_nuc4_pkernel (DevCtx ctx, const __grid_constant__ ParamBlob<CAP> blob, BlobOffsets off, DevResult *out, int seq)
 {
     const char *b = blob.bytes;
-    nuc4_small_body<K, NT> (ctx, reinterpret_cast<const DevEval *>(b + off.eval), reinterpret_cast<const double *>(b + off.dbl),
-                            reinterpret_cast<const DevMat *>(b + off.mat), reinterpret_cast<const DevOp *>(b + off.op), out, seq);
-}
-
-// bandwidth path
-template <int K, int NT>
-__global__ void __launch_bounds__(NT, (2048 / NT > 12 ? 12 : 2048 / NT))
-eval_nuc4_stream_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
-                         const DevMat *__restrict__ mats, const DevOp *__restrict__ ops, DevResult *out, int seq)
-{
-    nuc4_stream_body<K, NT> (ctx, evals, dvals, mats, ops, out, seq);
+    nuc4_body<K, NT, true> (ctx, reinterpret_cast<const DevEval *>(b + off.eval), reinterpret_cast<const double *>(b + off.dbl),
+                            reinterpret_cast<const DevChunk *>(b + off.chunk), reinterpret_cast<const DevMat *>(b + off.cmat),
+                            reinterpret_cast<const DevOp *>(b + off.op), out, seq);
 }
 
 // ---------------------------------------------------------------------------------------

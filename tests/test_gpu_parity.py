@@ -237,3 +237,21 @@ def test_full_size_subset_equals_oracle_on_subset(engine_lib, oracle_lib, name, 
     with small.create(oracle_lib) as o:
         (l_o,), _ = o.evaluate(small.full_evaluation(0))
     assert rel(l_sub, l_o) < LNL_RTOL
+
+
+@pytest.mark.parametrize("tips,K", [(40, 4), (90, 4), (150, 1), (70, 8)])
+def test_large_trees_span_several_chunks(engine_lib, oracle_lib, tips, K):
+    """Operation lists longer than one shared-memory chunk (more nodes / more branches than the
+    kernel's P(t) slots): full evaluations and partial updates against the oracle."""
+    pr = workloads.make_problem(4, K, 150, tips, 1, seed=tips)
+    rng = np.random.default_rng(3)
+    with pr.create(engine_lib) as e, pr.create(oracle_lib) as o:
+        o.set_arith(1)
+        sp = pr.full_evaluation(0)
+        (le,), _ = e.evaluate(sp); (lo,), _ = o.evaluate(sp)
+        assert rel(le, lo) < SYN_RTOL
+        _compare_state(e, o, sp, 4)
+        for it in range(6):
+            sp = pr.random_branch_update(0, rng)
+            (le,), _ = e.evaluate(sp); (lo,), _ = o.evaluate(sp)
+            assert rel(le, lo) < SYN_RTOL
