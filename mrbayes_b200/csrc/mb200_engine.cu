@@ -6,6 +6,7 @@
 #include "mb200.h"
 #include "mb200_device.cuh"
 #include "mb200_kernels.cuh"
+#include "mb200_kernels_tc.cuh"
 
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -44,6 +45,9 @@ struct Instance
     uint64_t     *dTip64 = nullptr;
     int          *dTipPartAmbig = nullptr;
     int           seq = 0;               // launch sequence number stamped into results
+    float        *dSplit = nullptr;      // tensor-core path: pre-split (hi, lo) canonical images of every P(t)
+    int           tcS = 0;               // 20 or 61 when the tcgen05 kernel serves this instance, else 0
+    size_t        smemTc = 0;
     float        *dPartials = nullptr, *dMatrices = nullptr, *dScalers = nullptr, *dWeights = nullptr;
     double       *dEigen = nullptr;
     uint64_t     *dInvMask = nullptr;
@@ -483,6 +487,23 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams)
             rc = launchNuc4 (I, ctx, grid, de, dd, dc, dm, dops, res, seq, b.fused);
         if (rc != MB200_SUCCESS) return rc;
         }
+    else if (I->tcS)
+        {
+        // tensor-core path: refresh the pre-split images of the matrices just rebuilt, then prune
+        if (b.nDirty > 0)
+            {
+            dim3 sg (b.nMat, ctx.K);
+            if (I->tcS == 61) tc_split_kernel<61><<<sg, 128, 0, I->stream>>> (I->dMatrices, I->dSplit, du, 0, ctx.K);
+            else              tc_split_kernel<20><<<sg, 128, 0, I->stream>>> (I->dMatrices, I->dSplit, du, 0, ctx.K);
+            CK (cudaGetLastError ());
+            I->launches++;
+            }
+        ctx.tilePatterns = 128;
+        ctx.numTiles = (ctx.C + 127) / 128;
+        dim3 grid (ctx.numTiles, b.nEval);
+        if (I->tcS == 61) eval_tc_kernel<61><<<grid, 128, I->smemTc, I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
+        else              eval_tc_kernel<20><<<grid, 128, I->smemTc, I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
+        }
     else
         {
         eval_gen_kernel<NT_GEN><<<dim3 (ctx.numTiles, b.nEval), NT_GEN, I->smemGen, I->stream>>> (ctx, de, dd, dops, res, seq);
@@ -572,7 +593,7 @@ void destroy (Instance *I)
     if (I->stream) cudaStreamSynchronize (I->stream);
     freeBatch (I->scratch);
     for (Batch *b : I->batches) if (b) { freeBatch (*b); delete b; }
-    cudaFree (I->dTip8); cudaFree (I->dTip64); cudaFree (I->dTipPartAmbig); cudaFree (I->dPartials); cudaFree (I->dMatrices);
+    cudaFree (I->dTip8); cudaFree (I->dTip64); cudaFree (I->dTipPartAmbig); cudaFree (I->dSplit); cudaFree (I->dPartials); cudaFree (I->dMatrices);
     cudaFree (I->dScalers); cudaFree (I->dWeights); cudaFree (I->dEigen); cudaFree (I->dInvMask);
     cudaFree (I->dTilePartial); cudaFree (I->dTileAbort); cudaFree (I->dTicket); cudaFree (I->dDbg);
     if (I->hostStage) cudaFreeHost (I->hostStage);
@@ -657,7 +678,12 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     while (TP > 1 && smemFor (TP) > 96*1024) TP >>= 1;
     I->smemGen = smemFor (TP);
     const bool nuc4 = (S == 4 && K <= 8);
-    I->maxTiles = nuc4 ? (C + nuc4PatternsPerBlock (K, false) - 1) / nuc4PatternsPerBlock (K, false) : (C + TP - 1) / TP;
+    if (!getenv ("MB200_DISABLE_TC"))
+        {
+        if (S == 61 && K == 1) I->tcS = 61;      // 61-state codon, tcgen05 path
+        if (S == 20 && K <= 4) I->tcS = 20;      // 20-state amino acids, tcgen05 path
+        }
+    I->maxTiles = I->tcS ? (C + 127) / 128 : nuc4 ? (C + nuc4PatternsPerBlock (K, false) - 1) / nuc4PatternsPerBlock (K, false) : (C + TP - 1) / TP;
 
 #define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc ((void **)&(ptr), (bytes)); if (e_ != cudaSuccess) { \
         cudaGetLastError (); destroy (I); return (e_ == cudaErrorMemoryAllocation) ? MB200_ERROR_OUT_OF_MEMORY : MB200_ERROR_CUDA; } } while (0)
@@ -670,6 +696,18 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     ALLOC (I->dScalers,  (size_t)cfg->scaler_count * C * sizeof(float));
     ALLOC (I->dWeights,  (size_t)cfg->weight_rows * C * sizeof(float));
     ALLOC (I->dEigen,    (size_t)cfg->eigen_count * I->eigenStride * sizeof(double));
+    if (I->tcS)
+        {
+        const size_t fl = (I->tcS == 61) ? tc_split_floats<61> () : tc_split_floats<20> ();
+        ALLOC (I->dSplit, (size_t)cfg->matrix_count * K * fl * sizeof(float));
+        cudaMemsetAsync (I->dSplit, 0, (size_t)cfg->matrix_count * K * fl * sizeof(float), I->stream);
+        const int NPv = (I->tcS == 61) ? 64 : 32, KPv = (I->tcS == 61) ? 64 : 24;
+        I->smemTc = (size_t)(2 * 128 * KPv + 2 * NPv * KPv) * sizeof(float);
+        cudaError_t ea = (I->tcS == 61)
+            ? cudaFuncSetAttribute (eval_tc_kernel<61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) I->smemTc)
+            : cudaFuncSetAttribute (eval_tc_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) I->smemTc);
+        if (ea != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
+        }
     ALLOC (I->dInvMask,  (size_t)C * sizeof(uint64_t));
     ALLOC (I->dTilePartial, (size_t)I->maxEval * I->maxTiles * sizeof(double));
     ALLOC (I->dTileAbort,   (size_t)I->maxEval * I->maxTiles * sizeof(int));
@@ -697,7 +735,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     x.S = S; x.Sp = Sp; x.K = K; x.C = C;
     x.tipCount = cfg->tip_count; x.partialsCount = cfg->partials_count; x.matrixCount = cfg->matrix_count;
     x.scalerCount = cfg->scaler_count; x.eigenCount = cfg->eigen_count; x.weightRows = cfg->weight_rows;
-    x.tilePatterns = nuc4 ? nuc4PatternsPerBlock (K, false) : TP;
+    x.tilePatterns = I->tcS ? 128 : nuc4 ? nuc4PatternsPerBlock (K, false) : TP;
     x.numTiles = I->maxTiles;
     x.tip8 = I->dTip8; x.tip64 = I->dTip64; x.tipPartAmbig = I->dTipPartAmbig; x.partials = I->dPartials; x.matrices = I->dMatrices;
     x.scalers = I->dScalers; x.eigen = I->dEigen; x.weights = I->dWeights; x.invMask = I->dInvMask;
@@ -945,6 +983,13 @@ int mb200_set_transition_matrix (int instance, int matrix, const float *in)
     int rc = use (I); if (rc) return rc;
     const size_t n = (size_t)I->cfg.category_count * I->cfg.state_count * I->cfg.state_count;
     CK (cudaMemcpyAsync (I->dMatrices + (size_t)matrix * n, in, n * sizeof(float), cudaMemcpyHostToDevice, I->stream));
+    if (I->tcS)
+        {
+        dim3 sg (1, I->cfg.category_count);
+        if (I->tcS == 61) tc_split_kernel<61><<<sg, 128, 0, I->stream>>> (I->dMatrices, I->dSplit, nullptr, matrix, I->cfg.category_count);
+        else              tc_split_kernel<20><<<sg, 128, 0, I->stream>>> (I->dMatrices, I->dSplit, nullptr, matrix, I->cfg.category_count);
+        I->launches++;
+        }
     CK (cudaStreamSynchronize (I->stream));
     return MB200_SUCCESS;
 }

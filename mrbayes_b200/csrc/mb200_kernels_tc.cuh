@@ -1,0 +1,340 @@
+// mb200_kernels_tc.cuh -- tensor-core (tcgen05 / TMEM) pruning kernel for the state counts where a
+// node update really is a dense contraction: 20-state amino-acid and 61-state codon models
+// (CondLikeDown/Root_Gen*, CondLikeScaler_Gen*, Likelihood_Gen*; reference src/likelihood.c:204,
+// 2152, 4939, 5764).
+//
+// Per node, per rate category, per child:   D[128 patterns][S] = CL_child[128][S] * P^T[S][S]
+// is one 128 x NP x KP tcgen05.mma chain (kind::tf32, FP32 accumulate in TMEM), NP/KP = S padded to
+// the MMA granularity (61 -> 64/64, 20 -> 32/24).  FP32 accuracy is recovered with the 3xTF32 split
+//     x = hi + lo,  hi = rna_tf32(x),  lo = rna_tf32(x - hi):   A*B ~= Ahi*Bhi + (Ahi*Blo + Alo*Bhi)
+// (plain TF32 would cost ~2e-4 per product; the split leaves ~7e-7, see tests/probes/umma_probe.cu).
+// The large term and the two small correction terms go to SEPARATE TMEM accumulators so that the
+// tensor core's truncating accumulation bias is paid on KP/8 steps only, and are added in FP32 (RN)
+// in the epilogue.
+//
+// CTA = 128 threads = one tile of 128 site patterns; grid = (tiles, evaluations); like the other
+// pruning kernels the CTA walks the evaluation's whole operation list for its tile, no inter-CTA sync.
+//   operands  A (child CLs): loaded from HBM with 512-byte-coalesced LDG.128, split hi/lo in registers,
+//             written to shared memory in the canonical K-major core-matrix layout (umma_common.cuh);
+//             the child that is the previous node's result comes straight from registers; tips are
+//             expanded from their state masks (exact in TF32, no lo term).
+//             B (P(t), pre-split hi/lo in canonical layout by tiprobs_kernel): one bulk async copy
+//             (TMA engine, mbarrier complete_tx) per child and category.
+//   MMA       one elected thread issues 3 * KP/8 tcgen05.mma; tcgen05.commit -> mbarrier.
+//   epilogue  thread t = pattern row t = TMEM lane t: tcgen05.ld, product over children in registers,
+//             max / divide / log, coalesced-row float4 stores, site-scaler bookkeeping, root integration.
+#pragma once
+#include "mb200_device.cuh"
+#include "umma_common.cuh"
+
+template <int S> struct TcGeom;
+template <> struct TcGeom<61> { static constexpr int NP = 64, KP = 64, KMAX = 1; };
+template <> struct TcGeom<20> { static constexpr int NP = 32, KP = 24, KMAX = 4; };
+
+// floats per pre-split matrix image: hi then lo, each NP x KP in canonical layout
+template <int S> __host__ __device__ constexpr int tc_split_floats () { return 2 * TcGeom<S>::NP * TcGeom<S>::KP; }
+
+// P(t) [S][S] row-major (row = ancestral state i) -> hi/lo images of B[n = i][k = j] in canonical layout
+template <int S>
+__device__ __forceinline__ void tc_write_split_entry (float *img, int i, int j, float p)
+{
+    constexpr int NP = TcGeom<S>::NP, KP = TcGeom<S>::KP;
+    const float hi = umma::to_tf32 (p), lo = umma::to_tf32 (p - hi);
+    const uint32_t off = umma::canon_off (i, j, NP) / 4;
+    img[off] = hi;
+    img[NP * KP + off] = lo;
+}
+
+// split images of matrices already present in the matrix buffer (set_transition_matrix, or a
+// tiprobs launch predating the split buffer): grid = (matrices, K)
+template <int S>
+__global__ void tc_split_kernel (const float *__restrict__ matrices, float *__restrict__ split, const DevMat *__restrict__ upd,
+                                 int first, int K)
+{
+    constexpr int NP = TcGeom<S>::NP, KP = TcGeom<S>::KP;
+    const int m = upd ? upd[blockIdx.x].matrix : first + blockIdx.x, k = blockIdx.y;
+    const float *P = matrices + ((size_t)m * K + k) * S * S;
+    float *img = split + ((size_t)m * K + k) * tc_split_floats<S> ();
+    for (int idx = threadIdx.x; idx < NP * KP; idx += blockDim.x)
+        {
+        const int i = idx / KP, j = idx % KP;
+        tc_write_split_entry<S> (img, i, j, (i < S && j < S) ? P[i * S + j] : 0.0f);
+        }
+}
+
+template <int S>
+__global__ void __launch_bounds__(128, 1)
+eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
+                const DevOp *__restrict__ ops, const float *__restrict__ split, DevResult *out, int seq)
+{
+    using namespace umma;
+    constexpr int NP = TcGeom<S>::NP, KP = TcGeom<S>::KP, KMAX = TcGeom<S>::KMAX;
+    constexpr int TM = 128;                                   // patterns per tile = MMA M
+    constexpr int TMEM_COLS = (2 * NP <= 64) ? 64 : 128;      // main + correction accumulators
+    constexpr uint32_t LBO_A = (TM / 8) * 128, LBO_B = (NP / 8) * 128, SBO = 128;
+
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    float *sAhi = reinterpret_cast<float *>(tc_smem);            // TM x KP, canonical
+    float *sAlo = sAhi + TM * KP;
+    float *sB   = sAlo + TM * KP;                             // hi image then lo image, NP x KP each
+    __shared__ uint64_t barB, barM;
+    __shared__ uint32_t tmemBase;
+    __shared__ DevEval sEv;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Sp = ctx.Sp, K = ctx.K, C = ctx.C;
+    if (tid < (int)(sizeof(DevEval) / 4))
+        reinterpret_cast<int *>(&sEv)[tid] = reinterpret_cast<const int *>(evals + blockIdx.y)[tid];
+    if (warp == 0)
+        tmem_alloc<TMEM_COLS> (&tmemBase);
+    if (tid == 0)
+        { mbar_init (&barB, 1); mbar_init (&barM, 1); mbar_fence_init (); }
+    fence_before_sync ();
+    __syncthreads ();
+    fence_after_sync ();
+    const uint32_t tMain = tmemBase, tCorr = tmemBase + NP;
+    const uint32_t laneSel = (uint32_t)(warp * 32) << 16;      // this warp's TMEM lane quadrant
+    uint32_t parB = 0, parM = 0;
+
+    const double *catW = dvals + sEv.dOff + K, *freqs = dvals + sEv.dOff + 2*K;
+    const int   c0 = blockIdx.x * TM;
+    const int   np = min (TM, C - c0);
+    const int   c  = c0 + tid;                                 // this thread's pattern (epilogue role)
+    const bool  active = tid < np;
+    const size_t bufStride = (size_t)K * C * Sp;
+    const bool  shortcutFlag = (sEv.flags & MB200_SHORTCUT_FLAG) != 0;
+    const uint64_t fullMask = (S == 64) ? ~(uint64_t)0 : ((((uint64_t)1) << S) - 1);
+    constexpr uint32_t idesc = make_idesc_tf32 (TM, NP);
+
+    float site = (active && sEv.siteSrc >= 0) ? ctx.scalers[(size_t)sEv.siteSrc * C + c] : 0.0f;
+    float prod[KMAX][S];                                       // this pattern's node result, all categories
+    int   curBuf = -2;
+
+    for (int o = 0; o < sEv.nOp; o++)
+        {
+        const DevOp op = ops[sEv.opOff + o];
+        const int nChild = (op.c3 >= 0) ? 3 : 2;
+        float res[KMAX][S];
+
+        #pragma unroll
+        for (int k = 0; k < KMAX; k++)
+            {
+            if (k >= K) break;
+            for (int ch = 0; ch < nChild; ch++)
+                {
+                const int child = (ch == 0) ? op.c1 : (ch == 1) ? op.c2 : op.c3;
+                const int mat   = (ch == 0) ? op.m1 : (ch == 1) ? op.m2 : op.m3;
+                const bool isTip = child < ctx.tipCount;
+
+                // ---- B: pre-split P(t) image, bulk async copy ----
+                if (tid == 0)
+                    {
+                    mbar_expect_tx (&barB, (uint32_t)(tc_split_floats<S> () * 4));
+                    bulk_g2s (sB, split + ((size_t)mat * K + k) * tc_split_floats<S> (), (uint32_t)(tc_split_floats<S> () * 4), &barB);
+                    }
+
+                // ---- A: child tile -> hi / lo canonical images ----
+                bool tipFull = false;                          // scalar-kernel shortcut applies to my pattern
+                if (isTip)
+                    {
+                    // thread t expands pattern t's state mask: 0/1 are exact in TF32, lo image unused
+                    const uint64_t m = active ? ctx.tip64[(size_t)child * C + c] : 0;
+                    tipFull = shortcutFlag && active && m == fullMask && !ctx.tipPartAmbig[child];
+                    #pragma unroll
+                    for (int q = 0; q < KP / 4; q++)
+                        {
+                        float4 h;
+                        h.x = ((m >> (q*4 + 0)) & 1) ? 1.f : 0.f; h.y = ((m >> (q*4 + 1)) & 1) ? 1.f : 0.f;
+                        h.z = ((m >> (q*4 + 2)) & 1) ? 1.f : 0.f; h.w = ((m >> (q*4 + 3)) & 1) ? 1.f : 0.f;
+                        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sAhi) + canon_off (tid, q*4, TM)) = h;
+                        }
+                    }
+                else if (child == curBuf)
+                    {
+                    // the previous node's result: my row is still in registers
+                    #pragma unroll
+                    for (int q = 0; q < KP / 4; q++)
+                        {
+                        float x[4], h[4], l[4];
+                        #pragma unroll
+                        for (int e = 0; e < 4; e++)
+                            {
+                            x[e] = (q*4 + e < S && active) ? prod[k][(q*4 + e < S) ? q*4 + e : 0] : 0.f;
+                            h[e] = to_tf32 (x[e]); l[e] = to_tf32 (x[e] - h[e]);
+                            }
+                        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sAhi) + canon_off (tid, q*4, TM)) = make_float4 (h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sAlo) + canon_off (tid, q*4, TM)) = make_float4 (l[0], l[1], l[2], l[3]);
+                        }
+                    }
+                else
+                    {
+                    // HBM -> registers -> shared: a warp covers 8 rows x 4 chunks (64 contiguous bytes per
+                    // row: full 32-byte sectors) and stores 8 x 16 B contiguous per quarter-warp (no conflicts)
+                    const float *src = ctx.partials + (size_t)(child - ctx.tipCount) * bufStride + ((size_t)k * C + c0) * Sp;
+                    constexpr int QB = (KP / 4 + 3) / 4;       // chunk blocks of 4
+                    for (int it = warp; it < (TM / 8) * QB; it += 4)
+                        {
+                        const int rb = it / QB, qb = it % QB;
+                        const int r = rb * 8 + (lane & 7), q = qb * 4 + (lane >> 3);
+                        if (q < KP / 4)
+                            {
+                            float4 x = make_float4 (0.f, 0.f, 0.f, 0.f);
+                            if (r < np && q * 4 < Sp)
+                                x = *reinterpret_cast<const float4 *>(src + (size_t)r * Sp + q * 4);
+                            const float4 h = make_float4 (to_tf32 (x.x), to_tf32 (x.y), to_tf32 (x.z), to_tf32 (x.w));
+                            const float4 l = make_float4 (to_tf32 (x.x - h.x), to_tf32 (x.y - h.y), to_tf32 (x.z - h.z), to_tf32 (x.w - h.w));
+                            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sAhi) + canon_off (r, q*4, TM)) = h;
+                            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sAlo) + canon_off (r, q*4, TM)) = l;
+                            }
+                        }
+                    }
+                fence_async_smem ();                           // generic-proxy stores -> async proxy (MMA)
+                mbar_wait (&barB, parB); parB ^= 1;            // B image landed
+                fence_before_sync ();
+                __syncthreads ();
+                fence_after_sync ();
+
+                // ---- MMA: main = Ahi*Bhi ; corr = Ahi*Blo (+ Alo*Bhi) ----
+                if (tid == 0)
+                    {
+                    const uint32_t aHi = smem_u32 (sAhi), aLo = smem_u32 (sAlo), bHi = smem_u32 (sB), bLo = smem_u32 (sB + NP * KP);
+                    #pragma unroll
+                    for (int ks = 0; ks < KP / 8; ks++)
+                        mma_tf32 (tMain, make_desc (aHi + ks * 2 * LBO_A, LBO_A, SBO), make_desc (bHi + ks * 2 * LBO_B, LBO_B, SBO), idesc, ks > 0);
+                    #pragma unroll
+                    for (int ks = 0; ks < KP / 8; ks++)
+                        mma_tf32 (tCorr, make_desc (aHi + ks * 2 * LBO_A, LBO_A, SBO), make_desc (bLo + ks * 2 * LBO_B, LBO_B, SBO), idesc, ks > 0);
+                    if (!isTip)
+                        {
+                        #pragma unroll
+                        for (int ks = 0; ks < KP / 8; ks++)
+                            mma_tf32 (tCorr, make_desc (aLo + ks * 2 * LBO_A, LBO_A, SBO), make_desc (bHi + ks * 2 * LBO_B, LBO_B, SBO), idesc, true);
+                        }
+                    mma_commit (&barM);
+                    }
+                mbar_wait (&barM, parM); parM ^= 1;
+                fence_after_sync ();
+
+                // ---- epilogue part 1: my row of D, times what the other children gave ----
+                #pragma unroll
+                for (int cb = 0; cb < NP; cb += 16)
+                    {
+                    float vm[16], vc[16];
+                    tmem_ld16 (tMain + laneSel + cb, vm);
+                    tmem_ld16 (tCorr + laneSel + cb, vc);
+                    #pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        if (cb + i < S)
+                            {
+                            float v = vm[i] + vc[i];
+                            if (tipFull) v = 1.0f;             // preLike shortcut (src/likelihood.c:257-258)
+                            res[k][cb + i] = (ch == 0) ? v : res[k][cb + i] * v;
+                            }
+                    }
+                fence_before_sync ();                          // TMEM reads ordered before the next MMA
+                __syncthreads ();                              // shared operands free for the next child
+                fence_after_sync ();
+                }
+            }
+
+        // ---- epilogue part 2: scaler bookkeeping, rescale, store (one thread = one pattern) ----
+        if (active)
+            {
+            if (op.sr >= 0)
+                site -= ctx.scalers[(size_t)op.sr * C + c];
+            if (op.sw >= 0)
+                {
+                float m = 0.0f;
+                #pragma unroll
+                for (int k = 0; k < KMAX; k++)
+                    if (k < K)
+                        {
+                        #pragma unroll
+                        for (int i = 0; i < S; i++) m = fmaxf (m, res[k][i]);
+                        }
+                #pragma unroll
+                for (int k = 0; k < KMAX; k++)
+                    if (k < K)
+                        {
+                        #pragma unroll
+                        for (int i = 0; i < S; i++) res[k][i] /= m;
+                        }
+                const float sc = (float) log ((double) m);     // CondLikeScaler_Gen_SSE, src/likelihood.c:5055
+                ctx.scalers[(size_t)op.sw * C + c] = sc;
+                site += sc;
+                }
+            float *dstBase = ctx.partials + (size_t)(op.dest - ctx.tipCount) * bufStride;
+            #pragma unroll
+            for (int k = 0; k < KMAX; k++)
+                if (k < K)
+                    {
+                    float4 *dst = reinterpret_cast<float4 *>(dstBase + ((size_t)k * C + c) * Sp);
+                    #pragma unroll
+                    for (int q = 0; q < (S + 3) / 4; q++)
+                        {
+                        float4 v;
+                        v.x = res[k][q*4];
+                        v.y = (q*4 + 1 < S) ? res[k][(q*4 + 1 < S) ? q*4 + 1 : 0] : 0.f;
+                        v.z = (q*4 + 2 < S) ? res[k][(q*4 + 2 < S) ? q*4 + 2 : 0] : 0.f;
+                        v.w = (q*4 + 3 < S) ? res[k][(q*4 + 3 < S) ? q*4 + 3 : 0] : 0.f;
+                        dst[q] = v;
+                        }
+                    }
+            }
+        #pragma unroll
+        for (int k = 0; k < KMAX; k++)
+            #pragma unroll
+            for (int i = 0; i < S; i++) prod[k][i] = res[k][i];
+        curBuf = op.dest;
+        }
+
+    if (active && sEv.siteDst >= 0)
+        ctx.scalers[(size_t)sEv.siteDst * C + c] = site;
+
+    // TMEM no longer needed
+    fence_before_sync ();
+    __syncthreads ();
+    if (warp == 0)
+        tmem_dealloc<TMEM_COLS> (tmemBase);
+
+    if (sEv.root < 0)
+        return;
+
+    // ---- root integration (Likelihood_Gen, src/likelihood.c:5764-5916), double accumulation ----
+    double term = 0.0; int abortFlag = 0;
+    if (active)
+        {
+        if (sEv.root != curBuf)
+            {
+            const float *rootBase = ctx.partials + (size_t)(sEv.root - ctx.tipCount) * bufStride;
+            #pragma unroll
+            for (int k = 0; k < KMAX; k++)
+                if (k < K)
+                    {
+                    #pragma unroll
+                    for (int i = 0; i < S; i++) prod[k][i] = rootBase[((size_t)k * C + c) * Sp + i];
+                    }
+            }
+        double like = 0.0;
+        #pragma unroll
+        for (int k = 0; k < KMAX; k++)
+            if (k < K)
+                {
+                double s = 0.0;
+                #pragma unroll
+                for (int i = 0; i < S; i++) s += (double) prod[k][i] * freqs[i];
+                like += s * catW[k];
+                }
+        double likeI = 0.0;
+        if (sEv.hasPInvar)
+            {
+            const uint64_t im = ctx.invMask[c];
+            for (int i = 0; i < S; i++)
+                if ((im >> i) & 1) likeI += freqs[i];
+            likeI *= sEv.pInvar;
+            }
+        term = site_term (like, likeI, sEv.hasPInvar, sEv.flags & MB200_QUIRK_FLAG, site,
+                          ctx.weights[(size_t)sEv.weightsRow * C + c], abortFlag);
+        }
+    finish_lnl<128> (ctx, blockIdx.y, term, abortFlag, out, seq);
+}

@@ -18,6 +18,14 @@ LNL_RTOL = 1e-8
 # synthetic cases have |lnL| of a few hundred and, for S != 4, fused-vs-separate multiply-add
 # differences against the oracle's *_Gen_SSE arithmetic: still 5x inside the north-star bar
 SYN_RTOL = 2e-7
+# 20- and 61-state divisions run on the tensor cores with 3xTF32 operand splitting: each matvec
+# carries ~7e-7 relative error, mostly the tensor core's truncating FP32 accumulation (a small
+# negative bias), which shows up as ~1e-7 relative in lnL -- 5x inside the north-star bar of 1e-6
+TC_RTOL = 5e-7
+
+
+def lnl_tol(S, base):
+    return TC_RTOL if S in (20, 61) else base
 
 
 def rel(a, b):
@@ -30,7 +38,8 @@ def test_engine_matches_reference_records(engine_lib, oracle_lib, stem, arith):
     assert len(got) >= 40
     worst = max(rel(l, s.lnl_ref) for s, l, _ in got)
     assert all(st == abi.EVAL_OK for _, _, st in got)
-    assert worst < LNL_RTOL, f"{stem}: max relative lnL error vs reference {worst:.3e}"
+    tol = lnl_tol(len(got[0][0].freqs), LNL_RTOL)
+    assert worst < tol, f"{stem}: max relative lnL error vs reference {worst:.3e}"
 
 
 def test_transition_matrices_match_oracle(engine_lib, oracle_lib):
@@ -57,7 +66,7 @@ def test_transition_matrices_match_oracle(engine_lib, oracle_lib):
 def _compare_state(e, o, spec, S):
     for op in spec.ops:
         a, b = e.get_partials(int(op["dest"])), o.get_partials(int(op["dest"]))
-        assert np.allclose(a, b, rtol=2e-6, atol=1e-37), f"partials of buffer {op['dest']}"
+        assert np.allclose(a, b, rtol=(2e-5 if S in (20, 61) else 2e-6), atol=1e-37), f"partials of buffer {op['dest']}"
         if op["scale_write"] >= 0:
             sa, sb = e.get_scalers(int(op["scale_write"])), o.get_scalers(int(op["scale_write"]))
             assert np.allclose(sa, sb, atol=1e-6)
@@ -103,7 +112,7 @@ def test_engine_matches_oracle_synthetic(engine_lib, oracle_lib, S, K, C, tips, 
             (le,), (se,) = e.evaluate(sp)
             (lo,), (so,) = o.evaluate(sp)
             assert se == so == abi.EVAL_OK
-            assert rel(le, lo) < SYN_RTOL
+            assert rel(le, lo) < lnl_tol(S, SYN_RTOL)
             _compare_state(e, o, sp, S)
         for it in range(10):
             ch = it % nch
@@ -111,7 +120,7 @@ def test_engine_matches_oracle_synthetic(engine_lib, oracle_lib, S, K, C, tips, 
             sp = pr.random_branch_update(ch, rng)
             (le,), _ = e.evaluate(sp)
             (lo,), _ = o.evaluate(sp)
-            assert rel(le, lo) < SYN_RTOL, f"iteration {it}"
+            assert rel(le, lo) < lnl_tol(S, SYN_RTOL), f"iteration {it}"
             _compare_state(e, o, sp, S)
             if it % 3 == 2:
                 pr.reject(ch, sp, old)
@@ -236,7 +245,7 @@ def test_full_size_subset_equals_oracle_on_subset(engine_lib, oracle_lib, name, 
     small.masks = np.ascontiguousarray(small.masks[:, sub]); small.weights = small.weights[sub]; small.C = len(sub)
     with small.create(oracle_lib) as o:
         (l_o,), _ = o.evaluate(small.full_evaluation(0))
-    assert rel(l_sub, l_o) < LNL_RTOL
+    assert rel(l_sub, l_o) < lnl_tol(S, LNL_RTOL)
 
 
 @pytest.mark.parametrize("tips,K", [(40, 4), (90, 4), (150, 1), (70, 8)])
