@@ -701,8 +701,8 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
         const size_t fl = (I->tcS == 61) ? tc_split_floats<61> () : tc_split_floats<20> ();
         ALLOC (I->dSplit, (size_t)cfg->matrix_count * K * fl * sizeof(float));
         cudaMemsetAsync (I->dSplit, 0, (size_t)cfg->matrix_count * K * fl * sizeof(float), I->stream);
-        const int NPv = (I->tcS == 61) ? 64 : 32, KPv = (I->tcS == 61) ? 64 : 24;
-        I->smemTc = (size_t)(2 * 128 * KPv + 2 * NPv * KPv) * sizeof(float);
+        const int NPv = (I->tcS == 61) ? 64 : 32, KPv = (I->tcS == 61) ? 64 : 24, KMv = (I->tcS == 61) ? 1 : 4;
+        I->smemTc = (size_t)KMv * (2 * 128 * KPv + 2 * NPv * KPv) * sizeof(float);   // [k] A hi+lo images, [k] B images
         cudaError_t ea = (I->tcS == 61)
             ? cudaFuncSetAttribute (eval_tc_kernel<61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) I->smemTc)
             : cudaFuncSetAttribute (eval_tc_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) I->smemTc);

@@ -28,8 +28,8 @@
 #include "umma_common.cuh"
 
 template <int S> struct TcGeom;
-template <> struct TcGeom<61> { static constexpr int NP = 64, KP = 64, KMAX = 1; };
-template <> struct TcGeom<20> { static constexpr int NP = 32, KP = 24, KMAX = 4; };
+template <> struct TcGeom<61> { static constexpr int NP = 64, KP = 64, KMAX = 1, SP = 64; };
+template <> struct TcGeom<20> { static constexpr int NP = 32, KP = 24, KMAX = 4, SP = 20; };
 
 // floats per pre-split matrix image: hi then lo, each NP x KP in canonical layout
 template <int S> __host__ __device__ constexpr int tc_split_floats () { return 2 * TcGeom<S>::NP * TcGeom<S>::KP; }
@@ -70,13 +70,19 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
     using namespace umma;
     constexpr int NP = TcGeom<S>::NP, KP = TcGeom<S>::KP, KMAX = TcGeom<S>::KMAX;
     constexpr int TM = 128;                                   // patterns per tile = MMA M
-    constexpr int TMEM_COLS = (2 * NP <= 64) ? 64 : 128;      // main + correction accumulators
+    constexpr int TMEM_COLS = (2 * NP * KMAX <= 64) ? 64 : (2 * NP * KMAX <= 128) ? 128 : 256;
     constexpr uint32_t LBO_A = (TM / 8) * 128, LBO_B = (NP / 8) * 128, SBO = 128;
+    constexpr int A_FLOATS = TM * KP;                         // one hi (or lo) image
+    constexpr int B_FLOATS = 2 * NP * KP;                     // hi + lo image of one P(t)
+    constexpr int NQ = (S + 3) / 4;                           // 16-byte chunks per stored row
+    constexpr int SPC = TcGeom<S>::SP;                        // floats per global row (ctx.Sp)
 
+    // dynamic shared memory: [k][hi|lo] A images, then [k] B images; the A region doubles as the
+    // staging area of the node's result rows once its MMAs have completed
     extern __shared__ __align__(128) unsigned char tc_smem[];
-    float *sAhi = reinterpret_cast<float *>(tc_smem);            // TM x KP, canonical
-    float *sAlo = sAhi + TM * KP;
-    float *sB   = sAlo + TM * KP;                             // hi image then lo image, NP x KP each
+    float *sA = reinterpret_cast<float *>(tc_smem);           // KMAX x 2 x A_FLOATS
+    float *sB = sA + KMAX * 2 * A_FLOATS;                     // KMAX x B_FLOATS
+    float4 *sStage = reinterpret_cast<float4 *>(tc_smem);     // [k][q][TM+1] float4
     __shared__ uint64_t barB, barM;
     __shared__ uint32_t tmemBase;
     __shared__ DevEval sEv;
@@ -87,12 +93,13 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
         reinterpret_cast<int *>(&sEv)[tid] = reinterpret_cast<const int *>(evals + blockIdx.y)[tid];
     if (warp == 0)
         tmem_alloc<TMEM_COLS> (&tmemBase);
+    const int nIssuers = (2 * K < 4) ? 2 * K : 4;              // warps whose leader lane issues MMAs
     if (tid == 0)
-        { mbar_init (&barB, 1); mbar_init (&barM, 1); mbar_fence_init (); }
+        { mbar_init (&barB, 1); mbar_init (&barM, nIssuers); mbar_fence_init (); }
     fence_before_sync ();
     __syncthreads ();
     fence_after_sync ();
-    const uint32_t tMain = tmemBase, tCorr = tmemBase + NP;
+    const uint32_t tBase = tmemBase;                           // [k][main | corr] accumulators, NP columns each
     const uint32_t laneSel = (uint32_t)(warp * 32) << 16;      // this warp's TMEM lane quadrant
     uint32_t parB = 0, parM = 0;
 
@@ -107,137 +114,181 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
     constexpr uint32_t idesc = make_idesc_tf32 (TM, NP);
 
     float site = (active && sEv.siteSrc >= 0) ? ctx.scalers[(size_t)sEv.siteSrc * C + c] : 0.0f;
-    float prod[KMAX][S];                                       // this pattern's node result, all categories
-    int   curBuf = -2;
+
+    // operand descriptors never change: images live at fixed shared-memory addresses.  Only the
+    // start-address field (bits 0..13, 16-byte units) moves with the category and the K step.
+    const uint64_t dA0 = make_desc (smem_u32 (sA), LBO_A, SBO);      // hi image of category 0
+    const uint64_t dB0 = make_desc (smem_u32 (sB), LBO_B, SBO);
+    constexpr uint64_t A_LO = (A_FLOATS * 4) >> 4, A_K = (2 * A_FLOATS * 4) >> 4, A_KS = (2 * LBO_A) >> 4;
+    constexpr uint64_t B_LO = (NP * KP * 4) >> 4, B_K = (B_FLOATS * 4) >> 4, B_KS = (2 * LBO_B) >> 4;
+
+    int preloaded = -1;          // partials buffer whose hi/lo images already sit in sA (previous node's result)
 
     for (int o = 0; o < sEv.nOp; o++)
         {
         const DevOp op = ops[sEv.opOff + o];
         const int nChild = (op.c3 >= 0) ? 3 : 2;
-        float res[KMAX][S];
+        float res[KMAX][S];                                    // this pattern's node result, all categories
 
-        #pragma unroll
-        for (int k = 0; k < KMAX; k++)
+        // the child that is the previous node's result goes first: its images are already in place
+        int first = 0;
+        if (preloaded >= 0)
+            first = (op.c1 == preloaded) ? 0 : (op.c2 == preloaded) ? 1 : (op.c3 == preloaded) ? 2 : 0;
+        for (int cc = 0; cc < nChild; cc++)
             {
-            if (k >= K) break;
-            for (int ch = 0; ch < nChild; ch++)
+            const int ch = (cc == 0) ? first : (cc <= first) ? cc - 1 : cc;
+            const int child = (ch == 0) ? op.c1 : (ch == 1) ? op.c2 : op.c3;
+            const int mat   = (ch == 0) ? op.m1 : (ch == 1) ? op.m2 : op.m3;
+            const bool isTip = child < ctx.tipCount;
+            const bool inPlace = (cc == 0 && child == preloaded);
+#ifdef MB200_PHASE_TIMING
+#define TC_STAMP(SLOT_) do { if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 8 + ch*8 + (SLOT_)] = mb200_now (); } while (0)
+#else
+#define TC_STAMP(SLOT_) do { } while (0)
+#endif
+            TC_STAMP (0);
+            // ---- B: the K pre-split P(t) images of this branch, one bulk async copy (contiguous) ----
+            if (tid == 0)
                 {
-                const int child = (ch == 0) ? op.c1 : (ch == 1) ? op.c2 : op.c3;
-                const int mat   = (ch == 0) ? op.m1 : (ch == 1) ? op.m2 : op.m3;
-                const bool isTip = child < ctx.tipCount;
+                mbar_expect_tx (&barB, (uint32_t)(K * B_FLOATS * 4));
+                bulk_g2s (sB, split + (size_t)mat * K * B_FLOATS, (uint32_t)(K * B_FLOATS * 4), &barB);
+                }
 
-                // ---- B: pre-split P(t) image, bulk async copy ----
-                if (tid == 0)
+            // ---- A: child tiles of all K categories -> hi / lo canonical images ----
+            bool tipFull = false;                              // scalar-kernel shortcut applies to my pattern
+            if (isTip)
+                {
+                // thread t expands pattern t's state mask (identical for every category): 0/1 are exact
+                // in TF32, the lo image is not used
+                const uint64_t m = active ? ctx.tip64[(size_t)child * C + c] : 0;
+                tipFull = shortcutFlag && active && m == fullMask && !ctx.tipPartAmbig[child];
+                #pragma unroll
+                for (int q = 0; q < KP / 4; q++)
                     {
-                    mbar_expect_tx (&barB, (uint32_t)(tc_split_floats<S> () * 4));
-                    bulk_g2s (sB, split + ((size_t)mat * K + k) * tc_split_floats<S> (), (uint32_t)(tc_split_floats<S> () * 4), &barB);
+                    float4 h;
+                    h.x = ((m >> (q*4 + 0)) & 1) ? 1.f : 0.f; h.y = ((m >> (q*4 + 1)) & 1) ? 1.f : 0.f;
+                    h.z = ((m >> (q*4 + 2)) & 1) ? 1.f : 0.f; h.w = ((m >> (q*4 + 3)) & 1) ? 1.f : 0.f;
+                    *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sA) + canon_off (tid, q*4, TM)) = h;
                     }
-
-                // ---- A: child tile -> hi / lo canonical images ----
-                bool tipFull = false;                          // scalar-kernel shortcut applies to my pattern
-                if (isTip)
+                }
+            else if (!inPlace)
+                {
+                // HBM/L2 -> registers -> shared: a warp covers 8 rows x 4 chunks (64 contiguous bytes per
+                // row: full 32-byte sectors) and stores 8 x 16 B contiguous per quarter-warp (no conflicts).
+                // All loads of a category are issued before the first one is used (memory-level
+                // parallelism: one round trip per category instead of one per chunk).
+                constexpr int QB = (KP / 4 + 3) / 4;           // chunk blocks of 4
+                constexpr int NIT = (TM / 8) * QB / 4;         // items per warp and category
+                for (int k = 0; k < K; k++)
                     {
-                    // thread t expands pattern t's state mask: 0/1 are exact in TF32, lo image unused
-                    const uint64_t m = active ? ctx.tip64[(size_t)child * C + c] : 0;
-                    tipFull = shortcutFlag && active && m == fullMask && !ctx.tipPartAmbig[child];
-                    #pragma unroll
-                    for (int q = 0; q < KP / 4; q++)
-                        {
-                        float4 h;
-                        h.x = ((m >> (q*4 + 0)) & 1) ? 1.f : 0.f; h.y = ((m >> (q*4 + 1)) & 1) ? 1.f : 0.f;
-                        h.z = ((m >> (q*4 + 2)) & 1) ? 1.f : 0.f; h.w = ((m >> (q*4 + 3)) & 1) ? 1.f : 0.f;
-                        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sAhi) + canon_off (tid, q*4, TM)) = h;
-                        }
-                    }
-                else if (child == curBuf)
-                    {
-                    // the previous node's result: my row is still in registers
-                    #pragma unroll
-                    for (int q = 0; q < KP / 4; q++)
-                        {
-                        float x[4], h[4], l[4];
-                        #pragma unroll
-                        for (int e = 0; e < 4; e++)
-                            {
-                            x[e] = (q*4 + e < S && active) ? prod[k][(q*4 + e < S) ? q*4 + e : 0] : 0.f;
-                            h[e] = to_tf32 (x[e]); l[e] = to_tf32 (x[e] - h[e]);
-                            }
-                        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sAhi) + canon_off (tid, q*4, TM)) = make_float4 (h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sAlo) + canon_off (tid, q*4, TM)) = make_float4 (l[0], l[1], l[2], l[3]);
-                        }
-                    }
-                else
-                    {
-                    // HBM -> registers -> shared: a warp covers 8 rows x 4 chunks (64 contiguous bytes per
-                    // row: full 32-byte sectors) and stores 8 x 16 B contiguous per quarter-warp (no conflicts)
                     const float *src = ctx.partials + (size_t)(child - ctx.tipCount) * bufStride + ((size_t)k * C + c0) * Sp;
-                    constexpr int QB = (KP / 4 + 3) / 4;       // chunk blocks of 4
-                    for (int it = warp; it < (TM / 8) * QB; it += 4)
+                    unsigned char *base = reinterpret_cast<unsigned char *>(sA + (size_t)k * 2 * A_FLOATS);
+                    float4 x[NIT];
+                    #pragma unroll
+                    for (int n = 0; n < NIT; n++)
                         {
+                        const int it = warp + 4 * n;
+                        const int rb = it / QB, qb = it % QB;
+                        const int r = rb * 8 + (lane & 7), q = qb * 4 + (lane >> 3);
+                        x[n] = make_float4 (0.f, 0.f, 0.f, 0.f);
+                        if (q < KP / 4 && r < np && q * 4 < SPC)
+                            x[n] = __ldcg (reinterpret_cast<const float4 *>(src + (size_t)r * SPC + q * 4));
+                        }
+                    #pragma unroll
+                    for (int n = 0; n < NIT; n++)
+                        {
+                        const int it = warp + 4 * n;
                         const int rb = it / QB, qb = it % QB;
                         const int r = rb * 8 + (lane & 7), q = qb * 4 + (lane >> 3);
                         if (q < KP / 4)
                             {
-                            float4 x = make_float4 (0.f, 0.f, 0.f, 0.f);
-                            if (r < np && q * 4 < Sp)
-                                x = *reinterpret_cast<const float4 *>(src + (size_t)r * Sp + q * 4);
-                            const float4 h = make_float4 (to_tf32 (x.x), to_tf32 (x.y), to_tf32 (x.z), to_tf32 (x.w));
-                            const float4 l = make_float4 (to_tf32 (x.x - h.x), to_tf32 (x.y - h.y), to_tf32 (x.z - h.z), to_tf32 (x.w - h.w));
-                            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sAhi) + canon_off (r, q*4, TM)) = h;
-                            *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sAlo) + canon_off (r, q*4, TM)) = l;
+                            const float4 h = make_float4 (to_tf32 (x[n].x), to_tf32 (x[n].y), to_tf32 (x[n].z), to_tf32 (x[n].w));
+                            const float4 l = make_float4 (to_tf32 (x[n].x - h.x), to_tf32 (x[n].y - h.y), to_tf32 (x[n].z - h.z), to_tf32 (x[n].w - h.w));
+                            *reinterpret_cast<float4 *>(base + canon_off (r, q*4, TM)) = h;
+                            *reinterpret_cast<float4 *>(base + A_FLOATS * 4 + canon_off (r, q*4, TM)) = l;
                             }
                         }
                     }
-                fence_async_smem ();                           // generic-proxy stores -> async proxy (MMA)
-                mbar_wait (&barB, parB); parB ^= 1;            // B image landed
-                fence_before_sync ();
-                __syncthreads ();
-                fence_after_sync ();
+                }
+            TC_STAMP (1);
+            fence_async_smem ();                               // generic-proxy stores -> async proxy (MMA)
+            mbar_wait (&barB, parB); parB ^= 1;                // B images landed
+            TC_STAMP (2);
+            fence_before_sync ();
+            __syncthreads ();
+            fence_after_sync ();
 
-                // ---- MMA: main = Ahi*Bhi ; corr = Ahi*Blo (+ Alo*Bhi) ----
-                if (tid == 0)
+            // ---- MMA, all categories: main[k] = Ahi*Bhi ; corr[k] = Ahi*Blo (+ Alo*Bhi) ----
+            // issue is the bottleneck of these small MMAs (~35 ns each from one thread), so the
+            // 2K independent accumulators are spread over the four warps' leader lanes; each issuer
+            // commits to the same mbarrier (initialised with the number of issuers)
+            if (lane == 0 && warp < nIssuers)
+                {
+                for (int item = warp; item < 2 * K; item += 4)
                     {
-                    const uint32_t aHi = smem_u32 (sAhi), aLo = smem_u32 (sAlo), bHi = smem_u32 (sB), bLo = smem_u32 (sB + NP * KP);
-                    #pragma unroll
-                    for (int ks = 0; ks < KP / 8; ks++)
-                        mma_tf32 (tMain, make_desc (aHi + ks * 2 * LBO_A, LBO_A, SBO), make_desc (bHi + ks * 2 * LBO_B, LBO_B, SBO), idesc, ks > 0);
-                    #pragma unroll
-                    for (int ks = 0; ks < KP / 8; ks++)
-                        mma_tf32 (tCorr, make_desc (aHi + ks * 2 * LBO_A, LBO_A, SBO), make_desc (bLo + ks * 2 * LBO_B, LBO_B, SBO), idesc, ks > 0);
-                    if (!isTip)
+                    const int k = item >> 1, corr = item & 1;
+                    const uint64_t aHi = dA0 + (isTip ? 0 : (uint64_t)k * A_K), aLo = aHi + A_LO;
+                    const uint64_t bHi = dB0 + (uint64_t)k * B_K, bLo = bHi + B_LO;
+                    const uint32_t tAcc = tBase + k * 2 * NP + corr * NP;
+                    if (!corr)
                         {
                         #pragma unroll
                         for (int ks = 0; ks < KP / 8; ks++)
-                            mma_tf32 (tCorr, make_desc (aLo + ks * 2 * LBO_A, LBO_A, SBO), make_desc (bHi + ks * 2 * LBO_B, LBO_B, SBO), idesc, true);
+                            mma_tf32 (tAcc, aHi + ks * A_KS, bHi + ks * B_KS, idesc, ks > 0);
                         }
-                    mma_commit (&barM);
+                    else
+                        {
+                        #pragma unroll
+                        for (int ks = 0; ks < KP / 8; ks++)
+                            mma_tf32 (tAcc, aHi + ks * A_KS, bLo + ks * B_KS, idesc, ks > 0);
+                        if (!isTip)
+                            {
+                            #pragma unroll
+                            for (int ks = 0; ks < KP / 8; ks++)
+                                mma_tf32 (tAcc, aLo + ks * A_KS, bHi + ks * B_KS, idesc, true);
+                            }
+                        }
                     }
-                mbar_wait (&barM, parM); parM ^= 1;
-                fence_after_sync ();
+                mma_commit (&barM);
+                }
+            TC_STAMP (3);
+            mbar_wait (&barM, parM); parM ^= 1;
+            fence_after_sync ();
+            TC_STAMP (4);
 
-                // ---- epilogue part 1: my row of D, times what the other children gave ----
+            // ---- epilogue part 1: my row of D (all categories), times what the other children gave ----
+            #pragma unroll
+            for (int k = 0; k < KMAX; k++)
+                {
+                if (k >= K) break;
                 #pragma unroll
-                for (int cb = 0; cb < NP; cb += 16)
+                for (int cb = 0; cb < NP; cb += 32)
                     {
-                    float vm[16], vc[16];
-                    tmem_ld16 (tMain + laneSel + cb, vm);
-                    tmem_ld16 (tCorr + laneSel + cb, vc);
+                    uint32_t vm[32], vc[32];
+                    tmem_ld32_nowait (tBase + k * 2 * NP + laneSel + cb, vm);
+                    tmem_ld32_nowait (tBase + k * 2 * NP + NP + laneSel + cb, vc);
+                    tmem_ld_wait ();
                     #pragma unroll
-                    for (int i = 0; i < 16; i++)
+                    for (int i = 0; i < 32; i++)
                         if (cb + i < S)
                             {
-                            float v = vm[i] + vc[i];
+                            float v = __uint_as_float (vm[i]) + __uint_as_float (vc[i]);
                             if (tipFull) v = 1.0f;             // preLike shortcut (src/likelihood.c:257-258)
-                            res[k][cb + i] = (ch == 0) ? v : res[k][cb + i] * v;
+                            res[k][cb + i] = (cc == 0) ? v : res[k][cb + i] * v;
                             }
                     }
-                fence_before_sync ();                          // TMEM reads ordered before the next MMA
-                __syncthreads ();                              // shared operands free for the next child
-                fence_after_sync ();
                 }
+            TC_STAMP (5);
+            fence_before_sync ();                              // TMEM reads ordered before the next MMA
+            __syncthreads ();                                  // shared operands free for the next child
+            fence_after_sync ();
+            TC_STAMP (6);
             }
+#ifdef MB200_PHASE_TIMING
+        if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 40] = mb200_now ();
+#endif
 
-        // ---- epilogue part 2: scaler bookkeeping, rescale, store (one thread = one pattern) ----
+        // ---- epilogue part 2: scaler bookkeeping and rescale (one thread = one pattern) ----
         if (active)
             {
             if (op.sr >= 0)
@@ -252,40 +303,99 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
                         #pragma unroll
                         for (int i = 0; i < S; i++) m = fmaxf (m, res[k][i]);
                         }
+                // one IEEE reciprocal, then multiplies: 1 ulp from the reference's divisions, far below
+                // the 3xTF32 operand error of this path
+                const float rcp = 1.0f / m;
                 #pragma unroll
                 for (int k = 0; k < KMAX; k++)
                     if (k < K)
                         {
                         #pragma unroll
-                        for (int i = 0; i < S; i++) res[k][i] /= m;
+                        for (int i = 0; i < S; i++) res[k][i] *= rcp;
                         }
                 const float sc = (float) log ((double) m);     // CondLikeScaler_Gen_SSE, src/likelihood.c:5055
                 ctx.scalers[(size_t)op.sw * C + c] = sc;
                 site += sc;
                 }
-            float *dstBase = ctx.partials + (size_t)(op.dest - ctx.tipCount) * bufStride;
-            #pragma unroll
-            for (int k = 0; k < KMAX; k++)
-                if (k < K)
-                    {
-                    float4 *dst = reinterpret_cast<float4 *>(dstBase + ((size_t)k * C + c) * Sp);
-                    #pragma unroll
-                    for (int q = 0; q < (S + 3) / 4; q++)
-                        {
-                        float4 v;
-                        v.x = res[k][q*4];
-                        v.y = (q*4 + 1 < S) ? res[k][(q*4 + 1 < S) ? q*4 + 1 : 0] : 0.f;
-                        v.z = (q*4 + 2 < S) ? res[k][(q*4 + 2 < S) ? q*4 + 2 : 0] : 0.f;
-                        v.w = (q*4 + 3 < S) ? res[k][(q*4 + 3 < S) ? q*4 + 3 : 0] : 0.f;
-                        dst[q] = v;
-                        }
-                    }
             }
+#ifdef MB200_PHASE_TIMING
+        if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 44] = mb200_now ();
+#endif
+        // ---- store: rows go through shared memory (chunk-major, conflict-free) so that the global
+        //      writes are fully coalesced 16-byte-per-lane runs of the contiguous tile ----
         #pragma unroll
         for (int k = 0; k < KMAX; k++)
+            if (k < K)
+                {
+                #pragma unroll
+                for (int q = 0; q < NQ; q++)
+                    {
+                    float4 v;
+                    v.x = res[k][q*4];
+                    v.y = (q*4 + 1 < S) ? res[k][(q*4 + 1 < S) ? q*4 + 1 : 0] : 0.f;
+                    v.z = (q*4 + 2 < S) ? res[k][(q*4 + 2 < S) ? q*4 + 2 : 0] : 0.f;
+                    v.w = (q*4 + 3 < S) ? res[k][(q*4 + 3 < S) ? q*4 + 3 : 0] : 0.f;
+                    sStage[((size_t)k * NQ + q) * (TM + 1) + tid] = v;
+                    }
+                }
+        __syncthreads ();
+#ifdef MB200_PHASE_TIMING
+        if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 45] = mb200_now ();
+#endif
+        {
+        float *dstBase = ctx.partials + (size_t)(op.dest - ctx.tipCount) * bufStride;
+        constexpr int nq = SPC / 4;                            // chunks per global row (pad chunks are zero)
+        for (int k = 0; k < K; k++)
+            {
+            float4 *dst = reinterpret_cast<float4 *>(dstBase + ((size_t)k * C + c0) * SPC);
             #pragma unroll
-            for (int i = 0; i < S; i++) prod[k][i] = res[k][i];
-        curBuf = op.dest;
+            for (int n = 0; n < nq; n++)                       // 128 rows x nq chunks = nq rounds of 128 lanes
+                {
+                const int idx = n * 128 + tid;
+                const int r = idx / nq, q = idx % nq;
+                if (r < np)
+                    dst[idx] = (q < NQ) ? sStage[((size_t)k * NQ + q) * (TM + 1) + r] : make_float4 (0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+#ifdef MB200_PHASE_TIMING
+        if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 46] = mb200_now ();
+#endif
+        __syncthreads ();                                      // staging area is the A region again
+        // register forwarding: when the next node consumes this result, its hi/lo images are written
+        // straight from registers (no store -> load round trip through L2 on dependent chains)
+        preloaded = -1;
+        if (o + 1 < sEv.nOp)
+            {
+            const DevOp nx = ops[sEv.opOff + o + 1];
+            if (nx.c1 == op.dest || nx.c2 == op.dest || nx.c3 == op.dest)
+                {
+                preloaded = op.dest;
+                #pragma unroll
+                for (int k = 0; k < KMAX; k++)
+                    if (k < K)
+                        {
+                        unsigned char *base = reinterpret_cast<unsigned char *>(sA + (size_t)k * 2 * A_FLOATS);
+                        #pragma unroll
+                        for (int q = 0; q < KP / 4; q++)
+                            {
+                            float x[4], h[4], l[4];
+                            #pragma unroll
+                            for (int e = 0; e < 4; e++)
+                                {
+                                x[e] = (q*4 + e < S && active) ? res[k][(q*4 + e < S) ? q*4 + e : 0] : 0.f;
+                                h[e] = to_tf32 (x[e]); l[e] = to_tf32 (x[e] - h[e]);
+                                }
+                            *reinterpret_cast<float4 *>(base + canon_off (tid, q*4, TM)) = make_float4 (h[0], h[1], h[2], h[3]);
+                            *reinterpret_cast<float4 *>(base + A_FLOATS * 4 + canon_off (tid, q*4, TM)) = make_float4 (l[0], l[1], l[2], l[3]);
+                            }
+                        }
+                }
+            }
+#ifdef MB200_PHASE_TIMING
+        if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 41] = mb200_now ();
+        if (blockIdx.x == 0 && tid == 0 && o < 2) ctx.dbg[blockIdx.y*64 + 42 + o] = mb200_now ();
+#endif
         }
 
     if (active && sEv.siteDst >= 0)
@@ -304,27 +414,23 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
     double term = 0.0; int abortFlag = 0;
     if (active)
         {
-        if (sEv.root != curBuf)
-            {
-            const float *rootBase = ctx.partials + (size_t)(sEv.root - ctx.tipCount) * bufStride;
-            #pragma unroll
-            for (int k = 0; k < KMAX; k++)
-                if (k < K)
-                    {
-                    #pragma unroll
-                    for (int i = 0; i < S; i++) prod[k][i] = rootBase[((size_t)k * C + c) * Sp + i];
-                    }
-            }
+        const float *rootBase = ctx.partials + (size_t)(sEv.root - ctx.tipCount) * bufStride;
         double like = 0.0;
-        #pragma unroll
-        for (int k = 0; k < KMAX; k++)
-            if (k < K)
+        for (int k = 0; k < K; k++)
+            {
+            const float4 *row = reinterpret_cast<const float4 *>(rootBase + ((size_t)k * C + c) * Sp);
+            double s = 0.0;
+            #pragma unroll
+            for (int q = 0; q < NQ; q++)
                 {
-                double s = 0.0;
-                #pragma unroll
-                for (int i = 0; i < S; i++) s += (double) prod[k][i] * freqs[i];
-                like += s * catW[k];
+                const float4 v = __ldcg (row + q);
+                s += (double) v.x * freqs[q*4];
+                if (q*4 + 1 < S) s += (double) v.y * freqs[q*4 + 1];
+                if (q*4 + 2 < S) s += (double) v.z * freqs[q*4 + 2];
+                if (q*4 + 3 < S) s += (double) v.w * freqs[q*4 + 3];
                 }
+            like += s * catW[k];
+            }
         double likeI = 0.0;
         if (sEv.hasPInvar)
             {
