@@ -464,8 +464,16 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams)
         }
     if (b.nDirty > 0 && !b.fused)
         {
-        dim3 grid (b.nMat, ctx.K);
-        tiprobs_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, b.nEval, dd, du);
+        if (ctx.S > 32)
+            {
+            dim3 grid (b.nMat, ctx.K, (ctx.S + 3) / 4);
+            tiprobs_wide_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, b.nEval, dd, du);
+            }
+        else
+            {
+            dim3 grid (b.nMat, ctx.K);
+            tiprobs_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, b.nEval, dd, du);
+            }
         CK (cudaGetLastError ());
         I->launches++;
         }

@@ -94,6 +94,68 @@ tiprobs_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, const 
         }
 }
 
+// K1 for large state counts (61-state codon): the same sum, organised for memory parallelism.
+// grid = (matrix updates, K, ceil(S/4)); one warp per ancestral state i: for each j the 32 lanes
+// read the S consecutive doubles c[i][j][.] (coalesced), multiply by exp(lambda_s t) from shared
+// memory and tree-reduce with shuffles.  (Summation order differs from the reference's sequential
+// loop by O(1e-16) relative, invisible after the cast to float.)
+__global__ void __launch_bounds__(128)
+tiprobs_wide_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, const double *__restrict__ dvals,
+                     const DevMat *__restrict__ mats)
+{
+    __shared__ double sExp[MB200_DEV_MAX_STATES];
+    __shared__ int sEvalIdx;
+    const DevMat   mu = mats[blockIdx.x];
+    const int      k  = blockIdx.y;
+    const int      S  = ctx.S;
+    const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0)
+        {
+        int e = 0;
+        while (e + 1 < nEval && (int) blockIdx.x >= evals[e + 1].matOff)
+            e++;
+        while (e > 0 && evals[e].nMat == 0)
+            e--;
+        sEvalIdx = e;
+        }
+    __syncthreads ();
+    const DevEval *ev = evals + sEvalIdx;
+    if (ev->fuseP)
+        return;
+    const double  *rates = dvals + ev->dOff;
+    const double  *freqs = rates + 2*ctx.K;
+    const double   t  = mu.length * rates[k];
+    const int      i  = blockIdx.z * 4 + warp;
+    float         *P  = ctx.matrices + ((size_t)mu.matrix * ctx.K + k) * S * S;
+    if (t < MB200_TIME_MIN || t > MB200_TIME_MAX)
+        {
+        if (i < S)
+            for (int j = lane; j < S; j += 32)
+                P[i*S + j] = (t < MB200_TIME_MIN) ? ((i == j) ? 1.0f : 0.0f) : (float) freqs[j];
+        return;
+        }
+    const double *lam = ctx.eigen + (size_t)mu.eigen * (2*(size_t)S + (size_t)S*S*S);
+    const double *cij = lam + 2*S;
+    if (threadIdx.x < S)
+        sExp[threadIdx.x] = exp (lam[threadIdx.x] * t);
+    __syncthreads ();
+    if (i >= S)
+        return;
+    const double e0 = (lane < S) ? sExp[lane] : 0.0, e1 = (lane + 32 < S) ? sExp[lane + 32] : 0.0;
+    for (int j = 0; j < S; j++)
+        {
+        const double *c = cij + ((size_t)i * S + j) * S;
+        double sum = 0.0;
+        if (lane < S)      sum  = c[lane] * e0;
+        if (lane + 32 < S) sum += c[lane + 32] * e1;
+        #pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            sum += __shfl_xor_sync (0xffffffffu, sum, off);
+        if (lane == 0)
+            P[i*S + j] = (float) ((sum < 0.0) ? 0.0 : sum);
+        }
+}
+
 // c_ijk = V[i][k] * Vinv[k][j]  (CalcCijk, src/utils.c:9734-9746)
 __global__ void cijk_kernel (double *block, const double *V, const double *Vinv, const double *lambda, int S)
 {
