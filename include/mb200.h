@@ -77,6 +77,7 @@ extern "C" {
 #define MB200_MAX_STATES             64   /* numModelStates; 61-state codon fits   */
 #define MB200_MAX_CATEGORIES         20   /* MAX_RATE_CATS (src/bayes.h:316)       */
 #define MB200_NONE                  (-1)  /* "no buffer" sentinel, like BEAGLE_OP_NONE */
+#define MB200_EIGEN_INLINE          (-2)  /* mb200_matrix_update.eigen: use mb200_evaluation.inline_eigen */
 
 /* evaluation flags */
 /* Root integration follows Likelihood_NUC4_{SSE,AVX,FMA}: when the site scaler is
@@ -158,6 +159,12 @@ typedef struct mb200_evaluation
     /* stationary frequencies of the model states (covarion-adjusted by the caller,
        src/likelihood.c:5797-5818) */
     double                      state_freqs[MB200_MAX_STATES];
+    /* Optional eigensystem travelling with the evaluation instead of living in an eigen slot: a
+     * cijk block [lambda_re(S), lambda_im(S), c_ijk(S^3)] for matrix updates whose eigen field is
+     * MB200_EIGEN_INLINE.  Used for the models MrBayes keeps no eigensystem for (nst = 1, 2:
+     * TiProbs_JukesCantor / _Fels / _Hky closed forms, src/likelihood.c:9289-9960); the seam derives
+     * the eigensystem of their rate matrix per evaluation.  4-state models only.  NULL otherwise. */
+    const double               *inline_eigen;
 } mb200_evaluation;
 
 /* ---- library ---------------------------------------------------------------------- */

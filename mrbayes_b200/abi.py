@@ -22,6 +22,7 @@ ORACLE_LIB = ROOT / "oracle" / "liboracle.so"
 MAX_STATES = 64
 MAX_CATEGORIES = 20
 NONE = -1
+EIGEN_INLINE = -2
 FLAG_NUC4_PINVAR_QUIRK = 1
 FLAG_TIP_SHORTCUTS = 2
 EVAL_OK = 0
@@ -63,6 +64,7 @@ class Evaluation(C.Structure):
         ("category_rates", C.c_double * MAX_CATEGORIES),
         ("category_weights", C.c_double * MAX_CATEGORIES),
         ("state_freqs", C.c_double * MAX_STATES),
+        ("inline_eigen", C.POINTER(C.c_double)),
     ]
 
 
@@ -185,11 +187,11 @@ class EvalSpec:
 
     __slots__ = ("mats", "ops", "site_dst", "site_src", "root", "weights_row", "flags",
                  "p_invar", "has_p_invar", "rates", "cat_weights", "freqs", "chain", "division",
-                 "lnl_ref", "aborted")
+                 "lnl_ref", "aborted", "inline_eigen")
 
     def __init__(self, mats=None, ops=None, site_dst=NONE, site_src=NONE, root=NONE, weights_row=0,
                  flags=0, p_invar=0.0, has_p_invar=0, rates=(), cat_weights=(), freqs=(),
-                 chain=0, division=0, lnl_ref=None, aborted=0):
+                 chain=0, division=0, lnl_ref=None, aborted=0, inline_eigen=None):
         self.mats = np.ascontiguousarray(mats if mats is not None else np.zeros(0, MAT_DTYPE), MAT_DTYPE)
         self.ops = np.ascontiguousarray(ops if ops is not None else np.zeros(0, OP_DTYPE), OP_DTYPE)
         self.site_dst, self.site_src, self.root, self.weights_row = site_dst, site_src, root, weights_row
@@ -198,6 +200,7 @@ class EvalSpec:
         self.cat_weights = np.asarray(cat_weights, np.float64)
         self.freqs = np.asarray(freqs, np.float64)
         self.chain, self.division, self.lnl_ref, self.aborted = chain, division, lnl_ref, aborted
+        self.inline_eigen = None if inline_eigen is None else np.ascontiguousarray(inline_eigen, np.float64)
 
     def fill(self, ev: Evaluation):
         ev.matrix_update_count = len(self.mats)
@@ -213,6 +216,7 @@ class EvalSpec:
             ev.category_weights[k] = v
         for s, v in enumerate(self.freqs):
             ev.state_freqs[s] = v
+        ev.inline_eigen = _ptr(self.inline_eigen, C.c_double) if self.inline_eigen is not None else None
 
     @property
     def node_updates(self) -> int:

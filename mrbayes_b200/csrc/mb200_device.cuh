@@ -41,7 +41,8 @@ struct DevEval                      // one LaunchLogLikeForDivision (96 bytes)
     double pInvar;
     int    fuseP;                   // 1: the pruning kernel rebuilds this evaluation's P(t) itself
     int    nChunk;                  // 4-state path: chunk0 below + (nChunk-1) entries at chunkOff
-    int    eigen0;                  // eigen slot of the first matrix update (normally of all of them)
+    int    eigen0;                  // eigen slot of the first matrix update (normally of all of them);
+                                    // -2: the evaluation carries its own cijk block after freqs in the doubles
     int    chunkOff;
     DevChunk chunk0;
     int    pad[2];

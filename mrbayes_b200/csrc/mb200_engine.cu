@@ -206,8 +206,13 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         for (int i = 0; i < ev.matrix_update_count; i++)
             {
             const mb200_matrix_update &u = ev.matrix_updates[i];
-            if (u.matrix < 0 || u.matrix >= c.matrix_count || u.eigen < 0 || u.eigen >= c.eigen_count)
+            const bool inl = (u.eigen == MB200_EIGEN_INLINE);
+            if (u.matrix < 0 || u.matrix >= c.matrix_count || (!inl && (u.eigen < 0 || u.eigen >= c.eigen_count)))
                 { rcv = MB200_ERROR_OUT_OF_RANGE; break; }
+            if (inl && (!ev.inline_eigen || S != 4))
+                { rcv = MB200_ERROR_UNSUPPORTED; break; }
+            if (inl != (ev.matrix_updates[0].eigen == MB200_EIGEN_INLINE))
+                { rcv = MB200_ERROR_UNSUPPORTED; break; }       // all or none of an evaluation's updates
             I->dirtyOf[u.matrix] = i;
             }
         // chunking
@@ -292,8 +297,12 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     const int nUpd = fused ? 0 : nMat;                 // update list only feeds the stand-alone P(t) kernel
     int nExtraChunks = 0;
     for (int e = 0; e < count; e++) nExtraChunks += (nChunkOf[e] > 1) ? nChunkOf[e] - 1 : 0;
-    const int perEvalDbl = 2*K + S;
-    const int nDbl = perEvalDbl * count;
+    // per evaluation: rates[K], catW[K], freqs[S] and, when the evaluation carries its own
+    // eigensystem, the cijk block [2S + S^3]
+    int nDbl = 0;
+    for (int e = 0; e < count; e++)
+        nDbl += 2*K + S + (evs[e].inline_eigen ? 2*S + S*S*S : 0);
+    nDbl = (nDbl + 1) & ~1;
     size_t offEval  = mb200_align16 (sizeof(DevBatchHeader));
     size_t offDbl   = mb200_align16 (offEval + sizeof(DevEval) * (size_t)count);
     size_t offUpd   = mb200_align16 (offDbl + sizeof(double) * (size_t)nDbl);
@@ -315,7 +324,7 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     if (!cmats.empty ())
         memcpy (dm, cmats.data (), sizeof(DevMat) * cmats.size ());
 
-    int mOff = 0, oOff = 0, chunkPos = 0, extraPos = 0;
+    int mOff = 0, oOff = 0, chunkPos = 0, extraPos = 0, dblPos = 0;
     size_t slotPos = 0;
     b.needInv = false;
     for (int e = 0; e < count; e++)
@@ -329,7 +338,8 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         d.root = ev.root_buffer;         d.weightsRow = ev.weights_row;
         d.flags = ev.flags;              d.hasPInvar = ev.has_p_invar ? 1 : 0;
         d.pInvar = ev.p_invar;
-        d.dOff = e * perEvalDbl;
+        d.dOff = dblPos;
+        dblPos += 2*K + S + (ev.inline_eigen ? 2*S + S*S*S : 0);
         d.fuseP = fused ? 1 : 0;
         d.eigen0 = (ev.matrix_update_count > 0) ? ev.matrix_updates[0].eigen : 0;
         d.nChunk = nChunkOf[e];
@@ -353,6 +363,12 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         d.equalWeights = eq ? 1 : 0;
         for (int s = 0; s < S; s++)
             dv[2*K + s] = ev.state_freqs[s];
+        if (ev.inline_eigen)
+            {
+            memcpy (dv + 2*K + S, ev.inline_eigen, sizeof(double) * (size_t)(2*S + S*S*S));
+            if (ev.matrix_update_count > 0 && ev.matrix_updates[0].eigen == MB200_EIGEN_INLINE)
+                d.eigen0 = MB200_EIGEN_INLINE;
+            }
         if (!fused)
             for (int i = 0; i < ev.matrix_update_count; i++)
                 {

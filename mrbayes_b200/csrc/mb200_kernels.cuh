@@ -79,7 +79,8 @@ tiprobs_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, const 
             P[idx] = (float) freqs[idx % S];
         return;
         }
-    const double *lam = ctx.eigen + (size_t)mu.eigen * (2*(size_t)S + (size_t)S*S*S);
+    const double *lam = (mu.eigen == -2) ? (freqs + S)            // eigensystem carried by the evaluation
+                                         : ctx.eigen + (size_t)mu.eigen * (2*(size_t)S + (size_t)S*S*S);
     const double *cij = lam + 2*S;
     if (threadIdx.x < S)
         sExp[threadIdx.x] = exp (lam[threadIdx.x] * t);
@@ -401,7 +402,8 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
     if (threadIdx.x < 2*K + 4)
         sD[threadIdx.x] = dvals[sEv.dOff + threadIdx.x];
     if (FUSE && threadIdx.x < 72)
-        sEig[threadIdx.x] = ctx.eigen[(size_t)eig0 * 72 + threadIdx.x];
+        sEig[threadIdx.x] = (eig0 == -2) ? dvals[sEv.dOff + 2*K + 4 + threadIdx.x]     // carried by the evaluation
+                                          : ctx.eigen[(size_t)eig0 * 72 + threadIdx.x];
     float  lnScaler = (sEv.siteSrc >= 0) ? ctx.scalers[(size_t)sEv.siteSrc * C + cc] : 0.0f;
 
     float4 cur = make_float4 (0.f, 0.f, 0.f, 0.f);
@@ -464,7 +466,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             {
             const int s = r & 3, k = (r >> 2) % K, m = r / (4*K);
             const int eg = sMat[m].eigen;
-            if (FUSE && eg >= 0)
+            if (FUSE && eg != -1)
                 {
                 const double lam = (eg == eig0) ? sEig[s] : ctx.eigen[(size_t)eg * 72 + s];
                 sExp[m][k][s] = exp (lam * (sMat[m].length * sD[k]));
@@ -479,7 +481,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 {
                 const int i = r & 3, k = (r >> 2) % K, m = r / (4*K);
                 const int eg = sMat[m].eigen;
-                if (eg < 0)
+                if (eg == -1)
                     continue;
                 const double t = sMat[m].length * sD[k];
                 float4 row;

@@ -66,6 +66,7 @@ def load(path):
     pos = 12
     divisions: dict[int, Division] = {}
     events: list[Event] = []
+    pending_inline = None
     while pos < len(data):
         tag = data[pos:pos + 4]
         (nb,) = struct.unpack_from("<I", data, pos + 4)
@@ -88,7 +89,10 @@ def load(path):
         elif tag == b"CIJK":
             d, eig, S = struct.unpack_from("<3i", body, 0)
             a = np.frombuffer(body, "<f8", 2 * S + S ** 3, 12).copy()
-            events.append(Event("cijk", d, eig, block=a))
+            if eig == abi.EIGEN_INLINE:
+                pending_inline = a                # travels with the next evaluation
+            else:
+                events.append(Event("cijk", d, eig, block=a))
         elif tag == b"EVAL":
             (d, chain, nmat, nop, sdst, ssrc, root, wrow, flags, haspi, K, S) = struct.unpack_from("<12i", body, 0)
             off = 48
@@ -102,7 +106,9 @@ def load(path):
             (aborted, _pad) = struct.unpack_from("<2i", body, off)
             spec = abi.EvalSpec(mats=mats, ops=ops, site_dst=sdst, site_src=ssrc, root=root, weights_row=wrow,
                                 flags=flags, p_invar=pinv, has_p_invar=haspi, rates=rates, cat_weights=catw,
-                                freqs=freqs, chain=chain, division=d, lnl_ref=lnl, aborted=aborted)
+                                freqs=freqs, chain=chain, division=d, lnl_ref=lnl, aborted=aborted,
+                                inline_eigen=pending_inline)
+            pending_inline = None
             events.append(Event("eval", d, spec=spec))
         else:
             raise ValueError(f"{path}: unknown chunk {tag!r}")

@@ -53,6 +53,8 @@ typedef struct
     mb200_operation     *ops;
     mb200_matrix_update *mats;
     mb200_evaluation     ev;                /* evaluation being assembled            */
+    int                  inlineEigen;       /* nst = 1, 2: eigensystem derived per evaluation */
+    double               eigenBlock[72];    /* [lambda_re(4), lambda_im(4), c_ijk(64)] */
     long long            clUpdates;         /* node*pattern*rate updates issued      */
     } SeamDivision;
 
@@ -111,6 +113,69 @@ int MB200SeamInstance (int division)
     return seamDiv[division].instance;
 }
 
+/* 4x4 nucleotide models with nst = 1 or 2 (JC69, F81, K80, HKY85): the reference evaluates
+ * them with closed forms (TiProbs_JukesCantor / _Fels / _Hky, src/likelihood.c:9289, 9709, 9846)
+ * and keeps no eigensystem for them in non-BEAGLE builds (InitEigenSystemInfo, src/mcmc.c:6540-6552).
+ * The seam derives the eigensystem of their rate matrix for every evaluation and ships it with
+ * the call (mb200_evaluation.inline_eigen), so the engine needs no extra kernel. */
+int MB200SeamClosedFormModel (ModelInfo *m)
+{
+    if ((m->dataType == DNA || m->dataType == RNA) && m->nucModelId == NUCMODEL_4BY4 &&
+        (m->nst == 1 || m->nst == 2) && m->numModelStates == 4 && m->switchRates == NULL && m->nCijkParts == 0)
+        return YES;
+    return NO;
+}
+
+/* Q of HKY85 (kappa = 1: F81 / JC69), scaled to one expected substitution per unit time -- the
+ * same normalisation as TiProbs_Hky's beta (src/likelihood.c:9745) -- then GetEigens + CalcCijk,
+ * the two public utilities UpDateCijk itself uses (src/likelihood.c:10626-10661) */
+static int SeamClosedFormEigen (ModelInfo *m, int chain, double *block)
+{
+    int             i, j, isComplex;
+    MrBFlt          kappa, *bs, scaler, mult, **q, **eigvecs, **inverseEigvecs, eigenValues[4], eigvalsImag[4];
+    MrBComplex      **Ceigvecs, **CinverseEigvecs;
+
+    bs = GetParamSubVals (m->stateFreq, chain, state[chain]);
+    kappa = (m->nst == 2) ? *GetParamVals (m->tRatio, chain, state[chain]) : 1.0;
+    q = AllocateSquareDoubleMatrix (4);
+    eigvecs = AllocateSquareDoubleMatrix (4);
+    inverseEigvecs = AllocateSquareDoubleMatrix (4);
+    Ceigvecs = AllocateSquareComplexMatrix (4);
+    CinverseEigvecs = AllocateSquareComplexMatrix (4);
+    for (i=0; i<4; i++)
+        q[i][i] = 0.0;
+    scaler = 0.0;
+    for (i=0; i<4; i++)
+        for (j=i+1; j<4; j++)
+            {
+            mult = ((i == 0 && j == 2) || (i == 1 && j == 3)) ? kappa : 1.0;   /* A<->G, C<->T */
+            q[i][i] -= (q[i][j] = bs[j] * mult);
+            q[j][j] -= (q[j][i] = bs[i] * mult);
+            scaler += bs[i] * q[i][j];
+            scaler += bs[j] * q[j][i];
+            }
+    scaler = 1.0 / scaler;
+    for (i=0; i<4; i++)
+        for (j=0; j<4; j++)
+            q[i][j] *= scaler;
+    isComplex = GetEigens (4, q, eigenValues, eigvalsImag, eigvecs, inverseEigvecs, Ceigvecs, CinverseEigvecs);
+    if (isComplex == NO)
+        {
+        for (i=0; i<4; i++)
+            {
+            block[i] = eigenValues[i];
+            block[4+i] = eigvalsImag[i];
+            }
+        CalcCijk (4, block + 8, eigvecs, inverseEigvecs);
+        }
+    FreeSquareDoubleMatrix (q);
+    FreeSquareDoubleMatrix (eigvecs);
+    FreeSquareDoubleMatrix (inverseEigvecs);
+    FreeSquareComplexMatrix (Ceigvecs);
+    FreeSquareComplexMatrix (CinverseEigvecs);
+    return (isComplex == NO) ? NO_ERROR : ERROR;
+}
+
 /* Which divisions the engine takes; everything else stays on the reference's own
  * function pointers, the way the reference keeps BEAGLE away from models it does
  * not cover (src/mcmc.c:5741-5775). */
@@ -120,7 +185,7 @@ int MB200SeamDivisionSupported (ModelInfo *m)
         return NO;
     if (m->dataType != DNA && m->dataType != RNA && m->dataType != PROTEIN)
         return NO;                              /* STANDARD / RESTRICTION / CONTINUOUS: next rows */
-    if (m->nCijkParts != 1)
+    if (m->nCijkParts != 1 && MB200SeamClosedFormModel (m) == NO)
         return NO;                              /* NY98 multi-omega, covarion+gamma (TiProbs_GenCov) */
     if (m->gibbsGamma == YES || m->switchRates != NULL || m->correlation != NULL)
         return NO;
@@ -160,7 +225,7 @@ int InitBeagleInstance (ModelInfo *m, int division)
     cfg.category_count  = m->numRateCats;
     cfg.matrix_count    = m->numTiProbs;
     cfg.scaler_count    = m->numScalers;
-    cfg.eigen_count     = numLocalChains + 1;
+    cfg.eigen_count     = numLocalChains + 1;    /* unused (but harmless) for the inline-eigen models */
     cfg.weight_rows     = chainParams.numChains;
     cfg.device          = 0;
     cfg.max_evaluations = 1;
@@ -256,7 +321,7 @@ static void SeamQueueMatrix (SeamDivision *sd, ModelInfo *m, TreeNode *p, int ch
     FlipTiProbsSpace (m, chain, p->index);
     u = &sd->mats[sd->ev.matrix_update_count++];
     u->matrix = m->tiProbsIndex[chain][p->index];
-    u->eigen  = m->cijkIndex[chain];
+    u->eigen  = (sd->inlineEigen == YES) ? MB200_EIGEN_INLINE : m->cijkIndex[chain];
     u->length = SeamBranchLength (m, p, chain);
 }
 
@@ -405,6 +470,7 @@ int TreeLikelihood_Beagle (Tree *t, int division, int chain, MrBFlt *lnL, int wh
     sd->ev.root_buffer = m->condLikeIndex[chain][t->root->left->index];
     sd->ev.weights_row = whichSitePats;
     sd->ev.flags       = 0;
+    sd->ev.inline_eigen = (sd->inlineEigen == YES) ? sd->eigenBlock : NULL;
 
     pInvar = 0.0;
     sd->ev.has_p_invar = NO;
@@ -487,6 +553,24 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
         return (NO);
 
     tree = GetTree (m->brlens, chain, state[chain]);
+
+    if (MB200SeamClosedFormModel (m) == YES)
+        {
+        /* no cijk bookkeeping in the reference for these models: derive the eigensystem of the
+           chain's current kappa / base frequencies and send it along with the evaluation */
+        sd->inlineEigen = YES;
+        if (m->upDateCijk == YES)
+            m->upDateAll = YES;                 /* what LaunchLogLikeForDivision does (src/likelihood.c:7864-7872) */
+        if (SeamClosedFormEigen (m, chain, sd->eigenBlock) == ERROR)
+            {
+            (*lnL) = MRBFLT_NEG_MAX;
+            abortMove = YES;
+            return (YES);
+            }
+        LaunchBEAGLELogLikeForDivision (chain, d, m, tree, lnL);
+        return (YES);
+        }
+    sd->inlineEigen = NO;
 
     if (m->upDateCijk == YES)
         {

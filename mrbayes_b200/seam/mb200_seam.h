@@ -17,6 +17,7 @@
  * must use the reference's own function-pointer path. */
 int       MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL);
 int       MB200SeamDivisionSupported (ModelInfo *m);
+int       MB200SeamClosedFormModel (ModelInfo *m);     /* nst = 1, 2 4x4 models: eigensystem sent inline */
 void      MB200SeamFinalize (void);
 long long MB200SeamUpdateCount (int division);   /* node*pattern*rate CL updates issued  */
 int       MB200SeamInstance (int division);      /* engine instance of a division, or -1 */

@@ -173,7 +173,8 @@ static void TiProbs (OrcInst *o, const mb200_matrix_update *mu, const mb200_eval
 {
     int     S = o->cfg.state_count, K = o->cfg.category_count, i, j, k, s, index;
     double  t, sum, e[MB200_MAX_STATES];
-    const double *lam = o->eigen + (size_t)mu->eigen * (2*(size_t)S + (size_t)S*S*S);
+    const double *lam = (mu->eigen == MB200_EIGEN_INLINE) ? ev->inline_eigen
+                                                          : o->eigen + (size_t)mu->eigen * (2*(size_t)S + (size_t)S*S*S);
     const double *ptr;
     float  *tiP = o->matrices + (size_t)mu->matrix * K * S * S;
 

@@ -24,7 +24,8 @@
  *   'TIPS' i32 division, i32 tip, i32 C, C x u64
  *   'WGHT' i32 division, i32 row, i32 C, C x f32
  *   'EIGN' i32 division, i32 eigen, i32 S, f64 lambda[S], V[S*S], Vinv[S*S]
- *   'CIJK' i32 division, i32 eigen, i32 S, f64 block[2S+S^3]   (when V/Vinv unavailable)
+ *   'CIJK' i32 division, i32 eigen, i32 S, f64 block[2S+S^3]   (when V/Vinv unavailable; eigen = -2:
+ *          the block travels inline with the NEXT 'EVAL' record)
  *   'EVAL' i32 division, i32 chain, i32 nMat, i32 nOp, i32 siteDst, i32 siteSrc,
  *          i32 root, i32 weightsRow, i32 flags, i32 hasPInvar, i32 K, i32 S,
  *          f64 pInvar, f64 rates[K], f64 weights[K], f64 freqs[S],
@@ -69,6 +70,7 @@ static struct
     int                  capOps, capMats;
     double               lnLGpu;
     int                  statusGpu;
+    double              *inlineEig;
     } hLast;
 
 static int hInstDivision[4096];     /* recorder instance id -> division */
@@ -198,6 +200,14 @@ static int rec_eval (int inst, const mb200_evaluation *e, int n, double *lnL, in
     for (i=0; i<e->matrix_update_count; i++)  hLast.mats[i] = e->matrix_updates[i];
     hLast.ev.operations = hLast.ops;
     hLast.ev.matrix_updates = hLast.mats;
+    if (e->inline_eigen != NULL)
+        {
+        int S = hInstCfg[inst].state_count;
+        size_t nb = (2*(size_t)S + (size_t)S*S*S) * sizeof(double);
+        hLast.inlineEig = (double *) realloc (hLast.inlineEig, nb);
+        memcpy (hLast.inlineEig, e->inline_eigen, nb);
+        hLast.ev.inline_eigen = hLast.inlineEig;
+        }
     hLast.instance = inst;
     hLast.valid = 1;
     lnL[0] = 0.0;
@@ -224,6 +234,12 @@ static void WriteEval (int division, int chain, double lnLRef, int aborted)
 
     if (!hDump || !hLast.valid)
         return;
+    if (e->inline_eigen != NULL)
+        {
+        int eh[3];
+        eh[0] = division; eh[1] = MB200_EIGEN_INLINE; eh[2] = S;
+        Chunk ("CIJK", eh, sizeof(eh), e->inline_eigen, (2*(size_t)S + (size_t)S*S*S) * sizeof(double));
+        }
     hdr[0] = division; hdr[1] = chain; hdr[2] = e->matrix_update_count; hdr[3] = e->operation_count;
     hdr[4] = e->site_scaler_dst; hdr[5] = e->site_scaler_src; hdr[6] = e->root_buffer; hdr[7] = e->weights_row;
     hdr[8] = e->flags; hdr[9] = e->has_p_invar; hdr[10] = K; hdr[11] = S;

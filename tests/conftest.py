@@ -16,6 +16,8 @@ GOLDEN_FILES = [
     ("primates_gtr_eq_fma", 1),
     ("ovomucoids_wag_g4_sse", 0),
     ("replicase_m0_sse", 0),
+    ("primates_hky_g4_fma", 1),      # nst=2: closed-form model, eigensystem sent inline
+    ("primates_f81_i_fma", 1),       # nst=1 + pInvar
 ]
 
 

@@ -22,5 +22,7 @@ run primates_gtr_ig4_fma  mb_b200    100 200 primates_gtr_ig4
 run primates_gtr_eq_fma   mb_b200    100 150 primates_gtr_eq
 run ovomucoids_wag_g4_sse mb_b200    100  80 ovomucoids_wag_g4
 run replicase_m0_sse      mb_b200    100  40 replicase_m0
+run primates_hky_g4_fma   mb_b200    100 200 primates_hky_g4
+run primates_f81_i_fma    mb_b200    100 150 primates_f81_i
 rm -rf $TMP
 ls -la $OUT/*.gold.gz

@@ -29,7 +29,7 @@ def test_struct_sizes_match_the_header():
     assert ctypes.sizeof(abi.MatrixUpdate) == 16
     assert ctypes.sizeof(abi.InstanceConfig) == 48
     # int, ptr, int, ptr, 5 ints, double, int, 20+20+64 doubles (natural alignment)
-    assert ctypes.sizeof(abi.Evaluation) == 8 + 8 + 8 + 8 + 24 + 8 + 8 + 8 * (20 + 20 + 64)
+    assert ctypes.sizeof(abi.Evaluation) == 8 + 8 + 8 + 8 + 24 + 8 + 8 + 8 * (20 + 20 + 64) + 8
 
 
 def test_no_cpu_fallback_without_device():
