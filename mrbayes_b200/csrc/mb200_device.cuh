@@ -89,6 +89,8 @@ struct DevCtx                       // instance geometry + buffer bases, passed 
     int tipCount, partialsCount, matrixCount, scalerCount, eigenCount, weightRows;
     int tilePatterns;               // patterns per CTA in the evaluation kernels
     int numTiles;
+    int hostSum;                    // 1: every tile writes its partial lnL to the (mapped) result buffer,
+                                    //    the host adds them up in tile order (small launches only)
     const uint8_t  *tip8;
     const uint64_t *tip64;
     const int      *tipPartAmbig;   // [tip] 1: some pattern is partially ambiguous (isPartAmbig)

@@ -9,6 +9,7 @@
 #include "mb200_kernels_tc.cuh"
 
 #include <cuda_runtime.h>
+#include <float.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -60,6 +61,7 @@ struct Instance
     size_t        eigenStride = 0;     // doubles per eigen slot
     size_t        smemGen = 0;         // dynamic smem of eval_gen_kernel
     long long     launches = 0;
+    int           lastHostSum = 0, lastTiles = 1;   // how the last launch delivers its results
     Batch         scratch;             // used by the synchronous entry points
     std::vector<Batch *> batches;      // resident batches (mb200_pack_evaluations)
     void         *hostStage = nullptr; // pinned staging for set/get calls
@@ -77,13 +79,14 @@ std::mutex               gLock;
 std::vector<Instance *>  gInstances;
 
 const int NT_GEN = 256;
+const int HOSTSUM_MAX_TILES = 8;    // latency path: up to this many tile partials per evaluation summed on the host
 // threads per CTA of the 4-state kernels: latency regime (FUSE) and bandwidth regime; both sizes are
 // compiled, MB200_NT_SMALL / MB200_NT_STREAM (128 or 256) pick at run time for tuning
 int ntFromEnv (const char *name, int dflt)
 {
     const char *v = getenv (name);
     int n = v ? atoi (v) : dflt;
-    return (n == 128 || n == 256) ? n : dflt;
+    return (n == 128 || n == 256 || n == 512) ? n : dflt;
 }
 const int NT_SMALL = ntFromEnv ("MB200_NT_SMALL", 256);
 const int NT_STREAM = ntFromEnv ("MB200_NT_STREAM", 256);
@@ -153,9 +156,9 @@ int reserveBatch (Batch &b, size_t bytes, int nEval)
         if (b.hRes) cudaFreeHost (b.hRes);
         b.capEval = 0;
         CK (cudaMalloc ((void **)&b.dRes, sizeof(DevResult) * cap));
-        CK (cudaHostAlloc ((void **)&b.hRes, sizeof(DevResult) * cap, cudaHostAllocMapped));
+        CK (cudaHostAlloc ((void **)&b.hRes, sizeof(DevResult) * cap * HOSTSUM_MAX_TILES, cudaHostAllocMapped));
         CK (cudaHostGetDevicePointer ((void **)&b.hResDev, b.hRes, 0));
-        memset (b.hRes, 0, sizeof(DevResult) * cap);
+        memset (b.hRes, 0, sizeof(DevResult) * cap * HOSTSUM_MAX_TILES);
         b.capEval = cap;
         }
     return MB200_SUCCESS;
@@ -425,8 +428,9 @@ int launchNuc4T (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, c
 int launchNuc4 (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const double *dd, const DevChunk *dc,
                 const DevMat *dm, const DevOp *dops, DevResult *res, int seq, bool fused)
 {
-    const int nt = fused ? NT_SMALL : NT_STREAM;
-    return (nt == 256) ? launchNuc4T<256> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, fused)
+    const int nt = fused ? NT_SMALL : (NT_STREAM == 512 ? 256 : NT_STREAM);
+    return (nt == 512) ? launchNuc4T<512> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, true)
+         : (nt == 256) ? launchNuc4T<256> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, fused)
                        : launchNuc4T<128> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, fused);
 }
 
@@ -449,7 +453,8 @@ int launchNuc4ParamT (Instance *I, const DevCtx &ctx, dim3 grid, const Batch &b,
 template <int CAP>
 int launchNuc4Param (Instance *I, const DevCtx &ctx, dim3 grid, const Batch &b, DevResult *res, int seq)
 {
-    return (NT_SMALL == 256) ? launchNuc4ParamT<CAP, 256> (I, ctx, grid, b, res, seq)
+    return (NT_SMALL == 512) ? launchNuc4ParamT<CAP, 512> (I, ctx, grid, b, res, seq)
+         : (NT_SMALL == 256) ? launchNuc4ParamT<CAP, 256> (I, ctx, grid, b, res, seq)
                              : launchNuc4ParamT<CAP, 128> (I, ctx, grid, b, res, seq);
 }
 
@@ -462,7 +467,7 @@ bool paramEligible (const Instance *I, const Batch &b)
 
 // launch the fused pass for a packed batch; fromHost: the job lives in b.hBlob only and is
 // delivered through the parameter block when it fits (otherwise the caller has copied it to dBlob)
-int launch (Instance *I, Batch &b, DevResult *res, bool viaParams)
+int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum = false)
 {
     const DevEval  *de = (const DevEval  *)(b.dBlob + b.offEval);
     const double   *dd = (const double   *)(b.dBlob + b.offDbl);
@@ -500,6 +505,8 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams)
         {
         ctx.tilePatterns = nuc4PatternsPerBlock (ctx.K, b.fused);
         ctx.numTiles = (ctx.C + ctx.tilePatterns - 1) / ctx.tilePatterns;
+        ctx.hostSum = (hostSum && ctx.numTiles <= HOSTSUM_MAX_TILES) ? 1 : 0;
+        I->lastHostSum = ctx.hostSum; I->lastTiles = ctx.numTiles;
         dim3 grid (ctx.numTiles, b.nEval);
         int rc;
         if (viaParams)
@@ -542,13 +549,13 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams)
     return MB200_SUCCESS;
 }
 
-// wait until the kernel has written every result of the batch into the mapped host buffer
-int waitResults (Instance *I, Batch &b, int count)
+// wait until the kernel has written `slots` results into the mapped host buffer
+int waitResults (Instance *I, Batch &b, int slots)
 {
     const int seq = I->seq;
     volatile DevResult *r = b.hRes;
     unsigned long long spins = 0;
-    for (int e = 0; e < count; e++)
+    for (int e = 0; e < slots; e++)
         {
         while (r[e].seq != seq)
             {
@@ -583,13 +590,15 @@ int runSync (Instance *I, const mb200_evaluation *evs, int count, double *lnL, i
     const bool viaParams = paramEligible (I, b);
     if (!viaParams)
         CK (cudaMemcpyAsync (b.dBlob, b.hBlob, b.bytes, cudaMemcpyHostToDevice, I->stream));
-    rc = launch (I, b, b.hResDev, viaParams);
-    if (rc != MB200_SUCCESS) return rc;
     bool allRoot = true;
     for (int e = 0; e < count; e++) if (evs[e].root_buffer == MB200_NONE) allRoot = false;
+    I->lastHostSum = 0; I->lastTiles = 1;
+    rc = launch (I, b, b.hResDev, viaParams, allRoot && b.fused);
+    if (rc != MB200_SUCCESS) return rc;
     if (allRoot)
         {
-        rc = waitResults (I, b, count);           // results land in pinned host memory; no D2H copy
+        // results land in pinned host memory; no D2H copy, no stream synchronisation
+        rc = waitResults (I, b, I->lastHostSum ? count * I->lastTiles : count);
         if (rc != MB200_SUCCESS) return rc;
         }
     else
@@ -598,8 +607,23 @@ int runSync (Instance *I, const mb200_evaluation *evs, int count, double *lnL, i
         {
         if (evs[e].root_buffer != MB200_NONE)
             {
-            if (lnL)    lnL[e] = b.hRes[e].lnL;
-            if (status) status[e] = b.hRes[e].status;
+            if (I->lastHostSum)
+                {
+                // the tiles' partial sums, added left to right (the order the device uses too)
+                double tot = 0.0; int ab = 0;
+                for (int t = 0; t < I->lastTiles; t++)
+                    {
+                    tot += b.hRes[e * I->lastTiles + t].lnL;
+                    ab  |= b.hRes[e * I->lastTiles + t].status;
+                    }
+                if (lnL)    lnL[e] = ab ? -DBL_MAX : tot;
+                if (status) status[e] = ab ? MB200_EVAL_UNDERFLOW : MB200_EVAL_OK;
+                }
+            else
+                {
+                if (lnL)    lnL[e] = b.hRes[e].lnL;
+                if (status) status[e] = b.hRes[e].status;
+                }
             }
         else
             {

@@ -212,17 +212,48 @@ __device__ __forceinline__ void finish_lnl (const DevCtx &ctx, int evalIdx, doub
         double s = 0.0; int a = 0;
         #pragma unroll
         for (int w = 0; w < NT/32; w++) { s += sSum[w]; a |= sAb[w]; }
+        if (ctx.hostSum)
+            {
+            // latency path: no ticket, no second pass -- the tile's partial goes straight to the
+            // caller (one 16-byte store into mapped host memory), which sums the few tiles itself
+            int4 pkt;
+            pkt.x = __double2loint (s); pkt.y = __double2hiint (s); pkt.z = a; pkt.w = seq;
+            *reinterpret_cast<int4 *>(&out[(size_t)evalIdx*ctx.numTiles + blockIdx.x]) = pkt;
+            sLast = 0;
+            }
+        else
+            {
         ctx.tilePartial[(size_t)evalIdx*ctx.numTiles + blockIdx.x] = s;
         ctx.tileAbort  [(size_t)evalIdx*ctx.numTiles + blockIdx.x] = a;
         __threadfence ();
         unsigned int t = atomicAdd (&ctx.ticket[evalIdx], 1u);
         sLast = (t == (unsigned int)ctx.numTiles - 1u);
+            }
         }
     __syncthreads ();
     if (!sLast)
         return;
     __threadfence ();
     // last CTA of this evaluation: fixed-order sum over the tiles
+    if (ctx.numTiles <= 8)
+        {
+        // few tiles: plain left-to-right sum, the order the host uses in hostSum mode
+        if (threadIdx.x == 0)
+            {
+            double tot = 0.0; int ab = 0;
+            for (int tIdx = 0; tIdx < ctx.numTiles; tIdx++)
+                {
+                tot += __ldcg (&ctx.tilePartial[(size_t)evalIdx*ctx.numTiles + tIdx]);
+                ab  |= __ldcg (&ctx.tileAbort  [(size_t)evalIdx*ctx.numTiles + tIdx]);
+                }
+            const double lnL = ab ? -DBL_MAX : tot;
+            int4 pkt;
+            pkt.x = __double2loint (lnL); pkt.y = __double2hiint (lnL); pkt.z = ab ? 1 : 0; pkt.w = seq;
+            *reinterpret_cast<int4 *>(&out[evalIdx]) = pkt;
+            ctx.ticket[evalIdx] = 0u;
+            }
+        return;
+        }
     double s = 0.0; int a = 0;
     for (int tIdx = threadIdx.x; tIdx < ctx.numTiles; tIdx += NT)
         {
