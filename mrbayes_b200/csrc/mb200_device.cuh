@@ -45,7 +45,8 @@ struct DevEval                      // one LaunchLogLikeForDivision (96 bytes)
                                     // -2: the evaluation carries its own cijk block after freqs in the doubles
     int    chunkOff;
     DevChunk chunk0;
-    int    pad[2];
+    int    rootFwd;                 // 4-state path: the root buffer is the last node's result
+    unsigned rootOff;               // 4-state path: float4 index of the root buffer
 };
 
 struct DevMat                       // one branch (16 bytes)
@@ -61,6 +62,26 @@ struct DevOp                        // one interior-node update (48 bytes)
     int dest, c1, m1, c2, m2, c3, m3, sw, sr;
     int s1, s2, s3;                 // fused launches: shared-memory slot of m1/m2/m3 (index into the
                                     // evaluation's matrix list, dirty first, then clean); else -1
+};
+
+// 4-state kernels: the same 48-byte record with everything address-like precomputed by pack(),
+// so the node loop is  base + uniform offset  and nothing else
+#define NUC_NONE     0u
+#define NUC_LOAD     1u             // interior child, read from the partials buffer
+#define NUC_TIP      2u             // tip child: 1-byte state mask
+#define NUC_TIP_ONE  6u             // tip child under the scalar kernels' shortcut: a missing observation contributes exactly 1
+#define NUC_FWD      8u             // the previous node's result: stays in registers
+#define NUC_RESCALE  0x1000u
+struct NucOp
+{
+    unsigned a1, a2, a3;            // child operand: float4 index of its partials buffer ((child - tips) * K * C)
+                                    // or byte index of its tip row (child * C)
+    unsigned kinds;                 // bits 0-3 / 4-7 / 8-11: kind of child 1 / 2 / 3; bit 12: rescale this node
+    unsigned destOff;               // float4 index of the destination buffer
+    unsigned sp1, sp2, sp3;         // byte offset of the branch's P(t) slot in shared memory
+    int sw, sr;                     // node scaler to write / to remove (-1: none)
+    int dest;
+    int pad;
 };
 
 struct DevResult                    // 16 bytes per evaluation

@@ -35,6 +35,7 @@ struct Batch                       // packed evaluations (device job format)
     bool    fused = false;         // 4-state latency path: P(t) rebuilt inside the pruning kernel
     bool    needInv = false;
     bool    used = false;
+    int     tipEpoch = 0;          // Instance::tipEpoch at pack time (4-state records embed tip kinds)
 };
 
 struct Instance
@@ -61,6 +62,8 @@ struct Instance
     size_t        eigenStride = 0;     // doubles per eigen slot
     size_t        smemGen = 0;         // dynamic smem of eval_gen_kernel
     long long     launches = 0;
+    std::vector<int> tipPartAmbig;  // host copy (operand kinds of the 4-state records)
+    int           tipEpoch = 0;
     int           lastHostSum = 0, lastTiles = 1;   // how the last launch delivers its results
     Batch         scratch;             // used by the synchronous entry points
     std::vector<Batch *> batches;      // resident batches (mb200_pack_evaluations)
@@ -101,6 +104,12 @@ int nuc4PatternsPerBlock (int K, bool small)
 {
     int L = (K <= 1) ? 1 : (K <= 2) ? 2 : (K <= 4) ? 4 : 8;
     return (small ? NT_SMALL : NT_STREAM) / L;
+}
+
+int nuc4MinPatternsPerBlock (int K)
+{
+    int a = nuc4PatternsPerBlock (K, true), b = nuc4PatternsPerBlock (K, false);
+    return a < b ? a : b;
 }
 
 Instance *get (int id)
@@ -379,6 +388,42 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
                 DevMat &m = du[mOff + i];
                 m.matrix = u.matrix; m.eigen = u.eigen; m.length = u.length;
                 }
+        if (nuc4)
+            {
+            // 4-state kernels: address-like quantities precomputed, operand kinds resolved
+            const unsigned bufStride = (unsigned) K * (unsigned) c.pattern_count;       // float4 per buffer
+            const unsigned slotBytes = (unsigned) K * 80u;                              // sP[slot][K][5] float4
+            const bool shortcuts = (ev.flags & MB200_FLAG_TIP_SHORTCUTS) != 0;
+            int prevDest = -2;
+            auto operand = [&] (int child, unsigned &a) -> unsigned
+                {
+                if (child == MB200_NONE) { a = 0; return NUC_NONE; }
+                if (child < c.tip_count)
+                    {
+                    a = (unsigned) child * (unsigned) c.pattern_count;
+                    return (shortcuts && !I->tipPartAmbig[child]) ? NUC_TIP_ONE : NUC_TIP;
+                    }
+                a = (unsigned)(child - c.tip_count) * bufStride;
+                return (child == prevDest) ? NUC_FWD : NUC_LOAD;
+                };
+            for (int i = 0; i < ev.operation_count; i++)
+                {
+                const mb200_operation &op = ev.operations[i];
+                NucOp &o = reinterpret_cast<NucOp *>(dops)[oOff + i];
+                const unsigned k1 = operand (op.child1, o.a1), k2 = operand (op.child2, o.a2), k3 = operand (op.child3, o.a3);
+                o.kinds = k1 | (k2 << 4) | (k3 << 8) | (op.scale_write >= 0 ? NUC_RESCALE : 0u);
+                o.destOff = (unsigned)(op.dest - c.tip_count) * bufStride;
+                o.sp1 = (unsigned) slots[slotPos] * slotBytes;
+                o.sp2 = (unsigned) slots[slotPos + 1] * slotBytes;
+                o.sp3 = (slots[slotPos + 2] >= 0) ? (unsigned) slots[slotPos + 2] * slotBytes : 0u;
+                o.sw = op.scale_write; o.sr = op.scale_remove; o.dest = op.dest; o.pad = 0;
+                slotPos += 3;
+                prevDest = op.dest;
+                }
+            d.rootFwd = (ev.root_buffer != MB200_NONE && ev.root_buffer == prevDest) ? 1 : 0;
+            d.rootOff = (ev.root_buffer != MB200_NONE) ? (unsigned)(ev.root_buffer - c.tip_count) * bufStride : 0u;
+            }
+        else
         for (int i = 0; i < ev.operation_count; i++)
             {
             const mb200_operation &op = ev.operations[i];
@@ -393,7 +438,7 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         oOff += ev.operation_count;
         }
     b.bytes = bytes; b.nEval = count; b.nMat = nUpd; b.nOp = nOp; b.nDbl = nDbl;
-    b.nDirty = nMat; b.fused = fused;
+    b.nDirty = nMat; b.fused = fused; b.tipEpoch = I->tipEpoch;
     b.offEval = offEval; b.offDbl = offDbl; b.offUpd = offUpd; b.offChunk = offChunk; b.offCmat = offCmat; b.offOp = offOp;
     return MB200_SUCCESS;
 }
@@ -726,12 +771,14 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     while (TP > 1 && smemFor (TP) > 96*1024) TP >>= 1;
     I->smemGen = smemFor (TP);
     const bool nuc4 = (S == 4 && K <= 8);
+    if (nuc4 && (nInt * K * C >= (1ull << 32) || (size_t)cfg->tip_count * C >= (1ull << 32)))
+        { delete I; return MB200_ERROR_OUT_OF_RANGE; }      // 4-state records carry 32-bit element offsets (64 GB of partials)
     if (!getenv ("MB200_DISABLE_TC"))
         {
         if (S == 61 && K == 1) I->tcS = 61;      // 61-state codon, tcgen05 path
         if (S == 20 && K <= 4) I->tcS = 20;      // 20-state amino acids, tcgen05 path
         }
-    I->maxTiles = I->tcS ? (C + 127) / 128 : nuc4 ? (C + nuc4PatternsPerBlock (K, false) - 1) / nuc4PatternsPerBlock (K, false) : (C + TP - 1) / TP;
+    I->maxTiles = I->tcS ? (C + 127) / 128 : nuc4 ? (C + nuc4MinPatternsPerBlock (K) - 1) / nuc4MinPatternsPerBlock (K) : (C + TP - 1) / TP;
 
 #define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc ((void **)&(ptr), (bytes)); if (e_ != cudaSuccess) { \
         cudaGetLastError (); destroy (I); return (e_ == cudaErrorMemoryAllocation) ? MB200_ERROR_OUT_OF_MEMORY : MB200_ERROR_CUDA; } } while (0)
@@ -765,6 +812,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     cudaMemsetAsync (I->dTip8, 0, (size_t)cfg->tip_count * C, I->stream);
     cudaMemsetAsync (I->dTip64, 0, (size_t)cfg->tip_count * C * sizeof(uint64_t), I->stream);
     cudaMemsetAsync (I->dTipPartAmbig, 0, (size_t)cfg->tip_count * sizeof(int), I->stream);
+    I->tipPartAmbig.assign (cfg->tip_count, 0);
     cudaMemsetAsync (I->dPartials, 0, nInt * K * C * Sp * sizeof(float), I->stream);
     cudaMemsetAsync (I->dMatrices, 0, (size_t)cfg->matrix_count * K * S * S * sizeof(float), I->stream);
     cudaMemsetAsync (I->dScalers, 0, (size_t)cfg->scaler_count * C * sizeof(float), I->stream);
@@ -833,6 +881,8 @@ int mb200_set_tip_states (int instance, int tip, const uint64_t *masks)
             partAmbig = 1;
         }
     CK (cudaMemcpyAsync (I->dTipPartAmbig + tip, &partAmbig, sizeof(int), cudaMemcpyHostToDevice, I->stream));
+    I->tipPartAmbig[tip] = partAmbig;
+    I->tipEpoch++;                  // packed 4-state batches carry the tip kinds: re-pack after this
     CK (cudaMemcpyAsync (I->dTip64 + (size_t)tip * C, h64, (size_t)C * 8, cudaMemcpyHostToDevice, I->stream));
     CK (cudaMemcpyAsync (I->dTip8 + (size_t)tip * C, h8, (size_t)C, cudaMemcpyHostToDevice, I->stream));
     CK (cudaStreamSynchronize (I->stream));
@@ -1094,6 +1144,8 @@ int mb200_replay (int instance, int batch)
     if (batch < 0 || batch >= (int) I->batches.size () || !I->batches[batch]) return MB200_ERROR_OUT_OF_RANGE;
     int rc = use (I); if (rc) return rc;
     Batch &rb = *I->batches[batch];
+    if (rb.tipEpoch != I->tipEpoch)
+        return MB200_ERROR_OUT_OF_RANGE;           // tip states changed since mb200_pack_evaluations: pack again
     return launch (I, rb, rb.dRes, false);
 }
 

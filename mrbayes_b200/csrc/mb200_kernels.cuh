@@ -331,6 +331,27 @@ __device__ __forceinline__ double site_term (double like, double likeI, int hasP
 // only in the final lnL reduction.  Every global access is a fully coalesced 16-byte (CL),
 // 4-byte (scalers, weights) or 1-byte (tip codes) per-thread access.
 // ---------------------------------------------------------------------------------------
+// r / m for the four states of a rescaled vector (CondLikeScaler_NUC4, src/likelihood.c:5169-5200):
+// one reciprocal refined to < 1 ulp, then per element the quotient with one exact-remainder
+// correction -- the correctly rounded quotient an IEEE divide returns, at a third of the
+// instructions of four divisions.  Outside the exponent range where that argument holds: plain '/'.
+__device__ __forceinline__ void scale4 (float4 &r, float m)
+{
+    if (m > 1.0e-30f && m < 1.0e30f)
+        {
+        float rc;
+        asm ("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(m));
+        rc = fmaf (rc, fmaf (-m, rc, 1.0f), rc);
+        float q, rem;
+        q = r.x * rc; rem = fmaf (-m, q, r.x); r.x = fmaf (rem, rc, q);
+        q = r.y * rc; rem = fmaf (-m, q, r.y); r.y = fmaf (rem, rc, q);
+        q = r.z * rc; rem = fmaf (-m, q, r.z); r.z = fmaf (rem, rc, q);
+        q = r.w * rc; rem = fmaf (-m, q, r.w); r.w = fmaf (rem, rc, q);
+        }
+    else
+        { r.x /= m; r.y /= m; r.z /= m; r.w /= m; }
+}
+
 __device__ __forceinline__ float dot4_fma (const float4 p, const float4 x)
 {
     // same operation order as CondLikeDown_NUC4_FMA (src/likelihood.c:1149-1169)
@@ -340,6 +361,21 @@ __device__ __forceinline__ float dot4_fma (const float4 p, const float4 x)
 __device__ __forceinline__ float4 matvec4 (const float4 *rows, const float4 x)
 {
     return make_float4 (dot4_fma (rows[0], x), dot4_fma (rows[1], x), dot4_fma (rows[2], x), dot4_fma (rows[3], x));
+}
+
+// the same with the four rows of P(t) read from shared memory at a 32-bit shared address
+// (rows 16 bytes apart): keeps one live register per base instead of a generic pointer
+__device__ __forceinline__ float4 lds128 (unsigned saddr)
+{
+    float4 v;
+    asm volatile ("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
+__device__ __forceinline__ float4 matvec4s (unsigned saddr, const float4 x)
+{
+    const float4 r0 = lds128 (saddr), r1 = lds128 (saddr + 16), r2 = lds128 (saddr + 32), r3 = lds128 (saddr + 48);
+    return make_float4 (dot4_fma (r0, x), dot4_fma (r1, x), dot4_fma (r2, x), dot4_fma (r3, x));
 }
 
 // contribution of a tip child: sum of the P columns its state set selects == the dense 0/1
@@ -422,9 +458,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
     const int   c      = c0 + pl;
     const bool  active = (c < C) && (lk < K);
     const int   cc     = (c < C) ? c : C - 1;
-    const size_t bufStride = (size_t)K * C;                 // float4 per partials buffer
     float4 *partials4 = reinterpret_cast<float4 *>(ctx.partials);
-    const bool  shortcutFlag = (sEv.flags & MB200_SHORTCUT_FLAG) != 0;
     const unsigned groupBase = (threadIdx.x & 31) & ~(L - 1);
     const int   eig0 = sEv.eigen0;
     const int   nChunk = sEv.nChunk;
@@ -438,36 +472,32 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
     float  lnScaler = (sEv.siteSrc >= 0) ? ctx.scalers[(size_t)sEv.siteSrc * C + cc] : 0.0f;
 
     float4 cur = make_float4 (0.f, 0.f, 0.f, 0.f);
-    int    curBuf = -2;
-    float4 xn[3];                                 // prefetched child vectors of the next node
-    int    tn[3];                                 // -1: vector in xn, -2: take `cur`, 16: tip shortcut (all ones)
 
-    auto issue = [&] (const DevOp &op, int prevDest)
+    // per-thread addressing: everything in the node loop is  base + (uniform offset from the op record)
+    // (32-bit element offsets: pack() guarantees they fit; one live register per base)
+    const unsigned       tOff  = (unsigned) kk * (unsigned) C + (unsigned) cc;
+    const unsigned       sPk   = (unsigned) __cvta_generic_to_shared (&sP[0][kk][0]);
+    float               *sNewT = &sNew[0][pl];
+    const NucOp         *nops  = reinterpret_cast<const NucOp *>(sOps);
+
+    // operand of a node: interior child -> one 16-byte load; tip -> its 1-byte state mask, parked in
+    // x.x until the node consumes it (expanding it here would stall on the load just issued)
+    auto fetch = [&] (unsigned kind, unsigned a, float4 &x)
         {
-        #pragma unroll
-        for (int ch = 0; ch < 3; ch++)
-            {
-            tn[ch] = -1;
-            xn[ch] = make_float4 (0.f, 0.f, 0.f, 0.f);
-            const int child = (ch == 0) ? op.c1 : (ch == 1) ? op.c2 : op.c3;
-            if (child < 0)
-                continue;
-            if (child < ctx.tipCount)
-                {
-                // tip: 1-byte state mask -> 0/1 vector; the dense matvec then equals the reference's
-                // 0/1 matvec bit for bit (products by 0 and 1 are exact)
-                const int mask = ctx.tip8[(size_t)child * C + cc];
-                xn[ch] = make_float4 ((mask & 1) ? 1.f : 0.f, (mask & 2) ? 1.f : 0.f, (mask & 4) ? 1.f : 0.f, (mask & 8) ? 1.f : 0.f);
-                // scalar-kernel shortcut: a missing observation on a tip without partial ambiguity
-                // contributes exactly 1.0 (preLike tables, src/likelihood.c:816-832)
-                if (shortcutFlag && (mask & 15) == 15 && !ctx.tipPartAmbig[child])
-                    tn[ch] = 16;
-                }
-            else if (child == prevDest)
-                tn[ch] = -2;
-            else
-                xn[ch] = partials4[(size_t)(child - ctx.tipCount) * bufStride + (size_t)kk * C + cc];
-            }
+        if (kind == NUC_LOAD)
+            x = partials4[tOff + a];
+        else if (kind & NUC_TIP)
+            x.x = __uint_as_float ((unsigned) ctx.tip8[(unsigned) cc + a]);
+        };
+    // tip operand: state mask -> 0/1 vector (the dense matvec then equals the reference's 0/1 matvec
+    // bit for bit: products by 0 and 1 are exact); returns true when, under the scalar kernels'
+    // shortcut, a missing observation on a tip without partial ambiguity contributes exactly 1.0
+    // (preLike tables, src/likelihood.c:816-832)
+    auto expand = [&] (float4 &x, bool shortcut) -> bool
+        {
+        const unsigned mask = __float_as_uint (x.x);
+        x = make_float4 ((mask & 1) ? 1.f : 0.f, (mask & 2) ? 1.f : 0.f, (mask & 4) ? 1.f : 0.f, (mask & 8) ? 1.f : 0.f);
+        return shortcut && (mask & 15) == 15;
         };
 
     for (int ci = 0; ci < nChunk; ci++)
@@ -542,51 +572,89 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
         __syncthreads ();
         if (ci == 0) MB200_STAMP (3);
 
-        // ---- 3. node loop: no barrier, a thread only ever touches its own pattern ----
+        // ---- 3. node loop: no barrier, a thread only ever touches its own pattern.  The operands of
+        //      node n+1 are fetched while node n computes; the two operand sets alternate (xa, xb) so
+        //      that no register copies are needed ----
         const int nOp = ch.nOp;
-        if (nOp > 0)
-            issue (sOps[0], curBuf);
-        for (int oo = 0; oo < nOp; oo++)
+        float4   xa[3], xb[3];
+        auto node = [&] (int oo, const float4 (&xi)[3], float4 (&xo)[3])
             {
-            const DevOp op = sOps[oo];
-            float4 x0 = (tn[0] == -2) ? cur : xn[0];
-            float4 x1 = (tn[1] == -2) ? cur : xn[1];
-            float4 x2 = (tn[2] == -2) ? cur : xn[2];
-            const int t0 = tn[0], t1 = tn[1], t2 = tn[2];
+            const uint4 oa = reinterpret_cast<const uint4 *>(nops + oo)[0];     // a1 a2 a3 kinds
+            const uint4 ob = reinterpret_cast<const uint4 *>(nops + oo)[1];     // destOff sp1 sp2 sp3
+            const unsigned kinds = oa.w;
+            unsigned nk = 0;
             if (oo + 1 < nOp)
-                issue (sOps[oo + 1], op.dest);    // next node's loads in flight
-
-            float4 res = matvec4 (sP[op.s1][kk], x0);
-            float4 v   = matvec4 (sP[op.s2][kk], x1);
-            if (shortcutFlag)
                 {
-                if (t0 == 16) res = make_float4 (1.f, 1.f, 1.f, 1.f);
-                if (t1 == 16) v   = make_float4 (1.f, 1.f, 1.f, 1.f);
+                const uint4 na = reinterpret_cast<const uint4 *>(nops + oo + 1)[0];
+                nk = na.w;
+                fetch (nk & 15u, na.x, xo[0]);
+                fetch ((nk >> 4) & 15u, na.y, xo[1]);
+                if (nk & 0xf00u)
+                    fetch ((nk >> 8) & 15u, na.z, xo[2]);
+                }
+            float4 x0 = xi[0], x1 = xi[1];
+            bool one0 = false, one1 = false;
+            if (kinds & 0x22u)                    // tip operands (uniform tests)
+                {
+                if (kinds & 0x02u) one0 = expand (x0, (kinds & 0x04u) != 0);
+                if (kinds & 0x20u) one1 = expand (x1, (kinds & 0x40u) != 0);
+                }
+            float4 res = matvec4s (sPk + ob.y, x0);
+            float4 v   = matvec4s (sPk + ob.z, x1);
+            if (kinds & 0x44u)
+                {
+                if (one0) res = make_float4 (1.f, 1.f, 1.f, 1.f);
+                if (one1) v   = make_float4 (1.f, 1.f, 1.f, 1.f);
                 }
             res.x *= v.x; res.y *= v.y; res.z *= v.z; res.w *= v.w;
-            if (op.c3 >= 0)                       // unrooted interior root: third neighbour
+            if (kinds & 0xf00u)                   // unrooted interior root: third neighbour
                 {
-                v = matvec4 (sP[op.s3][kk], x2);
-                if (shortcutFlag && t2 == 16) v = make_float4 (1.f, 1.f, 1.f, 1.f);
+                float4 x2 = xi[2];
+                bool one2 = false;
+                if (kinds & 0x200u) one2 = expand (x2, (kinds & 0x400u) != 0);
+                v = matvec4s (sPk + ob.w, x2);
+                if (one2) v = make_float4 (1.f, 1.f, 1.f, 1.f);
                 res.x *= v.x; res.y *= v.y; res.z *= v.z; res.w *= v.w;
                 }
             float m = 0.0f;                       // 0 marks "node not rescaled"
-            if (op.sw >= 0)
+            if (kinds & NUC_RESCALE)
                 {
-                m = (lk < K) ? fmaxf (fmaxf (res.x, res.y), fmaxf (res.z, res.w)) : 0.0f;
-                m = fmaxf (m, 0.0f);
+                // lanes beyond K (K not a power of two) hold a copy of category K-1: harmless in a max
+                m = fmaxf (fmaxf (fmaxf (res.x, res.y), fmaxf (res.z, res.w)), 0.0f);
                 #pragma unroll
                 for (int off = 1; off < L; off <<= 1)
                     m = fmaxf (m, __shfl_xor_sync (0xffffffffu, m, off));
-                res.x /= m; res.y /= m; res.z /= m; res.w /= m;
+                scale4 (res, m);
                 }
             if (lk == 0)
-                sNew[oo][pl] = m;
+                sNewT[oo * PPB] = m;
             if (active)
-                partials4[(size_t)(op.dest - ctx.tipCount) * bufStride + (size_t)kk * C + c] = res;
+                partials4[tOff + ob.x] = res;
+            if (nk & 0x888u)                      // the next node consumes this result (uniform test)
+                {
+                if (nk & NUC_FWD)         xo[0] = res;
+                if (nk & (NUC_FWD << 4))  xo[1] = res;
+                if (nk & (NUC_FWD << 8))  xo[2] = res;
+                }
             cur = res;
-            curBuf = op.dest;
             if (ci == 0) MB200_STAMP (8 + oo);
+            };
+        if (nOp > 0)
+            {
+            const uint4 na = reinterpret_cast<const uint4 *>(nops)[0];
+            fetch (na.w & 15u, na.x, xa[0]);
+            fetch ((na.w >> 4) & 15u, na.y, xa[1]);
+            if (na.w & 0xf00u)
+                fetch ((na.w >> 8) & 15u, na.z, xa[2]);
+            if (na.w & NUC_FWD)        xa[0] = cur;       // result of the previous chunk's last node
+            if (na.w & (NUC_FWD << 4)) xa[1] = cur;
+            if (na.w & (NUC_FWD << 8)) xa[2] = cur;
+            }
+        for (int oo = 0; oo < nOp; oo += 2)
+            {
+            node (oo, xa, xb);
+            if (oo + 1 < nOp)
+                node (oo + 1, xb, xa);
             }
 
         // ---- 4. batched scaler pass: logs with full ILP, node scalers out, old scalers in ----
@@ -595,7 +663,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             {
             const int oo = e / PPB, p = e % PPB;
             const int cp = c0 + p;
-            const int sw = sOps[oo].sw, sr = sOps[oo].sr;
+            const int sw = nops[oo].sw, sr = nops[oo].sr;
             float sc = 0.0f, old = 0.0f;
             if (cp < C)
                 {
@@ -620,7 +688,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             for (int oo = 0; oo < nOp; oo++)
                 {
                 lnScaler -= sOld[oo][pl];
-                if (sOps[oo].sw >= 0)
+                if (nops[oo].sw >= 0)
                     lnScaler += sNew[oo][pl];
                 }
         }
@@ -633,8 +701,8 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
         return;
 
     // ---- root integration (Likelihood_NUC4_FMA, src/likelihood.c:6468-6625) ----
-    if (sEv.root != curBuf)
-        cur = partials4[(size_t)(sEv.root - ctx.tipCount) * bufStride + (size_t)kk * C + cc];
+    if (!sEv.rootFwd)
+        cur = partials4[tOff + sEv.rootOff];
     const double *freqs = sD + 2*K, *catW = sD + K;
     const float fA = (float) freqs[0], fC = (float) freqs[1], fG = (float) freqs[2], fT = (float) freqs[3];
     // the reference accumulates one fused chain over k = 0..K-1 and the four states; the chain
@@ -690,7 +758,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
 // ---- kernel entry points of the 4-state path ----
 // job descriptors in global memory (device-resident batches, large jobs)
 template <int K, int NT, bool FUSE>
-__global__ void __launch_bounds__(NT, FUSE ? 1 : 1024 / NT)
+__global__ void __launch_bounds__(NT, FUSE ? 1 : 768 / NT)
 eval_nuc4_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
                   const DevChunk *__restrict__ chunks, const DevMat *__restrict__ cmats,
                   const DevOp *__restrict__ ops, DevResult *out, int seq)
