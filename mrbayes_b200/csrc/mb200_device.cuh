@@ -23,6 +23,7 @@
 #define MB200_DEV_MAX_STATES 64
 
 struct DevChunk                     // a run of nodes whose branches fit the shared-memory P(t) slots
+                                    // (4-state path: nMat = branches | tip operands << 16)
 {
     int opOff, nOp;                 // nodes    [opOff, opOff+nOp)   of the batch's operation array
     int matOff, nMat;               // branches [matOff, matOff+nMat) of the batch's chunk-matrix array
@@ -76,13 +77,17 @@ struct NucOp
 {
     unsigned a1, a2, a3;            // child operand: float4 index of its partials buffer ((child - tips) * K * C)
                                     // or byte index of its tip row (child * C)
-    unsigned kinds;                 // bits 0-3 / 4-7 / 8-11: kind of child 1 / 2 / 3; bit 12: rescale this node
+    unsigned kinds;                 // bits 0-3 / 4-7 / 8-11: kind of child 1 / 2 / 3; bit 12: rescale this node;
+                                    // bits 13-18 / 19-24 / 25-30: tip-table index (within the chunk) of child 1 / 2 / 3
     unsigned destOff;               // float4 index of the destination buffer
     unsigned sp1, sp2, sp3;         // byte offset of the branch's P(t) slot in shared memory
     int sw, sr;                     // node scaler to write / to remove (-1: none)
     int dest;
     int pad;
 };
+// tip operands of a chunk get a 16-entry lookup table each (state mask -> P(t) column sum, per rate
+// category): tables per chunk, as a function of K (24 KB of shared memory)
+#define NUC_MAXT(K) ((96 / (K)) > 64 ? 64 : (96 / (K)))
 
 struct DevResult                    // 16 bytes per evaluation
 {

@@ -72,7 +72,7 @@ struct Instance
     std::vector<int> slotOf;           // scratch: matrix index -> shared-memory slot in the current evaluation
     std::vector<int> touched;          // scratch: matrices whose slotOf entry is set
     std::vector<int> dirtyOf;          // scratch: matrix index -> index in the evaluation's update list
-    std::vector<DevChunk> chunkTmp; std::vector<DevMat> cmatTmp; std::vector<int> slotTmp, nChunkTmp;
+    std::vector<DevChunk> chunkTmp; std::vector<DevMat> cmatTmp; std::vector<int> slotTmp, nChunkTmp, tipIdxTmp;
     bool          timing = false;      // bracket the fused kernel with events
     std::vector<cudaEvent_t> evA, evB; // ring of event pairs
     long long     evCount = 0;         // pairs recorded since the last read
@@ -198,8 +198,10 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     std::vector<DevChunk> &chunks = I->chunkTmp;   // all evaluations, chunk0 of each included
     std::vector<DevMat>   &cmats  = I->cmatTmp;
     std::vector<int>      &slots  = I->slotTmp;    // 3 per operation
+    std::vector<int>      &tipIdx = I->tipIdxTmp;  // 3 per operation: tip-table index within the chunk (-1: not a tip)
+    const int  maxTips = NUC_MAXT (K > 0 ? K : 1);
     std::vector<int>      &nChunkOf = I->nChunkTmp;
-    chunks.clear (); cmats.clear (); slots.clear (); nChunkOf.assign (count, 0);
+    chunks.clear (); cmats.clear (); slots.clear (); tipIdx.clear (); nChunkOf.assign (count, 0);
 
     // ---- pass 1: validate; 4-state path: cut every operation list into chunks whose branches fit
     //      the kernel's shared-memory P(t) slots ----
@@ -229,15 +231,18 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
             }
         // chunking
         DevChunk cur = { nOp, 0, (int) cmats.size (), 0 };
+        int curTips = 0;
         std::vector<int> &touched = I->touched;
         touched.clear ();
         auto closeChunk = [&] ()
             {
             for (int m : touched) I->slotOf[m] = -1;
             touched.clear ();
-            chunks.push_back (cur);
+            DevChunk done = cur;
+            done.nMat |= curTips << 16;
+            chunks.push_back (done);
             nChunkOf[e]++;
-            cur.opOff += cur.nOp; cur.nOp = 0; cur.matOff = (int) cmats.size (); cur.nMat = 0;
+            cur.opOff += cur.nOp; cur.nOp = 0; cur.matOff = (int) cmats.size (); cur.nMat = 0; curTips = 0;
             };
         auto slotFor = [&] (int m) -> int
             {
@@ -270,11 +275,15 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
             if (I->slotOf[op.matrix1] < 0) need++;
             if (I->slotOf[op.matrix2] < 0 && op.matrix2 != op.matrix1) need++;
             if (m3 >= 0 && I->slotOf[m3] < 0 && m3 != op.matrix1 && m3 != op.matrix2) need++;
-            if (cur.nOp >= opc || cur.nMat + need > maxSlots)
+            const int tipsHere = (op.child1 < c.tip_count) + (op.child2 < c.tip_count) + (m3 >= 0 && op.child3 < c.tip_count);
+            if (cur.nOp >= opc || cur.nMat + need > maxSlots || curTips + tipsHere > maxTips)
                 closeChunk ();
             slots.push_back (slotFor (op.matrix1));
             slots.push_back (slotFor (op.matrix2));
             slots.push_back (m3 >= 0 ? slotFor (m3) : -1);
+            tipIdx.push_back (op.child1 < c.tip_count ? curTips++ : -1);
+            tipIdx.push_back (op.child2 < c.tip_count ? curTips++ : -1);
+            tipIdx.push_back ((m3 >= 0 && op.child3 < c.tip_count) ? curTips++ : -1);
             cur.nOp++;
             }
         if (nuc4 && rcv == MB200_SUCCESS)
@@ -412,6 +421,9 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
                 NucOp &o = reinterpret_cast<NucOp *>(dops)[oOff + i];
                 const unsigned k1 = operand (op.child1, o.a1), k2 = operand (op.child2, o.a2), k3 = operand (op.child3, o.a3);
                 o.kinds = k1 | (k2 << 4) | (k3 << 8) | (op.scale_write >= 0 ? NUC_RESCALE : 0u);
+                for (int j = 0; j < 3; j++)
+                    if (tipIdx[slotPos + j] >= 0)
+                        o.kinds |= (unsigned) tipIdx[slotPos + j] << (13 + 6 * j);
                 o.destOff = (unsigned)(op.dest - c.tip_count) * bufStride;
                 o.sp1 = (unsigned) slots[slotPos] * slotBytes;
                 o.sp2 = (unsigned) slots[slotPos + 1] * slotBytes;
@@ -455,19 +467,53 @@ int ensureInvMask (Instance *I)
     return MB200_SUCCESS;
 }
 
+// launch one instantiation of the 4-state kernel; the first launch per device opts it in to its
+// dynamic shared-memory size
+template <int KK, int NT, bool F>
+int launchNuc4K (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const double *dd, const DevChunk *dc,
+                 const DevMat *dm, const DevOp *dops, DevResult *res, int seq)
+{
+    static bool optedIn[64];
+    auto kern = eval_nuc4_kernel<KK, NT, F>;
+    constexpr int bytes = (int) sizeof(Nuc4Smem<KK, NT, F>);
+    if (!optedIn[I->cfg.device & 63])
+        {
+        CK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        optedIn[I->cfg.device & 63] = true;
+        }
+    kern<<<grid, NT, bytes, I->stream>>> (ctx, de, dd, dc, dm, dops, res, seq);
+    return MB200_SUCCESS;
+}
+
+template <int KK, int NT, int CAP>
+int launchNuc4PK (Instance *I, const DevCtx &ctx, dim3 grid, const ParamBlob<CAP> &blob, const BlobOffsets &off, DevResult *res, int seq)
+{
+    static bool optedIn[64];
+    auto kern = eval_nuc4_pkernel<KK, NT, CAP>;
+    constexpr int bytes = (int) sizeof(Nuc4Smem<KK, NT, true>);
+    if (!optedIn[I->cfg.device & 63])
+        {
+        CK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        optedIn[I->cfg.device & 63] = true;
+        }
+    kern<<<grid, NT, bytes, I->stream>>> (ctx, blob, off, res, seq);
+    return MB200_SUCCESS;
+}
+
 template <int NT>
 int launchNuc4T (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const double *dd, const DevChunk *dc,
                  const DevMat *dm, const DevOp *dops, DevResult *res, int seq, bool fused)
 {
+    int rcl = MB200_SUCCESS;
     switch (ctx.K)
         {
-#define MB200_CASE(KK) case KK: if (fused) eval_nuc4_kernel<KK, NT, true><<<grid, NT, 0, I->stream>>> (ctx, de, dd, dc, dm, dops, res, seq); \
-                                 else eval_nuc4_kernel<KK, NT, false><<<grid, NT, 0, I->stream>>> (ctx, de, dd, dc, dm, dops, res, seq); break;
+#define MB200_CASE(KK) case KK: rcl = fused ? launchNuc4K<KK, NT, true> (I, ctx, grid, de, dd, dc, dm, dops, res, seq) \
+                                             : launchNuc4K<KK, NT, false> (I, ctx, grid, de, dd, dc, dm, dops, res, seq); break;
         MB200_CASE(1) MB200_CASE(2) MB200_CASE(3) MB200_CASE(4) MB200_CASE(5) MB200_CASE(6) MB200_CASE(7) MB200_CASE(8)
 #undef MB200_CASE
         default: return MB200_ERROR_UNSUPPORTED;
         }
-    return MB200_SUCCESS;
+    return rcl;
 }
 
 int launchNuc4 (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const double *dd, const DevChunk *dc,
@@ -485,14 +531,15 @@ int launchNuc4ParamT (Instance *I, const DevCtx &ctx, dim3 grid, const Batch &b,
 {
     const ParamBlob<CAP> &blob = *reinterpret_cast<const ParamBlob<CAP> *>(b.hBlob);
     BlobOffsets off = { (int) b.offEval, (int) b.offDbl, (int) b.offUpd, (int) b.offChunk, (int) b.offCmat, (int) b.offOp };
+    int rcl = MB200_SUCCESS;
     switch (ctx.K)
         {
-#define MB200_CASE(KK) case KK: eval_nuc4_pkernel<KK, NT, CAP><<<grid, NT, 0, I->stream>>> (ctx, blob, off, res, seq); break;
+#define MB200_CASE(KK) case KK: rcl = launchNuc4PK<KK, NT, CAP> (I, ctx, grid, blob, off, res, seq); break;
         MB200_CASE(1) MB200_CASE(2) MB200_CASE(3) MB200_CASE(4) MB200_CASE(5) MB200_CASE(6) MB200_CASE(7) MB200_CASE(8)
 #undef MB200_CASE
         default: return MB200_ERROR_UNSUPPORTED;
         }
-    return MB200_SUCCESS;
+    return rcl;
 }
 
 template <int CAP>

@@ -423,6 +423,29 @@ template <int K> struct Nuc4Geom
     static constexpr int MAXS = (256 / K > 96) ? 96 : 256 / K;                 // P(t) slots per chunk
 };
 
+// shared memory of the 4-state kernel (dynamic: more than the 48 KB a static allocation may take)
+template <int K, int NT, bool FUSE> struct Nuc4Smem
+{
+    static constexpr int L    = Nuc4Geom<K>::L;
+    static constexpr int MAXS = Nuc4Geom<K>::MAXS;
+    static constexpr int PPB  = NT / L;
+    static constexpr int OPC  = (2048 / PPB > 32) ? 32 : (2048 / PPB < 8 ? 8 : 2048 / PPB);
+    static constexpr int MAXT = NUC_MAXT (K);
+    float4 sP[MAXS][K][5];                       // P(t) rows of every branch the chunk touches (4 rows + 1 pad: bank spread)
+    float4 sTab[MAXT][K][16];                    // per tip operand and category: state mask -> sum of the P(t) columns it selects
+    double sExp[FUSE ? MAXS : 1][K][4];          // exp(lambda_s t) of the dirty branches
+    double sD[2*K + 4];                          // rates[K], catW[K], freqs[4]
+    double sEig[FUSE ? 72 : 2];                  // lambda_re[4], lambda_im[4], c_ijk[64] of slot eigen0
+    DevMat sMat[MAXS];
+    DevOp  sOps[OPC];
+    DevEval sEv;
+    DevChunk sCh;
+    uint2  sTipInfo[MAXT];                       // .x: byte index of the tip row (| 1u<<31: shortcut applies), .y: P(t) slot offset
+    float  sNew[OPC][PPB];                       // per node: scaler maximum, later its logarithm
+    float  sOld[OPC][PPB];                       // per node: the old node scaler to remove
+    unsigned char sMask[MAXT][PPB];              // the chunk's tip state masks, this CTA's patterns
+};
+
 template <int K, int NT, bool FUSE>
 __device__ __forceinline__ void
 nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
@@ -434,16 +457,12 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
     constexpr int PPB  = NT / L;                 // patterns per CTA
     constexpr int OPC  = (2048 / PPB > 32) ? 32 : (2048 / PPB < 8 ? 8 : 2048 / PPB);   // nodes per chunk
     constexpr int LDR  = 5;                      // float4 per (slot,k): 4 rows + 1 pad (bank spread)
-    __shared__ float4 sP[MAXS][K][LDR];          // P(t) rows of every branch the chunk touches
-    __shared__ double sExp[FUSE ? MAXS : 1][K][4];   // exp(lambda_s t) of the dirty branches
-    __shared__ __align__(16) DevMat sMat[MAXS];
-    __shared__ __align__(16) DevOp  sOps[OPC];
-    __shared__ float  sNew[OPC][PPB];            // per node: scaler maximum, later its logarithm
-    __shared__ float  sOld[OPC][PPB];            // per node: the old node scaler to remove
-    __shared__ __align__(16) DevEval sEv;
-    __shared__ __align__(16) DevChunk sCh;
-    __shared__ __align__(16) double sD[2*K + 4]; // rates[K], catW[K], freqs[4]
-    __shared__ double sEig[FUSE ? 72 : 1];       // lambda_re[4], lambda_im[4], c_ijk[64] of slot eigen0
+    constexpr int MAXT = NUC_MAXT (K);           // tip operands per chunk
+    extern __shared__ __align__(16) unsigned char nuc_smem[];
+    Nuc4Smem<K, NT, FUSE> &sm = *reinterpret_cast<Nuc4Smem<K, NT, FUSE> *>(nuc_smem);
+    auto &sP = sm.sP;   auto &sExp = sm.sExp; auto &sTab = sm.sTab; auto &sMat = sm.sMat; auto &sOps = sm.sOps;
+    auto &sNew = sm.sNew; auto &sOld = sm.sOld; auto &sEv = sm.sEv; auto &sCh = sm.sCh; auto &sD = sm.sD;
+    auto &sEig = sm.sEig; auto &sTipInfo = sm.sTipInfo; auto &sMask = sm.sMask;
 
     MB200_STAMP (0);
     if (threadIdx.x < (int)(sizeof(DevEval) / 4))
@@ -480,25 +499,8 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
     float               *sNewT = &sNew[0][pl];
     const NucOp         *nops  = reinterpret_cast<const NucOp *>(sOps);
 
-    // operand of a node: interior child -> one 16-byte load; tip -> its 1-byte state mask, parked in
-    // x.x until the node consumes it (expanding it here would stall on the load just issued)
-    auto fetch = [&] (unsigned kind, unsigned a, float4 &x)
-        {
-        if (kind == NUC_LOAD)
-            x = partials4[tOff + a];
-        else if (kind & NUC_TIP)
-            x.x = __uint_as_float ((unsigned) ctx.tip8[(unsigned) cc + a]);
-        };
-    // tip operand: state mask -> 0/1 vector (the dense matvec then equals the reference's 0/1 matvec
-    // bit for bit: products by 0 and 1 are exact); returns true when, under the scalar kernels'
-    // shortcut, a missing observation on a tip without partial ambiguity contributes exactly 1.0
-    // (preLike tables, src/likelihood.c:816-832)
-    auto expand = [&] (float4 &x, bool shortcut) -> bool
-        {
-        const unsigned mask = __float_as_uint (x.x);
-        x = make_float4 ((mask & 1) ? 1.f : 0.f, (mask & 2) ? 1.f : 0.f, (mask & 4) ? 1.f : 0.f, (mask & 8) ? 1.f : 0.f);
-        return shortcut && (mask & 15) == 15;
-        };
+    const unsigned sTabK  = (unsigned) __cvta_generic_to_shared (&sTab[0][kk][0]);
+    const unsigned sMaskP = (unsigned) __cvta_generic_to_shared (&sMask[0][pl]);
 
     for (int ci = 0; ci < nChunk; ci++)
         {
@@ -515,15 +517,29 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             __syncthreads ();
             }
         const DevChunk ch = (ci == 0) ? sEv.chunk0 : sCh;
-        for (int e = threadIdx.x; e < ch.nMat * 4; e += NT)
+        const int nMatC = ch.nMat & 0xffff, nTipC = ch.nMat >> 16;
+        for (int e = threadIdx.x; e < nMatC * 4; e += NT)
             reinterpret_cast<int *>(sMat)[e] = reinterpret_cast<const int *>(cmats + ch.matOff)[e];
         for (int e = threadIdx.x; e < ch.nOp * (int)(sizeof(DevOp)/4); e += NT)
             reinterpret_cast<int *>(sOps)[e] = reinterpret_cast<const int *>(ops + ch.opOff)[e];
         __syncthreads ();
         if (ci == 0) MB200_STAMP (2);
 
-        // ---- 2. P(t) slots (K1 fused: TiProbs_Gen, src/likelihood.c:9499-9542) ----
-        for (int r = threadIdx.x; r < ch.nMat * K * 4; r += NT)
+        // ---- 2. P(t) slots (K1 fused: TiProbs_Gen, src/likelihood.c:9499-9542); tip operand list ----
+        if (threadIdx.x < ch.nOp)
+            {
+            const NucOp o = nops[threadIdx.x];
+            #pragma unroll
+            for (int j = 0; j < 3; j++)
+                {
+                const unsigned kind = (o.kinds >> (4*j)) & 15u;
+                if (kind & NUC_TIP)
+                    sTipInfo[(o.kinds >> (13 + 6*j)) & 63u] =
+                        make_uint2 (((j == 0) ? o.a1 : (j == 1) ? o.a2 : o.a3) | ((kind == NUC_TIP_ONE) ? 0x80000000u : 0u),
+                                    (j == 0) ? o.sp1 : (j == 1) ? o.sp2 : o.sp3);
+                }
+            }
+        for (int r = threadIdx.x; r < nMatC * K * 4; r += NT)
             {
             const int s = r & 3, k = (r >> 2) % K, m = r / (4*K);
             const int eg = sMat[m].eigen;
@@ -535,10 +551,33 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             else                                  // clean branch (or P(t) prepared by tiprobs_kernel): copy row s
                 sP[m][k][s] = reinterpret_cast<const float4 *>(ctx.matrices + (size_t)sMat[m].matrix * K * 16)[k*4 + s];
             }
+        __syncthreads ();
+        // the chunk's tip masks for this CTA's patterns (loads batched four deep: the bytes may come
+        // from HBM behind the write stream)
+        for (int e0 = threadIdx.x; e0 < nTipC * PPB; e0 += 4 * NT)
+            {
+            unsigned char mk[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++)
+                {
+                const int e = e0 + u * NT;
+                if (e < nTipC * PPB)
+                    {
+                    const int cp = c0 + (e % PPB);
+                    mk[u] = ctx.tip8[(sTipInfo[e / PPB].x & 0x7fffffffu) + (unsigned)((cp < C) ? cp : C - 1)];
+                    }
+                }
+            #pragma unroll
+            for (int u = 0; u < 4; u++)
+                {
+                const int e = e0 + u * NT;
+                if (e < nTipC * PPB)
+                    sMask[e / PPB][e % PPB] = mk[u];
+                }
+            }
         if (FUSE)
             {
-            __syncthreads ();
-            for (int r = threadIdx.x; r < ch.nMat * K * 4; r += NT)
+            for (int r = threadIdx.x; r < nMatC * K * 4; r += NT)
                 {
                 const int i = r & 3, k = (r >> 2) % K, m = r / (4*K);
                 const int eg = sMat[m].eigen;
@@ -568,15 +607,57 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 if (blockIdx.x == 0)              // tile 0 publishes the rebuilt matrices
                     reinterpret_cast<float4 *>(ctx.matrices + (size_t)sMat[m].matrix * K * 16)[k*4 + i] = row;
                 }
+            __syncthreads ();
+            }
+        // tip lookup tables: entry[mask][i] = sum over the states j in the mask of P[i][j], added in state
+        // order -- the value the reference's dense 0/1 matvec produces (CondLikeDown_NUC4*, products by
+        // 0 and 1 are exact), so the node loop replaces a tip's matvec by one 16-byte load.  Under the
+        // scalar kernels' shortcut a missing observation on a tip without partial ambiguity contributes
+        // exactly 1.0 (preLike tables, src/likelihood.c:816-832)
+        for (int e = threadIdx.x; e < nTipC * K * 16; e += NT)
+            {
+            const int mask = e & 15, k = (e >> 4) % K, t = e / (16*K);
+            const uint2 ti = sTipInfo[t];
+            const float4 *rows = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(&sP[0][k][0]) + ti.y);
+            float v[4];
+            #pragma unroll
+            for (int i = 0; i < 4; i++)
+                {
+                const float4 p = rows[i];
+                float acc = (mask & 1) ? p.x : 0.0f;      // same additions as fma(P3,x3,fma(P2,x2,fma(P1,x1,P0*x0))) with x in {0,1}
+                acc = acc + ((mask & 2) ? p.y : 0.0f);
+                acc = acc + ((mask & 4) ? p.z : 0.0f);
+                acc = acc + ((mask & 8) ? p.w : 0.0f);
+                v[i] = acc;
+                }
+            if ((ti.x & 0x80000000u) && mask == 15)
+                v[0] = v[1] = v[2] = v[3] = 1.0f;
+            sTab[t][k][mask] = make_float4 (v[0], v[1], v[2], v[3]);
             }
         __syncthreads ();
         if (ci == 0) MB200_STAMP (3);
 
-        // ---- 3. node loop: no barrier, a thread only ever touches its own pattern.  The operands of
-        //      node n+1 are fetched while node n computes; the two operand sets alternate (xa, xb) so
-        //      that no register copies are needed ----
+        // ---- 3. node loop: no barrier, a thread only ever touches its own pattern.  Interior operands
+        //      of node n+1 are fetched while node n computes; the two operand sets alternate (xa, xb)
+        //      so that no register copies are needed; tip operands are table lookups ----
         const int nOp = ch.nOp;
         float4   xa[3], xb[3];
+        auto fetch = [&] (unsigned kind, unsigned a, float4 &x)
+            {
+            if (kind == NUC_LOAD)
+                x = partials4[tOff + a];
+            };
+        auto operand = [&] (unsigned kinds, int j, unsigned sp, const float4 &x) -> float4
+            {
+            if ((kinds >> (4*j)) & NUC_TIP)
+                {
+                const unsigned t = (kinds >> (13 + 6*j)) & 63u;
+                unsigned mask;
+                asm volatile ("ld.shared.u8 %0, [%1];" : "=r"(mask) : "r"(sMaskP + t * PPB));
+                return lds128 (sTabK + t * (K * 256) + mask * 16);
+                }
+            return matvec4s (sPk + sp, x);
+            };
         auto node = [&] (int oo, const float4 (&xi)[3], float4 (&xo)[3])
             {
             const uint4 oa = reinterpret_cast<const uint4 *>(nops + oo)[0];     // a1 a2 a3 kinds
@@ -592,28 +673,12 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 if (nk & 0xf00u)
                     fetch ((nk >> 8) & 15u, na.z, xo[2]);
                 }
-            float4 x0 = xi[0], x1 = xi[1];
-            bool one0 = false, one1 = false;
-            if (kinds & 0x22u)                    // tip operands (uniform tests)
-                {
-                if (kinds & 0x02u) one0 = expand (x0, (kinds & 0x04u) != 0);
-                if (kinds & 0x20u) one1 = expand (x1, (kinds & 0x40u) != 0);
-                }
-            float4 res = matvec4s (sPk + ob.y, x0);
-            float4 v   = matvec4s (sPk + ob.z, x1);
-            if (kinds & 0x44u)
-                {
-                if (one0) res = make_float4 (1.f, 1.f, 1.f, 1.f);
-                if (one1) v   = make_float4 (1.f, 1.f, 1.f, 1.f);
-                }
+            float4 res = operand (kinds, 0, ob.y, xi[0]);
+            float4 v   = operand (kinds, 1, ob.z, xi[1]);
             res.x *= v.x; res.y *= v.y; res.z *= v.z; res.w *= v.w;
             if (kinds & 0xf00u)                   // unrooted interior root: third neighbour
                 {
-                float4 x2 = xi[2];
-                bool one2 = false;
-                if (kinds & 0x200u) one2 = expand (x2, (kinds & 0x400u) != 0);
-                v = matvec4s (sPk + ob.w, x2);
-                if (one2) v = make_float4 (1.f, 1.f, 1.f, 1.f);
+                v = operand (kinds, 2, ob.w, xi[2]);
                 res.x *= v.x; res.y *= v.y; res.z *= v.z; res.w *= v.w;
                 }
             float m = 0.0f;                       // 0 marks "node not rescaled"
