@@ -432,7 +432,8 @@ template <int K, int NT, bool FUSE> struct Nuc4Smem
     static constexpr int OPC  = (2048 / PPB > 32) ? 32 : (2048 / PPB < 8 ? 8 : 2048 / PPB);
     static constexpr int MAXT = NUC_MAXT (K);
     float4 sP[MAXS][K][5];                       // P(t) rows of every branch the chunk touches (4 rows + 1 pad: bank spread)
-    float4 sTab[MAXT][K][16];                    // per tip operand and category: state mask -> sum of the P(t) columns it selects
+    float4 sTab[MAXT][16][K];                    // per tip operand, state mask and category: sum of the P(t) columns the mask selects
+                                                 // (mask-major: the K lanes of a pattern read one contiguous 16K-byte line)
     double sExp[FUSE ? MAXS : 1][K][4];          // exp(lambda_s t) of the dirty branches
     double sD[2*K + 4];                          // rates[K], catW[K], freqs[4]
     double sEig[FUSE ? 72 : 2];                  // lambda_re[4], lambda_im[4], c_ijk[64] of slot eigen0
@@ -453,11 +454,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
            const DevOp *__restrict__ ops, DevResult *out, int seq)
 {
     constexpr int L    = Nuc4Geom<K>::L;
-    constexpr int MAXS = Nuc4Geom<K>::MAXS;
     constexpr int PPB  = NT / L;                 // patterns per CTA
-    constexpr int OPC  = (2048 / PPB > 32) ? 32 : (2048 / PPB < 8 ? 8 : 2048 / PPB);   // nodes per chunk
-    constexpr int LDR  = 5;                      // float4 per (slot,k): 4 rows + 1 pad (bank spread)
-    constexpr int MAXT = NUC_MAXT (K);           // tip operands per chunk
     extern __shared__ __align__(16) unsigned char nuc_smem[];
     Nuc4Smem<K, NT, FUSE> &sm = *reinterpret_cast<Nuc4Smem<K, NT, FUSE> *>(nuc_smem);
     auto &sP = sm.sP;   auto &sExp = sm.sExp; auto &sTab = sm.sTab; auto &sMat = sm.sMat; auto &sOps = sm.sOps;
@@ -499,7 +496,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
     float               *sNewT = &sNew[0][pl];
     const NucOp         *nops  = reinterpret_cast<const NucOp *>(sOps);
 
-    const unsigned sTabK  = (unsigned) __cvta_generic_to_shared (&sTab[0][kk][0]);
+    const unsigned sTabK  = (unsigned) __cvta_generic_to_shared (&sTab[0][0][kk]);
     const unsigned sMaskP = (unsigned) __cvta_generic_to_shared (&sMask[0][pl]);
 
     for (int ci = 0; ci < nChunk; ci++)
@@ -618,12 +615,12 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             {
             const int mask = e & 15, k = (e >> 4) % K, t = e / (16*K);
             const uint2 ti = sTipInfo[t];
-            const float4 *rows = reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(&sP[0][k][0]) + ti.y);
+            const unsigned rows = (unsigned) __cvta_generic_to_shared (&sP[0][0][0]) + (unsigned) k * 80u + ti.y;
             float v[4];
             #pragma unroll
             for (int i = 0; i < 4; i++)
                 {
-                const float4 p = rows[i];
+                const float4 p = lds128 (rows + 16u * i);
                 float acc = (mask & 1) ? p.x : 0.0f;      // same additions as fma(P3,x3,fma(P2,x2,fma(P1,x1,P0*x0))) with x in {0,1}
                 acc = acc + ((mask & 2) ? p.y : 0.0f);
                 acc = acc + ((mask & 4) ? p.z : 0.0f);
@@ -632,7 +629,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 }
             if ((ti.x & 0x80000000u) && mask == 15)
                 v[0] = v[1] = v[2] = v[3] = 1.0f;
-            sTab[t][k][mask] = make_float4 (v[0], v[1], v[2], v[3]);
+            sTab[t][mask][k] = make_float4 (v[0], v[1], v[2], v[3]);
             }
         __syncthreads ();
         if (ci == 0) MB200_STAMP (3);
@@ -642,20 +639,25 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
         //      so that no register copies are needed; tip operands are table lookups ----
         const int nOp = ch.nOp;
         float4   xa[3], xb[3];
-        auto fetch = [&] (unsigned kind, unsigned a, float4 &x)
+        // operand j of a node, fetched one node ahead: interior child -> its conditional likelihoods
+        // (one 16-byte load); tip child -> its contribution, looked up by state mask
+        auto fetch = [&] (unsigned kinds, int j, unsigned a, float4 &x)
             {
+            const unsigned kind = (kinds >> (4*j)) & 15u;
             if (kind == NUC_LOAD)
                 x = partials4[tOff + a];
-            };
-        auto operand = [&] (unsigned kinds, int j, unsigned sp, const float4 &x) -> float4
-            {
-            if ((kinds >> (4*j)) & NUC_TIP)
+            else if (kind & NUC_TIP)
                 {
                 const unsigned t = (kinds >> (13 + 6*j)) & 63u;
                 unsigned mask;
                 asm volatile ("ld.shared.u8 %0, [%1];" : "=r"(mask) : "r"(sMaskP + t * PPB));
-                return lds128 (sTabK + t * (K * 256) + mask * 16);
+                x = lds128 (sTabK + (t * 16 + mask) * (K * 16));
                 }
+            };
+        auto operand = [&] (unsigned kinds, int j, unsigned sp, const float4 &x) -> float4
+            {
+            if ((kinds >> (4*j)) & NUC_TIP)
+                return x;
             return matvec4s (sPk + sp, x);
             };
         auto node = [&] (int oo, const float4 (&xi)[3], float4 (&xo)[3])
@@ -668,10 +670,10 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 {
                 const uint4 na = reinterpret_cast<const uint4 *>(nops + oo + 1)[0];
                 nk = na.w;
-                fetch (nk & 15u, na.x, xo[0]);
-                fetch ((nk >> 4) & 15u, na.y, xo[1]);
+                fetch (nk, 0, na.x, xo[0]);
+                fetch (nk, 1, na.y, xo[1]);
                 if (nk & 0xf00u)
-                    fetch ((nk >> 8) & 15u, na.z, xo[2]);
+                    fetch (nk, 2, na.z, xo[2]);
                 }
             float4 res = operand (kinds, 0, ob.y, xi[0]);
             float4 v   = operand (kinds, 1, ob.z, xi[1]);
@@ -707,10 +709,10 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
         if (nOp > 0)
             {
             const uint4 na = reinterpret_cast<const uint4 *>(nops)[0];
-            fetch (na.w & 15u, na.x, xa[0]);
-            fetch ((na.w >> 4) & 15u, na.y, xa[1]);
+            fetch (na.w, 0, na.x, xa[0]);
+            fetch (na.w, 1, na.y, xa[1]);
             if (na.w & 0xf00u)
-                fetch ((na.w >> 8) & 15u, na.z, xa[2]);
+                fetch (na.w, 2, na.z, xa[2]);
             if (na.w & NUC_FWD)        xa[0] = cur;       // result of the previous chunk's last node
             if (na.w & (NUC_FWD << 4)) xa[1] = cur;
             if (na.w & (NUC_FWD << 8)) xa[2] = cur;
