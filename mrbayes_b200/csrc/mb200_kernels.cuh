@@ -436,7 +436,7 @@ template <int K, int NT, bool FUSE> struct Nuc4Smem
                                                  // (mask-major: the K lanes of a pattern read one contiguous 16K-byte line)
     double sExp[FUSE ? MAXS : 1][K][4];          // exp(lambda_s t) of the dirty branches
     double sD[2*K + 4];                          // rates[K], catW[K], freqs[4]
-    double sEig[FUSE ? 72 : 2];                  // lambda_re[4], lambda_im[4], c_ijk[64] of slot eigen0
+    double sEig[72];                               // lambda_re[4], lambda_im[4], c_ijk[64] of slot eigen0
     DevMat sMat[MAXS];
     DevOp  sOps[OPC];
     DevEval sEv;
@@ -519,21 +519,36 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             reinterpret_cast<int *>(sMat)[e] = reinterpret_cast<const int *>(cmats + ch.matOff)[e];
         for (int e = threadIdx.x; e < ch.nOp * (int)(sizeof(DevOp)/4); e += NT)
             reinterpret_cast<int *>(sOps)[e] = reinterpret_cast<const int *>(ops + ch.opOff)[e];
-        __syncthreads ();
-        if (ci == 0) MB200_STAMP (2);
-
-        // ---- 2. P(t) slots (K1 fused: TiProbs_Gen, src/likelihood.c:9499-9542); tip operand list ----
-        if (threadIdx.x < ch.nOp)
+        if (threadIdx.x < ch.nOp)                 // tip operand list of the chunk
             {
-            const NucOp o = nops[threadIdx.x];
+            const NucOp &o = reinterpret_cast<const NucOp *>(ops + ch.opOff)[threadIdx.x];
+            const unsigned kinds = o.kinds;
             #pragma unroll
             for (int j = 0; j < 3; j++)
                 {
-                const unsigned kind = (o.kinds >> (4*j)) & 15u;
+                const unsigned kind = (kinds >> (4*j)) & 15u;
                 if (kind & NUC_TIP)
-                    sTipInfo[(o.kinds >> (13 + 6*j)) & 63u] =
+                    sTipInfo[(kinds >> (13 + 6*j)) & 63u] =
                         make_uint2 (((j == 0) ? o.a1 : (j == 1) ? o.a2 : o.a3) | ((kind == NUC_TIP_ONE) ? 0x80000000u : 0u),
                                     (j == 0) ? o.sp1 : (j == 1) ? o.sp2 : o.sp3);
+                }
+            }
+        __syncthreads ();
+        if (ci == 0) MB200_STAMP (2);
+
+        // ---- 2. P(t) slots (K1 fused: TiProbs_Gen, src/likelihood.c:9499-9542); the chunk's tip masks
+        //      for this CTA's patterns: the loads go out first, eight deep (the bytes may come from HBM
+        //      behind the write stream), and land in shared memory after the P(t) work ----
+        constexpr int MKD = 8;
+        unsigned char mk[MKD];
+        #pragma unroll
+        for (int u = 0; u < MKD; u++)
+            {
+            const int e = threadIdx.x + u * NT;
+            if (e < nTipC * PPB)
+                {
+                const int cp = c0 + (e % PPB);
+                mk[u] = ctx.tip8[(sTipInfo[e / PPB].x & 0x7fffffffu) + (unsigned)((cp < C) ? cp : C - 1)];
                 }
             }
         for (int r = threadIdx.x; r < nMatC * K * 4; r += NT)
@@ -548,30 +563,19 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             else                                  // clean branch (or P(t) prepared by tiprobs_kernel): copy row s
                 sP[m][k][s] = reinterpret_cast<const float4 *>(ctx.matrices + (size_t)sMat[m].matrix * K * 16)[k*4 + s];
             }
-        __syncthreads ();
-        // the chunk's tip masks for this CTA's patterns (loads batched four deep: the bytes may come
-        // from HBM behind the write stream)
-        for (int e0 = threadIdx.x; e0 < nTipC * PPB; e0 += 4 * NT)
+        #pragma unroll
+        for (int u = 0; u < MKD; u++)
             {
-            unsigned char mk[4];
-            #pragma unroll
-            for (int u = 0; u < 4; u++)
-                {
-                const int e = e0 + u * NT;
-                if (e < nTipC * PPB)
-                    {
-                    const int cp = c0 + (e % PPB);
-                    mk[u] = ctx.tip8[(sTipInfo[e / PPB].x & 0x7fffffffu) + (unsigned)((cp < C) ? cp : C - 1)];
-                    }
-                }
-            #pragma unroll
-            for (int u = 0; u < 4; u++)
-                {
-                const int e = e0 + u * NT;
-                if (e < nTipC * PPB)
-                    sMask[e / PPB][e % PPB] = mk[u];
-                }
+            const int e = threadIdx.x + u * NT;
+            if (e < nTipC * PPB)
+                sMask[e / PPB][e % PPB] = mk[u];
             }
+        for (int e = threadIdx.x + MKD * NT; e < nTipC * PPB; e += NT)      // more than eight per thread: K < 4 only
+            {
+            const int cp = c0 + (e % PPB);
+            sMask[e / PPB][e % PPB] = ctx.tip8[(sTipInfo[e / PPB].x & 0x7fffffffu) + (unsigned)((cp < C) ? cp : C - 1)];
+            }
+        __syncthreads ();
         if (FUSE)
             {
             for (int r = threadIdx.x; r < nMatC * K * 4; r += NT)
@@ -607,29 +611,31 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             __syncthreads ();
             }
         // tip lookup tables: entry[mask][i] = sum over the states j in the mask of P[i][j], added in state
-        // order -- the value the reference's dense 0/1 matvec produces (CondLikeDown_NUC4*, products by
-        // 0 and 1 are exact), so the node loop replaces a tip's matvec by one 16-byte load.  Under the
-        // scalar kernels' shortcut a missing observation on a tip without partial ambiguity contributes
-        // exactly 1.0 (preLike tables, src/likelihood.c:816-832)
-        for (int e = threadIdx.x; e < nTipC * K * 16; e += NT)
+        // order -- the value the reference's dense 0/1 matvec produces (CondLikeDown_NUC4*: products by
+        // 0 and 1 are exact, adding 0 changes nothing), so the node loop replaces a tip's matvec by one
+        // 16-byte load.  One thread per (tip operand, category, row i): entry[m] = entry[m without its
+        // highest state] + P[i][highest state].  Under the scalar kernels' shortcut a missing
+        // observation on a tip without partial ambiguity contributes exactly 1.0 (preLike tables,
+        // src/likelihood.c:816-832)
+        for (int e = threadIdx.x; e < nTipC * K * 4; e += NT)
             {
-            const int mask = e & 15, k = (e >> 4) % K, t = e / (16*K);
+            const int i = e & 3, k = (e >> 2) % K, t = e / (4*K);
             const uint2 ti = sTipInfo[t];
-            const unsigned rows = (unsigned) __cvta_generic_to_shared (&sP[0][0][0]) + (unsigned) k * 80u + ti.y;
-            float v[4];
+            const float4 p = lds128 ((unsigned) __cvta_generic_to_shared (&sP[0][0][0]) + (unsigned) k * 80u + ti.y + 16u * i);
+            float E[16];
+            E[0] = 0.0f;
+            E[1] = p.x;  E[2] = p.y;  E[4] = p.z;  E[8] = p.w;
+            E[3] = E[1] + p.y;
+            E[5] = E[1] + p.z;  E[6] = E[2] + p.z;  E[7] = E[3] + p.z;
             #pragma unroll
-            for (int i = 0; i < 4; i++)
-                {
-                const float4 p = lds128 (rows + 16u * i);
-                float acc = (mask & 1) ? p.x : 0.0f;      // same additions as fma(P3,x3,fma(P2,x2,fma(P1,x1,P0*x0))) with x in {0,1}
-                acc = acc + ((mask & 2) ? p.y : 0.0f);
-                acc = acc + ((mask & 4) ? p.z : 0.0f);
-                acc = acc + ((mask & 8) ? p.w : 0.0f);
-                v[i] = acc;
-                }
-            if ((ti.x & 0x80000000u) && mask == 15)
-                v[0] = v[1] = v[2] = v[3] = 1.0f;
-            sTab[t][mask][k] = make_float4 (v[0], v[1], v[2], v[3]);
+            for (int m = 1; m < 8; m++)
+                E[8 + m] = E[m] + p.w;
+            if (ti.x & 0x80000000u)
+                E[15] = 1.0f;
+            float *dst = reinterpret_cast<float *>(&sTab[t][0][k]) + i;
+            #pragma unroll
+            for (int m = 0; m < 16; m++)
+                dst[m * K * 4] = E[m];
             }
         __syncthreads ();
         if (ci == 0) MB200_STAMP (3);
@@ -724,31 +730,30 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 node (oo + 1, xb, xa);
             }
 
-        // ---- 4. batched scaler pass: logs with full ILP, node scalers out, old scalers in ----
-        __syncthreads ();
-        for (int e = threadIdx.x; e < nOp * PPB; e += NT)
+        // ---- 4. batched scaler pass: logs with full ILP, node scalers out, old scalers in.  The L lanes
+        //      of a pattern share its nodes, so only warp-level synchronisation is needed ----
+        __syncwarp ();
+        for (int oo = lk; oo < nOp; oo += L)
             {
-            const int oo = e / PPB, p = e % PPB;
-            const int cp = c0 + p;
             const int sw = nops[oo].sw, sr = nops[oo].sr;
             float sc = 0.0f, old = 0.0f;
-            if (cp < C)
+            if (c < C)
                 {
                 if (sw >= 0)
                     {
                     // (float) log (double): CondLikeScaler_NUC4 / _SSE (src/likelihood.c:5183, 5328);
                     // the correctly rounded value, which the AVX variant's logf returns too in all
                     // but rare last-bit cases
-                    sc = (float) log ((double) sNew[oo][p]);
-                    ctx.scalers[(size_t)sw * C + cp] = sc;
+                    sc = (float) log ((double) sNewT[oo * PPB]);
+                    ctx.scalers[(size_t)sw * C + c] = sc;
                     }
                 if (sr >= 0)
-                    old = ctx.scalers[(size_t)sr * C + cp];
+                    old = ctx.scalers[(size_t)sr * C + c];
                 }
-            sNew[oo][p] = sc;
-            sOld[oo][p] = old;
+            sNewT[oo * PPB] = sc;
+            sOld[oo][pl] = old;
             }
-        __syncthreads ();
+        __syncwarp ();
         // site scaler: the reference's sequence  ... - old(o) + new(o) ...  (RemoveNodeScalers then
         // CondLikeScaler per node, src/likelihood.c:7938-7965), replayed per pattern
         if (lk == 0)
@@ -756,7 +761,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 {
                 lnScaler -= sOld[oo][pl];
                 if (nops[oo].sw >= 0)
-                    lnScaler += sNew[oo][pl];
+                    lnScaler += sNewT[oo * PPB];
                 }
         }
 
