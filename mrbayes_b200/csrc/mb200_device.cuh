@@ -87,7 +87,28 @@ struct NucOp
 };
 // tip operands of a chunk get a 16-entry lookup table each (state mask -> P(t) column sum, per rate
 // category): tables per chunk, as a function of K (24 KB of shared memory)
+#ifdef MB200_STREAM4                // experiment: geometry that fits four 256-thread CTAs per SM
+#define NUC_MAXT(K) ((64 / (K)) > 64 ? 64 : (64 / (K)))
+#define NUC_OPC(PPB) ((1536 / (PPB) > 24) ? 24 : (1536 / (PPB) < 8 ? 8 : 1536 / (PPB)))
+#define NUC_STREAM_THREADS 1024
+#else
 #define NUC_MAXT(K) ((96 / (K)) > 64 ? 64 : (96 / (K)))
+#define NUC_OPC(PPB) ((2048 / (PPB) > 32) ? 32 : (2048 / (PPB) < 8 ? 8 : 2048 / (PPB)))   // nodes per chunk
+#define NUC_STREAM_THREADS 768      // resident threads per SM the streaming variant is compiled for
+#endif
+
+// Where the first chunk of each evaluation lives in the job blob, passed BY VALUE as a kernel
+// parameter: the 4-state kernel can then issue every staging load of a CTA (evaluation header,
+// branch list, node list, rates/frequencies, eigensystem) in one round instead of first fetching
+// the header and then what it points to -- one memory round trip less on the latency path.
+#define MB200_JOB_INDEX_MAX 16
+struct JobIndexEntry { int matOff, nMat, opOff, nOp, dOff, eigen0; };     // nMat = branches | tip operands << 16
+struct JobIndex
+{
+    int n;                          // evaluations covered (0: none, kernels read the headers first)
+    int pad[3];
+    JobIndexEntry e[MB200_JOB_INDEX_MAX];
+};
 
 struct DevResult                    // 16 bytes per evaluation
 {
@@ -99,7 +120,7 @@ struct DevResult                    // 16 bytes per evaluation
 
 // Job descriptors handed over as a kernel parameter (constant bank) instead of a host->device
 // copy: removes one stream operation from the latency path of small evaluations.
-template <int CAP> struct ParamBlob { char bytes[CAP]; };
+template <int CAP> struct alignas(16) ParamBlob { char bytes[CAP]; };
 struct BlobOffsets { int eval, dbl, upd, chunk, cmat, op; };
 
 struct DevBatchHeader

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <float.h>
 #include <stdio.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 #include <mutex>
@@ -36,6 +37,7 @@ struct Batch                       // packed evaluations (device job format)
     bool    needInv = false;
     bool    used = false;
     int     tipEpoch = 0;          // Instance::tipEpoch at pack time (4-state records embed tip kinds)
+    JobIndex jx;                   // 4-state latency path: where each evaluation's first chunk lives
 };
 
 struct Instance
@@ -89,7 +91,7 @@ int ntFromEnv (const char *name, int dflt)
 {
     const char *v = getenv (name);
     int n = v ? atoi (v) : dflt;
-    return (n == 128 || n == 256 || n == 512) ? n : dflt;
+    return (n == 128 || n == 256) ? n : dflt;
 }
 const int NT_SMALL = ntFromEnv ("MB200_NT_SMALL", 256);
 const int NT_STREAM = ntFromEnv ("MB200_NT_STREAM", 256);
@@ -192,7 +194,7 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     const bool fused = nuc4 && ctas <= 4L * I->numSMs;          // small launch: latency-bound regime
     const int  ppb  = nuc4 ? nuc4PatternsPerBlock (K, fused) : 1;
     const int  maxSlots = (256 / K > 96) ? 96 : 256 / K;        // Nuc4Geom<K>::MAXS
-    const int  opc = (2048 / ppb > 32) ? 32 : (2048 / ppb < 8 ? 8 : 2048 / ppb);   // nodes per chunk, as in the kernel
+    const int  opc = NUC_OPC (ppb);                             // nodes per chunk, as in the kernel
     if ((int) I->slotOf.size () < c.matrix_count)
         { I->slotOf.assign (c.matrix_count, -1); I->dirtyOf.assign (c.matrix_count, -1); }
     std::vector<DevChunk> &chunks = I->chunkTmp;   // all evaluations, chunk0 of each included
@@ -346,6 +348,7 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         memcpy (dm, cmats.data (), sizeof(DevMat) * cmats.size ());
 
     int mOff = 0, oOff = 0, chunkPos = 0, extraPos = 0, dblPos = 0;
+    b.jx.n = (nuc4 && fused && count <= MB200_JOB_INDEX_MAX) ? count : 0;
     size_t slotPos = 0;
     b.needInv = false;
     for (int e = 0; e < count; e++)
@@ -372,6 +375,12 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
                 dc[extraPos++] = chunks[chunkPos + q];
             chunkPos += nChunkOf[e];
             }
+        if (nuc4 && fused && count <= MB200_JOB_INDEX_MAX && nChunkOf[e] > 0)
+            {
+            JobIndexEntry &je = b.jx.e[e];
+            je.matOff = d.chunk0.matOff; je.nMat = d.chunk0.nMat; je.opOff = d.chunk0.opOff; je.nOp = d.chunk0.nOp;
+            je.dOff = d.dOff; je.eigen0 = 0;      // eigen0: set below, once known
+            }
         if (d.root != MB200_NONE && d.hasPInvar) b.needInv = true;
         double *dv = dd + d.dOff;
         bool eq = true;
@@ -390,6 +399,8 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
             if (ev.matrix_update_count > 0 && ev.matrix_updates[0].eigen == MB200_EIGEN_INLINE)
                 d.eigen0 = MB200_EIGEN_INLINE;
             }
+        if (e < MB200_JOB_INDEX_MAX)
+            b.jx.e[e].eigen0 = d.eigen0;
         if (!fused)
             for (int i = 0; i < ev.matrix_update_count; i++)
                 {
@@ -471,7 +482,7 @@ int ensureInvMask (Instance *I)
 // dynamic shared-memory size
 template <int KK, int NT, bool F>
 int launchNuc4K (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const double *dd, const DevChunk *dc,
-                 const DevMat *dm, const DevOp *dops, DevResult *res, int seq)
+                 const DevMat *dm, const DevOp *dops, DevResult *res, int seq, const JobIndex &jx)
 {
     static bool optedIn[64];
     auto kern = eval_nuc4_kernel<KK, NT, F>;
@@ -481,12 +492,13 @@ int launchNuc4K (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, c
         CK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         optedIn[I->cfg.device & 63] = true;
         }
-    kern<<<grid, NT, bytes, I->stream>>> (ctx, de, dd, dc, dm, dops, res, seq);
+    kern<<<grid, NT, bytes, I->stream>>> (ctx, de, dd, dc, dm, dops, res, seq, jx);
     return MB200_SUCCESS;
 }
 
 template <int KK, int NT, int CAP>
-int launchNuc4PK (Instance *I, const DevCtx &ctx, dim3 grid, const ParamBlob<CAP> &blob, const BlobOffsets &off, DevResult *res, int seq)
+int launchNuc4PK (Instance *I, const DevCtx &ctx, dim3 grid, const ParamBlob<CAP> &blob, const BlobOffsets &off, DevResult *res, int seq,
+                  const JobIndex &jx)
 {
     static bool optedIn[64];
     auto kern = eval_nuc4_pkernel<KK, NT, CAP>;
@@ -496,19 +508,19 @@ int launchNuc4PK (Instance *I, const DevCtx &ctx, dim3 grid, const ParamBlob<CAP
         CK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         optedIn[I->cfg.device & 63] = true;
         }
-    kern<<<grid, NT, bytes, I->stream>>> (ctx, blob, off, res, seq);
+    kern<<<grid, NT, bytes, I->stream>>> (ctx, off, res, seq, jx, blob);
     return MB200_SUCCESS;
 }
 
 template <int NT>
 int launchNuc4T (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const double *dd, const DevChunk *dc,
-                 const DevMat *dm, const DevOp *dops, DevResult *res, int seq, bool fused)
+                 const DevMat *dm, const DevOp *dops, DevResult *res, int seq, bool fused, const JobIndex &jx)
 {
     int rcl = MB200_SUCCESS;
     switch (ctx.K)
         {
-#define MB200_CASE(KK) case KK: rcl = fused ? launchNuc4K<KK, NT, true> (I, ctx, grid, de, dd, dc, dm, dops, res, seq) \
-                                             : launchNuc4K<KK, NT, false> (I, ctx, grid, de, dd, dc, dm, dops, res, seq); break;
+#define MB200_CASE(KK) case KK: rcl = fused ? launchNuc4K<KK, NT, true> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, jx) \
+                                             : launchNuc4K<KK, NT, false> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, jx); break;
         MB200_CASE(1) MB200_CASE(2) MB200_CASE(3) MB200_CASE(4) MB200_CASE(5) MB200_CASE(6) MB200_CASE(7) MB200_CASE(8)
 #undef MB200_CASE
         default: return MB200_ERROR_UNSUPPORTED;
@@ -517,12 +529,11 @@ int launchNuc4T (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, c
 }
 
 int launchNuc4 (Instance *I, const DevCtx &ctx, dim3 grid, const DevEval *de, const double *dd, const DevChunk *dc,
-                const DevMat *dm, const DevOp *dops, DevResult *res, int seq, bool fused)
+                const DevMat *dm, const DevOp *dops, DevResult *res, int seq, bool fused, const JobIndex &jx)
 {
-    const int nt = fused ? NT_SMALL : (NT_STREAM == 512 ? 256 : NT_STREAM);
-    return (nt == 512) ? launchNuc4T<512> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, true)
-         : (nt == 256) ? launchNuc4T<256> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, fused)
-                       : launchNuc4T<128> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, fused);
+    const int nt = fused ? NT_SMALL : NT_STREAM;
+    return (nt == 256) ? launchNuc4T<256> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, fused, jx)
+                       : launchNuc4T<128> (I, ctx, grid, de, dd, dc, dm, dops, res, seq, fused, jx);
 }
 
 // the same kernel with the job descriptors riding in the parameter block (no H2D copy)
@@ -534,7 +545,7 @@ int launchNuc4ParamT (Instance *I, const DevCtx &ctx, dim3 grid, const Batch &b,
     int rcl = MB200_SUCCESS;
     switch (ctx.K)
         {
-#define MB200_CASE(KK) case KK: rcl = launchNuc4PK<KK, NT, CAP> (I, ctx, grid, blob, off, res, seq); break;
+#define MB200_CASE(KK) case KK: rcl = launchNuc4PK<KK, NT, CAP> (I, ctx, grid, blob, off, res, seq, b.jx); break;
         MB200_CASE(1) MB200_CASE(2) MB200_CASE(3) MB200_CASE(4) MB200_CASE(5) MB200_CASE(6) MB200_CASE(7) MB200_CASE(8)
 #undef MB200_CASE
         default: return MB200_ERROR_UNSUPPORTED;
@@ -545,12 +556,11 @@ int launchNuc4ParamT (Instance *I, const DevCtx &ctx, dim3 grid, const Batch &b,
 template <int CAP>
 int launchNuc4Param (Instance *I, const DevCtx &ctx, dim3 grid, const Batch &b, DevResult *res, int seq)
 {
-    return (NT_SMALL == 512) ? launchNuc4ParamT<CAP, 512> (I, ctx, grid, b, res, seq)
-         : (NT_SMALL == 256) ? launchNuc4ParamT<CAP, 256> (I, ctx, grid, b, res, seq)
+    return (NT_SMALL == 256) ? launchNuc4ParamT<CAP, 256> (I, ctx, grid, b, res, seq)
                              : launchNuc4ParamT<CAP, 128> (I, ctx, grid, b, res, seq);
 }
 
-const int PARAM_SMALL = 4096, PARAM_BIG = 30720;
+const int PARAM_SMALL = 4096, PARAM_MID = 10240, PARAM_BIG = 30720;   // parameter-block sizes compiled (the launch copies all of it)
 
 bool paramEligible (const Instance *I, const Batch &b)
 {
@@ -603,11 +613,12 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
         int rc;
         if (viaParams)
             {
-            if (b.bytes <= (size_t) PARAM_SMALL) rc = launchNuc4Param<PARAM_SMALL> (I, ctx, grid, b, res, seq);
-            else                                 rc = launchNuc4Param<PARAM_BIG> (I, ctx, grid, b, res, seq);
+            if (b.bytes <= (size_t) PARAM_SMALL)    rc = launchNuc4Param<PARAM_SMALL> (I, ctx, grid, b, res, seq);
+            else if (b.bytes <= (size_t) PARAM_MID) rc = launchNuc4Param<PARAM_MID> (I, ctx, grid, b, res, seq);
+            else                                    rc = launchNuc4Param<PARAM_BIG> (I, ctx, grid, b, res, seq);
             }
         else
-            rc = launchNuc4 (I, ctx, grid, de, dd, dc, dm, dops, res, seq, b.fused);
+            rc = launchNuc4 (I, ctx, grid, de, dd, dc, dm, dops, res, seq, b.fused, b.jx);
         if (rc != MB200_SUCCESS) return rc;
         }
     else if (I->tcS)
@@ -674,10 +685,20 @@ int waitResults (Instance *I, Batch &b, int slots)
     return MB200_SUCCESS;
 }
 
+#ifdef MB200_PHASE_TIMING
+static double hostNow () { struct timespec ts; clock_gettime (CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+double gHostPhase[4] = {0, 0, 0, 0};   // pack, launch, wait, calls
+#define MB200_HOST_T(var) const double var = hostNow ()
+#else
+#define MB200_HOST_T(var) do { } while (0)
+#endif
+
 int runSync (Instance *I, const mb200_evaluation *evs, int count, double *lnL, int *status)
 {
     Batch &b = I->scratch;
+    MB200_HOST_T (tA);
     int rc = pack (I, b, evs, count);
+    MB200_HOST_T (tB);
     if (rc != MB200_SUCCESS) return rc;
     const bool viaParams = paramEligible (I, b);
     if (!viaParams)
@@ -686,6 +707,7 @@ int runSync (Instance *I, const mb200_evaluation *evs, int count, double *lnL, i
     for (int e = 0; e < count; e++) if (evs[e].root_buffer == MB200_NONE) allRoot = false;
     I->lastHostSum = 0; I->lastTiles = 1;
     rc = launch (I, b, b.hResDev, viaParams, allRoot && b.fused);
+    MB200_HOST_T (tC);
     if (rc != MB200_SUCCESS) return rc;
     if (allRoot)
         {
@@ -695,6 +717,9 @@ int runSync (Instance *I, const mb200_evaluation *evs, int count, double *lnL, i
         }
     else
         CK (cudaStreamSynchronize (I->stream));
+#ifdef MB200_PHASE_TIMING
+    { const double tD = hostNow (); gHostPhase[0] += tB - tA; gHostPhase[1] += tC - tB; gHostPhase[2] += tD - tC; gHostPhase[3] += 1.0; }
+#endif
     for (int e = 0; e < count; e++)
         {
         if (evs[e].root_buffer != MB200_NONE)
@@ -1250,6 +1275,10 @@ int mb200_get_launch_count (int instance, long long *launches)
     *launches = I->launches;
     return MB200_SUCCESS;
 }
+
+#ifdef MB200_PHASE_TIMING
+extern "C" int mb200_debug_host_phases (double *out4) { for (int i = 0; i < 4; i++) { out4[i] = gHostPhase[i]; gHostPhase[i] = 0; } return 0; }
+#endif
 
 // phase timestamps of the last launch (debug builds compiled with -DMB200_PHASE_TIMING only)
 int mb200_debug_read_stamps (int instance, unsigned long long *out, int evaluations)

@@ -429,7 +429,7 @@ template <int K, int NT, bool FUSE> struct Nuc4Smem
     static constexpr int L    = Nuc4Geom<K>::L;
     static constexpr int MAXS = Nuc4Geom<K>::MAXS;
     static constexpr int PPB  = NT / L;
-    static constexpr int OPC  = (2048 / PPB > 32) ? 32 : (2048 / PPB < 8 ? 8 : 2048 / PPB);
+    static constexpr int OPC  = NUC_OPC (PPB);
     static constexpr int MAXT = NUC_MAXT (K);
     float4 sP[MAXS][K][5];                       // P(t) rows of every branch the chunk touches (4 rows + 1 pad: bank spread)
     float4 sTab[MAXT][16][K];                    // per tip operand, state mask and category: sum of the P(t) columns the mask selects
@@ -451,7 +451,7 @@ template <int K, int NT, bool FUSE>
 __device__ __forceinline__ void
 nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
            const DevChunk *__restrict__ chunks, const DevMat *__restrict__ cmats,
-           const DevOp *__restrict__ ops, DevResult *out, int seq)
+           const DevOp *__restrict__ ops, DevResult *out, int seq, const JobIndex &jx)
 {
     constexpr int L    = Nuc4Geom<K>::L;
     constexpr int PPB  = NT / L;                 // patterns per CTA
@@ -462,59 +462,28 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
     auto &sEig = sm.sEig; auto &sTipInfo = sm.sTipInfo; auto &sMask = sm.sMask;
 
     MB200_STAMP (0);
+    // ---- 0. staging of the evaluation and of its first chunk.  With a job index (small launches) all
+    //      of it is one round of independent loads; otherwise the header comes first ----
+    const bool indexed = (int) blockIdx.y < jx.n;
+    DevChunk ch0;
+    int dOff0, eig0;
+    if (indexed)
+        {
+        const JobIndexEntry je = jx.e[blockIdx.y];
+        ch0.opOff = je.opOff; ch0.nOp = je.nOp; ch0.matOff = je.matOff; ch0.nMat = je.nMat;
+        dOff0 = je.dOff; eig0 = je.eigen0;
+        }
     if (threadIdx.x < (int)(sizeof(DevEval) / 4))
         reinterpret_cast<int *>(&sEv)[threadIdx.x] = reinterpret_cast<const int *>(evals + blockIdx.y)[threadIdx.x];
-    __syncthreads ();
-    MB200_STAMP (1);
-    const int   C      = ctx.C;
-    const int   lk     = threadIdx.x % L;                   // this lane's rate category
-    const int   kk     = (lk < K) ? lk : K - 1;
-    const int   pl     = threadIdx.x / L;                   // pattern slot within the CTA
-    const int   c0     = blockIdx.x * PPB;
-    const int   c      = c0 + pl;
-    const bool  active = (c < C) && (lk < K);
-    const int   cc     = (c < C) ? c : C - 1;
-    float4 *partials4 = reinterpret_cast<float4 *>(ctx.partials);
-    const unsigned groupBase = (threadIdx.x & 31) & ~(L - 1);
-    const int   eig0 = sEv.eigen0;
-    const int   nChunk = sEv.nChunk;
-
-    // evaluation-wide inputs, one round of independent loads (together with chunk 0's lists below)
-    if (threadIdx.x < 2*K + 4)
-        sD[threadIdx.x] = dvals[sEv.dOff + threadIdx.x];
-    if (FUSE && threadIdx.x < 72)
-        sEig[threadIdx.x] = (eig0 == -2) ? dvals[sEv.dOff + 2*K + 4 + threadIdx.x]     // carried by the evaluation
-                                          : ctx.eigen[(size_t)eig0 * 72 + threadIdx.x];
-    float  lnScaler = (sEv.siteSrc >= 0) ? ctx.scalers[(size_t)sEv.siteSrc * C + cc] : 0.0f;
-
-    float4 cur = make_float4 (0.f, 0.f, 0.f, 0.f);
-
-    // per-thread addressing: everything in the node loop is  base + (uniform offset from the op record)
-    // (32-bit element offsets: pack() guarantees they fit; one live register per base)
-    const unsigned       tOff  = (unsigned) kk * (unsigned) C + (unsigned) cc;
-    const unsigned       sPk   = (unsigned) __cvta_generic_to_shared (&sP[0][kk][0]);
-    float               *sNewT = &sNew[0][pl];
-    const NucOp         *nops  = reinterpret_cast<const NucOp *>(sOps);
-
-    const unsigned sTabK  = (unsigned) __cvta_generic_to_shared (&sTab[0][0][kk]);
-    const unsigned sMaskP = (unsigned) __cvta_generic_to_shared (&sMask[0][pl]);
-
-    for (int ci = 0; ci < nChunk; ci++)
+    if (!indexed)
         {
-        // ---- 1. chunk descriptor, node list, branch list ----
-        if (ci == 0)
-            {
-            ;
-            }
-        else
-            {
-            __syncthreads ();                     // previous chunk completely done: shared arrays free
-            if (threadIdx.x < 4)
-                reinterpret_cast<int *>(&sCh)[threadIdx.x] = reinterpret_cast<const int *>(chunks + sEv.chunkOff + ci - 1)[threadIdx.x];
-            __syncthreads ();
-            }
-        const DevChunk ch = (ci == 0) ? sEv.chunk0 : sCh;
-        const int nMatC = ch.nMat & 0xffff, nTipC = ch.nMat >> 16;
+        __syncthreads ();
+        ch0 = sEv.chunk0; dOff0 = sEv.dOff; eig0 = sEv.eigen0;
+        }
+    MB200_STAMP (1);
+    auto stageChunk = [&] (const DevChunk &ch)
+        {
+        const int nMatC = ch.nMat & 0xffff;
         for (int e = threadIdx.x; e < nMatC * 4; e += NT)
             reinterpret_cast<int *>(sMat)[e] = reinterpret_cast<const int *>(cmats + ch.matOff)[e];
         for (int e = threadIdx.x; e < ch.nOp * (int)(sizeof(DevOp)/4); e += NT)
@@ -533,7 +502,53 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                                     (j == 0) ? o.sp1 : (j == 1) ? o.sp2 : o.sp3);
                 }
             }
-        __syncthreads ();
+        };
+    stageChunk (ch0);
+    if (threadIdx.x < 2*K + 4)
+        sD[threadIdx.x] = dvals[dOff0 + threadIdx.x];
+    if (FUSE && threadIdx.x < 72)
+        sEig[threadIdx.x] = (eig0 == -2) ? dvals[dOff0 + 2*K + 4 + threadIdx.x]     // carried by the evaluation
+                                          : ctx.eigen[(size_t)eig0 * 72 + threadIdx.x];
+    __syncthreads ();
+    const int   C      = ctx.C;
+    const int   lk     = threadIdx.x % L;                   // this lane's rate category
+    const int   kk     = (lk < K) ? lk : K - 1;
+    const int   pl     = threadIdx.x / L;                   // pattern slot within the CTA
+    const int   c0     = blockIdx.x * PPB;
+    const int   c      = c0 + pl;
+    const bool  active = (c < C) && (lk < K);
+    const int   cc     = (c < C) ? c : C - 1;
+    float4 *partials4 = reinterpret_cast<float4 *>(ctx.partials);
+    const unsigned groupBase = (threadIdx.x & 31) & ~(L - 1);
+    const int   nChunk = sEv.nChunk;
+    float  lnScaler = (sEv.siteSrc >= 0) ? ctx.scalers[(size_t)sEv.siteSrc * C + cc] : 0.0f;
+
+    float4 cur = make_float4 (0.f, 0.f, 0.f, 0.f);
+
+    // per-thread addressing: everything in the node loop is  base + (uniform offset from the op record)
+    // (32-bit element offsets: pack() guarantees they fit; one live register per base)
+    const unsigned       tOff  = (unsigned) kk * (unsigned) C + (unsigned) cc;
+    const unsigned       sPk   = (unsigned) __cvta_generic_to_shared (&sP[0][kk][0]);
+    float               *sNewT = &sNew[0][pl];
+    const NucOp         *nops  = reinterpret_cast<const NucOp *>(sOps);
+
+    const unsigned sTabK  = (unsigned) __cvta_generic_to_shared (&sTab[0][0][kk]);
+    const unsigned sMaskP = (unsigned) __cvta_generic_to_shared (&sMask[0][pl]);
+
+    for (int ci = 0; ci < nChunk; ci++)
+        {
+        // ---- 1. chunk descriptor, node list, branch list (chunk 0: staged above) ----
+        if (ci > 0)
+            {
+            __syncthreads ();                     // previous chunk completely done: shared arrays free
+            if (threadIdx.x < 4)
+                reinterpret_cast<int *>(&sCh)[threadIdx.x] = reinterpret_cast<const int *>(chunks + sEv.chunkOff + ci - 1)[threadIdx.x];
+            __syncthreads ();
+            stageChunk (sCh);
+            __syncthreads ();
+            }
+        const DevChunk ch = (ci == 0) ? ch0 : sCh;
+        const int nMatC = ch.nMat & 0xffff, nTipC = ch.nMat >> 16;
         if (ci == 0) MB200_STAMP (2);
 
         // ---- 2. P(t) slots (K1 fused: TiProbs_Gen, src/likelihood.c:9499-9542); the chunk's tip masks
@@ -576,6 +591,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             sMask[e / PPB][e % PPB] = ctx.tip8[(sTipInfo[e / PPB].x & 0x7fffffffu) + (unsigned)((cp < C) ? cp : C - 1)];
             }
         __syncthreads ();
+        if (ci == 0) MB200_STAMP (50);
         if (FUSE)
             {
             for (int r = threadIdx.x; r < nMatC * K * 4; r += NT)
@@ -592,15 +608,29 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                     row = make_float4 ((float) sD[2*K], (float) sD[2*K+1], (float) sD[2*K+2], (float) sD[2*K+3]);
                 else
                     {
-                    const double *cij = (eg == eig0) ? (sEig + 8 + i*16) : (ctx.eigen + (size_t)eg * 72 + 8 + i*16);
                     const double e0 = sExp[m][k][0], e1 = sExp[m][k][1], e2 = sExp[m][k][2], e3 = sExp[m][k][3];
                     float v[4];
-                    #pragma unroll
-                    for (int j = 0; j < 4; j++)
+                    if (eg == eig0)               // the evaluation's own eigensystem: staged in shared memory
                         {
-                        double sum = 0.0;
-                        sum += cij[j*4+0] * e0; sum += cij[j*4+1] * e1; sum += cij[j*4+2] * e2; sum += cij[j*4+3] * e3;
-                        v[j] = (float) ((sum < 0.0) ? 0.0 : sum);
+                        const double *cij = sEig + 8 + i*16;
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            {
+                            double sum = 0.0;
+                            sum += cij[j*4+0] * e0; sum += cij[j*4+1] * e1; sum += cij[j*4+2] * e2; sum += cij[j*4+3] * e3;
+                            v[j] = (float) ((sum < 0.0) ? 0.0 : sum);
+                            }
+                        }
+                    else
+                        {
+                        const double *cij = ctx.eigen + (size_t)eg * 72 + 8 + i*16;
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            {
+                            double sum = 0.0;
+                            sum += cij[j*4+0] * e0; sum += cij[j*4+1] * e1; sum += cij[j*4+2] * e2; sum += cij[j*4+3] * e3;
+                            v[j] = (float) ((sum < 0.0) ? 0.0 : sum);
+                            }
                         }
                     row = make_float4 (v[0], v[1], v[2], v[3]);
                     }
@@ -609,6 +639,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                     reinterpret_cast<float4 *>(ctx.matrices + (size_t)sMat[m].matrix * K * 16)[k*4 + i] = row;
                 }
             __syncthreads ();
+            if (ci == 0) MB200_STAMP (51);
             }
         // tip lookup tables: entry[mask][i] = sum over the states j in the mask of P[i][j], added in state
         // order -- the value the reference's dense 0/1 matvec produces (CondLikeDown_NUC4*: products by
@@ -830,24 +861,26 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
 // ---- kernel entry points of the 4-state path ----
 // job descriptors in global memory (device-resident batches, large jobs)
 template <int K, int NT, bool FUSE>
-__global__ void __launch_bounds__(NT, FUSE ? 1 : 768 / NT)
+__global__ void __launch_bounds__(NT, FUSE ? 1 : NUC_STREAM_THREADS / NT)
 eval_nuc4_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
                   const DevChunk *__restrict__ chunks, const DevMat *__restrict__ cmats,
-                  const DevOp *__restrict__ ops, DevResult *out, int seq)
+                  const DevOp *__restrict__ ops, DevResult *out, int seq, const __grid_constant__ JobIndex jx)
 {
-    nuc4_body<K, NT, FUSE> (ctx, evals, dvals, chunks, cmats, ops, out, seq);
+    nuc4_body<K, NT, FUSE> (ctx, evals, dvals, chunks, cmats, ops, out, seq, jx);
 }
 
 // job descriptors delivered in the kernel parameter block (host call path of small evaluations):
 // no host->device copy on the way in
 template <int K, int NT, int CAP>
 __global__ void __launch_bounds__(NT, 1)
-eval_nuc4_pkernel (DevCtx ctx, const __grid_constant__ ParamBlob<CAP> blob, BlobOffsets off, DevResult *out, int seq)
+eval_nuc4_pkernel (DevCtx ctx, BlobOffsets off, DevResult *out, int seq, const __grid_constant__ JobIndex jx,
+                   const __grid_constant__ ParamBlob<CAP> blob)       // small uniform parameters first: they share the
+                                                                       // constant-cache lines the kernel touches anyway
 {
     const char *b = blob.bytes;
     nuc4_body<K, NT, true> (ctx, reinterpret_cast<const DevEval *>(b + off.eval), reinterpret_cast<const double *>(b + off.dbl),
                             reinterpret_cast<const DevChunk *>(b + off.chunk), reinterpret_cast<const DevMat *>(b + off.cmat),
-                            reinterpret_cast<const DevOp *>(b + off.op), out, seq);
+                            reinterpret_cast<const DevOp *>(b + off.op), out, seq, jx);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -22,4 +22,4 @@ for rep in range(2):
     for e in range(8):
         nop=len(specs[e].ops); nm=len(specs[e].mats)
         r=a[e]; ops=[int(r[8+o]-r[3]) if o==0 else int(r[8+o]-r[8+o-1]) for o in range(nop)]
-        print(f" eval{e} nOp={nop:2d} nMat={nm:2d} start+{r[0]-t0:6d} hdr={r[1]-r[0]:5d} sD={r[2]-r[1]:5d} P={r[3]-r[2]:6d} ops={ops} tail={r[5]-r[4]:5d} fin={r[6]-r[5]:5d} total={r[6]-r[0]:6d} | op3: sync={r[41]-r[40]} loads+mv={r[42]-r[41]} scale={r[43]-r[42]} rest={r[8+3]-r[43]} pre={r[40]-r[8+2]}" if nop>3 else "")
+        print(f" eval{e} nOp={nop:2d} nMat={nm:2d} start+{r[0]-t0:6d} hdr={r[1]-r[0]:5d} stage={r[2]-r[1]:5d} exp={r[50]-r[2]:5d} rows={r[51]-r[50]:5d} tab={r[3]-r[51]:5d} ops={ops} scal={r[4]-r[8+nop-1] if nop else 0:5d} tail={r[5]-r[4]:5d} fin={r[6]-r[5]:5d} total={r[6]-r[0]:6d}")
