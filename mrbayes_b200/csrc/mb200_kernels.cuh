@@ -473,24 +473,54 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
         ch0.opOff = je.opOff; ch0.nOp = je.nOp; ch0.matOff = je.matOff; ch0.nMat = je.nMat;
         dOff0 = je.dOff; eig0 = je.eigen0;
         }
-    if (threadIdx.x < (int)(sizeof(DevEval) / 4))
-        reinterpret_cast<int *>(&sEv)[threadIdx.x] = reinterpret_cast<const int *>(evals + blockIdx.y)[threadIdx.x];
     if (!indexed)
         {
+        if (threadIdx.x < (int)(sizeof(DevEval) / 4))
+            reinterpret_cast<int *>(&sEv)[threadIdx.x] = reinterpret_cast<const int *>(evals + blockIdx.y)[threadIdx.x];
         __syncthreads ();
         ch0 = sEv.chunk0; dOff0 = sEv.dOff; eig0 = sEv.eigen0;
         }
     MB200_STAMP (1);
-    auto stageChunk = [&] (const DevChunk &ch)
+    // chunk lists -> shared memory.  All loads of a thread are issued before its first store (a load
+    // followed by its store, loop after loop, would serialise one cold miss per list)
+    auto stageChunk = [&] (const DevChunk &ch, bool withEval)
         {
-        const int nMatC = ch.nMat & 0xffff;
-        for (int e = threadIdx.x; e < nMatC * 4; e += NT)
-            reinterpret_cast<int *>(sMat)[e] = reinterpret_cast<const int *>(cmats + ch.matOff)[e];
-        for (int e = threadIdx.x; e < ch.nOp * (int)(sizeof(DevOp)/4); e += NT)
-            reinterpret_cast<int *>(sOps)[e] = reinterpret_cast<const int *>(ops + ch.opOff)[e];
-        if (threadIdx.x < ch.nOp)                 // tip operand list of the chunk
+        const int nMatW = (ch.nMat & 0xffff) * 4, nOpW = ch.nOp * (int)(sizeof(DevOp)/4);
+        const int *srcE = reinterpret_cast<const int *>(evals + blockIdx.y);
+        const int *srcM = reinterpret_cast<const int *>(cmats + ch.matOff);
+        const int *srcO = reinterpret_cast<const int *>(ops + ch.opOff);
+        int vE = 0, vM = 0, vO = 0, vO2 = 0;
+        double vD = 0.0, vG = 0.0;
+        const int t = threadIdx.x;
+        if (withEval)
             {
-            const NucOp &o = reinterpret_cast<const NucOp *>(ops + ch.opOff)[threadIdx.x];
+            if (indexed && t < (int)(sizeof(DevEval) / 4)) vE = srcE[t];
+            if (t < 2*K + 4) vD = dvals[dOff0 + t];
+            if (FUSE && t < 72)
+                vG = (eig0 == -2) ? dvals[dOff0 + 2*K + 4 + t]          // eigensystem carried by the evaluation
+                                  : ctx.eigen[(size_t)eig0 * 72 + t];
+            }
+        if (t < nMatW)      vM  = srcM[t];
+        if (t < nOpW)       vO  = srcO[t];
+        if (t + NT < nOpW)  vO2 = srcO[t + NT];
+        if (withEval)
+            {
+            if (indexed && t < (int)(sizeof(DevEval) / 4)) reinterpret_cast<int *>(&sEv)[t] = vE;
+            if (t < 2*K + 4) sD[t] = vD;
+            if (FUSE && t < 72) sEig[t] = vG;
+            }
+        if (t < nMatW)      reinterpret_cast<int *>(sMat)[t] = vM;
+        if (t < nOpW)       reinterpret_cast<int *>(sOps)[t] = vO;
+        if (t + NT < nOpW)  reinterpret_cast<int *>(sOps)[t + NT] = vO2;
+        for (int e = t + NT; e < nMatW; e += NT)      reinterpret_cast<int *>(sMat)[e] = srcM[e];
+        for (int e = t + 2 * NT; e < nOpW; e += NT)   reinterpret_cast<int *>(sOps)[e] = srcO[e];
+        };
+    // tip operand list of the chunk, from the staged node list
+    auto listTips = [&] (int nOp)
+        {
+        if (threadIdx.x < nOp)
+            {
+            const NucOp &o = reinterpret_cast<const NucOp *>(sOps)[threadIdx.x];
             const unsigned kinds = o.kinds;
             #pragma unroll
             for (int j = 0; j < 3; j++)
@@ -503,12 +533,9 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 }
             }
         };
-    stageChunk (ch0);
-    if (threadIdx.x < 2*K + 4)
-        sD[threadIdx.x] = dvals[dOff0 + threadIdx.x];
-    if (FUSE && threadIdx.x < 72)
-        sEig[threadIdx.x] = (eig0 == -2) ? dvals[dOff0 + 2*K + 4 + threadIdx.x]     // carried by the evaluation
-                                          : ctx.eigen[(size_t)eig0 * 72 + threadIdx.x];
+    stageChunk (ch0, true);
+    __syncthreads ();
+    listTips (ch0.nOp);
     __syncthreads ();
     const int   C      = ctx.C;
     const int   lk     = threadIdx.x % L;                   // this lane's rate category
@@ -544,7 +571,9 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             if (threadIdx.x < 4)
                 reinterpret_cast<int *>(&sCh)[threadIdx.x] = reinterpret_cast<const int *>(chunks + sEv.chunkOff + ci - 1)[threadIdx.x];
             __syncthreads ();
-            stageChunk (sCh);
+            stageChunk (sCh, false);
+            __syncthreads ();
+            listTips (sCh.nOp);
             __syncthreads ();
             }
         const DevChunk ch = (ci == 0) ? ch0 : sCh;
