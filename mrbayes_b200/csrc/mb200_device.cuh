@@ -110,6 +110,10 @@ struct JobIndex
     JobIndexEntry e[MB200_JOB_INDEX_MAX];
 };
 
+// evaluations with at most this many pattern tiles add their tile partials left to right -- on the
+// device (last CTA) or, on the host-call latency path, on the host: the same order, the same bits
+#define MB200_SEQ_SUM_TILES 16
+
 struct DevResult                    // 16 bytes per evaluation
 {
     double lnL;

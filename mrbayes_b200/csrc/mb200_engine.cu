@@ -66,6 +66,7 @@ struct Instance
     long long     launches = 0;
     std::vector<int> tipPartAmbig;  // host copy (operand kinds of the 4-state records)
     int           tipEpoch = 0;
+    int           writtenStamp = 0;
     int           lastHostSum = 0, lastTiles = 1;   // how the last launch delivers its results
     Batch         scratch;             // used by the synchronous entry points
     std::vector<Batch *> batches;      // resident batches (mb200_pack_evaluations)
@@ -74,7 +75,7 @@ struct Instance
     std::vector<int> slotOf;           // scratch: matrix index -> shared-memory slot in the current evaluation
     std::vector<int> touched;          // scratch: matrices whose slotOf entry is set
     std::vector<int> dirtyOf;          // scratch: matrix index -> index in the evaluation's update list
-    std::vector<DevChunk> chunkTmp; std::vector<DevMat> cmatTmp; std::vector<int> slotTmp, nChunkTmp, tipIdxTmp;
+    std::vector<DevChunk> chunkTmp; std::vector<DevMat> cmatTmp; std::vector<int> slotTmp, nChunkTmp, tipIdxTmp, writtenTmp;
     bool          timing = false;      // bracket the fused kernel with events
     std::vector<cudaEvent_t> evA, evB; // ring of event pairs
     long long     evCount = 0;         // pairs recorded since the last read
@@ -84,7 +85,7 @@ std::mutex               gLock;
 std::vector<Instance *>  gInstances;
 
 const int NT_GEN = 256;
-const int HOSTSUM_MAX_TILES = 8;    // latency path: up to this many tile partials per evaluation summed on the host
+const int HOSTSUM_MAX_TILES = MB200_SEQ_SUM_TILES;   // latency path: up to this many tile partials per evaluation summed on the host
 // threads per CTA of the 4-state kernels: latency regime (FUSE) and bandwidth regime; both sizes are
 // compiled, MB200_NT_SMALL / MB200_NT_STREAM (128 or 256) pick at run time for tuning
 int ntFromEnv (const char *name, int dflt)
@@ -415,6 +416,10 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
             const unsigned slotBytes = (unsigned) K * 80u;                              // sP[slot][K][5] float4
             const bool shortcuts = (ev.flags & MB200_FLAG_TIP_SHORTCUTS) != 0;
             int prevDest = -2;
+            std::vector<int> &written = I->writtenTmp;      // [buffer] == stamp: produced earlier in this evaluation
+            if ((int) written.size () < c.partials_count) written.assign (c.partials_count, 0);
+            const int stamp = ++I->writtenStamp;
+            auto isWritten = [&] (int buf) { return written[buf] == stamp; };
             auto operand = [&] (int child, unsigned &a) -> unsigned
                 {
                 if (child == MB200_NONE) { a = 0; return NUC_NONE; }
@@ -439,9 +444,13 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
                 o.sp1 = (unsigned) slots[slotPos] * slotBytes;
                 o.sp2 = (unsigned) slots[slotPos + 1] * slotBytes;
                 o.sp3 = (slots[slotPos + 2] >= 0) ? (unsigned) slots[slotPos + 2] * slotBytes : 0u;
-                o.sw = op.scale_write; o.sr = op.scale_remove; o.dest = op.dest; o.pad = 0;
+                o.sw = op.scale_write; o.sr = op.scale_remove; o.dest = op.dest;
+                // operands read from buffers this evaluation does not write: worth prefetching (latency path)
+                o.pad = ((k1 == NUC_LOAD && !isWritten (op.child1)) ? 1 : 0) | ((k2 == NUC_LOAD && !isWritten (op.child2)) ? 2 : 0) |
+                        ((k3 == NUC_LOAD && !isWritten (op.child3)) ? 4 : 0);
                 slotPos += 3;
                 prevDest = op.dest;
+                written[op.dest] = stamp;
                 }
             d.rootFwd = (ev.root_buffer != MB200_NONE && ev.root_buffer == prevDest) ? 1 : 0;
             d.rootOff = (ev.root_buffer != MB200_NONE) ? (unsigned)(ev.root_buffer - c.tip_count) * bufStride : 0u;

@@ -235,7 +235,7 @@ __device__ __forceinline__ void finish_lnl (const DevCtx &ctx, int evalIdx, doub
         return;
     __threadfence ();
     // last CTA of this evaluation: fixed-order sum over the tiles
-    if (ctx.numTiles <= 8)
+    if (ctx.numTiles <= MB200_SEQ_SUM_TILES)
         {
         // few tiles: plain left-to-right sum, the order the host uses in hostSum mode
         if (threadIdx.x == 0)

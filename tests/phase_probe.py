@@ -21,5 +21,13 @@ for rep in range(2):
     print("rep",rep,"step",si)
     for e in range(8):
         nop=len(specs[e].ops); nm=len(specs[e].mats)
+        ntips = inst.cfg['tip_count'] if hasattr(inst,'cfg') else 12
+        kinds=[]; prev=-9
+        for o in specs[e].ops:
+            k=''
+            for ch in (o['child1'],o['child2'],o['child3']):
+                if ch < 0: continue
+                k += 'T' if ch < ntips else ('F' if ch == prev else 'L')
+            kinds.append(k); prev=o['dest']
         r=a[e]; ops=[int(r[8+o]-r[3]) if o==0 else int(r[8+o]-r[8+o-1]) for o in range(nop)]
-        print(f" eval{e} nOp={nop:2d} nMat={nm:2d} start+{r[0]-t0:6d} hdr={r[1]-r[0]:5d} stage={r[2]-r[1]:5d} exp={r[50]-r[2]:5d} rows={r[51]-r[50]:5d} tab={r[3]-r[51]:5d} ops={ops} scal={r[4]-r[8+nop-1] if nop else 0:5d} tail={r[5]-r[4]:5d} fin={r[6]-r[5]:5d} total={r[6]-r[0]:6d}")
+        print(f" eval{e} nOp={nop:2d} nMat={nm:2d} start+{r[0]-t0:6d} hdr={r[1]-r[0]:5d} stage={r[2]-r[1]:5d} exp={r[50]-r[2]:5d} rows={r[51]-r[50]:5d} tab={r[3]-r[51]:5d} ops={ops} kinds={kinds} scal={r[4]-r[8+nop-1] if nop else 0:5d} tail={r[5]-r[4]:5d} fin={r[6]-r[5]:5d} total={r[6]-r[0]:6d}")
