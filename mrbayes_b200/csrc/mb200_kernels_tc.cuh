@@ -62,8 +62,10 @@ __global__ void tc_split_kernel (const float *__restrict__ matrices, float *__re
         }
 }
 
+// resident CTAs per SM: the 61-state tile needs 96 KB of shared memory and 128 TMEM columns, so two
+// fit and hide each other's load / MMA / read-out phases; the 20-state tile (4 categories) needs 123 KB
 template <int S>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, (S == 61) ? 2 : 1)
 eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
                 const DevOp *__restrict__ ops, const float *__restrict__ split, DevResult *out, int seq)
 {

@@ -21,7 +21,7 @@ for rep in range(2):
     print("rep",rep,"step",si)
     for e in range(8):
         nop=len(specs[e].ops); nm=len(specs[e].mats)
-        ntips = inst.cfg['tip_count'] if hasattr(inst,'cfg') else 12
+        ntips = pr.n_tips
         kinds=[]; prev=-9
         for o in specs[e].ops:
             k=''
