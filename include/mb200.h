@@ -216,6 +216,15 @@ int mb200_root_log_likelihood (int instance, int root_buffer, int site_scaler,
 int mb200_evaluate (int instance, const mb200_evaluation *evaluations, int count,
                     double *lnL, int *status);
 
+/* The same call in two halves, so that the divisions (partitions) of one chain -- separate
+ * instances, separate streams -- are in flight together and their launch latencies overlap:
+ * begin() validates, packs and launches and returns at once; end() waits for the results.
+ * One evaluation may be in flight per instance.  This is what the reference's partition-batched
+ * accelerator entry does in one BEAGLE call (LaunchBEAGLELogLikeMultiPartition, src/mbbeagle.h:29;
+ * LaunchLogLikeForBeagleMultiPartition, src/likelihood.c:7792). */
+int mb200_evaluate_begin (int instance, const mb200_evaluation *evaluations, int count);
+int mb200_evaluate_end   (int instance, double *lnL, int *status);
+
 /* ---- read-back / seeding (parity tests, debugging) --------------------------------- */
 /* host layout of partials: [k][c][s] floats, the reference's scalar layout
  * (src/mcmc.c:5756, 6397-6413) */

@@ -67,6 +67,9 @@ struct Instance
     std::vector<int> tipPartAmbig;  // host copy (operand kinds of the 4-state records)
     int           tipEpoch = 0;
     int           writtenStamp = 0;
+    int           pendingCount = 0;            // evaluations started by mb200_evaluate_begin, not yet collected
+    bool          pendingAllRoot = false;
+    std::vector<char> pendingHasRoot;
     int           lastHostSum = 0, lastTiles = 1;   // how the last launch delivers its results
     Batch         scratch;             // used by the synchronous entry points
     std::vector<Batch *> batches;      // resident batches (mb200_pack_evaluations)
@@ -702,8 +705,11 @@ double gHostPhase[4] = {0, 0, 0, 0};   // pack, launch, wait, calls
 #define MB200_HOST_T(var) do { } while (0)
 #endif
 
-int runSync (Instance *I, const mb200_evaluation *evs, int count, double *lnL, int *status)
+// first half of an evaluation: validate, pack, launch.  Returns as soon as the work is queued.
+int runBegin (Instance *I, const mb200_evaluation *evs, int count)
 {
+    if (I->pendingCount > 0)
+        return MB200_ERROR_OUT_OF_RANGE;               // one evaluation in flight per instance
     Batch &b = I->scratch;
     MB200_HOST_T (tA);
     int rc = pack (I, b, evs, count);
@@ -713,25 +719,46 @@ int runSync (Instance *I, const mb200_evaluation *evs, int count, double *lnL, i
     if (!viaParams)
         CK (cudaMemcpyAsync (b.dBlob, b.hBlob, b.bytes, cudaMemcpyHostToDevice, I->stream));
     bool allRoot = true;
-    for (int e = 0; e < count; e++) if (evs[e].root_buffer == MB200_NONE) allRoot = false;
+    if ((int) I->pendingHasRoot.size () < count) I->pendingHasRoot.resize (count);
+    for (int e = 0; e < count; e++)
+        {
+        I->pendingHasRoot[e] = (evs[e].root_buffer != MB200_NONE);
+        if (!I->pendingHasRoot[e]) allRoot = false;
+        }
     I->lastHostSum = 0; I->lastTiles = 1;
     rc = launch (I, b, b.hResDev, viaParams, allRoot && b.fused);
     MB200_HOST_T (tC);
     if (rc != MB200_SUCCESS) return rc;
-    if (allRoot)
+    I->pendingCount = count; I->pendingAllRoot = allRoot;
+#ifdef MB200_PHASE_TIMING
+    gHostPhase[0] += tB - tA; gHostPhase[1] += tC - tB; gHostPhase[3] += 1.0;
+#endif
+    return MB200_SUCCESS;
+}
+
+// second half: wait for the results of the evaluation started by runBegin
+int runEnd (Instance *I, double *lnL, int *status)
+{
+    const int count = I->pendingCount;
+    if (count <= 0)
+        return MB200_ERROR_OUT_OF_RANGE;
+    I->pendingCount = 0;
+    Batch &b = I->scratch;
+    MB200_HOST_T (tC);
+    if (I->pendingAllRoot)
         {
         // results land in pinned host memory; no D2H copy, no stream synchronisation
-        rc = waitResults (I, b, I->lastHostSum ? count * I->lastTiles : count);
+        int rc = waitResults (I, b, I->lastHostSum ? count * I->lastTiles : count);
         if (rc != MB200_SUCCESS) return rc;
         }
     else
         CK (cudaStreamSynchronize (I->stream));
 #ifdef MB200_PHASE_TIMING
-    { const double tD = hostNow (); gHostPhase[0] += tB - tA; gHostPhase[1] += tC - tB; gHostPhase[2] += tD - tC; gHostPhase[3] += 1.0; }
+    { const double tD = hostNow (); gHostPhase[2] += tD - tC; }
 #endif
     for (int e = 0; e < count; e++)
         {
-        if (evs[e].root_buffer != MB200_NONE)
+        if (I->pendingHasRoot[e])
             {
             if (I->lastHostSum)
                 {
@@ -758,6 +785,13 @@ int runSync (Instance *I, const mb200_evaluation *evs, int count, double *lnL, i
             }
         }
     return MB200_SUCCESS;
+}
+
+int runSync (Instance *I, const mb200_evaluation *evs, int count, double *lnL, int *status)
+{
+    int rc = runBegin (I, evs, count);
+    if (rc != MB200_SUCCESS) return rc;
+    return runEnd (I, lnL, status);
 }
 
 void destroy (Instance *I)
@@ -1103,6 +1137,24 @@ int mb200_evaluate (int instance, const mb200_evaluation *evaluations, int count
     if (!evaluations || !lnL || !status) return MB200_ERROR_OUT_OF_RANGE;
     int rc = use (I); if (rc) return rc;
     return runSync (I, evaluations, count, lnL, status);
+}
+
+int mb200_evaluate_begin (int instance, const mb200_evaluation *evaluations, int count)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (!evaluations) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    return runBegin (I, evaluations, count);
+}
+
+int mb200_evaluate_end (int instance, double *lnL, int *status)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (!lnL || !status) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    return runEnd (I, lnL, status);
 }
 
 // ---- read-back / seeding ---------------------------------------------------------------

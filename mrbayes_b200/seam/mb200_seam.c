@@ -56,6 +56,9 @@ typedef struct
     int                  inlineEigen;       /* nst = 1, 2: eigensystem derived per evaluation */
     double               eigenBlock[72];    /* [lambda_re(4), lambda_im(4), c_ijk(64)] */
     long long            clUpdates;         /* node*pattern*rate updates issued      */
+    int                  pending;           /* launched by a deferred evaluation, result not yet collected */
+    double               syncValue;         /* backend without begin/end: the result, kept until collected */
+    int                  syncStatus, syncRc;
     } SeamDivision;
 
 static SeamDivision seamDiv[SEAM_MAX_DIVISIONS];
@@ -72,14 +75,17 @@ static int be_tips (int i, int t, const uint64_t *m)                   { return 
 static int be_weights (int i, int r, const float *w)                   { return mb200_set_pattern_weights (i, r, w); }
 static int be_cijk (int i, int e, const double *b)                     { return mb200_set_cijk (i, e, b); }
 static int be_eval (int i, const mb200_evaluation *e, int n, double *l, int *s) { return mb200_evaluate (i, e, n, l, s); }
+static int be_begin (int i, const mb200_evaluation *e, int n)          { return mb200_evaluate_begin (i, e, n); }
+static int be_end (int i, double *l, int *s)                           { return mb200_evaluate_end (i, l, s); }
 
-static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval };
+static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end };
+static int seamDeferred = NO;   /* YES: TreeLikelihood_Beagle only launches; SeamCollect fetches the result */
 
 void MB200SeamSetBackend (const MB200SeamBackend *backend)
 {
     if (backend == NULL)
         {
-        MB200SeamBackend def = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval };
+        MB200SeamBackend def = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end };
         seamBackend = def;
         }
     else
@@ -455,6 +461,8 @@ int TreeCondLikes_Beagle_Rescale_All (Tree *t, int division, int chain)
     return TreeCondLikes_Beagle_Always_Rescale (t, division, chain);
 }
 
+static int SeamApplyResult (int division, int rc, double value, int status, MrBFlt *lnL);
+
 /* ---- TreeLikelihood_Beagle (src/mbbeagle.c:1117): root integration; launches ------- */
 int TreeLikelihood_Beagle (Tree *t, int division, int chain, MrBFlt *lnL, int whichSitePats)
 {
@@ -499,7 +507,23 @@ int TreeLikelihood_Beagle (Tree *t, int division, int chain, MrBFlt *lnL, int wh
     for (s=0; s<m->numModelStates; s++)
         sd->ev.state_freqs[s] = bs[s];
 
+    if (seamDeferred == YES)
+        {
+        /* partition-batched evaluation: launch only, MB200LogLike collects */
+        if (seamBackend.evaluate_begin != NULL && seamBackend.evaluate_end != NULL)
+            sd->syncRc = seamBackend.evaluate_begin (sd->instance, &sd->ev, 1);
+        else
+            sd->syncRc = seamBackend.evaluate (sd->instance, &sd->ev, 1, &sd->syncValue, &sd->syncStatus);
+        sd->pending = YES;
+        return (NO_ERROR);
+        }
     rc = seamBackend.evaluate (sd->instance, &sd->ev, 1, &value, &status);
+    return SeamApplyResult (division, rc, value, status, lnL);
+}
+
+/* result of an evaluation -> the reference's conventions */
+static int SeamApplyResult (int division, int rc, double value, int status, MrBFlt *lnL)
+{
     if (rc != MB200_SUCCESS)
         {
         MrBayesPrint ("%s   B200 engine: evaluation failed for division %d (%s)\n", spacer, division+1, mb200_error_string (rc));
@@ -598,4 +622,99 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
 
     LaunchBEAGLELogLikeForDivision (chain, d, m, tree, lnL);
     return (YES);
+}
+
+/* collect the result of a deferred evaluation of division d */
+static int SeamCollect (int d, MrBFlt *lnL)
+{
+    SeamDivision *sd = &seamDiv[d];
+    double        value = 0.0;
+    int           status = MB200_EVAL_OK, rc = sd->syncRc;
+
+    sd->pending = NO;
+    if (seamBackend.evaluate_begin != NULL && seamBackend.evaluate_end != NULL)
+        {
+        if (rc == MB200_SUCCESS)
+            rc = seamBackend.evaluate_end (sd->instance, &value, &status);
+        }
+    else
+        { value = sd->syncValue; status = sd->syncStatus; }
+    return SeamApplyResult (d, rc, value, status, lnL);
+}
+
+/* ---- replacement for the division loop of LogLike (src/mcmc.c:7421-7441) ------------ */
+MrBFlt MB200LogLike (int chain, void (*cpuPath) (int chain, int d, MrBFlt *lnL))
+{
+    int         d;
+    ModelInfo  *m;
+    MrBFlt      chainLnLike = 0.0;
+
+    /* pass 1: launch every division that needs updating (engine) or compute it (reference path) */
+    seamDeferred = YES;
+    for (d=0; d<numCurrentDivisions; d++)
+        {
+        m = &modelSettings[d];
+        if (m->upDateCl != YES)
+            continue;
+        if (MB200LaunchLogLikeForDivision (chain, d, &(m->lnLike[2*chain + state[chain]])) == NO)
+            {
+            seamDeferred = NO;
+            cpuPath (chain, d, &(m->lnLike[2*chain + state[chain]]));
+            seamDeferred = YES;
+            }
+        }
+    seamDeferred = NO;
+
+    /* pass 2: collect */
+    for (d=0; d<numCurrentDivisions; d++)
+        {
+        m = &modelSettings[d];
+        if (d < SEAM_MAX_DIVISIONS && seamDiv[d].pending == YES)
+            SeamCollect (d, &(m->lnLike[2*chain + state[chain]]));
+        }
+    if (abortMove == YES)
+        return MRBFLT_NEG_MAX;
+    for (d=0; d<numCurrentDivisions; d++)
+        chainLnLike += modelSettings[d].lnLike[2*chain + state[chain]];
+    return chainLnLike;
+}
+
+/* ---- LaunchBEAGLELogLikeMultiPartition (src/mbbeagle.h:29, called from
+ *      LaunchLogLikeForBeagleMultiPartition, src/likelihood.c:7792-7843, which has already run
+ *      UpDateCijk for the divisions it passes): all of them in flight together ---------- */
+void LaunchBEAGLELogLikeMultiPartition (int *divisions, int divisionCount, int chain, MrBFlt *lnL)
+{
+    int         i, d, hadCijk;
+    ModelInfo  *m;
+
+    (*lnL) = 0.0;
+    seamDeferred = YES;
+    for (i=0; i<divisionCount; i++)
+        {
+        d = divisions[i];
+        m = &modelSettings[d];
+        hadCijk = m->upDateCijk;
+        if (MB200SeamClosedFormModel (m) == NO)
+            m->upDateCijk = NO;                 /* the caller flipped and rebuilt the cijk space already ... */
+        if (hadCijk == YES && d < SEAM_MAX_DIVISIONS)
+            memset (seamCijkSeen[d], 0, sizeof(seamCijkSeen[d]));   /* ... so only the upload is left */
+        if (MB200LaunchLogLikeForDivision (chain, d, &(m->lnLike[2*chain + state[chain]])) == NO)
+            {
+            MrBayesPrint ("%s   B200 engine: division %d is outside the engine's coverage\n", spacer, d+1);
+            m->lnLike[2*chain + state[chain]] = MRBFLT_NEG_MAX;
+            abortMove = YES;
+            }
+        m->upDateCijk = hadCijk;
+        }
+    seamDeferred = NO;
+    for (i=0; i<divisionCount; i++)
+        {
+        d = divisions[i];
+        m = &modelSettings[d];
+        if (d < SEAM_MAX_DIVISIONS && seamDiv[d].pending == YES)
+            SeamCollect (d, &(m->lnLike[2*chain + state[chain]]));
+        (*lnL) += m->lnLike[2*chain + state[chain]];
+        }
+    if (abortMove == YES)
+        (*lnL) = MRBFLT_NEG_MAX;
 }

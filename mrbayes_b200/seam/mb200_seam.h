@@ -18,6 +18,12 @@
 int       MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL);
 int       MB200SeamDivisionSupported (ModelInfo *m);
 int       MB200SeamClosedFormModel (ModelInfo *m);     /* nst = 1, 2 4x4 models: eigensystem sent inline */
+/* Replacement for the division loop of LogLike (src/mcmc.c:7421-7441): every division of `chain`
+ * that needs updating is launched before any result is waited for, so the partitions of a chain
+ * overlap on the device.  Divisions outside the engine's coverage go to `cpuPath` (the reference's
+ * own LaunchLogLikeForDivision body).  Returns the chain's log likelihood (MRBFLT_NEG_MAX and
+ * abortMove = YES on a numerical failure, like the reference). */
+MrBFlt    MB200LogLike (int chain, void (*cpuPath) (int chain, int d, MrBFlt *lnL));
 void      MB200SeamFinalize (void);
 long long MB200SeamUpdateCount (int division);   /* node*pattern*rate CL updates issued  */
 int       MB200SeamInstance (int division);      /* engine instance of a division, or -1 */
@@ -33,6 +39,9 @@ typedef struct
     int (*set_cijk)            (int instance, int eigen, const double *block);
     int (*evaluate)            (int instance, const mb200_evaluation *evaluations, int count,
                                 double *lnL, int *status);
+    /* optional (may be NULL: the seam then evaluates synchronously) */
+    int (*evaluate_begin)      (int instance, const mb200_evaluation *evaluations, int count);
+    int (*evaluate_end)        (int instance, double *lnL, int *status);
     } MB200SeamBackend;
 
 void      MB200SeamSetBackend (const MB200SeamBackend *backend);   /* NULL = the engine  */

@@ -43,11 +43,13 @@
 #include <time.h>
 
 void __real_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL);
+MrBFlt __real_LogLike (int chain);
 void __real_CalcCijk (int dim, MrBFlt *c_ijk, MrBFlt **u, MrBFlt **v);
 
 enum { MODE_CPU, MODE_DUMP, MODE_SHADOW, MODE_GPU };
 
 static int        hMode = -1;
+static int        hMultiPart = 1;    /* gpu mode: all divisions of a chain in flight together (MB200LogLike) */
 static FILE      *hDump = NULL;
 static long       hDumpMax = -1, hDumped = 0;
 static double     hTol = 1e-6;
@@ -293,6 +295,7 @@ static void Setup (void)
     if (s && !strcmp (s, "shadow")) hMode = MODE_SHADOW;
     if (s && !strcmp (s, "gpu"))    hMode = MODE_GPU;
     if ((s = getenv ("MB200_TOL")) != NULL)      hTol = atof (s);
+    if ((s = getenv ("MB200_MULTIPART")) != NULL) hMultiPart = atoi (s);
     if ((s = getenv ("MB200_DUMP_MAX")) != NULL) hDumpMax = atol (s);
     memset (&hLast, 0, sizeof(hLast));
     if (hMode == MODE_DUMP)
@@ -372,6 +375,41 @@ static long long CountDirty (Tree *t)
         if (t->intDownPass[i]->upDateCl == YES)
             n++;
     return n;
+}
+
+/* LogLike (src/mcmc.c:7396): in gpu mode the division loop is the seam's partition-batched one */
+static void CpuPathTimed (int chain, int d, MrBFlt *lnL)
+{
+    hUnsupported++;
+    __real_LaunchLogLikeForDivision (chain, d, lnL);
+}
+
+MrBFlt __wrap_LogLike (int chain)
+{
+    int     d;
+    double  t0;
+    MrBFlt  v;
+
+    if (hMode < 0)
+        Setup ();
+    if (hMode != MODE_GPU || hMultiPart == 0 || chainParams.runWithData == NO)
+        return __real_LogLike (chain);
+    for (d=0; d<numCurrentDivisions; d++)
+        {
+        ModelInfo *m = &modelSettings[d];
+        if (m->upDateCl == YES)
+            {
+            long long dirty = CountDirty (GetTree (m->brlens, chain, state[chain]));
+            hCalls++;
+            hNodeUpdates += dirty;
+            hUpdates += dirty * m->numChars * m->numRateCats;
+            }
+        }
+    t0 = Now ();
+    v = MB200LogLike (chain, CpuPathTimed);
+    hSecGpu += Now () - t0;
+    if (abortMove == YES) hAborts++;
+    return v;
 }
 
 void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
