@@ -23,7 +23,7 @@
 #define MB200_DEV_MAX_STATES 64
 
 struct DevChunk                     // a run of nodes whose branches fit the shared-memory P(t) slots
-                                    // (4-state path: nMat = branches | tip operands << 16)
+                                    // (4-state path: nMat = branches | tip operands << 16 | early-fetched operands << 24)
 {
     int opOff, nOp;                 // nodes    [opOff, opOff+nOp)   of the batch's operation array
     int matOff, nMat;               // branches [matOff, matOff+nMat) of the batch's chunk-matrix array
@@ -71,7 +71,10 @@ struct DevOp                        // one interior-node update (48 bytes)
 #define NUC_LOAD     1u             // interior child, read from the partials buffer
 #define NUC_TIP      2u             // tip child: 1-byte state mask
 #define NUC_TIP_ONE  6u             // tip child under the scalar kernels' shortcut: a missing observation contributes exactly 1
+#define NUC_PRE      4u             // interior child this evaluation does not write, latency path: fetched into shared
+                                    // memory when the chunk starts (slot in NucOp::pad), off the node chain
 #define NUC_FWD      8u             // the previous node's result: stays in registers
+#define NUC_MAXPRE   8              // such operands per chunk
 #define NUC_RESCALE  0x1000u
 struct NucOp
 {
@@ -83,7 +86,7 @@ struct NucOp
     unsigned sp1, sp2, sp3;         // byte offset of the branch's P(t) slot in shared memory
     int sw, sr;                     // node scaler to write / to remove (-1: none)
     int dest;
-    int pad;
+    int pad;                        // bits 4j..4j+3: shared-memory slot of operand j when its kind is NUC_PRE
 };
 // tip operands of a chunk get a 16-entry lookup table each (state mask -> P(t) column sum, per rate
 // category): tables per chunk, as a function of K (24 KB of shared memory)

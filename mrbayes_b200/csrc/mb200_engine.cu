@@ -419,6 +419,7 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
             const unsigned slotBytes = (unsigned) K * 80u;                              // sP[slot][K][5] float4
             const bool shortcuts = (ev.flags & MB200_FLAG_TIP_SHORTCUTS) != 0;
             int prevDest = -2;
+            int chunkIdx = chunkPos - nChunkOf[e], opsLeft = (nChunkOf[e] > 0) ? chunks[chunkIdx].nOp : 0, nPre = 0;
             std::vector<int> &written = I->writtenTmp;      // [buffer] == stamp: produced earlier in this evaluation
             if ((int) written.size () < c.partials_count) written.assign (c.partials_count, 0);
             const int stamp = ++I->writtenStamp;
@@ -448,13 +449,36 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
                 o.sp2 = (unsigned) slots[slotPos + 1] * slotBytes;
                 o.sp3 = (slots[slotPos + 2] >= 0) ? (unsigned) slots[slotPos + 2] * slotBytes : 0u;
                 o.sw = op.scale_write; o.sr = op.scale_remove; o.dest = op.dest;
-                // operands read from buffers this evaluation does not write: worth prefetching (latency path)
-                o.pad = ((k1 == NUC_LOAD && !isWritten (op.child1)) ? 1 : 0) | ((k2 == NUC_LOAD && !isWritten (op.child2)) ? 2 : 0) |
-                        ((k3 == NUC_LOAD && !isWritten (op.child3)) ? 4 : 0);
+                // latency path: interior operands read from buffers this evaluation does not write are
+                // fetched into shared memory when the chunk starts, off the node-to-node chain
+                while (opsLeft == 0 && chunkIdx + 1 < chunkPos)
+                    {
+                    (chunkIdx == chunkPos - nChunkOf[e] ? d.chunk0.nMat : dc[d.chunkOff + chunkIdx - (chunkPos - nChunkOf[e]) - 1].nMat) |= nPre << 24;
+                    chunkIdx++; opsLeft = chunks[chunkIdx].nOp; nPre = 0;
+                    }
+                o.pad = 0;
+                if (fused)
+                    {
+                    unsigned kj[3] = { k1, k2, k3 };
+                    const int cj[3] = { op.child1, op.child2, op.child3 };
+                    for (int j = 0; j < 3; j++)
+                        if (kj[j] == NUC_LOAD && !isWritten (cj[j]) && nPre < NUC_MAXPRE)
+                            {
+                            kj[j] = NUC_PRE;
+                            o.pad |= nPre << (4 * j);
+                            nPre++;
+                            }
+                    o.kinds = (o.kinds & ~0xfffu) | kj[0] | (kj[1] << 4) | (kj[2] << 8);
+                    }
+                opsLeft--;
                 slotPos += 3;
                 prevDest = op.dest;
                 written[op.dest] = stamp;
                 }
+            if (nChunkOf[e] > 0)
+                (chunkIdx == chunkPos - nChunkOf[e] ? d.chunk0.nMat : dc[d.chunkOff + chunkIdx - (chunkPos - nChunkOf[e]) - 1].nMat) |= nPre << 24;
+            if (e < MB200_JOB_INDEX_MAX && b.jx.n > 0)
+                b.jx.e[e].nMat = d.chunk0.nMat;
             d.rootFwd = (ev.root_buffer != MB200_NONE && ev.root_buffer == prevDest) ? 1 : 0;
             d.rootOff = (ev.root_buffer != MB200_NONE) ? (unsigned)(ev.root_buffer - c.tip_count) * bufStride : 0u;
             }

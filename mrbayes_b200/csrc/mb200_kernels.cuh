@@ -445,6 +445,8 @@ template <int K, int NT, bool FUSE> struct Nuc4Smem
     float  sNew[OPC][PPB];                       // per node: scaler maximum, later its logarithm
     float  sOld[OPC][PPB];                       // per node: the old node scaler to remove
     unsigned char sMask[MAXT][PPB];              // the chunk's tip state masks, this CTA's patterns
+    unsigned sPreList[NUC_MAXPRE];               // latency path: buffer offsets of the operands fetched at chunk start
+    float4 sPre[FUSE ? NUC_MAXPRE : 1][NT];      // ... and their vectors, one per thread (thread-private: no barrier needed)
 };
 
 template <int K, int NT, bool FUSE>
@@ -459,7 +461,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
     Nuc4Smem<K, NT, FUSE> &sm = *reinterpret_cast<Nuc4Smem<K, NT, FUSE> *>(nuc_smem);
     auto &sP = sm.sP;   auto &sExp = sm.sExp; auto &sTab = sm.sTab; auto &sMat = sm.sMat; auto &sOps = sm.sOps;
     auto &sNew = sm.sNew; auto &sOld = sm.sOld; auto &sEv = sm.sEv; auto &sCh = sm.sCh; auto &sD = sm.sD;
-    auto &sEig = sm.sEig; auto &sTipInfo = sm.sTipInfo; auto &sMask = sm.sMask;
+    auto &sEig = sm.sEig; auto &sTipInfo = sm.sTipInfo; auto &sMask = sm.sMask; auto &sPreList = sm.sPreList; auto &sPre = sm.sPre;
 
     MB200_STAMP (0);
     // ---- 0. staging of the evaluation and of its first chunk.  With a job index (small launches) all
@@ -530,6 +532,8 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                     sTipInfo[(kinds >> (13 + 6*j)) & 63u] =
                         make_uint2 (((j == 0) ? o.a1 : (j == 1) ? o.a2 : o.a3) | ((kind == NUC_TIP_ONE) ? 0x80000000u : 0u),
                                     (j == 0) ? o.sp1 : (j == 1) ? o.sp2 : o.sp3);
+                if (FUSE && kind == NUC_PRE)
+                    sPreList[((unsigned) o.pad >> (4*j)) & 15u] = (j == 0) ? o.a1 : (j == 1) ? o.a2 : o.a3;
                 }
             }
         };
@@ -577,7 +581,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             __syncthreads ();
             }
         const DevChunk ch = (ci == 0) ? ch0 : sCh;
-        const int nMatC = ch.nMat & 0xffff, nTipC = ch.nMat >> 16;
+        const int nMatC = ch.nMat & 0xffff, nTipC = (ch.nMat >> 16) & 0xff, nPreC = FUSE ? (int)((unsigned) ch.nMat >> 24) : 0;
         if (ci == 0) MB200_STAMP (2);
 
         // ---- 2. P(t) slots (K1 fused: TiProbs_Gen, src/likelihood.c:9499-9542); the chunk's tip masks
@@ -594,6 +598,15 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 const int cp = c0 + (e % PPB);
                 mk[u] = ctx.tip8[(sTipInfo[e / PPB].x & 0x7fffffffu) + (unsigned)((cp < C) ? cp : C - 1)];
                 }
+            }
+        // latency path: interior operands from buffers this evaluation does not write, requested now
+        float4 pre[NUC_MAXPRE];
+        if (FUSE)
+            {
+            #pragma unroll
+            for (int u = 0; u < NUC_MAXPRE; u++)
+                if (u < nPreC)
+                    pre[u] = partials4[tOff + sPreList[u]];
             }
         for (int r = threadIdx.x; r < nMatC * K * 4; r += NT)
             {
@@ -613,6 +626,13 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             const int e = threadIdx.x + u * NT;
             if (e < nTipC * PPB)
                 sMask[e / PPB][e % PPB] = mk[u];
+            }
+        if (FUSE)
+            {
+            #pragma unroll
+            for (int u = 0; u < NUC_MAXPRE; u++)
+                if (u < nPreC)
+                    sPre[u][threadIdx.x] = pre[u];     // thread-private slot: read back by this thread only
             }
         for (int e = threadIdx.x + MKD * NT; e < nTipC * PPB; e += NT)      // more than eight per thread: K < 4 only
             {
@@ -707,11 +727,14 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
         float4   xa[3], xb[3];
         // operand j of a node, fetched one node ahead: interior child -> its conditional likelihoods
         // (one 16-byte load); tip child -> its contribution, looked up by state mask
-        auto fetch = [&] (unsigned kinds, int j, unsigned a, float4 &x)
+        const unsigned sPreT = (unsigned) __cvta_generic_to_shared (&sPre[0][FUSE ? threadIdx.x : 0]);
+        auto fetch = [&] (unsigned kinds, int j, unsigned a, float4 &x, unsigned pad)
             {
             const unsigned kind = (kinds >> (4*j)) & 15u;
             if (kind == NUC_LOAD)
                 x = partials4[tOff + a];
+            else if (FUSE && kind == NUC_PRE)
+                x = lds128 (sPreT + ((pad >> (4*j)) & 15u) * (NT * 16));
             else if (kind & NUC_TIP)
                 {
                 const unsigned t = (kinds >> (13 + 6*j)) & 63u;
@@ -736,10 +759,11 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 {
                 const uint4 na = reinterpret_cast<const uint4 *>(nops + oo + 1)[0];
                 nk = na.w;
-                fetch (nk, 0, na.x, xo[0]);
-                fetch (nk, 1, na.y, xo[1]);
+                const unsigned npad = FUSE ? (unsigned) nops[oo + 1].pad : 0u;
+                fetch (nk, 0, na.x, xo[0], npad);
+                fetch (nk, 1, na.y, xo[1], npad);
                 if (nk & 0xf00u)
-                    fetch (nk, 2, na.z, xo[2]);
+                    fetch (nk, 2, na.z, xo[2], npad);
                 }
             float4 res = operand (kinds, 0, ob.y, xi[0]);
             float4 v   = operand (kinds, 1, ob.z, xi[1]);
@@ -775,10 +799,11 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
         if (nOp > 0)
             {
             const uint4 na = reinterpret_cast<const uint4 *>(nops)[0];
-            fetch (na.w, 0, na.x, xa[0]);
-            fetch (na.w, 1, na.y, xa[1]);
+            const unsigned npad = FUSE ? (unsigned) nops[0].pad : 0u;
+            fetch (na.w, 0, na.x, xa[0], npad);
+            fetch (na.w, 1, na.y, xa[1], npad);
             if (na.w & 0xf00u)
-                fetch (na.w, 2, na.z, xa[2]);
+                fetch (na.w, 2, na.z, xa[2], npad);
             if (na.w & NUC_FWD)        xa[0] = cur;       // result of the previous chunk's last node
             if (na.w & (NUC_FWD << 4)) xa[1] = cur;
             if (na.w & (NUC_FWD << 8)) xa[2] = cur;
