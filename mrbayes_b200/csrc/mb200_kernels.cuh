@@ -348,6 +348,14 @@ __device__ __forceinline__ void scale4 (float4 &r, float m)
         q = r.z * rc; rem = fmaf (-m, q, r.z); r.z = fmaf (rem, rc, q);
         q = r.w * rc; rem = fmaf (-m, q, r.w); r.w = fmaf (rem, rc, q);
         }
+    else if (m == 0.0f)
+        {
+        // every state of every category is zero (a dead pattern): the reference's 0/0.  No reason to
+        // spend four slow-path divisions on it
+        const float q = __int_as_float (0x7fc00000);
+        r.x = (r.x == 0.0f) ? q : r.x / m; r.y = (r.y == 0.0f) ? q : r.y / m;
+        r.z = (r.z == 0.0f) ? q : r.z / m; r.w = (r.w == 0.0f) ? q : r.w / m;
+        }
     else
         { r.x /= m; r.y /= m; r.z /= m; r.w /= m; }
 }
