@@ -302,6 +302,22 @@ class Instance:
         self._call("evaluate", arr, n, _ptr(lnl, C.c_double), _ptr(st, C.c_int))
         return lnl, st
 
+    def evaluate_begin(self, specs):
+        """First half of evaluate(): validate, pack, launch; returns at once (one in flight per instance)."""
+        if isinstance(specs, EvalSpec):
+            specs = [specs]
+        self._pending = make_eval_array(specs)          # keep the host structs alive until end()
+        self._pending_n = len(specs)
+        self._call("evaluate_begin", self._pending, self._pending_n)
+
+    def evaluate_end(self):
+        n = self._pending_n
+        lnl = np.zeros(n, np.float64)
+        st = np.zeros(n, np.int32)
+        self._call("evaluate_end", _ptr(lnl, C.c_double), _ptr(st, C.c_int))
+        self._pending = None
+        return lnl, st
+
     def pack(self, specs) -> int:
         arr = make_eval_array(specs)
         b = C.c_int(-1)

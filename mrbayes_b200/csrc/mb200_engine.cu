@@ -671,8 +671,14 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
         ctx.tilePatterns = 128;
         ctx.numTiles = (ctx.C + 127) / 128;
         dim3 grid (ctx.numTiles, b.nEval);
-        if (I->tcS == 61) eval_tc_kernel<61><<<grid, 128, I->smemTc, I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
-        else              eval_tc_kernel<20><<<grid, 128, I->smemTc, I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
+        // 61 states: two children in flight per CTA when the grid is at most one CTA per SM anyway
+        static const bool oneSlot = getenv ("MB200_TC_ONE_SLOT") != nullptr;      // A/B switch for measurements
+        if (I->tcS == 61 && !oneSlot && (long) grid.x * grid.y <= (long) I->numSMs)
+            eval_tc_kernel<61, 2><<<grid, 128, tc_smem_bytes<61, 2> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
+        else if (I->tcS == 61)
+            eval_tc_kernel<61, 1><<<grid, 128, tc_smem_bytes<61, 1> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
+        else
+            eval_tc_kernel<20, 1><<<grid, 128, tc_smem_bytes<20, 1> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
         }
     else
         {
@@ -935,11 +941,15 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
         const size_t fl = (I->tcS == 61) ? tc_split_floats<61> () : tc_split_floats<20> ();
         ALLOC (I->dSplit, (size_t)cfg->matrix_count * K * fl * sizeof(float));
         cudaMemsetAsync (I->dSplit, 0, (size_t)cfg->matrix_count * K * fl * sizeof(float), I->stream);
-        const int NPv = (I->tcS == 61) ? 64 : 32, KPv = (I->tcS == 61) ? 64 : 24, KMv = (I->tcS == 61) ? 1 : 4;
-        I->smemTc = (size_t)KMv * (2 * 128 * KPv + 2 * NPv * KPv) * sizeof(float);   // [k] A hi+lo images, [k] B images
-        cudaError_t ea = (I->tcS == 61)
-            ? cudaFuncSetAttribute (eval_tc_kernel<61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) I->smemTc)
-            : cudaFuncSetAttribute (eval_tc_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) I->smemTc);
+        cudaError_t ea;
+        if (I->tcS == 61)
+            {
+            ea = cudaFuncSetAttribute (eval_tc_kernel<61, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc_smem_bytes<61, 1> ());
+            if (ea == cudaSuccess)
+                ea = cudaFuncSetAttribute (eval_tc_kernel<61, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc_smem_bytes<61, 2> ());
+            }
+        else
+            ea = cudaFuncSetAttribute (eval_tc_kernel<20, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc_smem_bytes<20, 1> ());
         if (ea != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
         }
     ALLOC (I->dInvMask,  (size_t)C * sizeof(uint64_t));

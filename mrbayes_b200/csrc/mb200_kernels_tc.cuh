@@ -31,6 +31,15 @@ template <int S> struct TcGeom;
 template <> struct TcGeom<61> { static constexpr int NP = 64, KP = 64, KMAX = 1, SP = 64; };
 template <> struct TcGeom<20> { static constexpr int NP = 32, KP = 24, KMAX = 4, SP = 20; };
 
+// SLOTS: children whose operands are staged and whose MMAs are in flight at the same time.  Two slots
+// (one barrier round, one MMA wait and one read-out per node: 28 % less time per CTA, measured on
+// the 61-state tile) need twice the shared memory, i.e. one CTA per SM: the engine uses them for
+// small grids (at most one CTA per SM anyway) and one slot -- two co-resident CTAs -- for large ones.
+template <int S, int SLOTS> __host__ __device__ constexpr size_t tc_smem_bytes ()
+{
+    return (size_t) SLOTS * TcGeom<S>::KMAX * (2 * 128 * TcGeom<S>::KP + 2 * TcGeom<S>::NP * TcGeom<S>::KP) * sizeof(float);
+}
+
 // floats per pre-split matrix image: hi then lo, each NP x KP in canonical layout
 template <int S> __host__ __device__ constexpr int tc_split_floats () { return 2 * TcGeom<S>::NP * TcGeom<S>::KP; }
 
@@ -62,28 +71,29 @@ __global__ void tc_split_kernel (const float *__restrict__ matrices, float *__re
         }
 }
 
-// resident CTAs per SM: the 61-state tile needs 96 KB of shared memory and 128 TMEM columns, so two
-// fit and hide each other's load / MMA / read-out phases; the 20-state tile (4 categories) needs 123 KB
-template <int S>
-__global__ void __launch_bounds__(128, (S == 61) ? 2 : 1)
+template <int S, int SLOTS>
+__global__ void __launch_bounds__(128, 1)
 eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
                 const DevOp *__restrict__ ops, const float *__restrict__ split, DevResult *out, int seq)
 {
     using namespace umma;
     constexpr int NP = TcGeom<S>::NP, KP = TcGeom<S>::KP, KMAX = TcGeom<S>::KMAX;
     constexpr int TM = 128;                                   // patterns per tile = MMA M
-    constexpr int TMEM_COLS = (2 * NP * KMAX <= 64) ? 64 : (2 * NP * KMAX <= 128) ? 128 : 256;
+    constexpr int ACC_COLS = 2 * NP * KMAX;                   // TMEM columns of one child's accumulators
+    constexpr int TMEM_COLS = (SLOTS * ACC_COLS <= 64) ? 64 : (SLOTS * ACC_COLS <= 128) ? 128 : (SLOTS * ACC_COLS <= 256) ? 256 : 512;
     constexpr uint32_t LBO_A = (TM / 8) * 128, LBO_B = (NP / 8) * 128, SBO = 128;
     constexpr int A_FLOATS = TM * KP;                         // one hi (or lo) image
     constexpr int B_FLOATS = 2 * NP * KP;                     // hi + lo image of one P(t)
     constexpr int NQ = (S + 3) / 4;                           // 16-byte chunks per stored row
     constexpr int SPC = TcGeom<S>::SP;                        // floats per global row (ctx.Sp)
+    constexpr int A_SLOT = KMAX * 2 * A_FLOATS;               // floats of one child's A images
+    constexpr int B_SLOT = KMAX * B_FLOATS;
 
-    // dynamic shared memory: [k][hi|lo] A images, then [k] B images; the A region doubles as the
-    // staging area of the node's result rows once its MMAs have completed
+    // dynamic shared memory: [slot][k][hi|lo] A images, then [slot][k] B images; the first A slot
+    // doubles as the staging area of the node's result rows once the MMAs have completed
     extern __shared__ __align__(128) unsigned char tc_smem[];
-    float *sA = reinterpret_cast<float *>(tc_smem);           // KMAX x 2 x A_FLOATS
-    float *sB = sA + KMAX * 2 * A_FLOATS;                     // KMAX x B_FLOATS
+    float *sA = reinterpret_cast<float *>(tc_smem);           // SLOTS x A_SLOT
+    float *sB = sA + SLOTS * A_SLOT;                          // SLOTS x B_SLOT
     float4 *sStage = reinterpret_cast<float4 *>(tc_smem);     // [k][q][TM+1] float4
     __shared__ uint64_t barB, barM;
     __shared__ uint32_t tmemBase;
@@ -95,13 +105,15 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
         reinterpret_cast<int *>(&sEv)[tid] = reinterpret_cast<const int *>(evals + blockIdx.y)[tid];
     if (warp == 0)
         tmem_alloc<TMEM_COLS> (&tmemBase);
-    const int nIssuers = (2 * K < 4) ? 2 * K : 4;              // warps whose leader lane issues MMAs
+    // warps whose leader lane issues MMAs (one slot: the 2K accumulators of a child; two slots: all four
+    // leaders arrive on the barrier, with or without work)
+    const int nIssuers = (SLOTS == 1) ? ((2 * K < 4) ? 2 * K : 4) : 4;
     if (tid == 0)
         { mbar_init (&barB, 1); mbar_init (&barM, nIssuers); mbar_fence_init (); }
     fence_before_sync ();
     __syncthreads ();
     fence_after_sync ();
-    const uint32_t tBase = tmemBase;                           // [k][main | corr] accumulators, NP columns each
+    const uint32_t tBase = tmemBase;                           // [slot][k][main | corr] accumulators, NP columns each
     const uint32_t laneSel = (uint32_t)(warp * 32) << 16;      // this warp's TMEM lane quadrant
     uint32_t parB = 0, parM = 0;
 
@@ -118,13 +130,116 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
     float site = (active && sEv.siteSrc >= 0) ? ctx.scalers[(size_t)sEv.siteSrc * C + c] : 0.0f;
 
     // operand descriptors never change: images live at fixed shared-memory addresses.  Only the
-    // start-address field (bits 0..13, 16-byte units) moves with the category and the K step.
-    const uint64_t dA0 = make_desc (smem_u32 (sA), LBO_A, SBO);      // hi image of category 0
+    // start-address field (bits 0..13, 16-byte units) moves with the slot, the category and the K step.
+    const uint64_t dA0 = make_desc (smem_u32 (sA), LBO_A, SBO);      // hi image of slot 0, category 0
     const uint64_t dB0 = make_desc (smem_u32 (sB), LBO_B, SBO);
-    constexpr uint64_t A_LO = (A_FLOATS * 4) >> 4, A_K = (2 * A_FLOATS * 4) >> 4, A_KS = (2 * LBO_A) >> 4;
-    constexpr uint64_t B_LO = (NP * KP * 4) >> 4, B_K = (B_FLOATS * 4) >> 4, B_KS = (2 * LBO_B) >> 4;
+    constexpr uint64_t A_LO = (A_FLOATS * 4) >> 4, A_K = (2 * A_FLOATS * 4) >> 4, A_KS = (2 * LBO_A) >> 4, A_SL = ((uint64_t) A_SLOT * 4) >> 4;
+    constexpr uint64_t B_LO = (NP * KP * 4) >> 4, B_K = (B_FLOATS * 4) >> 4, B_KS = (2 * LBO_B) >> 4, B_SL = ((uint64_t) B_SLOT * 4) >> 4;
 
-    int preloaded = -1;          // partials buffer whose hi/lo images already sit in sA (previous node's result)
+    int preloaded = -1;          // partials buffer whose hi/lo images already sit in A slot 0 (previous node's result)
+
+    // ---- helpers ----
+    // B: the K pre-split P(t) images of a branch, one bulk async copy (contiguous) into slot `sl`
+    auto stageB = [&] (int sl, int mat)
+        {
+        bulk_g2s (sB + sl * B_SLOT, split + (size_t)mat * K * B_FLOATS, (uint32_t)(K * B_FLOATS * 4), &barB);
+        };
+    // A: child tiles of all K categories -> hi / lo canonical images in slot `sl`; returns whether the
+    // scalar-kernel tip shortcut applies to this thread's pattern
+    auto stageA = [&] (int sl, int child, bool isTip) -> bool
+        {
+        float *slotA = sA + sl * A_SLOT;
+        if (isTip)
+            {
+            // thread t expands pattern t's state mask (identical for every category): 0/1 are exact
+            // in TF32, the lo image is not used
+            const uint64_t m = active ? ctx.tip64[(size_t)child * C + c] : 0;
+            #pragma unroll
+            for (int q = 0; q < KP / 4; q++)
+                {
+                float4 h;
+                h.x = ((m >> (q*4 + 0)) & 1) ? 1.f : 0.f; h.y = ((m >> (q*4 + 1)) & 1) ? 1.f : 0.f;
+                h.z = ((m >> (q*4 + 2)) & 1) ? 1.f : 0.f; h.w = ((m >> (q*4 + 3)) & 1) ? 1.f : 0.f;
+                *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(slotA) + canon_off (tid, q*4, TM)) = h;
+                }
+            return shortcutFlag && active && m == fullMask && !ctx.tipPartAmbig[child];
+            }
+        // HBM/L2 -> registers -> shared: a warp covers 8 rows x 4 chunks (64 contiguous bytes per
+        // row: full 32-byte sectors) and stores 8 x 16 B contiguous per quarter-warp (no conflicts).
+        // All loads of a category are issued before the first one is used (memory-level
+        // parallelism: one round trip per category instead of one per chunk).
+        constexpr int QB = (KP / 4 + 3) / 4;           // chunk blocks of 4
+        constexpr int NIT = (TM / 8) * QB / 4;         // items per warp and category
+        for (int k = 0; k < K; k++)
+            {
+            const float *src = ctx.partials + (size_t)(child - ctx.tipCount) * bufStride + ((size_t)k * C + c0) * Sp;
+            unsigned char *base = reinterpret_cast<unsigned char *>(slotA + (size_t)k * 2 * A_FLOATS);
+            float4 x[NIT];
+            #pragma unroll
+            for (int n = 0; n < NIT; n++)
+                {
+                const int it = warp + 4 * n;
+                const int rb = it / QB, qb = it % QB;
+                const int r = rb * 8 + (lane & 7), q = qb * 4 + (lane >> 3);
+                x[n] = make_float4 (0.f, 0.f, 0.f, 0.f);
+                if (q < KP / 4 && r < np && q * 4 < SPC)
+                    x[n] = __ldcg (reinterpret_cast<const float4 *>(src + (size_t)r * SPC + q * 4));
+                }
+            #pragma unroll
+            for (int n = 0; n < NIT; n++)
+                {
+                const int it = warp + 4 * n;
+                const int rb = it / QB, qb = it % QB;
+                const int r = rb * 8 + (lane & 7), q = qb * 4 + (lane >> 3);
+                if (q < KP / 4)
+                    {
+                    const float4 h = make_float4 (to_tf32 (x[n].x), to_tf32 (x[n].y), to_tf32 (x[n].z), to_tf32 (x[n].w));
+                    const float4 l = make_float4 (to_tf32 (x[n].x - h.x), to_tf32 (x[n].y - h.y), to_tf32 (x[n].z - h.z), to_tf32 (x[n].w - h.w));
+                    *reinterpret_cast<float4 *>(base + canon_off (r, q*4, TM)) = h;
+                    *reinterpret_cast<float4 *>(base + A_FLOATS * 4 + canon_off (r, q*4, TM)) = l;
+                    }
+                }
+            }
+        return false;
+        };
+    // MMA for the children staged in slots [0, nSl): main[k] = Ahi*Bhi ; corr[k] = Ahi*Blo (+ Alo*Bhi).
+    // Issue is the bottleneck of these small MMAs (~35 ns each from one thread), so the independent
+    // accumulators are spread over the four warps' leader lanes; every leader arrives on barM
+    auto issueMMA = [&] (int nSl, unsigned tipBits)
+        {
+        if (lane != 0 || warp >= nIssuers)
+            return;
+        bool any = false;
+        for (int item = warp; item < nSl * 2 * K; item += 4)
+            {
+            const int sl = (SLOTS == 1) ? 0 : item / (2 * K), k = (SLOTS == 1) ? (item >> 1) : (item >> 1) % K, corr = item & 1;
+            const bool isTip = (tipBits >> sl) & 1u;
+            const uint64_t aHi = dA0 + (uint64_t) sl * A_SL + (isTip ? 0 : (uint64_t)k * A_K), aLo = aHi + A_LO;
+            const uint64_t bHi = dB0 + (uint64_t) sl * B_SL + (uint64_t)k * B_K, bLo = bHi + B_LO;
+            const uint32_t tAcc = tBase + sl * ACC_COLS + k * 2 * NP + corr * NP;
+            if (!corr)
+                {
+                #pragma unroll
+                for (int ks = 0; ks < KP / 8; ks++)
+                    mma_tf32 (tAcc, aHi + ks * A_KS, bHi + ks * B_KS, idesc, ks > 0);
+                }
+            else
+                {
+                #pragma unroll
+                for (int ks = 0; ks < KP / 8; ks++)
+                    mma_tf32 (tAcc, aHi + ks * A_KS, bLo + ks * B_KS, idesc, ks > 0);
+                if (!isTip)
+                    {
+                    #pragma unroll
+                    for (int ks = 0; ks < KP / 8; ks++)
+                        mma_tf32 (tAcc, aLo + ks * A_KS, bHi + ks * B_KS, idesc, true);
+                    }
+                }
+            any = true;
+            }
+        if (any) mma_commit (&barM);
+        else     mbar_arrive (&barM);
+        };
 
     for (int o = 0; o < sEv.nOp; o++)
         {
@@ -132,133 +247,9 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
         const int nChild = (op.c3 >= 0) ? 3 : 2;
         float res[KMAX][S];                                    // this pattern's node result, all categories
 
-        // the child that is the previous node's result goes first: its images are already in place
-        int first = 0;
-        if (preloaded >= 0)
-            first = (op.c1 == preloaded) ? 0 : (op.c2 == preloaded) ? 1 : (op.c3 == preloaded) ? 2 : 0;
-        for (int cc = 0; cc < nChild; cc++)
+        // my row of D for the child in slot `sl` (all categories), times what the other children gave
+        auto readAcc = [&] (int sl, bool tipFull, bool firstChild)
             {
-            const int ch = (cc == 0) ? first : (cc <= first) ? cc - 1 : cc;
-            const int child = (ch == 0) ? op.c1 : (ch == 1) ? op.c2 : op.c3;
-            const int mat   = (ch == 0) ? op.m1 : (ch == 1) ? op.m2 : op.m3;
-            const bool isTip = child < ctx.tipCount;
-            const bool inPlace = (cc == 0 && child == preloaded);
-#ifdef MB200_PHASE_TIMING
-#define TC_STAMP(SLOT_) do { if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 8 + ch*8 + (SLOT_)] = mb200_now (); } while (0)
-#else
-#define TC_STAMP(SLOT_) do { } while (0)
-#endif
-            TC_STAMP (0);
-            // ---- B: the K pre-split P(t) images of this branch, one bulk async copy (contiguous) ----
-            if (tid == 0)
-                {
-                mbar_expect_tx (&barB, (uint32_t)(K * B_FLOATS * 4));
-                bulk_g2s (sB, split + (size_t)mat * K * B_FLOATS, (uint32_t)(K * B_FLOATS * 4), &barB);
-                }
-
-            // ---- A: child tiles of all K categories -> hi / lo canonical images ----
-            bool tipFull = false;                              // scalar-kernel shortcut applies to my pattern
-            if (isTip)
-                {
-                // thread t expands pattern t's state mask (identical for every category): 0/1 are exact
-                // in TF32, the lo image is not used
-                const uint64_t m = active ? ctx.tip64[(size_t)child * C + c] : 0;
-                tipFull = shortcutFlag && active && m == fullMask && !ctx.tipPartAmbig[child];
-                #pragma unroll
-                for (int q = 0; q < KP / 4; q++)
-                    {
-                    float4 h;
-                    h.x = ((m >> (q*4 + 0)) & 1) ? 1.f : 0.f; h.y = ((m >> (q*4 + 1)) & 1) ? 1.f : 0.f;
-                    h.z = ((m >> (q*4 + 2)) & 1) ? 1.f : 0.f; h.w = ((m >> (q*4 + 3)) & 1) ? 1.f : 0.f;
-                    *reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(sA) + canon_off (tid, q*4, TM)) = h;
-                    }
-                }
-            else if (!inPlace)
-                {
-                // HBM/L2 -> registers -> shared: a warp covers 8 rows x 4 chunks (64 contiguous bytes per
-                // row: full 32-byte sectors) and stores 8 x 16 B contiguous per quarter-warp (no conflicts).
-                // All loads of a category are issued before the first one is used (memory-level
-                // parallelism: one round trip per category instead of one per chunk).
-                constexpr int QB = (KP / 4 + 3) / 4;           // chunk blocks of 4
-                constexpr int NIT = (TM / 8) * QB / 4;         // items per warp and category
-                for (int k = 0; k < K; k++)
-                    {
-                    const float *src = ctx.partials + (size_t)(child - ctx.tipCount) * bufStride + ((size_t)k * C + c0) * Sp;
-                    unsigned char *base = reinterpret_cast<unsigned char *>(sA + (size_t)k * 2 * A_FLOATS);
-                    float4 x[NIT];
-                    #pragma unroll
-                    for (int n = 0; n < NIT; n++)
-                        {
-                        const int it = warp + 4 * n;
-                        const int rb = it / QB, qb = it % QB;
-                        const int r = rb * 8 + (lane & 7), q = qb * 4 + (lane >> 3);
-                        x[n] = make_float4 (0.f, 0.f, 0.f, 0.f);
-                        if (q < KP / 4 && r < np && q * 4 < SPC)
-                            x[n] = __ldcg (reinterpret_cast<const float4 *>(src + (size_t)r * SPC + q * 4));
-                        }
-                    #pragma unroll
-                    for (int n = 0; n < NIT; n++)
-                        {
-                        const int it = warp + 4 * n;
-                        const int rb = it / QB, qb = it % QB;
-                        const int r = rb * 8 + (lane & 7), q = qb * 4 + (lane >> 3);
-                        if (q < KP / 4)
-                            {
-                            const float4 h = make_float4 (to_tf32 (x[n].x), to_tf32 (x[n].y), to_tf32 (x[n].z), to_tf32 (x[n].w));
-                            const float4 l = make_float4 (to_tf32 (x[n].x - h.x), to_tf32 (x[n].y - h.y), to_tf32 (x[n].z - h.z), to_tf32 (x[n].w - h.w));
-                            *reinterpret_cast<float4 *>(base + canon_off (r, q*4, TM)) = h;
-                            *reinterpret_cast<float4 *>(base + A_FLOATS * 4 + canon_off (r, q*4, TM)) = l;
-                            }
-                        }
-                    }
-                }
-            TC_STAMP (1);
-            fence_async_smem ();                               // generic-proxy stores -> async proxy (MMA)
-            mbar_wait (&barB, parB); parB ^= 1;                // B images landed
-            TC_STAMP (2);
-            fence_before_sync ();
-            __syncthreads ();
-            fence_after_sync ();
-
-            // ---- MMA, all categories: main[k] = Ahi*Bhi ; corr[k] = Ahi*Blo (+ Alo*Bhi) ----
-            // issue is the bottleneck of these small MMAs (~35 ns each from one thread), so the
-            // 2K independent accumulators are spread over the four warps' leader lanes; each issuer
-            // commits to the same mbarrier (initialised with the number of issuers)
-            if (lane == 0 && warp < nIssuers)
-                {
-                for (int item = warp; item < 2 * K; item += 4)
-                    {
-                    const int k = item >> 1, corr = item & 1;
-                    const uint64_t aHi = dA0 + (isTip ? 0 : (uint64_t)k * A_K), aLo = aHi + A_LO;
-                    const uint64_t bHi = dB0 + (uint64_t)k * B_K, bLo = bHi + B_LO;
-                    const uint32_t tAcc = tBase + k * 2 * NP + corr * NP;
-                    if (!corr)
-                        {
-                        #pragma unroll
-                        for (int ks = 0; ks < KP / 8; ks++)
-                            mma_tf32 (tAcc, aHi + ks * A_KS, bHi + ks * B_KS, idesc, ks > 0);
-                        }
-                    else
-                        {
-                        #pragma unroll
-                        for (int ks = 0; ks < KP / 8; ks++)
-                            mma_tf32 (tAcc, aHi + ks * A_KS, bLo + ks * B_KS, idesc, ks > 0);
-                        if (!isTip)
-                            {
-                            #pragma unroll
-                            for (int ks = 0; ks < KP / 8; ks++)
-                                mma_tf32 (tAcc, aLo + ks * A_KS, bHi + ks * B_KS, idesc, true);
-                            }
-                        }
-                    }
-                mma_commit (&barM);
-                }
-            TC_STAMP (3);
-            mbar_wait (&barM, parM); parM ^= 1;
-            fence_after_sync ();
-            TC_STAMP (4);
-
-            // ---- epilogue part 1: my row of D (all categories), times what the other children gave ----
             #pragma unroll
             for (int k = 0; k < KMAX; k++)
                 {
@@ -267,8 +258,8 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
                 for (int cb = 0; cb < NP; cb += 32)
                     {
                     uint32_t vm[32], vc[32];
-                    tmem_ld32_nowait (tBase + k * 2 * NP + laneSel + cb, vm);
-                    tmem_ld32_nowait (tBase + k * 2 * NP + NP + laneSel + cb, vc);
+                    tmem_ld32_nowait (tBase + sl * ACC_COLS + k * 2 * NP + laneSel + cb, vm);
+                    tmem_ld32_nowait (tBase + sl * ACC_COLS + k * 2 * NP + NP + laneSel + cb, vc);
                     tmem_ld_wait ();
                     #pragma unroll
                     for (int i = 0; i < 32; i++)
@@ -276,19 +267,55 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
                             {
                             float v = __uint_as_float (vm[i]) + __uint_as_float (vc[i]);
                             if (tipFull) v = 1.0f;             // preLike shortcut (src/likelihood.c:257-258)
-                            res[k][cb + i] = (cc == 0) ? v : res[k][cb + i] * v;
+                            res[k][cb + i] = firstChild ? v : res[k][cb + i] * v;
                             }
                     }
                 }
-            TC_STAMP (5);
-            fence_before_sync ();                              // TMEM reads ordered before the next MMA
-            __syncthreads ();                                  // shared operands free for the next child
+            };
+
+        // the child that is the previous node's result goes first: its images are already in slot 0
+        int first = 0;
+        if (preloaded >= 0)
+            first = (op.c1 == preloaded) ? 0 : (op.c2 == preloaded) ? 1 : (op.c3 == preloaded) ? 2 : 0;
+        for (int cc = 0; cc < nChild; cc += SLOTS)
+            {
+            const int nSl = (nChild - cc < SLOTS) ? nChild - cc : SLOTS;
+            bool     tipFull[SLOTS];
+            unsigned tipBits = 0;
+            if (tid == 0)
+                mbar_expect_tx (&barB, (uint32_t)(nSl * K * B_FLOATS * 4));
+            #pragma unroll
+            for (int sl = 0; sl < SLOTS; sl++)
+                {
+                tipFull[sl] = false;
+                if (sl >= nSl) continue;
+                const int ci = cc + sl;
+                const int ch = (ci == 0) ? first : (ci <= first) ? ci - 1 : ci;
+                const int child = (ch == 0) ? op.c1 : (ch == 1) ? op.c2 : op.c3;
+                const int mat   = (ch == 0) ? op.m1 : (ch == 1) ? op.m2 : op.m3;
+                const bool isTip = child < ctx.tipCount;
+                if (tid == 0)
+                    stageB (sl, mat);
+                if (isTip) tipBits |= 1u << sl;
+                if (!(ci == 0 && child == preloaded))          // else: images already in place (slot 0)
+                    tipFull[sl] = stageA (sl, child, isTip);
+                }
+            fence_async_smem ();                               // generic-proxy stores -> async proxy (MMA)
+            mbar_wait (&barB, parB); parB ^= 1;                // B images landed
+            fence_before_sync ();
+            __syncthreads ();
             fence_after_sync ();
-            TC_STAMP (6);
+            issueMMA (nSl, tipBits);
+            mbar_wait (&barM, parM); parM ^= 1;
+            fence_after_sync ();
+            #pragma unroll
+            for (int sl = 0; sl < SLOTS; sl++)
+                if (sl < nSl)
+                    readAcc (sl, tipFull[sl], cc + sl == 0);
+            fence_before_sync ();                              // TMEM reads ordered before the next MMA
+            __syncthreads ();                                  // shared operands free for the next children
+            fence_after_sync ();
             }
-#ifdef MB200_PHASE_TIMING
-        if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 40] = mb200_now ();
-#endif
 
         // ---- epilogue part 2: scaler bookkeeping and rescale (one thread = one pattern) ----
         if (active)
@@ -320,9 +347,6 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
                 site += sc;
                 }
             }
-#ifdef MB200_PHASE_TIMING
-        if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 44] = mb200_now ();
-#endif
         // ---- store: rows go through shared memory (chunk-major, conflict-free) so that the global
         //      writes are fully coalesced 16-byte-per-lane runs of the contiguous tile ----
         #pragma unroll
@@ -341,9 +365,6 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
                     }
                 }
         __syncthreads ();
-#ifdef MB200_PHASE_TIMING
-        if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 45] = mb200_now ();
-#endif
         {
         float *dstBase = ctx.partials + (size_t)(op.dest - ctx.tipCount) * bufStride;
         constexpr int nq = SPC / 4;                            // chunks per global row (pad chunks are zero)
@@ -360,10 +381,7 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
                 }
             }
         }
-#ifdef MB200_PHASE_TIMING
-        if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 46] = mb200_now ();
-#endif
-        __syncthreads ();                                      // staging area is the A region again
+        __syncthreads ();                                      // staging area is A slot 0 again
         // register forwarding: when the next node consumes this result, its hi/lo images are written
         // straight from registers (no store -> load round trip through L2 on dependent chains)
         preloaded = -1;
@@ -394,10 +412,6 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
                         }
                 }
             }
-#ifdef MB200_PHASE_TIMING
-        if (o == 5 && blockIdx.x == 0 && tid == 0) ctx.dbg[blockIdx.y*64 + 41] = mb200_now ();
-        if (blockIdx.x == 0 && tid == 0 && o < 2) ctx.dbg[blockIdx.y*64 + 42 + o] = mb200_now ();
-#endif
         }
 
     if (active && sEv.siteDst >= 0)

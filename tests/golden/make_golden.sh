@@ -24,5 +24,6 @@ run ovomucoids_wag_g4_sse mb_b200    100  80 ovomucoids_wag_g4
 run replicase_m0_sse      mb_b200    100  40 replicase_m0
 run primates_hky_g4_fma   mb_b200    100 200 primates_hky_g4
 run primates_f81_i_fma    mb_b200    100 150 primates_f81_i
+run cynmix_part_fma       mb_b200     40 160 cynmix_part
 rm -rf $TMP
 ls -la $OUT/*.gold.gz

@@ -143,6 +143,38 @@ def test_chain_batched_launch_equals_serial(engine_lib, S, K, C, tips):
             assert np.array_equal(la, lb)
 
 
+def test_partition_batched_begin_end_equals_evaluate(engine_lib):
+    """The divisions of a chain (separate instances) launched together with evaluate_begin and
+    collected with evaluate_end give exactly what one evaluate() per division gives
+    (LaunchBEAGLELogLikeMultiPartition semantics, reference src/likelihood.c:7792)."""
+    shapes = [(4, 4, 537, 32), (4, 4, 125, 32), (4, 4, 205, 32), (20, 4, 90, 10)]
+    probs_a = [workloads.make_problem(S, K, C, tips, 1, seed=40 + i) for i, (S, K, C, tips) in enumerate(shapes)]
+    probs_b = [workloads.make_problem(S, K, C, tips, 1, seed=40 + i) for i, (S, K, C, tips) in enumerate(shapes)]
+    insts_a = [p.create(engine_lib) for p in probs_a]
+    insts_b = [p.create(engine_lib) for p in probs_b]
+    try:
+        rng_a, rng_b = np.random.default_rng(3), np.random.default_rng(3)
+        for gen in range(4):
+            specs_a = [p.full_evaluation(0) if gen == 0 else p.random_branch_update(0, rng_a) for p in probs_a]
+            specs_b = [p.full_evaluation(0) if gen == 0 else p.random_branch_update(0, rng_b) for p in probs_b]
+            for inst, sp in zip(insts_a, specs_a):
+                inst.evaluate_begin(sp)                       # all divisions in flight
+            got = [inst.evaluate_end() for inst in insts_a]
+            want = [inst.evaluate(sp) for inst, sp in zip(insts_b, specs_b)]
+            for (lg, sg), (lw, sw) in zip(got, want):
+                assert np.array_equal(lg, lw) and np.array_equal(sg, sw)
+        # protocol errors: a second begin before end, an end without begin
+        insts_a[0].evaluate_begin(probs_a[0].full_evaluation(0))
+        with pytest.raises(abi.AbiError):
+            insts_a[0].evaluate_begin(probs_a[0].full_evaluation(0))
+        insts_a[0].evaluate_end()
+        with pytest.raises(abi.AbiError):
+            insts_a[0].evaluate_end()
+    finally:
+        for inst in insts_a + insts_b:
+            inst.close()
+
+
 def test_resident_replay_equals_host_call(engine_lib):
     pr = workloads.make_problem(4, 4, 413, 12, 8, seed=9)
     with pr.create(engine_lib) as inst:
