@@ -1,30 +1,39 @@
 #!/usr/bin/env python
 """bench.py -- site-pattern conditional-likelihood updates per second (BASELINE.json's metric).
 
-Workload (N=1): BASELINE.json configs[1] -- primates.nex, 4-state GTR+G4, all 8 MC^3 chains
-(nruns=2 x nchains=4) on ONE B200.  A *step* is one MCMC generation: one proposal per chain,
-all 8 chains' likelihood evaluations issued as ONE chain-batched engine call (P(t) rebuild for
-the dirty branches, pruning over the dirty nodes with the rescaler fused, root integration,
-8 lnL values back).  The site patterns, pattern weights and GTR eigensystem are the reference's
-own (taken from the evaluation records in tests/golden, i.e. MrBayes' compressed matrix of
-primates.nex: 413 patterns, 898 sites); proposals are synthetic but MCMC-shaped: a branch move
-dirties one P(t) and the path to the root, a parameter move (15 %) dirties the whole tree,
-30 % of proposals are accepted, rejects undo the index flips on the host.
+Workload (N=1): BASELINE.json configs[1] -- primates.nex, 4-state GTR+G4, nruns=2 x nchains=4 = 8 MC^3
+chains per analysis -- with R independent analyses ("replicas", --replicas, default 32) in flight on
+ONE B200, the way the reference arm keeps one such analysis running on every host core.  A *step* is
+one MCMC generation of every replica: one proposal per chain, the 8 chains of a replica evaluated in
+ONE chain-batched engine call = one fused kernel launch (P(t) rebuild for the dirty branches, pruning
+over the dirty nodes with the rescaler fused, root integration, lnL reduction), R launches per step
+on R streams.  The site patterns, pattern weights and GTR eigensystem are the reference's own (taken
+from the evaluation records in tests/golden, i.e. MrBayes' compressed matrix of primates.nex: 413
+patterns, 898 sites); proposals are synthetic but MCMC-shaped: a branch move dirties one P(t) and the
+path to the root, a parameter move (15 %) dirties the whole tree, 30 % of proposals are accepted,
+rejects undo the index flips on the host.  `single_replica` in the output repeats the measurement
+with one analysis alone on the GPU (the latency-bound regime of a single MrBayes run).
 
-Legs, all on the same pre-generated cycle of steps:
-  value   device-resident replay: job descriptors already in HBM, results left in HBM; per-step
-          CUDA events on the engine's stream; L2 flushed between steps (a 256 MB memset)
-  e2e     the reference-facing C-ABI call (mb200_evaluate) with HOST structs: pack + H2D of the
-          job + kernels + D2H of 8 x (lnL, status), wall clock bracketed by synchronisation
-  roofline  the fused pruning kernel alone, bracketed by events inside the engine
+Legs, all on the same pre-generated cycle of steps, timed regions driven by a C host application
+(mrbayes_b200/host/mb200_host_loop.c, a plain client of the C-ABI):
+  value   device-resident replay (mb200_replay): job descriptors already in HBM, results left in HBM;
+          per-step CUDA events on a control stream that fans out to / joins the replicas' streams;
+          L2 flushed between steps (a 256 MB memset)
+  e2e     the reference-facing C-ABI with HOST structs (mb200_evaluate_begin / _end per replica and
+          generation: pack, launch with the job in the parameter block, 16-byte result records
+          written by the kernel into pinned host memory); wall clock; a replica's generation g+1
+          starts only after its generation g has returned its lnL values to the host;
+          --host-threads host threads share the replicas
+  roofline  algorithmic bytes of a step / device time of the step (value leg); avg_kernel_us is one
+          launch alone, bracketed by events inside the engine
   cpu_baseline  the reference's own CPU kernels (oracle/_ref, FMA build) timed inside
           LaunchLogLikeForDivision on one host core, bounded sample
 
 --impl reference times the reference's CPU path with every host core busy (N independent
 serial `mb` processes; the reference has no threading and MPI is not installed).
-Under torchrun (N>1) every rank drives its own GPU with its own 2 runs x 4 chains (weak
-scaling: independent runs never exchange state); one NCCL all-reduce of the per-run lnL sums
-(the marginal-likelihood reduce of the reference's MPI build) closes the timed region.
+Under torchrun (N>1) every rank drives its own GPU with its own R replicas (weak scaling:
+independent runs never exchange state); one NCCL all-reduce of the per-run lnL sums (the
+marginal-likelihood reduce of the reference's MPI build) closes the timed region.
 """
 from __future__ import annotations
 
@@ -250,20 +259,6 @@ def cpu_baseline():
 
 
 # ------------------------------------------------------------------------------ engine arm
-def time_resident(torch, inst, stream, batches, order, flush_buf):
-    """Per-step CUDA events on the engine's stream, optional L2 flush before each step."""
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in order]
-    with torch.cuda.stream(stream):
-        for (a, b), i in zip(evs, order):
-            if flush_buf is not None:
-                flush_buf.zero_()
-            a.record(stream)
-            inst.replay(batches[i])
-            b.record(stream)
-    inst.synchronize()
-    return sum(a.elapsed_time(b) for a, b in evs)          # ms
-
-
 def other_workload(torch, lib, name, peaks, device):
     """Large synthetic configs (inputs >> L2): full-tree evaluations, resident, event-timed."""
     pr = synthetic_problem(name, 1, 2026)
@@ -318,25 +313,47 @@ def bench_engine(args):
         raise SystemExit("bench.py: no sm_100 device; the engine has no CPU fallback")
 
     n_chains = 8
-    pr = primates_problem(n_chains, seed=20260924 + rank)
-    inst = pr.create(lib, device=local, max_evaluations=n_chains)
-    stream = torch.cuda.ExternalStream(inst.stream(), device=local)
+    R = max(1, args.replicas)
+    probs = [primates_problem(n_chains, seed=20260924 + 1000 * rank + r) for r in range(R)]
+    insts = [p.create(lib, device=local, max_evaluations=n_chains) for p in probs]
+    pr, inst = probs[0], insts[0]
     cycle_len = 128
-    steps = make_cycle(pr, inst, cycle_len, seed=7 + rank)
+    steps_r = [make_cycle(p, i, cycle_len, seed=7 + 1000 * rank + r) for r, (p, i) in enumerate(zip(probs, insts))]
+    steps = steps_r[0]
     K, W = args.steps, args.warmup
     order = [i % cycle_len for i in range(K)]
-    upd_per_step = [updates_of(s, pr.C, pr.K) for s in steps]
-    nodes_per_eval = float(np.mean([len(sp.ops) for s in steps for sp in s]))
+    upd_per_step = [sum(updates_of(sr[i], pr.C, pr.K) for sr in steps_r) for i in range(cycle_len)]
+    nodes_per_eval = float(np.mean([len(sp.ops) for sr in steps_r for s in sr for sp in s]))
     total_updates = sum(upd_per_step[i] for i in order)
 
     # device-resident job descriptors + host-side ctypes arrays, all built before timing
-    batches = [inst.pack(s) for s in steps]
-    host_arrays = [abi.make_eval_array(s) for s in steps]
-    lnl = np.zeros(n_chains); st = np.zeros(n_chains, np.int32)
+    batches_r = [[i.pack(s) for s in sr] for i, sr in zip(insts, steps_r)]
+    host_arrays_r = [[abi.make_eval_array(s) for s in sr] for sr in steps_r]
+    lnl = np.zeros(n_chains * R); st = np.zeros(n_chains * R, np.int32)
     p_lnl, p_st = lnl.ctypes.data_as(C.POINTER(C.c_double)), st.ctypes.data_as(C.POINTER(C.c_int))
-    evaluate = lib.fn("evaluate")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
-    sync_all = (lambda: (inst.synchronize(), torch.cuda.synchronize()))
+    sync_all = (lambda: ([i.synchronize() for i in insts], torch.cuda.synchronize()))
+
+    # the timed loops run in C (mrbayes_b200/host/mb200_host_loop.c), a plain client of the C-ABI
+    hl = C.CDLL(str(abi.ENGINE_LIB.parent / "libmb200_hostloop.so"))
+    hl.mb200_host_generation_loop.restype = C.c_double
+    hl.mb200_host_replay_loop.restype = C.c_double
+    HT = max(1, min(args.host_threads, R))              # host threads of the end-to-end loop
+    inst_ids = (C.c_int * R)(*[i.handle for i in insts])
+    batch_ids = (C.c_int * (R * cycle_len))(*[b for br in batches_r for b in br])
+    step_ptrs = (C.c_void_p * (R * cycle_len))(*[C.cast(a, C.c_void_p) for hr in host_arrays_r for a in hr])
+
+    def c_order(seq):
+        return (C.c_int * len(seq))(*seq), len(seq)
+
+    def replay_loop(seq, flush_buf):
+        arr, n = c_order(seq)
+        ms = hl.mb200_host_replay_loop(inst_ids, C.c_int(R), batch_ids, C.c_int(cycle_len), arr, C.c_int(n),
+                                       C.c_void_p(flush_buf.data_ptr() if flush_buf is not None else None),
+                                       C.c_size_t(flush_buf.numel() if flush_buf is not None else 0))
+        if ms < 0:
+            raise RuntimeError(f"mb200_host_replay_loop failed with code {ms}")
+        return ms
 
     def barrier():
         if dist is not None:
@@ -349,16 +366,14 @@ def bench_engine(args):
 
     # ---- warm-up: whole cycles so the state is back at the cycle start ------------------
     warm = max(W, 3)
-    for i in range(((warm + cycle_len - 1) // cycle_len) * cycle_len):
-        inst.replay(batches[i % cycle_len])
-    inst.synchronize()
+    replay_loop([i % cycle_len for i in range(((warm + cycle_len - 1) // cycle_len) * cycle_len)], None)
 
     # ---- value: resident replay, L2 flushed between steps ------------------------------
-    launches0 = inst.launch_count()
+    launches0 = sum(i.launch_count() for i in insts)
     barrier()
     t_clock0 = time.perf_counter()
-    ms_value = time_resident(torch, inst, stream, batches, order, flush)
-    launches = inst.launch_count() - launches0
+    ms_value = replay_loop(order, flush)
+    launches = sum(i.launch_count() for i in insts) - launches0
     run_lnl = torch.zeros(2, dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:      # final marginal-likelihood style reduce (1 double per run)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -366,42 +381,60 @@ def bench_engine(args):
         ms_value += a.elapsed_time(b)
     barrier()
     finish_cycle = (cycle_len - K % cycle_len) % cycle_len
-    for i in range(finish_cycle):                       # untimed: return to the cycle start
-        inst.replay(batches[(K + i) % cycle_len])
-    inst.synchronize()
+    finish_seq = [(K + i) % cycle_len for i in range(finish_cycle)]
+    if finish_seq:
+        replay_loop(finish_seq, None)                   # untimed: return to the cycle start
 
     # ---- warm-L2 variant (no flush), informational -------------------------------------
-    ms_warm = time_resident(torch, inst, stream, batches, order, None)
-    for i in range(finish_cycle):
-        inst.replay(batches[(K + i) % cycle_len])
-    inst.synchronize()
+    ms_warm = replay_loop(order, None)
+    if finish_seq:
+        replay_loop(finish_seq, None)
 
-    # ---- roofline of the fused kernel: events inside the engine, same steps, flushed ----
+    # ---- single-replica latency figures: one 8-chain analysis alone on the GPU ----------
+    single = None
+    if R > 1:
+        one_ids = (C.c_int * 1)(insts[0].handle)
+        arr, n = c_order(order)
+        ms1 = hl.mb200_host_replay_loop(one_ids, C.c_int(1), batch_ids, C.c_int(cycle_len), arr, C.c_int(n),
+                                        C.c_void_p(flush.data_ptr()), C.c_size_t(flush.numel()))
+        if finish_seq:
+            arrf, nf = c_order(finish_seq)
+            hl.mb200_host_replay_loop(one_ids, C.c_int(1), batch_ids, C.c_int(cycle_len), arrf, C.c_int(nf), C.c_void_p(None), C.c_size_t(0))
+        sec1 = hl.mb200_host_generation_loop(one_ids, C.c_int(1), step_ptrs, C.c_int(cycle_len), C.c_int(n_chains), arr, C.c_int(n), p_lnl, p_st, C.c_int(HT))
+        if finish_seq:
+            hl.mb200_host_generation_loop(one_ids, C.c_int(1), step_ptrs, C.c_int(cycle_len), C.c_int(n_chains), arrf, C.c_int(nf), p_lnl, p_st, C.c_int(1))
+        upd1 = sum(updates_of(steps[i], pr.C, pr.K) for i in order)
+        single = {"replicas": 1, "value": upd1 / (ms1 * 1e-3), "ms_per_step": ms1 / K,
+                  "e2e": upd1 / sec1, "e2e_ms_per_step": sec1 * 1e3 / K, "unit": UNIT,
+                  "note": "one nruns=2 x nchains=4 analysis alone on the GPU: the latency-bound regime"}
+
+    # ---- roofline of the fused kernel: events inside the engine, replica 0 alone, flushed ----
     inst.set_kernel_timing(True)
+    stream = torch.cuda.ExternalStream(inst.stream(), device=local)
     kt_ms, kt_n, kt_updates = 0.0, 0, 0
     for chunk0 in range(0, min(K, 4096), 1024):
         sub = order[chunk0:chunk0 + 1024]
         with torch.cuda.stream(stream):
             for i in sub:
                 flush.zero_()
-                inst.replay(batches[i])
+                inst.replay(batches_r[0][i])
         ms, n = inst.kernel_time()
-        kt_ms += ms; kt_n += n; kt_updates += sum(upd_per_step[i] for i in sub)
+        kt_ms += ms; kt_n += n; kt_updates += sum(updates_of(steps[i], pr.C, pr.K) for i in sub)
     inst.set_kernel_timing(False)
     done = min(K, 4096)
     for i in range((cycle_len - done % cycle_len) % cycle_len):
-        inst.replay(batches[(done + i) % cycle_len])
+        inst.replay(batches_r[0][(done + i) % cycle_len])
     inst.synchronize()
 
     # ---- e2e: the C-ABI call with host structs ------------------------------------------
-    for i in range(cycle_len):                          # warm the host path, end at cycle start
-        evaluate(inst.handle, host_arrays[i], n_chains, p_lnl, p_st)
+    arr, n = c_order(list(range(cycle_len)))            # warm the host path, end at cycle start
+    hl.mb200_host_generation_loop(inst_ids, C.c_int(R), step_ptrs, C.c_int(cycle_len), C.c_int(n_chains), arr, C.c_int(n), p_lnl, p_st, C.c_int(HT))
     barrier()
-    t0 = time.perf_counter()
-    for i in order:
-        evaluate(inst.handle, host_arrays[i], n_chains, p_lnl, p_st)
+    arr, n = c_order(order)
+    sec_e2e = hl.mb200_host_generation_loop(inst_ids, C.c_int(R), step_ptrs, C.c_int(cycle_len), C.c_int(n_chains), arr, C.c_int(n), p_lnl, p_st, C.c_int(HT))
+    if sec_e2e < 0:
+        raise RuntimeError(f"mb200_host_generation_loop failed with code {int(sec_e2e)}")
     sync_all()
-    sec_e2e = time.perf_counter() - t0
     t_clock1 = time.perf_counter()
     barrier()
     if rank == 0:
@@ -418,45 +451,55 @@ def bench_engine(args):
     else:
         ms_e2e, all_updates, all_launches = sec_e2e * 1e3, float(total_updates), launches
 
-    h2d = float(np.mean([mb.bytes for mb in (pack_bytes(s) for s in steps)]))
+    h2d = float(np.mean([sum(pack_bytes(sr[i]).bytes for sr in steps_r) for i in range(cycle_len)]))
     nt_small = int(os.environ.get("MB200_NT_SMALL", "256"))
     tiles = -(-pr.C // (nt_small // 4))
-    d2h = n_chains * 16 * (tiles if tiles <= 16 else 1)   # 16-byte result records written into mapped host memory
+    d2h = R * n_chains * 16 * (tiles if tiles <= 16 else 1)   # 16-byte result records written into mapped host memory
     if rank == 0:
         clocks = sampler.summary(t_clock0, t_clock1)
         if clocks.get("samples", 0) < 3:
             clocks["note"] = "timed region shorter than the 100 ms sampling period; nearest samples used"
         k_avg_s = (kt_ms / max(kt_n, 1)) * 1e-3
-        k_updates = kt_updates / max(kt_n, 1)
-        ach = k_updates * BYTES_PER_UPDATE[4] / k_avg_s / 1e9 if kt_n else None
+        # dominant (only) kernel: the fused pruning kernel, R launches per step running concurrently;
+        # achieved = algorithmic bytes of a step / device time of the step (events, value leg)
+        ach = (all_updates / world) * BYTES_PER_UPDATE[4] / (ms_value * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": all_updates / (ms_value * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": warm, "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32",
             "data": "primates.nex site patterns/weights/GTR eigensystem from the reference's own run (tests/golden); synthetic MCMC-shaped proposals",
-            "config": {"workload": "primates.nex 4-state GTR+G4, nruns=2 x nchains=4 = 8 chains per GPU, one chain-batched launch per generation (BASELINE configs[1])",
-                       "patterns": pr.C, "rate_categories": pr.K, "states": pr.S, "taxa": pr.n_tips, "chains_per_gpu": n_chains,
+            "config": {"workload": f"primates.nex 4-state GTR+G4, nruns=2 x nchains=4 = 8 chains per analysis (BASELINE configs[1]), "
+                                   f"{R} independent analyses (replicas) in flight per GPU, one chain-batched launch per analysis and generation; "
+                                   f"the reference arm runs one such analysis per host core",
+                       "replicas_per_gpu": R,
+                       "patterns": pr.C, "rate_categories": pr.K, "states": pr.S, "taxa": pr.n_tips, "chains_per_gpu": n_chains * R,
                        "mean_dirty_nodes_per_evaluation": nodes_per_eval, "cycle_steps": cycle_len,
                        "l2": "flushed between timed steps (256 MB memset); warm-L2 figure in value_l2_warm",
                        "sharding": "independent runs per GPU, no data-path collective; one NCCL all-reduce of per-run lnL sums in the timed region (N>1)"},
             "value_l2_warm": all_updates / (ms_warm * 1e-3),
             "e2e": {"value": all_updates / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
-                    "api": "mb200_evaluate (C-ABI, host structs in, 8 x lnL out)"},
+                    "api": "mb200_evaluate_begin / _end per analysis and generation (C-ABI, host structs in, 8 x lnL out), "
+                           f"{HT} host thread(s), C generation loop (mrbayes_b200/host/mb200_host_loop.c); an analysis' results of generation g are on the host before its generation g+1 starts"},
             "gpu_launches": all_launches,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": (ach / peaks["hbm_gbs"]) if ach else None, "traffic": None,
-                         "kernel": f"eval_nuc4_kernel<K=4,NT={nt_small},FUSE=true> (device-resident replay)", "avg_kernel_us": k_avg_s * 1e6, "launches_timed": kt_n,
+                         "kernel": f"eval_nuc4_kernel<K=4,NT={nt_small},FUSE=true> (device-resident replay), {R} concurrent launches per step",
+                         "avg_kernel_us": k_avg_s * 1e6, "launches_timed": kt_n,
                          "bytes_per_update": BYTES_PER_UPDATE[4], "peak_source": peaks["which"],
-                         "note": "latency-bound by construction: 2.7 MB working set, ~42 dirty nodes x 413 patterns per launch"},
+                         "note": "avg_kernel_us: one launch alone (events around it, launch latency included); each launch is latency-bound by construction "
+                                 "(2.7 MB working set, ~36 dirty nodes x 413 patterns); the step is bounded by how many such launches the SMs hold"},
             "clocks": clocks,
         }
+        if single is not None:
+            line["single_replica"] = single
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         if args.other and world == 1:
             line["other_workloads"] = [other_workload(torch, lib, n, peaks, local) for n in args.other.split(",")]
         print(json.dumps(line), flush=True)
-    inst.close()
+    for i in insts:
+        i.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -480,6 +523,10 @@ def main():
     ap.add_argument("--steps", type=int, default=4096)
     ap.add_argument("--warmup", type=int, default=128)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--host-threads", type=int, default=8,
+                    help="host threads the end-to-end loop deals the replicas out to (the reference arm uses every host core)")
+    ap.add_argument("--replicas", type=int, default=32,
+                    help="independent analyses (engine instances) in flight per GPU; 1 = a single analysis (latency regime)")
     ap.add_argument("--other", default="nuc200k,aa50k,codon20k",
                     help="comma list of extra large workloads reported under other_workloads ('' = none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -921,9 +921,12 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
 }
 
 // ---- kernel entry points of the 4-state path ----
+#ifndef MB200_FUSE_CTAS
+#define MB200_FUSE_CTAS 2          // resident CTAs per SM the latency-path variants are compiled for
+#endif
 // job descriptors in global memory (device-resident batches, large jobs)
 template <int K, int NT, bool FUSE>
-__global__ void __launch_bounds__(NT, FUSE ? 1 : NUC_STREAM_THREADS / NT)
+__global__ void __launch_bounds__(NT, FUSE ? MB200_FUSE_CTAS : NUC_STREAM_THREADS / NT)
 eval_nuc4_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__restrict__ dvals,
                   const DevChunk *__restrict__ chunks, const DevMat *__restrict__ cmats,
                   const DevOp *__restrict__ ops, DevResult *out, int seq, const __grid_constant__ JobIndex jx)
@@ -934,7 +937,7 @@ eval_nuc4_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *_
 // job descriptors delivered in the kernel parameter block (host call path of small evaluations):
 // no host->device copy on the way in
 template <int K, int NT, int CAP>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, MB200_FUSE_CTAS)
 eval_nuc4_pkernel (DevCtx ctx, BlobOffsets off, DevResult *out, int seq, const __grid_constant__ JobIndex jx,
                    const __grid_constant__ ParamBlob<CAP> blob)       // small uniform parameters first: they share the
                                                                        // constant-cache lines the kernel touches anyway

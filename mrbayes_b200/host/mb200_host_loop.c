@@ -1,0 +1,153 @@
+/*
+ * mb200_host_loop.c -- a host application in C on top of the C-ABI (it links against libmb200.so like
+ * any other client; it is not part of the engine).  bench.py drives its timed regions through it, so
+ * that the numbers are what a C caller (the reference is C99) gets, not what Python's ctypes adds.
+ *
+ * R independent replicas of the analysis (one engine instance each: its own chains, its own stream)
+ * advance generation by generation, the way the reference's RunChain (src/mcmc.c:16718) advances one:
+ *
+ *   mb200_host_generation_loop   host structs in, lnL out (the end-to-end path): per generation a host
+ *                                thread launches the evaluations of its replicas (mb200_evaluate_begin),
+ *                                then collects every result (mb200_evaluate_end) -- nothing of a
+ *                                replica's generation g+1 starts before its generation g has returned
+ *                                its lnL to the host;
+ *   mb200_host_replay_loop       device-resident job descriptors (mb200_replay), timed per generation
+ *                                with CUDA events on a control stream, optional L2 flush before each.
+ */
+#include <stdlib.h>
+#include <time.h>
+#include <pthread.h>
+#include <cuda_runtime_api.h>
+#include "mb200.h"
+
+/* steps[r * cycle + i]: evaluations of replica r in step i of the cycle (count each).  order[g] is the
+ * cycle step of generation g.  lnL / status: R * count entries, results of the last generation.
+ * The replicas are independent analyses, so they are dealt out to `threads` host threads (the
+ * reference arm uses every host core; this side needs a handful): each thread advances its own
+ * replicas generation by generation.  Returns wall-clock seconds, or a negative engine error code. */
+typedef struct
+{
+    const int *instances; int first, last;          /* replicas [first, last) */
+    const mb200_evaluation *const *steps; int cycle, count;
+    const int *order; int n_generations;
+    double *lnL; int *status; int rc;
+} LoopSlice;
+
+static void *run_slice (void *arg)
+{
+    LoopSlice *s = (LoopSlice *) arg;
+    int g, r, rc;
+
+    s->rc = MB200_SUCCESS;
+    for (g = 0; g < s->n_generations; g++)
+        {
+        if (s->last - s->first == 1)
+            {
+            r = s->first;
+            rc = mb200_evaluate (s->instances[r], s->steps[(size_t) r * s->cycle + s->order[g]], s->count,
+                                 s->lnL + (size_t) r * s->count, s->status + (size_t) r * s->count);
+            if (rc != MB200_SUCCESS) { s->rc = rc; return NULL; }
+            continue;
+            }
+        for (r = s->first; r < s->last; r++)
+            {
+            rc = mb200_evaluate_begin (s->instances[r], s->steps[(size_t) r * s->cycle + s->order[g]], s->count);
+            if (rc != MB200_SUCCESS) { s->rc = rc; return NULL; }
+            }
+        for (r = s->first; r < s->last; r++)
+            {
+            rc = mb200_evaluate_end (s->instances[r], s->lnL + (size_t) r * s->count, s->status + (size_t) r * s->count);
+            if (rc != MB200_SUCCESS) { s->rc = rc; return NULL; }
+            }
+        }
+    return NULL;
+}
+
+double mb200_host_generation_loop (const int *instances, int replicas, const mb200_evaluation *const *steps, int cycle,
+                                   int count, const int *order, int n_generations, double *lnL, int *status, int threads)
+{
+    struct timespec t0, t1;
+    LoopSlice slice[64];
+    pthread_t tid[64];
+    int t, rc = MB200_SUCCESS;
+
+    if (threads < 1) threads = 1;
+    if (threads > replicas) threads = replicas;
+    if (threads > 64) threads = 64;
+    for (t = 0; t < threads; t++)
+        {
+        LoopSlice *s = &slice[t];
+        s->instances = instances; s->first = (int)((long) replicas * t / threads); s->last = (int)((long) replicas * (t + 1) / threads);
+        s->steps = steps; s->cycle = cycle; s->count = count; s->order = order; s->n_generations = n_generations;
+        s->lnL = lnL; s->status = status; s->rc = MB200_SUCCESS;
+        }
+    clock_gettime (CLOCK_MONOTONIC, &t0);
+    for (t = 1; t < threads; t++)
+        if (pthread_create (&tid[t], NULL, run_slice, &slice[t]) != 0)
+            return -1.0;
+    run_slice (&slice[0]);
+    for (t = 1; t < threads; t++)
+        pthread_join (tid[t], NULL);
+    clock_gettime (CLOCK_MONOTONIC, &t1);
+    for (t = 0; t < threads; t++)
+        if (slice[t].rc != MB200_SUCCESS) rc = slice[t].rc;
+    if (rc != MB200_SUCCESS)
+        return (double) rc;
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+/* batches[r * cycle + i]: packed batch of replica r for cycle step i.  Per generation: [flush L2 on the
+ * control stream] -> start event -> every replica's stream waits for it and replays its batch ->
+ * the control stream waits for all of them -> stop event.  Returns the sum of the per-generation
+ * device times in milliseconds, or a negative error code. */
+double mb200_host_replay_loop (const int *instances, int replicas, const int *batches, int cycle, const int *order,
+                               int n_generations, void *flush_buffer, size_t flush_bytes)
+{
+    cudaStream_t ctl = NULL, *streams;
+    cudaEvent_t *start, *stop, *done;
+    double total = 0.0;
+    int g, r, rc = 0;
+
+    streams = (cudaStream_t *) calloc ((size_t) replicas, sizeof(cudaStream_t));
+    done  = (cudaEvent_t *) calloc ((size_t) replicas, sizeof(cudaEvent_t));
+    start = (cudaEvent_t *) calloc ((size_t) n_generations, sizeof(cudaEvent_t));
+    stop  = (cudaEvent_t *) calloc ((size_t) n_generations, sizeof(cudaEvent_t));
+    if (!streams || !done || !start || !stop) return -1.0;
+    for (r = 0; r < replicas; r++)
+        {
+        void *s = NULL;
+        if (mb200_get_stream (instances[r], &s) != MB200_SUCCESS) return -2.0;
+        streams[r] = (cudaStream_t) s;
+        if (cudaEventCreateWithFlags (&done[r], cudaEventDisableTiming) != cudaSuccess) return -3.0;
+        }
+    if (cudaStreamCreateWithFlags (&ctl, cudaStreamNonBlocking) != cudaSuccess) return -3.0;
+    for (g = 0; g < n_generations; g++)
+        if (cudaEventCreate (&start[g]) != cudaSuccess || cudaEventCreate (&stop[g]) != cudaSuccess) return -3.0;
+
+    for (g = 0; g < n_generations && rc == 0; g++)
+        {
+        if (flush_buffer != NULL)
+            cudaMemsetAsync (flush_buffer, g & 0xff, flush_bytes, ctl);
+        cudaEventRecord (start[g], ctl);
+        for (r = 0; r < replicas; r++)
+            {
+            cudaStreamWaitEvent (streams[r], start[g], 0);
+            if (mb200_replay (instances[r], batches[(size_t) r * cycle + order[g]]) != MB200_SUCCESS) { rc = -4; break; }
+            cudaEventRecord (done[r], streams[r]);
+            cudaStreamWaitEvent (ctl, done[r], 0);
+            }
+        cudaEventRecord (stop[g], ctl);
+        }
+    if (cudaStreamSynchronize (ctl) != cudaSuccess) rc = -5;
+    for (r = 0; r < replicas; r++) mb200_synchronize (instances[r]);
+    for (g = 0; g < n_generations; g++)
+        {
+        float ms = 0.0f;
+        if (rc == 0 && cudaEventElapsedTime (&ms, start[g], stop[g]) == cudaSuccess) total += ms;
+        cudaEventDestroy (start[g]); cudaEventDestroy (stop[g]);
+        }
+    for (r = 0; r < replicas; r++) cudaEventDestroy (done[r]);
+    cudaStreamDestroy (ctl);
+    free (streams); free (done); free (start); free (stop);
+    return (rc == 0) ? total : (double) rc;
+}
