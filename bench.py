@@ -485,7 +485,10 @@ def bench_engine(args):
                            f"{HT} host thread(s), C generation loop (mrbayes_b200/host/mb200_host_loop.c); an analysis' results of generation g are on the host before its generation g+1 starts"},
             "gpu_launches": all_launches,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": (ach / peaks["hbm_gbs"]) if ach else None, "traffic": None,
+                         "frac": (ach / peaks["hbm_gbs"]) if ach else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel, `ncu --set full`
+                         # (profiles/r01_launches_bench_primates.md: 8 full-tree evaluations = 6.7 MB algorithmic, L2 warm)
+                         "traffic": 70400, "traffic_unit": "bytes per launch (ncu, L2 warm: the 2.7 MB working set of an analysis lives in L2)",
                          "kernel": f"eval_nuc4_kernel<K=4,NT={nt_small},FUSE=true> (device-resident replay), {R} concurrent launches per step",
                          "avg_kernel_us": k_avg_s * 1e6, "launches_timed": kt_n,
                          "bytes_per_update": BYTES_PER_UPDATE[4], "peak_source": peaks["which"],
