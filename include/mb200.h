@@ -79,6 +79,13 @@ extern "C" {
 #define MB200_NONE                  (-1)  /* "no buffer" sentinel, like BEAGLE_OP_NONE */
 #define MB200_EIGEN_INLINE          (-2)  /* mb200_matrix_update.eigen: use mb200_evaluation.inline_eigen */
 
+/* instance flags.  Models whose categories have their own rate matrices (codon NY98 / M3: one
+ * eigensystem per omega category, m->nCijkParts = numOmegaCats, TiProbs_GenCov,
+ * src/likelihood.c:9568) keep `parts` consecutive [2S + S^3] blocks per cijk slot, the layout of
+ * m->cijks[] (cijkLength = parts * (2S + S^3)); category k uses part k.  parts must be 1 or equal to
+ * category_count. */
+#define MB200_CONFIG_CIJK_PARTS(n) (((n) & 0xff) << 8)
+
 /* evaluation flags */
 /* Root integration follows Likelihood_NUC4_{SSE,AVX,FMA}: when the site scaler is
  * below -200 and likeI > 1e-70 the pattern contributes (lnScaler + log(likeI))
@@ -105,7 +112,7 @@ typedef struct mb200_instance_config
     int weight_rows;      /* rows of numSitesOfPat (1, or numChains when reweighting)     */
     int device;           /* CUDA device ordinal                                          */
     int max_evaluations;  /* largest `count` ever passed to mb200_evaluate (>=1)          */
-    int flags;            /* reserved, 0                                                  */
+    int flags;            /* MB200_CONFIG_CIJK_PARTS(n) for models with one eigensystem per category, else 0 */
 } mb200_instance_config;
 
 /* One interior-node update: what CondLikeDown / CondLikeRoot + RemoveNodeScalers +

@@ -235,11 +235,12 @@ class Instance:
 
     def __init__(self, lib: Library, *, tip_count, partials_count, state_count, pattern_count,
                  category_count, matrix_count, scaler_count, eigen_count, weight_rows=1, device=0,
-                 max_evaluations=1):
+                 max_evaluations=1, flags=0):
         self.lib = lib
         self.cfg = InstanceConfig(tip_count, partials_count, state_count, pattern_count, category_count,
                                   matrix_count, scaler_count, eigen_count, weight_rows, device,
-                                  max_evaluations, 0)
+                                  max_evaluations, flags)
+        self.cijk_parts = max(1, (flags >> 8) & 0xff)       # MB200_CONFIG_CIJK_PARTS
         h = C.c_int(-1)
         lib.check("create_instance", lib.fn("create_instance")(C.byref(self.cfg), C.byref(h)))
         self.handle = h.value
@@ -279,7 +280,7 @@ class Instance:
 
     def set_cijk(self, eigen: int, block):
         b = np.ascontiguousarray(block, np.float64)
-        assert b.size == 2 * self.S + self.S ** 3
+        assert b.size == self.cijk_parts * (2 * self.S + self.S ** 3)
         self._call("set_cijk", eigen, _ptr(b, C.c_double))
 
     def set_eigen_decomposition(self, eigen: int, V, Vinv, lam):

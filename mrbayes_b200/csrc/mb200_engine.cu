@@ -61,7 +61,8 @@ struct Instance
     unsigned long long *dDbg = nullptr;
     bool          invMaskValid = false;
     int           maxEval = 1, maxTiles = 1, numSMs = 148;
-    size_t        eigenStride = 0;     // doubles per eigen slot
+    size_t        eigenStride = 0;     // doubles per eigen slot (all parts)
+    int           cijkParts = 1;       // eigensystems per slot (one per category for NY98-type models)
     size_t        smemGen = 0;         // dynamic smem of eval_gen_kernel
     long long     launches = 0;
     std::vector<int> tipPartAmbig;  // host copy (operand kinds of the 4-state records)
@@ -908,7 +909,9 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     const int S = cfg->state_count, K = cfg->category_count, C = cfg->pattern_count;
     const int Sp = (S + 3) & ~3;
     const size_t nInt = (size_t)(cfg->partials_count - cfg->tip_count);
-    I->eigenStride = 2*(size_t)S + (size_t)S*S*S;
+    I->cijkParts = ((cfg->flags >> 8) & 0xff) > 1 ? ((cfg->flags >> 8) & 0xff) : 1;
+    if (I->cijkParts != 1 && (I->cijkParts != K || S == 4)) { delete I; return MB200_ERROR_UNSUPPORTED; }
+    I->eigenStride = (size_t) I->cijkParts * (2*(size_t)S + (size_t)S*S*S);
 
     // tile geometry of the generic kernel: keep P + child tile + product under ~96 KB
     int TP = 32;
@@ -984,6 +987,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     x.numTiles = I->maxTiles;
     x.tip8 = I->dTip8; x.tip64 = I->dTip64; x.tipPartAmbig = I->dTipPartAmbig; x.partials = I->dPartials; x.matrices = I->dMatrices;
     x.scalers = I->dScalers; x.eigen = I->dEigen; x.weights = I->dWeights; x.invMask = I->dInvMask;
+    x.cijkParts = I->cijkParts; x.pad0 = 0;
     x.tilePartial = I->dTilePartial; x.tileAbort = I->dTileAbort; x.ticket = I->dTicket; x.dbg = I->dDbg;
 
     if (cudaStreamSynchronize (I->stream) != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
@@ -1068,6 +1072,7 @@ int mb200_set_eigen_decomposition (int instance, int eigen, const double *V, con
     Instance *I = get (instance);
     if (!I) return MB200_ERROR_BAD_INSTANCE;
     if (eigen < 0 || eigen >= I->cfg.eigen_count || !V || !Vinv || !lambda) return MB200_ERROR_OUT_OF_RANGE;
+    if (I->cijkParts != 1) return MB200_ERROR_UNSUPPORTED;        // multi-part slots are uploaded whole (mb200_set_cijk)
     int rc = use (I); if (rc) return rc;
     const int S = I->cfg.state_count;
     const size_t n2 = (size_t)S * S;

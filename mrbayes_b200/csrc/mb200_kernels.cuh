@@ -79,8 +79,9 @@ tiprobs_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, const 
             P[idx] = (float) freqs[idx % S];
         return;
         }
+    const size_t   partLen = 2*(size_t)S + (size_t)S*S*S;
     const double *lam = (mu.eigen == -2) ? (freqs + S)            // eigensystem carried by the evaluation
-                                         : ctx.eigen + (size_t)mu.eigen * (2*(size_t)S + (size_t)S*S*S);
+                                         : ctx.eigen + ((size_t)mu.eigen * ctx.cijkParts + (ctx.cijkParts > 1 ? k : 0)) * partLen;
     const double *cij = lam + 2*S;
     if (threadIdx.x < S)
         sExp[threadIdx.x] = exp (lam[threadIdx.x] * t);
@@ -135,7 +136,8 @@ tiprobs_wide_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, c
                 P[i*S + j] = (t < MB200_TIME_MIN) ? ((i == j) ? 1.0f : 0.0f) : (float) freqs[j];
         return;
         }
-    const double *lam = ctx.eigen + (size_t)mu.eigen * (2*(size_t)S + (size_t)S*S*S);
+    const size_t   partLen = 2*(size_t)S + (size_t)S*S*S;
+    const double *lam = ctx.eigen + ((size_t)mu.eigen * ctx.cijkParts + (ctx.cijkParts > 1 ? k : 0)) * partLen;
     const double *cij = lam + 2*S;
     if (threadIdx.x < S)
         sExp[threadIdx.x] = exp (lam[threadIdx.x] * t);

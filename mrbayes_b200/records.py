@@ -67,6 +67,7 @@ def load(path):
     divisions: dict[int, Division] = {}
     events: list[Event] = []
     pending_inline = None
+    pending_parts = []
     while pos < len(data):
         tag = data[pos:pos + 4]
         (nb,) = struct.unpack_from("<I", data, pos + 4)
@@ -84,11 +85,22 @@ def load(path):
         elif tag == b"EIGN":
             d, eig, S = struct.unpack_from("<3i", body, 0)
             a = np.frombuffer(body, "<f8", S + 2 * S * S, 12).copy()
-            events.append(Event("eigen", d, eig, lam=a[:S], V=a[S:S + S * S].reshape(S, S),
-                                Vinv=a[S + S * S:].reshape(S, S)))
+            parts, part, eig = (eig >> 24) & 0xff, (eig >> 16) & 0xff, eig & 0xffff
+            lam, V, Vinv = a[:S], a[S:S + S * S].reshape(S, S), a[S + S * S:].reshape(S, S)
+            if parts <= 1:
+                events.append(Event("eigen", d, eig, lam=lam, V=V, Vinv=Vinv))
+            else:
+                # one eigensystem per category (NY98): rebuild the slot's cijk block, part by part, the way
+                # CalcCijk does (src/utils.c:9734-9746: c[i][j][k] = u[i][k] * v[k][j]; IEEE products)
+                blk = np.concatenate([lam, np.zeros(S), (V[:, None, :] * Vinv.T[None, :, :]).ravel()])
+                if part == 0:
+                    pending_parts = []
+                pending_parts.append(blk)
+                if part == parts - 1:
+                    events.append(Event("cijk", d, eig, block=np.concatenate(pending_parts)))
         elif tag == b"CIJK":
             d, eig, S = struct.unpack_from("<3i", body, 0)
-            a = np.frombuffer(body, "<f8", 2 * S + S ** 3, 12).copy()
+            a = np.frombuffer(body, "<f8", (len(body) - 12) // 8, 12).copy()      # all parts of the slot
             if eig == abi.EIGEN_INLINE:
                 pending_inline = a                # travels with the next evaluation
             else:
@@ -118,7 +130,6 @@ def load(path):
 def make_instance(lib: abi.Library, div: Division, device: int = 0, max_evaluations: int = 1) -> abi.Instance:
     """Create an instance for a recorded division and load its tips and weights."""
     c = dict(div.cfg)
-    c.pop("flags", None)
     c["device"] = device
     c["max_evaluations"] = max(max_evaluations, 1)
     inst = abi.Instance(lib, **c)

@@ -182,6 +182,28 @@ static int SeamClosedFormEigen (ModelInfo *m, int chain, double *block)
     return (isComplex == NO) ? NO_ERROR : ERROR;
 }
 
+/* Codon models with omega categories (NY98, M3: lset omegavar=...): one rate matrix, hence one
+ * eigensystem, per category (nCijkParts = numOmegaCats, InitEigenSystemInfo src/mcmc.c:6573-6577);
+ * P(t) from TiProbs_GenCov (src/likelihood.c:9568), pruning CondLikeDown/Root/Scaler_NY98
+ * (:1575, :4010, :5413), root Likelihood_NY98 (:6975): the general-S arithmetic with
+ * K = numOmegaCats and the omega category frequencies as category weights. */
+static int SeamOmegaCategories (ModelInfo *m)
+{
+    if ((m->dataType != DNA && m->dataType != RNA) || m->nucModelId != NUCMODEL_CODON)
+        return NO;
+    if (m->numOmegaCats <= 1 || m->numOmegaCats > MB200_MAX_CATEGORIES || m->numRateCats != 1)
+        return NO;
+    if (m->nCijkParts != m->numOmegaCats || m->omega == NULL || m->pInvar != NULL)
+        return NO;
+    return YES;
+}
+
+/* rate / omega categories of the division as the engine sees them */
+static int SeamCategories (ModelInfo *m)
+{
+    return (SeamOmegaCategories (m) == YES) ? m->numOmegaCats : m->numRateCats;
+}
+
 /* Which divisions the engine takes; everything else stays on the reference's own
  * function pointers, the way the reference keeps BEAGLE away from models it does
  * not cover (src/mcmc.c:5741-5775). */
@@ -191,13 +213,15 @@ int MB200SeamDivisionSupported (ModelInfo *m)
         return NO;
     if (m->dataType != DNA && m->dataType != RNA && m->dataType != PROTEIN)
         return NO;                              /* STANDARD / RESTRICTION / CONTINUOUS: next rows */
-    if (m->nCijkParts != 1 && MB200SeamClosedFormModel (m) == NO)
-        return NO;                              /* NY98 multi-omega, covarion+gamma (TiProbs_GenCov) */
+    if (m->nCijkParts != 1 && MB200SeamClosedFormModel (m) == NO && SeamOmegaCategories (m) == NO)
+        return NO;                              /* covarion+gamma and the other TiProbs_GenCov users: next */
     if (m->gibbsGamma == YES || m->switchRates != NULL || m->correlation != NULL)
         return NO;
     if (m->numModelStates < 2 || m->numModelStates > MB200_MAX_STATES)
         return NO;
-    if (m->numRateCats < 1 || m->numRateCats > MB200_MAX_CATEGORIES || m->numOmegaCats != 1)
+    if (m->numRateCats < 1 || m->numRateCats > MB200_MAX_CATEGORIES)
+        return NO;
+    if (m->numOmegaCats != 1 && SeamOmegaCategories (m) == NO)
         return NO;
     if (m->nParsIntsPerSite != 1)
         return NO;
@@ -228,7 +252,8 @@ int InitBeagleInstance (ModelInfo *m, int division)
     cfg.partials_count  = m->numCondLikes;
     cfg.state_count     = m->numModelStates;
     cfg.pattern_count   = m->numChars;
-    cfg.category_count  = m->numRateCats;
+    cfg.category_count  = SeamCategories (m);
+    cfg.flags           = (SeamOmegaCategories (m) == YES) ? MB200_CONFIG_CIJK_PARTS (m->nCijkParts) : 0;
     cfg.matrix_count    = m->numTiProbs;
     cfg.scaler_count    = m->numScalers;
     cfg.eigen_count     = numLocalChains + 1;    /* unused (but harmless) for the inline-eigen models */
@@ -382,6 +407,9 @@ int TreeTiProbs_Beagle (Tree *t, int division, int chain)
         catRate = &theRate;
     for (k=0; k<m->numRateCats; k++)
         sd->ev.category_rates[k] = baseRate * catRate[k] * corr;
+    if (SeamOmegaCategories (m) == YES)
+        for (k=0; k<m->numOmegaCats; k++)
+            sd->ev.category_rates[k] = corr;    /* TiProbs_GenCov: t = length * correctionFactor, nothing else */
 
     return (NO_ERROR);
 }
@@ -443,7 +471,7 @@ int TreeCondLikes_Beagle_Always_Rescale (Tree *t, int division, int chain)
         else
             op->scale_write = MB200_NONE;
 
-        sd->clUpdates += (long long) m->numChars * m->numRateCats;
+        sd->clUpdates += (long long) m->numChars * SeamCategories (m);
         }
 
     return (NO_ERROR);
@@ -502,6 +530,13 @@ int TreeLikelihood_Beagle (Tree *t, int division, int chain, MrBFlt *lnL, int wh
         freq = (1.0 - pInvar) / m->numRateCats;
     for (k=0; k<m->numRateCats; k++)
         sd->ev.category_weights[k] = freq;
+    if (SeamOmegaCategories (m) == YES)
+        {
+        /* Likelihood_NY98 (src/likelihood.c:6998): the omega category frequencies */
+        MrBFlt *omegaCatFreq = GetParamSubVals (m->omega, chain, state[chain]);
+        for (k=0; k<m->numOmegaCats; k++)
+            sd->ev.category_weights[k] = omegaCatFreq[k];
+        }
 
     bs = GetParamSubVals (m->stateFreq, chain, state[chain]);
     for (s=0; s<m->numModelStates; s++)

@@ -30,7 +30,8 @@ typedef struct
     float      *partials;    /* [interior buffer][K][C][S]                           */
     float      *matrices;    /* [matrix][K][S][S]                                    */
     float      *scalers;     /* [scaler][C]                                          */
-    double     *eigen;       /* [slot][2S+S^3]                                       */
+    double     *eigen;       /* [slot][parts][2S+S^3]                                */
+    int         parts;       /* eigensystems per slot (1, or K for NY98-type models)  */
     float      *weights;     /* [row][C]                                             */
     float      *tmp[3];      /* per-child matvec results [K][C][S]                   */
     long long   updates;
@@ -72,7 +73,8 @@ int orc_create_instance (const mb200_instance_config *c, int *instance)
     o->partials     = (float *)    calloc (nInt * K * C * S, sizeof(float));
     o->matrices     = (float *)    calloc ((size_t)c->matrix_count * K * S * S, sizeof(float));
     o->scalers      = (float *)    calloc ((size_t)c->scaler_count * C, sizeof(float));
-    o->eigen        = (double *)   calloc ((size_t)c->eigen_count * (2*S + S*S*S), sizeof(double));
+    o->parts        = (((c->flags >> 8) & 0xff) > 1) ? ((c->flags >> 8) & 0xff) : 1;
+    o->eigen        = (double *)   calloc ((size_t)c->eigen_count * o->parts * (2*S + S*S*S), sizeof(double));
     o->weights      = (float *)    calloc ((size_t)c->weight_rows * C, sizeof(float));
     for (i=0; i<3; i++)
         o->tmp[i]   = (float *)    calloc (K * C * S, sizeof(float));
@@ -144,7 +146,7 @@ int orc_set_cijk (int instance, int eigen, const double *block)
     OrcInst *o = Get (instance);
     if (!o) return MB200_ERROR_BAD_INSTANCE;
     if (eigen < 0 || eigen >= o->cfg.eigen_count || !block) return MB200_ERROR_OUT_OF_RANGE;
-    S = (size_t)o->cfg.state_count; n = 2*S + S*S*S;
+    S = (size_t)o->cfg.state_count; n = (size_t)o->parts * (2*S + S*S*S);
     memcpy (o->eigen + (size_t)eigen * n, block, n * sizeof(double));
     return MB200_SUCCESS;
 }
@@ -157,6 +159,7 @@ int orc_set_eigen_decomposition (int instance, int eigen, const double *u, const
     OrcInst *o = Get (instance);
     if (!o) return MB200_ERROR_BAD_INSTANCE;
     if (eigen < 0 || eigen >= o->cfg.eigen_count || !u || !v || !lam) return MB200_ERROR_OUT_OF_RANGE;
+    if (o->parts != 1) return MB200_ERROR_UNSUPPORTED;
     S = (size_t)o->cfg.state_count; n = 2*S + S*S*S;
     b = o->eigen + (size_t)eigen * n;
     for (i=0; i<S; i++) { b[i] = lam[i]; b[S+i] = 0.0; }
@@ -173,13 +176,17 @@ static void TiProbs (OrcInst *o, const mb200_matrix_update *mu, const mb200_eval
 {
     int     S = o->cfg.state_count, K = o->cfg.category_count, i, j, k, s, index;
     double  t, sum, e[MB200_MAX_STATES];
-    const double *lam = (mu->eigen == MB200_EIGEN_INLINE) ? ev->inline_eigen
-                                                          : o->eigen + (size_t)mu->eigen * (2*(size_t)S + (size_t)S*S*S);
+    const size_t partLen = 2*(size_t)S + (size_t)S*S*S;
+    const double *lam0 = (mu->eigen == MB200_EIGEN_INLINE) ? ev->inline_eigen
+                                                           : o->eigen + (size_t)mu->eigen * o->parts * partLen;
+    const double *lam = lam0;
     const double *ptr;
     float  *tiP = o->matrices + (size_t)mu->matrix * K * S * S;
 
     for (k=index=0; k<K; k++)
         {
+        /* TiProbs_GenCov (src/likelihood.c:9568-9690): one eigensystem per category */
+        lam = lam0 + ((o->parts > 1) ? (size_t)k * partLen : 0);
         t = mu->length * ev->category_rates[k];
         if (t < ORC_TIME_MIN)
             {

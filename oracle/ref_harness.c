@@ -61,6 +61,9 @@ static long long  hCompared = 0, hFailed = 0;
 /* last eigensystem seen by CalcCijk */
 static int        hEigDim = 0;
 static double    *hEigU = NULL, *hEigV = NULL;
+#define HRING 8                       /* the last few CalcCijk inputs: multi-part slots (NY98) call it once per part */
+static double    *hRingU[HRING], *hRingV[HRING];
+static int        hRingDim[HRING], hRingPos = 0;
 
 /* evaluation stashed by the recorder until the reference value is known */
 static struct
@@ -151,11 +154,13 @@ static int rec_cijk (int inst, int eigen, const double *block)
     int     hdr[3], S = hInstCfg[inst].state_count, i, j, k, same = 0;
     size_t  n3 = (size_t)S * S * S;
 
+    const int parts = (((hInstCfg[inst].flags >> 8) & 0xff) > 1) ? ((hInstCfg[inst].flags >> 8) & 0xff) : 1;
+
     hdr[0] = hInstDivision[inst]; hdr[1] = eigen; hdr[2] = S;
     if (hDump)
         {
         /* prefer the compact (lambda, V, V^-1) form when it reproduces the block exactly */
-        if (hEigDim == S && hEigU != NULL)
+        if (parts == 1 && hEigDim == S && hEigU != NULL)
             {
             const double *c = block + 2*S;
             same = 1;
@@ -173,6 +178,42 @@ static int rec_cijk (int inst, int eigen, const double *block)
             memcpy (buf + S + S*S, hEigV, (size_t)S*S * sizeof(double));
             Chunk ("EIGN", hdr, sizeof(hdr), buf, (size_t)(S + 2*S*S) * sizeof(double));
             free (buf);
+            }
+        else if (parts > 1)
+            {
+            /* one (lambda, V, V^-1) triple per part when the recent CalcCijk inputs reproduce every part
+               exactly (they do: UpDateCijk calls CalcCijk once per omega category); else the raw blocks */
+            int     found[32], p, r, ok = 1;
+            const size_t partLen = 2*(size_t)S + n3;
+            for (p=0; p<parts && p<32 && ok; p++)
+                {
+                const double *c = block + (size_t)p * partLen + 2*S;
+                found[p] = -1;
+                for (r=0; r<HRING && found[p] < 0; r++)
+                    {
+                    int match = (hRingDim[r] == S && hRingU[r] != NULL);
+                    for (i=0; i<S && match; i++)
+                        for (j=0; j<S && match; j++)
+                            for (k=0; k<S; k++)
+                                if (c[((size_t)i*S + j)*S + k] != hRingU[r][i*S+k] * hRingV[r][k*S+j])
+                                    { match = 0; break; }
+                    if (match) found[p] = r;
+                    }
+                if (found[p] < 0) ok = 0;
+                }
+            if (ok && parts <= 32)
+                for (p=0; p<parts; p++)
+                    {
+                    int ph[3] = { hdr[0], eigen | (p << 16) | (parts << 24), S };
+                    double *buf = (double *) malloc ((size_t)(S + 2*S*S) * sizeof(double));
+                    memcpy (buf, block + (size_t)p * partLen, (size_t)S * sizeof(double));
+                    memcpy (buf + S, hRingU[found[p]], (size_t)S*S * sizeof(double));
+                    memcpy (buf + S + S*S, hRingV[found[p]], (size_t)S*S * sizeof(double));
+                    Chunk ("EIGN", ph, sizeof(ph), buf, (size_t)(S + 2*S*S) * sizeof(double));
+                    free (buf);
+                    }
+            else
+                Chunk ("CIJK", hdr, sizeof(hdr), block, (size_t)parts * partLen * sizeof(double));
             }
         else
             Chunk ("CIJK", hdr, sizeof(hdr), block, (2*(size_t)S + n3) * sizeof(double));
@@ -333,6 +374,19 @@ void __wrap_CalcCijk (int dim, MrBFlt *c_ijk, MrBFlt **u, MrBFlt **v)
                 hEigU[i*dim+j] = u[i][j];
                 hEigV[i*dim+j] = v[i][j];
                 }
+        {
+        const int r = hRingPos % HRING;
+        if (hRingDim[r] != dim)
+            {
+            free (hRingU[r]); free (hRingV[r]);
+            hRingU[r] = (double *) malloc ((size_t)dim*dim*sizeof(double));
+            hRingV[r] = (double *) malloc ((size_t)dim*dim*sizeof(double));
+            hRingDim[r] = dim;
+            }
+        memcpy (hRingU[r], hEigU, (size_t)dim*dim*sizeof(double));
+        memcpy (hRingV[r], hEigV, (size_t)dim*dim*sizeof(double));
+        hRingPos++;
+        }
         }
     __real_CalcCijk (dim, c_ijk, u, v);
 }
@@ -402,7 +456,7 @@ MrBFlt __wrap_LogLike (int chain)
             long long dirty = CountDirty (GetTree (m->brlens, chain, state[chain]));
             hCalls++;
             hNodeUpdates += dirty;
-            hUpdates += dirty * m->numChars * m->numRateCats;
+            hUpdates += dirty * m->numChars * m->numRateCats * m->numOmegaCats;
             }
         }
     t0 = Now ();
@@ -426,7 +480,7 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
     dirty = CountDirty (tree);
     hCalls++;
     hNodeUpdates += dirty;
-    hUpdates += dirty * m->numChars * m->numRateCats;
+    hUpdates += dirty * m->numChars * m->numRateCats * m->numOmegaCats;
 
     if (hMode == MODE_CPU || (hMode == MODE_DUMP && hDumpMax >= 0 && hDumped >= hDumpMax))
         {
@@ -474,13 +528,15 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
         mb200_instance_config c;
         memset (&c, 0, sizeof(c));
         c.tip_count = numLocalTaxa; c.partials_count = m->numCondLikes; c.state_count = m->numModelStates;
-        c.pattern_count = m->numChars; c.category_count = m->numRateCats; c.matrix_count = m->numTiProbs;
+        c.pattern_count = m->numChars; c.matrix_count = m->numTiProbs;
+        c.category_count = (m->numOmegaCats > 1) ? m->numOmegaCats : m->numRateCats;     /* as InitBeagleInstance in the seam */
         c.scaler_count = m->numScalers;
         {
         extern int numLocalChains;
         c.eigen_count = numLocalChains + 1;
         }
-        c.weight_rows = chainParams.numChains; c.device = 0; c.max_evaluations = 1; c.flags = 0;
+        c.weight_rows = chainParams.numChains; c.device = 0; c.max_evaluations = 1;
+        c.flags = (m->numOmegaCats > 1) ? MB200_CONFIG_CIJK_PARTS (m->nCijkParts) : 0;
         memcpy (hdr + 1, &c, 12 * sizeof(int));
         }
         Chunk ("INST", hdr, sizeof(hdr), NULL, 0);

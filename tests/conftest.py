@@ -18,6 +18,7 @@ GOLDEN_FILES = [
     ("replicase_m0_sse", 0),
     ("primates_hky_g4_fma", 1),      # nst=2: closed-form model, eigensystem sent inline
     ("primates_f81_i_fma", 1),       # nst=1 + pInvar
+    ("replicase_ny98_sse", 0),       # codon NY98: one eigensystem per omega category (TiProbs_GenCov, *_NY98)
     ("cynmix_part_fma", 1),          # cynmix, 4 unlinked GTR+I+G4 DNA partitions (32 taxa), interleaved evaluations
 ]
 
