@@ -25,6 +25,6 @@ run replicase_m0_sse      mb_b200    100  40 replicase_m0
 run primates_hky_g4_fma   mb_b200    100 200 primates_hky_g4
 run primates_f81_i_fma    mb_b200    100 150 primates_f81_i
 run cynmix_part_fma       mb_b200     40 160 cynmix_part
-run replicase_ny98_sse    mb_b200     60  30 replicase_ny98
+run replicase_ny98_sse    mb_b200     60  40 replicase_ny98
 rm -rf $TMP
 ls -la $OUT/*.gold.gz
