@@ -290,6 +290,22 @@ def other_workload(torch, lib, name, peaks, device):
                              "tflops": flops / (kms / kn * 1e-3) / 1e12}}
 
 
+def replica_seeds(rank: int, replicas: int):
+    """(problem seed, proposal-cycle seed) of every replica of a rank: disjoint across ranks, so that
+    under torchrun every GPU drives its own independent analyses (weak scaling)."""
+    return [(20260924 + 1000 * rank + r, 7 + 1000 * rank + r) for r in range(replicas)]
+
+
+def reduce_over_ranks(torch, dist, device, ms_value, ms_warm, ms_e2e, updates, launches):
+    """The multi-rank contract of the bench line: times are the MAX over ranks, work is the SUM."""
+    if dist is None:
+        return ms_value, ms_warm, ms_e2e, float(updates), int(launches)
+    vals = torch.tensor([ms_value, ms_warm, ms_e2e, float(updates), float(launches)], dtype=torch.float64, device=device)
+    mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    return mx[0].item(), mx[1].item(), mx[2].item(), sm[3].item(), int(sm[4].item())
+
+
 def bench_engine(args):
     import torch
     from mrbayes_b200 import abi
@@ -314,11 +330,12 @@ def bench_engine(args):
 
     n_chains = 8
     R = max(1, args.replicas)
-    probs = [primates_problem(n_chains, seed=20260924 + 1000 * rank + r) for r in range(R)]
+    seeds = replica_seeds(rank, R)
+    probs = [primates_problem(n_chains, seed=sd[0]) for sd in seeds]
     insts = [p.create(lib, device=local, max_evaluations=n_chains) for p in probs]
     pr, inst = probs[0], insts[0]
     cycle_len = 128
-    steps_r = [make_cycle(p, i, cycle_len, seed=7 + 1000 * rank + r) for r, (p, i) in enumerate(zip(probs, insts))]
+    steps_r = [make_cycle(p, i, cycle_len, seed=sd[1]) for sd, p, i in zip(seeds, probs, insts)]
     steps = steps_r[0]
     K, W = args.steps, args.warmup
     order = [i % cycle_len for i in range(K)]
@@ -441,15 +458,8 @@ def bench_engine(args):
         sampler.stop()
 
     # ---- reduce over ranks: MAX time, SUM work -------------------------------------------
-    vals = torch.tensor([ms_value, ms_warm, sec_e2e * 1e3, float(total_updates), float(launches)],
-                        dtype=torch.float64, device=f"cuda:{local}")
-    if dist is not None:
-        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms_value, ms_warm, ms_e2e = mx[0].item(), mx[1].item(), mx[2].item()
-        all_updates, all_launches = sm[3].item(), int(sm[4].item())
-    else:
-        ms_e2e, all_updates, all_launches = sec_e2e * 1e3, float(total_updates), launches
+    ms_value, ms_warm, ms_e2e, all_updates, all_launches = reduce_over_ranks(
+        torch, dist, f"cuda:{local}", ms_value, ms_warm, sec_e2e * 1e3, total_updates, launches)
 
     h2d = float(np.mean([sum(pack_bytes(sr[i]).bytes for sr in steps_r) for i in range(cycle_len)]))
     nt_small = int(os.environ.get("MB200_NT_SMALL", "256"))
