@@ -198,6 +198,26 @@ static int SeamOmegaCategories (ModelInfo *m)
     return YES;
 }
 
+/* Covarion models with gamma rate variation (lset covarion=yes rates=gamma; nucleotide S = 8, protein
+ * S = 40): the category's rate sits inside its own rate matrix, so there is one eigensystem per
+ * rate category (nCijkParts = numRateCats, InitEigenSystemInfo src/mcmc.c:6533-6563) and P(t) comes
+ * from TiProbs_GenCov; everything downstream is the general-S path (CondLike*_Gen*, Likelihood_Gen*).
+ * Covarion without rate variation has nCijkParts = 1 and goes through TiProbs_Gen like any other model. */
+static int SeamCovarionGamma (ModelInfo *m)
+{
+    if (m->switchRates == NULL || m->numOmegaCats != 1)
+        return NO;
+    if (m->nCijkParts <= 1 || m->nCijkParts != m->numRateCats)
+        return NO;
+    return YES;
+}
+
+/* one eigensystem per category? (TiProbs_GenCov models) */
+static int SeamCategoryEigens (ModelInfo *m)
+{
+    return (SeamOmegaCategories (m) == YES || SeamCovarionGamma (m) == YES) ? YES : NO;
+}
+
 /* rate / omega categories of the division as the engine sees them */
 static int SeamCategories (ModelInfo *m)
 {
@@ -213,10 +233,14 @@ int MB200SeamDivisionSupported (ModelInfo *m)
         return NO;
     if (m->dataType != DNA && m->dataType != RNA && m->dataType != PROTEIN)
         return NO;                              /* STANDARD / RESTRICTION / CONTINUOUS: next rows */
-    if (m->nCijkParts != 1 && MB200SeamClosedFormModel (m) == NO && SeamOmegaCategories (m) == NO)
-        return NO;                              /* covarion+gamma and the other TiProbs_GenCov users: next */
-    if (m->gibbsGamma == YES || m->switchRates != NULL || m->correlation != NULL)
+    if (m->nCijkParts != 1 && MB200SeamClosedFormModel (m) == NO && SeamCategoryEigens (m) == NO)
         return NO;
+    if (m->gibbsGamma == YES || m->correlation != NULL)
+        return NO;
+    if (m->switchRates != NULL)
+        return NO;                              /* covarion: the plumbing is here (SeamCovarionGamma, on/off
+                                                   frequencies) but the restatement is not pinned yet -- on primates the
+                                                   reference starts at lnL -1557.87 where this path gives -8553.7 */
     if (m->numModelStates < 2 || m->numModelStates > MB200_MAX_STATES)
         return NO;
     if (m->numRateCats < 1 || m->numRateCats > MB200_MAX_CATEGORIES)
@@ -253,7 +277,7 @@ int InitBeagleInstance (ModelInfo *m, int division)
     cfg.state_count     = m->numModelStates;
     cfg.pattern_count   = m->numChars;
     cfg.category_count  = SeamCategories (m);
-    cfg.flags           = (SeamOmegaCategories (m) == YES) ? MB200_CONFIG_CIJK_PARTS (m->nCijkParts) : 0;
+    cfg.flags           = (SeamCategoryEigens (m) == YES) ? MB200_CONFIG_CIJK_PARTS (m->nCijkParts) : 0;
     cfg.matrix_count    = m->numTiProbs;
     cfg.scaler_count    = m->numScalers;
     cfg.eigen_count     = numLocalChains + 1;    /* unused (but harmless) for the inline-eigen models */
@@ -407,8 +431,8 @@ int TreeTiProbs_Beagle (Tree *t, int division, int chain)
         catRate = &theRate;
     for (k=0; k<m->numRateCats; k++)
         sd->ev.category_rates[k] = baseRate * catRate[k] * corr;
-    if (SeamOmegaCategories (m) == YES)
-        for (k=0; k<m->numOmegaCats; k++)
+    if (SeamCategoryEigens (m) == YES)
+        for (k=0; k<SeamCategories (m); k++)
             sd->ev.category_rates[k] = corr;    /* TiProbs_GenCov: t = length * correctionFactor, nothing else */
 
     return (NO_ERROR);
@@ -541,6 +565,19 @@ int TreeLikelihood_Beagle (Tree *t, int division, int chain, MrBFlt *lnL, int wh
     bs = GetParamSubVals (m->stateFreq, chain, state[chain]);
     for (s=0; s<m->numModelStates; s++)
         sd->ev.state_freqs[s] = bs[s];
+    if (m->switchRates != NULL)
+        {
+        /* covarion: stationary frequencies of the on / off copies of every state, on-states first
+           (Likelihood_Gen, src/likelihood.c:5799-5818) */
+        MrBFlt *swr = GetParamVals (m->switchRates, chain, state[chain]);
+        MrBFlt  probOn = swr[0] / (swr[0] + swr[1]), probOff = 1.0 - probOn;
+        int     half = m->numModelStates / 2;
+        for (s=0; s<half; s++)
+            {
+            sd->ev.state_freqs[s]        = bs[s] * probOn;
+            sd->ev.state_freqs[s + half] = bs[s] * probOff;
+            }
+        }
 
     if (seamDeferred == YES)
         {

@@ -536,7 +536,7 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
         c.eigen_count = numLocalChains + 1;
         }
         c.weight_rows = chainParams.numChains; c.device = 0; c.max_evaluations = 1;
-        c.flags = (m->numOmegaCats > 1) ? MB200_CONFIG_CIJK_PARTS (m->nCijkParts) : 0;
+        c.flags = (m->nCijkParts > 1) ? MB200_CONFIG_CIJK_PARTS (m->nCijkParts) : 0;            /* NY98, covarion + gamma */
         memcpy (hdr + 1, &c, 12 * sizeof(int));
         }
         Chunk ("INST", hdr, sizeof(hdr), NULL, 0);

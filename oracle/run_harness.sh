@@ -10,7 +10,7 @@ sed -e "s/NGEN/$NGEN/" -e "s#OUTPREFIX#$TMP/out#" tests/golden/cmd/$STEM.nex > $
 BIN=oracle/_ref/mb_b200
 [ "${SSE:-0}" = "1" ] && BIN=oracle/_ref/mb_b200_sse
 START=$(date +%s.%N)
-MB200_MODE=$MODE MB200_REPORT=$TMP/report.json $BIN $TMP/run.nex > $TMP/run.log 2>$TMP/run.err || { tail -5 $TMP/run.log $TMP/run.err; exit 1; }
+MB200_MODE=$MODE MB200_REPORT=$TMP/report.json timeout -s KILL ${MB200_TIMEOUT:-900} $BIN $TMP/run.nex > $TMP/run.log 2>$TMP/run.err || { tail -5 $TMP/run.log $TMP/run.err; exit 1; }
 END=$(date +%s.%N)
 grep -E "Using B200|Using standard|likelihood calculator" $TMP/run.log | head -3 || true
 head -5 $TMP/run.err || true
