@@ -332,7 +332,9 @@ def bench_engine(args):
     R = max(1, args.replicas)
     seeds = replica_seeds(rank, R)
     probs = [primates_problem(n_chains, seed=sd[0]) for sd in seeds]
-    insts = [p.create(lib, device=local, max_evaluations=n_chains) for p in probs]
+    # several analyses share the GPU: SM time counts, not the latency of one launch
+    inst_flags = abi.CONFIG_THROUGHPUT if (R > 1 and args.throughput_tiling) else 0
+    insts = [p.create(lib, device=local, max_evaluations=n_chains, flags=inst_flags) for p in probs]
     pr, inst = probs[0], insts[0]
     cycle_len = 128
     steps_r = [make_cycle(p, i, cycle_len, seed=sd[1]) for sd, p, i in zip(seeds, probs, insts)]
@@ -540,6 +542,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--host-threads", type=int, default=8,
                     help="host threads the end-to-end loop deals the replicas out to (the reference arm uses every host core)")
+    ap.add_argument("--throughput-tiling", action="store_true",
+                    help="create the instances with MB200_CONFIG_THROUGHPUT (one CTA per evaluation walks all pattern "
+                         "tiles); measured slower than the default tiling at 32 replicas of this workload: 86 vs 75 us/step")
     ap.add_argument("--replicas", type=int, default=32,
                     help="independent analyses (engine instances) in flight per GPU; 1 = a single analysis (latency regime)")
     ap.add_argument("--other", default="nuc200k,aa50k,codon20k",

@@ -85,6 +85,10 @@ extern "C" {
  * m->cijks[] (cijkLength = parts * (2S + S^3)); category k uses part k.  parts must be 1 or equal to
  * category_count. */
 #define MB200_CONFIG_CIJK_PARTS(n) (((n) & 0xff) << 8)
+/* Favour throughput over the latency of one call: set it when several instances (independent
+ * analyses, or the partitions of a large data set) keep the GPU busy together.  4-state path: one
+ * CTA per evaluation walks all pattern tiles and rebuilds P(t) once instead of once per tile. */
+#define MB200_CONFIG_THROUGHPUT 1
 
 /* evaluation flags */
 /* Root integration follows Likelihood_NUC4_{SSE,AVX,FMA}: when the site scaler is
@@ -112,7 +116,7 @@ typedef struct mb200_instance_config
     int weight_rows;      /* rows of numSitesOfPat (1, or numChains when reweighting)     */
     int device;           /* CUDA device ordinal                                          */
     int max_evaluations;  /* largest `count` ever passed to mb200_evaluate (>=1)          */
-    int flags;            /* MB200_CONFIG_CIJK_PARTS(n) for models with one eigensystem per category, else 0 */
+    int flags;            /* MB200_CONFIG_THROUGHPUT | MB200_CONFIG_CIJK_PARTS(n), or 0                      */
 } mb200_instance_config;
 
 /* One interior-node update: what CondLikeDown / CondLikeRoot + RemoveNodeScalers +

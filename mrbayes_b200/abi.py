@@ -22,6 +22,7 @@ ORACLE_LIB = ROOT / "oracle" / "liboracle.so"
 MAX_STATES = 64
 MAX_CATEGORIES = 20
 NONE = -1
+CONFIG_THROUGHPUT = 1        # mb200_instance_config.flags: favour throughput over single-call latency
 EIGEN_INLINE = -2
 FLAG_NUC4_PINVAR_QUIRK = 1
 FLAG_TIP_SHORTCUTS = 2

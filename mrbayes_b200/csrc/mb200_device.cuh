@@ -159,7 +159,8 @@ struct DevCtx                       // instance geometry + buffer bases, passed 
     unsigned int   *ticket;         // [maxEval]
     unsigned long long *dbg;        // [maxEval][64] phase timestamps (MB200_PHASE_TIMING builds only)
     int    cijkParts;               // eigensystems per cijk slot: 1, or K (category k uses part k: NY98-type models)
-    int    pad0;
+    int    patternTiles;            // 4-state path: tiles of tilePatterns patterns; numTiles (CTAs per evaluation) may be
+                                    // smaller: a CTA then walks several tiles (throughput mode)
 };
 
 static inline size_t mb200_align16 (size_t x) { return (x + 15) & ~(size_t)15; }

@@ -35,6 +35,7 @@ struct Batch                       // packed evaluations (device job format)
     int     nDirty = 0;            // P(t) rebuilds in the batch
     bool    fused = false;         // 4-state latency path: P(t) rebuilt inside the pruning kernel
     bool    needInv = false;
+    bool    singleChunk = false;   // every evaluation of the batch fits one chunk (4-state path)
     bool    used = false;
     int     tipEpoch = 0;          // Instance::tipEpoch at pack time (4-state records embed tip kinds)
     JobIndex jx;                   // 4-state latency path: where each evaluation's first chunk lives
@@ -499,6 +500,8 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         }
     b.bytes = bytes; b.nEval = count; b.nMat = nUpd; b.nOp = nOp; b.nDbl = nDbl;
     b.nDirty = nMat; b.fused = fused; b.tipEpoch = I->tipEpoch;
+    b.singleChunk = true;
+    for (int e = 0; e < count; e++) if (nChunkOf[e] != 1) b.singleChunk = false;
     b.offEval = offEval; b.offDbl = offDbl; b.offUpd = offUpd; b.offChunk = offChunk; b.offCmat = offCmat; b.offOp = offOp;
     return MB200_SUCCESS;
 }
@@ -643,7 +646,13 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
     if (ctx.S == 4 && ctx.K <= 8)
         {
         ctx.tilePatterns = nuc4PatternsPerBlock (ctx.K, b.fused);
-        ctx.numTiles = (ctx.C + ctx.tilePatterns - 1) / ctx.tilePatterns;
+        ctx.patternTiles = (ctx.C + ctx.tilePatterns - 1) / ctx.tilePatterns;
+        ctx.numTiles = ctx.patternTiles;
+        // throughput mode (MB200_CONFIG_THROUGHPUT): several analyses share the GPU, so SM time counts, not
+        // the latency of one launch -- one CTA per evaluation walks all its tiles and builds P(t) once
+        // instead of once per tile.  Single-chunk evaluations only (per-pattern state lives in registers).
+        if (b.fused && (I->cfg.flags & MB200_CONFIG_THROUGHPUT) && b.singleChunk)
+            ctx.numTiles = 1;
         ctx.hostSum = (hostSum && ctx.numTiles <= HOSTSUM_MAX_TILES) ? 1 : 0;
         I->lastHostSum = ctx.hostSum; I->lastTiles = ctx.numTiles;
         dim3 grid (ctx.numTiles, b.nEval);
@@ -987,7 +996,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     x.numTiles = I->maxTiles;
     x.tip8 = I->dTip8; x.tip64 = I->dTip64; x.tipPartAmbig = I->dTipPartAmbig; x.partials = I->dPartials; x.matrices = I->dMatrices;
     x.scalers = I->dScalers; x.eigen = I->dEigen; x.weights = I->dWeights; x.invMask = I->dInvMask;
-    x.cijkParts = I->cijkParts; x.pad0 = 0;
+    x.cijkParts = I->cijkParts; x.patternTiles = 0;
     x.tilePartial = I->dTilePartial; x.tileAbort = I->dTileAbort; x.ticket = I->dTicket; x.dbg = I->dDbg;
 
     if (cudaStreamSynchronize (I->stream) != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }

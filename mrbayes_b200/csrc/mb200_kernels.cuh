@@ -555,10 +555,12 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
     const int   lk     = threadIdx.x % L;                   // this lane's rate category
     const int   kk     = (lk < K) ? lk : K - 1;
     const int   pl     = threadIdx.x / L;                   // pattern slot within the CTA
-    const int   c0     = blockIdx.x * PPB;
-    const int   c      = c0 + pl;
-    const bool  active = (c < C) && (lk < K);
-    const int   cc     = (c < C) ? c : C - 1;
+    // the pattern tile this CTA works on; in throughput mode (ctx.patternTiles > gridDim.x, single-chunk
+    // evaluations only) a CTA walks several tiles, reusing the P(t) slots and tip tables it built
+    int   c0     = blockIdx.x * PPB;
+    int   c      = c0 + pl;
+    bool  active = (c < C) && (lk < K);
+    int   cc     = (c < C) ? c : C - 1;
     float4 *partials4 = reinterpret_cast<float4 *>(ctx.partials);
     const unsigned groupBase = (threadIdx.x & 31) & ~(L - 1);
     const int   nChunk = sEv.nChunk;
@@ -568,7 +570,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
 
     // per-thread addressing: everything in the node loop is  base + (uniform offset from the op record)
     // (32-bit element offsets: pack() guarantees they fit; one live register per base)
-    const unsigned       tOff  = (unsigned) kk * (unsigned) C + (unsigned) cc;
+    unsigned             tOff  = (unsigned) kk * (unsigned) C + (unsigned) cc;
     const unsigned       sPk   = (unsigned) __cvta_generic_to_shared (&sP[0][kk][0]);
     float               *sNewT = &sNew[0][pl];
     const NucOp         *nops  = reinterpret_cast<const NucOp *>(sOps);
@@ -576,6 +578,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
     const unsigned sTabK  = (unsigned) __cvta_generic_to_shared (&sTab[0][0][kk]);
     const unsigned sMaskP = (unsigned) __cvta_generic_to_shared (&sMask[0][pl]);
 
+    double termAcc = 0.0; int abortAcc = 0;       // this thread's lnL terms over the tiles of the CTA
     for (int ci = 0; ci < nChunk; ci++)
         {
         // ---- 1. chunk descriptor, node list, branch list (chunk 0: staged above) ----
@@ -593,6 +596,17 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
         const DevChunk ch = (ci == 0) ? ch0 : sCh;
         const int nMatC = ch.nMat & 0xffff, nTipC = (ch.nMat >> 16) & 0xff, nPreC = FUSE ? (int)((unsigned) ch.nMat >> 24) : 0;
         if (ci == 0) MB200_STAMP (2);
+
+        for (int tIdx = blockIdx.x, firstTile = 1; tIdx < ctx.patternTiles; tIdx += gridDim.x, firstTile = 0)
+        {
+        if (!firstTile)
+            {
+            __syncthreads ();                     // the previous tile is done with sMask / sNew / sOld / sPre
+            c0 = tIdx * PPB; c = c0 + pl; active = (c < C) && (lk < K); cc = (c < C) ? c : C - 1;
+            tOff = (unsigned) kk * (unsigned) C + (unsigned) cc;
+            lnScaler = (sEv.siteSrc >= 0) ? ctx.scalers[(size_t)sEv.siteSrc * C + cc] : 0.0f;
+            cur = make_float4 (0.f, 0.f, 0.f, 0.f);
+            }
 
         // ---- 2. P(t) slots (K1 fused: TiProbs_Gen, src/likelihood.c:9499-9542); the chunk's tip masks
         //      for this CTA's patterns: the loads go out first, eight deep (the bytes may come from HBM
@@ -618,7 +632,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 if (u < nPreC)
                     pre[u] = partials4[tOff + sPreList[u]];
             }
-        for (int r = threadIdx.x; r < nMatC * K * 4; r += NT)
+        for (int r = threadIdx.x; firstTile && r < nMatC * K * 4; r += NT)
             {
             const int s = r & 3, k = (r >> 2) % K, m = r / (4*K);
             const int eg = sMat[m].eigen;
@@ -651,7 +665,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
             }
         __syncthreads ();
         if (ci == 0) MB200_STAMP (50);
-        if (FUSE)
+        if (FUSE && firstTile)
             {
             for (int r = threadIdx.x; r < nMatC * K * 4; r += NT)
                 {
@@ -707,7 +721,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
         // highest state] + P[i][highest state].  Under the scalar kernels' shortcut a missing
         // observation on a tip without partial ambiguity contributes exactly 1.0 (preLike tables,
         // src/likelihood.c:816-832)
-        for (int e = threadIdx.x; e < nTipC * K * 4; e += NT)
+        for (int e = threadIdx.x; firstTile && e < nTipC * K * 4; e += NT)
             {
             const int i = e & 3, k = (e >> 2) % K, t = e / (4*K);
             const uint2 ti = sTipInfo[t];
@@ -858,67 +872,76 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                 if (nops[oo].sw >= 0)
                     lnScaler += sNewT[oo * PPB];
                 }
+        // ---- 5. after the last chunk: site scalers out, root integration, this tile's lnL terms ----
+        if (ci < nChunk - 1)
+            continue;
+        {
+        if (sEv.siteDst >= 0 && active && lk == 0)
+            ctx.scalers[(size_t)sEv.siteDst * C + c] = lnScaler;
+
+        if (sEv.root < 0)
+            continue;
+
+        // ---- root integration (Likelihood_NUC4_FMA, src/likelihood.c:6468-6625) ----
+        if (!sEv.rootFwd)
+            cur = partials4[tOff + sEv.rootOff];
+        const double *freqs = sD + 2*K, *catW = sD + K;
+        const float fA = (float) freqs[0], fC = (float) freqs[1], fG = (float) freqs[2], fT = (float) freqs[3];
+        // the reference accumulates one fused chain over k = 0..K-1 and the four states; the chain
+        // hops from lane to lane so that the rounding sequence is the same
+        float likeF = 0.0f;
+        if (sEv.equalWeights)
+            {
+            #pragma unroll
+            for (int k = 0; k < K; k++)
+                {
+                float mine = fmaf (cur.x, fA, likeF);
+                mine = fmaf (cur.y, fC, mine);
+                mine = fmaf (cur.z, fG, mine);
+                mine = fmaf (cur.w, fT, mine);
+                likeF = __shfl_sync (0xffffffffu, mine, groupBase + k);
+                }
+            likeF *= (float) catW[0];
+            }
+        else
+            {
+            float s = cur.x * fA;
+            s = fmaf (cur.y, fC, s);
+            s = fmaf (cur.z, fG, s);
+            s = fmaf (cur.w, fT, s);
+            #pragma unroll
+            for (int k = 0; k < K; k++)
+                {
+                const float mine = fmaf (s, (float) catW[kk], likeF);
+                likeF = __shfl_sync (0xffffffffu, mine, groupBase + k);
+                }
+            }
+        double likeI = 0.0;
+        if (sEv.hasPInvar)
+            {
+            const unsigned int im = (unsigned int) ctx.invMask[cc];
+            float li = (im & 1) ? fA : 0.0f;
+            li = fmaf ((im & 2) ? 1.0f : 0.0f, fC, li);
+            li = fmaf ((im & 4) ? 1.0f : 0.0f, fG, li);
+            li = fmaf ((im & 8) ? 1.0f : 0.0f, fT, li);
+            li *= (float) sEv.pInvar;
+            likeI = (double) li;
+            }
+        int    abortFlag = 0;
+        double term = 0.0;
+        if (active && lk == 0)
+            term = site_term ((double) likeF, likeI, sEv.hasPInvar, sEv.flags & MB200_QUIRK_FLAG, lnScaler,
+                              ctx.weights[(size_t)sEv.weightsRow * C + c], abortFlag);
+        termAcc += term; abortAcc |= abortFlag;
         }
+        }   // tiles of this CTA
+        }   // chunks
 
     MB200_STAMP (4);
-    if (sEv.siteDst >= 0 && active && lk == 0)
-        ctx.scalers[(size_t)sEv.siteDst * C + c] = lnScaler;
-
     if (sEv.root < 0)
         return;
-
-    // ---- root integration (Likelihood_NUC4_FMA, src/likelihood.c:6468-6625) ----
-    if (!sEv.rootFwd)
-        cur = partials4[tOff + sEv.rootOff];
-    const double *freqs = sD + 2*K, *catW = sD + K;
-    const float fA = (float) freqs[0], fC = (float) freqs[1], fG = (float) freqs[2], fT = (float) freqs[3];
-    // the reference accumulates one fused chain over k = 0..K-1 and the four states; the chain
-    // hops from lane to lane so that the rounding sequence is the same
-    float likeF = 0.0f;
-    if (sEv.equalWeights)
-        {
-        #pragma unroll
-        for (int k = 0; k < K; k++)
-            {
-            float mine = fmaf (cur.x, fA, likeF);
-            mine = fmaf (cur.y, fC, mine);
-            mine = fmaf (cur.z, fG, mine);
-            mine = fmaf (cur.w, fT, mine);
-            likeF = __shfl_sync (0xffffffffu, mine, groupBase + k);
-            }
-        likeF *= (float) catW[0];
-        }
-    else
-        {
-        float s = cur.x * fA;
-        s = fmaf (cur.y, fC, s);
-        s = fmaf (cur.z, fG, s);
-        s = fmaf (cur.w, fT, s);
-        #pragma unroll
-        for (int k = 0; k < K; k++)
-            {
-            const float mine = fmaf (s, (float) catW[kk], likeF);
-            likeF = __shfl_sync (0xffffffffu, mine, groupBase + k);
-            }
-        }
-    double likeI = 0.0;
-    if (sEv.hasPInvar)
-        {
-        const unsigned int im = (unsigned int) ctx.invMask[cc];
-        float li = (im & 1) ? fA : 0.0f;
-        li = fmaf ((im & 2) ? 1.0f : 0.0f, fC, li);
-        li = fmaf ((im & 4) ? 1.0f : 0.0f, fG, li);
-        li = fmaf ((im & 8) ? 1.0f : 0.0f, fT, li);
-        li *= (float) sEv.pInvar;
-        likeI = (double) li;
-        }
-    int    abortFlag = 0;
-    double term = 0.0;
-    if (active && lk == 0)
-        term = site_term ((double) likeF, likeI, sEv.hasPInvar, sEv.flags & MB200_QUIRK_FLAG, lnScaler,
-                          ctx.weights[(size_t)sEv.weightsRow * C + c], abortFlag);
     MB200_STAMP (5);
-    finish_lnl<NT> (ctx, blockIdx.y, term, abortFlag, out, seq);
+    finish_lnl<NT> (ctx, blockIdx.y, termAcc, abortAcc, out, seq);
     MB200_STAMP (6);
 }
 

@@ -237,8 +237,8 @@ class Problem:
             self.chains.append(ChainState(cl, cls, ti, tis, ns, nss, base + nI, base + 2 * nI + 1,
                                           np.zeros(nN, bool), eigen=0))
 
-    def create(self, lib: abi.Library, device=0, max_evaluations=None) -> abi.Instance:
-        inst = abi.Instance(lib, device=device, **self.config(max_evaluations))
+    def create(self, lib: abi.Library, device=0, max_evaluations=None, flags=0) -> abi.Instance:
+        inst = abi.Instance(lib, device=device, flags=flags, **self.config(max_evaluations))
         for t in range(self.n_tips):
             inst.set_tip_states(t, self.masks[t])
         inst.set_pattern_weights(0, self.weights)

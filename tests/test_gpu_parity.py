@@ -175,6 +175,30 @@ def test_partition_batched_begin_end_equals_evaluate(engine_lib):
             inst.close()
 
 
+@pytest.mark.parametrize("K,C", [(4, 413), (1, 700), (3, 65)])
+def test_throughput_mode_equals_latency_mode(engine_lib, K, C):
+    """MB200_CONFIG_THROUGHPUT: one CTA per evaluation walks all pattern tiles (P(t) built once).  Every
+    buffer must come out bit-identical to the default tiling; lnL only differs in the order of the final sum."""
+    nch = 4
+    a = workloads.make_problem(4, K, C, 12, nch, seed=77)
+    b = workloads.make_problem(4, K, C, 12, nch, seed=77)
+    rng_a, rng_b = np.random.default_rng(2), np.random.default_rng(2)
+    with a.create(engine_lib) as ia, b.create(engine_lib, flags=abi.CONFIG_THROUGHPUT) as ib:
+        for gen in range(4):
+            sa = [a.full_evaluation(ch) if gen == 0 else a.random_branch_update(ch, rng_a) for ch in range(nch)]
+            sb = [b.full_evaluation(ch) if gen == 0 else b.random_branch_update(ch, rng_b) for ch in range(nch)]
+            la, sta = ia.evaluate(sa)
+            lb, stb = ib.evaluate(sb)
+            assert not sta.any() and not stb.any()
+            assert np.allclose(la, lb, rtol=1e-13, atol=0.0)
+            for spa, spb in zip(sa, sb):
+                for opa, opb in zip(spa.ops, spb.ops):
+                    assert np.array_equal(ia.get_partials(int(opa["dest"])), ib.get_partials(int(opb["dest"])))
+                    if opa["scale_write"] >= 0:
+                        assert np.array_equal(ia.get_scalers(int(opa["scale_write"])), ib.get_scalers(int(opb["scale_write"])))
+                assert np.array_equal(ia.get_scalers(spa.site_dst), ib.get_scalers(spb.site_dst))
+
+
 def test_resident_replay_equals_host_call(engine_lib):
     pr = workloads.make_problem(4, 4, 413, 12, 8, seed=9)
     with pr.create(engine_lib) as inst:
