@@ -333,6 +333,36 @@ __device__ __forceinline__ double site_term (double like, double likeI, int hasP
 // only in the final lnL reduction.  Every global access is a fully coalesced 16-byte (CL),
 // 4-byte (scalers, weights) or 1-byte (tip codes) per-thread access.
 // ---------------------------------------------------------------------------------------
+// (float) log ((double) m) for the node scalers (CondLikeScaler_NUC4 / _SSE, src/likelihood.c:5183, 5328): the
+// library's double-precision log costs ~75 instructions, most of them for arguments that cannot occur
+// here.  m is a positive normal float (a rescaler maximum): m = 2^e f with f in [0.7071, 1.4142],
+// log f = 2 atanh s, s = (f-1)/(f+1) (|s| <= 0.1716), evaluated in double to ~1e-15 -- the float cast
+// then agrees with the library's in all but ~1e-7 of the arguments.  Anything else goes to the library.
+__device__ __forceinline__ float log_of_max (float m)
+{
+    const int bits = __float_as_int (m);
+    if (bits < 0x00800000 || bits >= 0x7f800000)
+        return (float) log ((double) m);
+    int   e = (bits >> 23) - 127;
+    float f = __int_as_float ((bits & 0x007fffff) | 0x3f800000);           // [1, 2)
+    if (f > 1.41421354f) { f *= 0.5f; e += 1; }
+    const double fd = (double) f, dp1 = fd + 1.0, dm1 = fd - 1.0;
+    float r0;
+    asm ("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(f + 1.0f));
+    double r = (double) r0;
+    r = fma (r, fma (-dp1, r, 1.0), r);                                    // 1 / (f + 1)
+    double sq = dm1 * r;
+    sq = fma (fma (-sq, dp1, dm1), r, sq);                                 // s = (f - 1) / (f + 1)
+    const double s2 = sq * sq;
+    double p = 1.0 / 19.0;
+    p = fma (p, s2, 1.0 / 17.0); p = fma (p, s2, 1.0 / 15.0); p = fma (p, s2, 1.0 / 13.0);
+    p = fma (p, s2, 1.0 / 11.0); p = fma (p, s2, 1.0 / 9.0);  p = fma (p, s2, 1.0 / 7.0);
+    p = fma (p, s2, 1.0 / 5.0);  p = fma (p, s2, 1.0 / 3.0);
+    const double two_s = sq + sq;
+    const double lf = fma (two_s, p * s2, two_s);                          // 2 atanh s
+    return (float) fma ((double) e, 0.69314718055994530942, lf);
+}
+
 // r / m for the four states of a rescaled vector (CondLikeScaler_NUC4, src/likelihood.c:5169-5200):
 // one reciprocal refined to < 1 ulp, then per element the quotient with one exact-remainder
 // correction -- the correctly rounded quotient an IEEE divide returns, at a third of the
@@ -853,7 +883,7 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                     // (float) log (double): CondLikeScaler_NUC4 / _SSE (src/likelihood.c:5183, 5328);
                     // the correctly rounded value, which the AVX variant's logf returns too in all
                     // but rare last-bit cases
-                    sc = (float) log ((double) sNewT[oo * PPB]);
+                    sc = log_of_max (sNewT[oo * PPB]);
                     ctx.scalers[(size_t)sw * C + c] = sc;
                     }
                 if (sr >= 0)
