@@ -193,6 +193,31 @@ def reference_sample(n_procs: int, ngen: int, seed0: int):
         return tot_rate, tot_upd, wall, float(np.mean(secs))
 
 
+def usable_cores() -> int:
+    """Host cores this process may actually use: the smaller of the CPU count, the scheduler affinity
+    mask and the cgroup CPU quota (a container often sees every core of the machine but is capped)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path, parse in (("/sys/fs/cgroup/cpu.max", lambda t: (t.split()[0], t.split()[1])),):
+        try:
+            quota, period = parse(Path(path).read_text())
+            if quota != "max":
+                n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+        except (OSError, ValueError, IndexError):
+            pass
+    try:
+        q = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+        per = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+        if q > 0 and per > 0:
+            n = min(n, max(1, int(q / per + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def bench_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -208,7 +233,7 @@ def bench_reference(args):
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
-    cores = os.cpu_count() or 1
+    cores = args.ref_procs if args.ref_procs > 0 else usable_cores()
     ngen = 1500                                     # ~0.7 s of in-kernel time per process
     for w in range(min(args.warmup, 1)):
         reference_sample(cores, 300, 900 + w)
@@ -540,6 +565,8 @@ def main():
     ap.add_argument("--steps", type=int, default=4096)
     ap.add_argument("--warmup", type=int, default=128)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-procs", type=int, default=0,
+                    help="--impl reference: concurrent serial reference processes (0 = every usable host core)")
     ap.add_argument("--host-threads", type=int, default=8,
                     help="host threads the end-to-end loop deals the replicas out to (the reference arm uses every host core)")
     ap.add_argument("--throughput-tiling", action="store_true",
