@@ -382,7 +382,8 @@ def bench_engine(args):
     hl = C.CDLL(str(abi.ENGINE_LIB.parent / "libmb200_hostloop.so"))
     hl.mb200_host_generation_loop.restype = C.c_double
     hl.mb200_host_replay_loop.restype = C.c_double
-    HT = max(1, min(args.host_threads, R))              # host threads of the end-to-end loop
+    # host threads of the end-to-end loop: the ranks of a node share the usable host cores
+    HT = max(1, min(args.host_threads, R, max(1, usable_cores() // max(world, 1))))
     inst_ids = (C.c_int * R)(*[i.handle for i in insts])
     batch_ids = (C.c_int * (R * cycle_len))(*[b for br in batches_r for b in br])
     step_ptrs = (C.c_void_p * (R * cycle_len))(*[C.cast(a, C.c_void_p) for hr in host_arrays_r for a in hr])
