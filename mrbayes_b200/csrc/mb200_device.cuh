@@ -74,7 +74,9 @@ struct DevOp                        // one interior-node update (48 bytes)
 #define NUC_PRE      4u             // interior child this evaluation does not write, latency path: fetched into shared
                                     // memory when the chunk starts (slot in NucOp::pad), off the node chain
 #define NUC_FWD      8u             // the previous node's result: stays in registers
+#ifndef NUC_MAXPRE
 #define NUC_MAXPRE   8              // such operands per chunk
+#endif
 #define NUC_RESCALE  0x1000u
 struct NucOp
 {
@@ -95,7 +97,10 @@ struct NucOp
 #define NUC_OPC(PPB) ((1536 / (PPB) > 24) ? 24 : (1536 / (PPB) < 8 ? 8 : 1536 / (PPB)))
 #define NUC_STREAM_THREADS 1024
 #else
-#define NUC_MAXT(K) ((96 / (K)) > 64 ? 64 : (96 / (K)))
+#ifndef NUC_TABKB
+#define NUC_TABKB 96              // tip tables per chunk: NUC_TABKB / K (256 K bytes each)
+#endif
+#define NUC_MAXT(K) ((NUC_TABKB / (K)) > 64 ? 64 : (NUC_TABKB / (K)))
 #define NUC_OPC(PPB) ((2048 / (PPB) > 32) ? 32 : (2048 / (PPB) < 8 ? 8 : 2048 / (PPB)))   // nodes per chunk
 #define NUC_STREAM_THREADS 768      // resident threads per SM the streaming variant is compiled for
 #endif
