@@ -320,3 +320,58 @@ def test_large_trees_span_several_chunks(engine_lib, oracle_lib, tips, K):
             sp = pr.random_branch_update(0, rng)
             (le,), _ = e.evaluate(sp); (lo,), _ = o.evaluate(sp)
             assert rel(le, lo) < SYN_RTOL
+
+
+def test_api_edge_cases(engine_lib, oracle_lib):
+    """Degenerate and invalid inputs at the C-ABI: a single site pattern, an evaluation that only
+    integrates at the root, an evaluation without a root, out-of-range indices, protocol misuse."""
+    # one pattern, one category, four states: the smallest instance
+    pr_e = workloads.make_problem(4, 1, 1, 3, 1, seed=3)
+    pr_o = workloads.make_problem(4, 1, 1, 3, 1, seed=3)
+    with pr_e.create(engine_lib) as e, pr_o.create(oracle_lib) as o:
+        le, se = e.evaluate(pr_e.full_evaluation(0))
+        lo, so = o.evaluate(pr_o.full_evaluation(0))
+        assert not se.any() and abs(le[0] - lo[0]) <= 2e-7 * abs(lo[0])
+
+    pr_e = workloads.make_problem(4, 4, 97, 7, 2, seed=8)
+    with pr_e.create(engine_lib, max_evaluations=2) as e:
+        full = pr_e.full_evaluation(0)
+        want, _ = e.evaluate(full)
+        # root integration only: no matrix updates, no node updates, same buffers -> same lnL, bit for bit
+        root_only = abi.EvalSpec(mats=full.mats[:0], ops=full.ops[:0], site_dst=abi.NONE, site_src=full.site_dst,
+                                 root=full.root, weights_row=full.weights_row, flags=full.flags, p_invar=full.p_invar,
+                                 has_p_invar=full.has_p_invar, rates=full.rates, cat_weights=full.cat_weights, freqs=full.freqs)
+        got, st = e.evaluate(root_only)
+        assert not st.any() and np.array_equal(got, want)
+        # no root: buffers are updated, lnL comes back as 0 / OK
+        other = pr_e.full_evaluation(1)
+        no_root = abi.EvalSpec(mats=other.mats, ops=other.ops, site_dst=other.site_dst, site_src=other.site_src,
+                               root=abi.NONE, weights_row=0, flags=other.flags, p_invar=other.p_invar,
+                               has_p_invar=other.has_p_invar, rates=other.rates, cat_weights=other.cat_weights, freqs=other.freqs)
+        l0, s0 = e.evaluate(no_root)
+        assert l0[0] == 0.0 and s0[0] == 0
+        # ... and a root-only pass over them gives what a fused evaluation gives
+        pr_f = workloads.make_problem(4, 4, 97, 7, 2, seed=8)
+        with pr_f.create(engine_lib, max_evaluations=2) as f:
+            f.evaluate(pr_f.full_evaluation(0))
+            wantf, _ = f.evaluate(pr_f.full_evaluation(1))
+        root_only1 = abi.EvalSpec(mats=other.mats[:0], ops=other.ops[:0], site_dst=abi.NONE, site_src=other.site_dst,
+                                  root=other.root, weights_row=other.weights_row, flags=other.flags, p_invar=other.p_invar,
+                                  has_p_invar=other.has_p_invar, rates=other.rates, cat_weights=other.cat_weights, freqs=other.freqs)
+        l1, s1 = e.evaluate(root_only1)
+        assert not s1.any() and np.array_equal(l1, wantf)
+
+        # invalid indices are refused before anything is launched
+        bad = pr_e.full_evaluation(0)
+        bad.ops = bad.ops.copy(); bad.ops[0]["dest"] = 10 ** 6
+        with pytest.raises(abi.AbiError):
+            e.evaluate(bad)
+        bad = pr_e.full_evaluation(0)
+        bad.mats = bad.mats.copy(); bad.mats[0]["matrix"] = -5
+        with pytest.raises(abi.AbiError):
+            e.evaluate(bad)
+        with pytest.raises(abi.AbiError):
+            e.evaluate([pr_e.full_evaluation(0)] * 3)          # more evaluations than max_evaluations
+        # the instance is still usable afterwards
+        again, st = e.evaluate(pr_e.full_evaluation(0))
+        assert not st.any() and np.isfinite(again).all()
