@@ -122,6 +122,30 @@ struct JobIndex
 // device (last CTA) or, on the host-call latency path, on the host: the same order, the same bits
 #define MB200_SEQ_SUM_TILES 16
 
+// chunk geometry of the 4-state kernels (shared by pack() and the kernels).  The latency-path (FUSE)
+// variants may be compiled with smaller shared-memory areas (-DNUC_FUSE_*) to fit more CTAs per SM.
+#ifndef NUC_FUSE_MAXS
+#define NUC_FUSE_MAXS 96
+#endif
+#ifndef NUC_FUSE_OPC
+#define NUC_FUSE_OPC 32
+#endif
+#ifndef NUC_FUSE_TABKB
+#define NUC_FUSE_TABKB NUC_TABKB
+#endif
+__host__ __device__ constexpr int nuc_maxs (int K, bool fuse)          // P(t) slots per chunk
+{
+    return ((256 / K > 96) ? 96 : 256 / K) > (fuse ? NUC_FUSE_MAXS : 96) ? (fuse ? NUC_FUSE_MAXS : 96) : ((256 / K > 96) ? 96 : 256 / K);
+}
+__host__ __device__ constexpr int nuc_opc (int ppb, bool fuse)         // nodes per chunk
+{
+    return (NUC_OPC (ppb) > (fuse ? NUC_FUSE_OPC : 32)) ? (fuse ? NUC_FUSE_OPC : 32) : NUC_OPC (ppb);
+}
+__host__ __device__ constexpr int nuc_maxt (int K, bool fuse)          // tip operands (lookup tables) per chunk
+{
+    return (((fuse ? NUC_FUSE_TABKB : NUC_TABKB) / K) > 64) ? 64 : ((fuse ? NUC_FUSE_TABKB : NUC_TABKB) / K);
+}
+
 struct DevResult                    // 16 bytes per evaluation
 {
     double lnL;

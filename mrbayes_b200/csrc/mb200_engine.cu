@@ -199,15 +199,15 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     const long ctas = (long)((c.pattern_count + ppbS - 1) / ppbS) * count;
     const bool fused = nuc4 && ctas <= 4L * I->numSMs;          // small launch: latency-bound regime
     const int  ppb  = nuc4 ? nuc4PatternsPerBlock (K, fused) : 1;
-    const int  maxSlots = (256 / K > 96) ? 96 : 256 / K;        // Nuc4Geom<K>::MAXS
-    const int  opc = NUC_OPC (ppb);                             // nodes per chunk, as in the kernel
+    const int  maxSlots = nuc_maxs (K > 0 ? K : 1, fused);      // as in the kernel
+    const int  opc = nuc_opc (ppb, fused);                      // nodes per chunk, as in the kernel
     if ((int) I->slotOf.size () < c.matrix_count)
         { I->slotOf.assign (c.matrix_count, -1); I->dirtyOf.assign (c.matrix_count, -1); }
     std::vector<DevChunk> &chunks = I->chunkTmp;   // all evaluations, chunk0 of each included
     std::vector<DevMat>   &cmats  = I->cmatTmp;
     std::vector<int>      &slots  = I->slotTmp;    // 3 per operation
     std::vector<int>      &tipIdx = I->tipIdxTmp;  // 3 per operation: tip-table index within the chunk (-1: not a tip)
-    const int  maxTips = NUC_MAXT (K > 0 ? K : 1);
+    const int  maxTips = nuc_maxt (K > 0 ? K : 1, fused);
     std::vector<int>      &nChunkOf = I->nChunkTmp;
     chunks.clear (); cmats.clear (); slots.clear (); tipIdx.clear (); nChunkOf.assign (count, 0);
 

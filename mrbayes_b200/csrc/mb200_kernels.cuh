@@ -467,10 +467,10 @@ template <int K> struct Nuc4Geom
 template <int K, int NT, bool FUSE> struct Nuc4Smem
 {
     static constexpr int L    = Nuc4Geom<K>::L;
-    static constexpr int MAXS = Nuc4Geom<K>::MAXS;
+    static constexpr int MAXS = nuc_maxs (K, FUSE);
     static constexpr int PPB  = NT / L;
-    static constexpr int OPC  = NUC_OPC (PPB);
-    static constexpr int MAXT = NUC_MAXT (K);
+    static constexpr int OPC  = nuc_opc (PPB, FUSE);
+    static constexpr int MAXT = nuc_maxt (K, FUSE);
     float4 sP[MAXS][K][5];                       // P(t) rows of every branch the chunk touches (4 rows + 1 pad: bank spread)
     float4 sTab[MAXT][16][K];                    // per tip operand, state mask and category: sum of the P(t) columns the mask selects
                                                  // (mask-major: the K lanes of a pattern read one contiguous 16K-byte line)
