@@ -197,7 +197,11 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     const bool nuc4 = (S == 4 && K <= 8);
     const int  ppbS = nuc4 ? nuc4PatternsPerBlock (K, true) : 1;
     const long ctas = (long)((c.pattern_count + ppbS - 1) / ppbS) * count;
-    const bool fused = nuc4 && ctas <= 4L * I->numSMs;          // small launch: latency-bound regime
+    // fused P(t) rebuild (every CTA rebuilds the dirty matrices of its evaluation): small launches (latency-
+    // bound regime), and launches of many evaluations over few pattern tiles each (the rebuild is repeated
+    // only tiles-per-evaluation times, and a second kernel + its launch gap would cost more)
+    const long tilesS = (c.pattern_count + ppbS - 1) / ppbS;
+    const bool fused = nuc4 && (ctas <= 4L * I->numSMs || tilesS <= 16);
     const int  ppb  = nuc4 ? nuc4PatternsPerBlock (K, fused) : 1;
     const int  maxSlots = nuc_maxs (K > 0 ? K : 1, fused);      // as in the kernel
     const int  opc = nuc_opc (ppb, fused);                      // nodes per chunk, as in the kernel
