@@ -239,8 +239,10 @@ int MB200SeamDivisionSupported (ModelInfo *m)
         return NO;
     if (m->switchRates != NULL)
         return NO;                              /* covarion: the plumbing is here (SeamCovarionGamma, on/off
-                                                   frequencies) but the restatement is not pinned yet -- on primates the
-                                                   reference starts at lnL -1557.87 where this path gives -8553.7 */
+                                                   frequencies) but the restatement is not pinned: on primates the reference
+                                                   (as built here) starts at lnL -1557.87, above anything the data
+                                                   allows, while this path and an independent float64 recomputation
+                                                   from the same inputs give -8553.72 */
     if (m->numModelStates < 2 || m->numModelStates > MB200_MAX_STATES)
         return NO;
     if (m->numRateCats < 1 || m->numRateCats > MB200_MAX_CATEGORIES)
