@@ -453,6 +453,25 @@ def bench_engine(args):
                   "e2e": upd1 / sec1, "e2e_ms_per_step": sec1 * 1e3 / K, "unit": UNIT,
                   "note": "one nruns=2 x nchains=4 analysis alone on the GPU: the latency-bound regime"}
 
+    # ---- the same chains as ONE analysis (nruns = 2R, nchains = 4) on ONE instance: one launch per generation ----
+    one_instance = None
+    if R > 1 and rank == 0 and not args.no_one_instance:
+        big = primates_problem(n_chains * R, seed=424242)
+        with big.create(lib, device=local, max_evaluations=n_chains * R) as bi:
+            bsteps = make_cycle(big, bi, 32, seed=99)
+            bb = [bi.pack(sp) for sp in bsteps]
+            ids1 = (C.c_int * 1)(bi.handle)
+            barr = (C.c_int * len(bb))(*bb)
+            seq = [i % len(bb) for i in range(max(64, min(K, 512)) // len(bb) * len(bb))]
+            arr1, n1 = c_order(seq)
+            hl.mb200_host_replay_loop(ids1, C.c_int(1), barr, C.c_int(len(bb)), arr1, C.c_int(n1), C.c_void_p(None), C.c_size_t(0))
+            msb = hl.mb200_host_replay_loop(ids1, C.c_int(1), barr, C.c_int(len(bb)), arr1, C.c_int(n1),
+                                            C.c_void_p(flush.data_ptr()), C.c_size_t(flush.numel()))
+            updb = sum(updates_of(bsteps[i], big.C, big.K) for i in seq)
+            one_instance = {"chains": n_chains * R, "value": updb / (msb * 1e-3), "ms_per_step": msb / n1, "unit": UNIT,
+                            "note": f"nruns={2 * R} x nchains=4 of the same alignment as ONE analysis on one instance: "
+                                    f"all chains of a generation in one launch (device-resident replay, L2 flushed)"}
+
     # ---- roofline of the fused kernel: events inside the engine, replica 0 alone, flushed ----
     inst.set_kernel_timing(True)
     stream = torch.cuda.ExternalStream(inst.stream(), device=local)
@@ -536,6 +555,8 @@ def bench_engine(args):
         }
         if single is not None:
             line["single_replica"] = single
+        if one_instance is not None:
+            line["all_chains_one_instance"] = one_instance
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         if args.other and world == 1:
@@ -570,6 +591,7 @@ def main():
                     help="--impl reference: concurrent serial reference processes (0 = every usable host core)")
     ap.add_argument("--host-threads", type=int, default=8,
                     help="host threads the end-to-end loop deals the replicas out to (the reference arm uses every host core)")
+    ap.add_argument("--no-one-instance", action="store_true", help="skip the informational all-chains-on-one-instance leg")
     ap.add_argument("--throughput-tiling", action="store_true",
                     help="create the instances with MB200_CONFIG_THROUGHPUT (one CTA per evaluation walks all pattern "
                          "tiles); measured slower than the default tiling at 32 replicas of this workload: 86 vs 75 us/step")
