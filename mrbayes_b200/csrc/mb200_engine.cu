@@ -634,7 +634,7 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
         if (ctx.S > 32)
             {
             dim3 grid (b.nMat, ctx.K, (ctx.S + 3) / 4);
-            tiprobs_wide_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, b.nEval, dd, du);
+            tiprobs_wide_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, b.nEval, dd, du, (I->tcS == 61) ? I->dSplit : nullptr);
             }
         else
             {
@@ -674,7 +674,8 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
     else if (I->tcS)
         {
         // tensor-core path: refresh the pre-split images of the matrices just rebuilt, then prune
-        if (b.nDirty > 0)
+        // (61 states: tiprobs_wide_kernel has written them already)
+        if (b.nDirty > 0 && I->tcS != 61)
             {
             dim3 sg (b.nMat, ctx.K);
             if (I->tcS == 61) tc_split_kernel<61><<<sg, 128, 0, I->stream>>> (I->dMatrices, I->dSplit, du, 0, ctx.K);

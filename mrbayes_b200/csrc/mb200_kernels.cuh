@@ -96,6 +96,24 @@ tiprobs_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, const 
         }
 }
 
+__device__ __forceinline__ float umma_to_tf32 (float x)      // round-to-nearest TF32, as umma::to_tf32
+{
+    unsigned r;
+    asm ("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+    return __uint_as_float (r);
+}
+
+// 61-state tensor-core path: entry (i, j) of a P(t) matrix -> the pre-split operand image of tc kernel B
+// (canonical K-major layout of a 64-row tile, hi image then lo image: umma_common.cuh canon_off; mb200_kernels_tc.cuh)
+__device__ __forceinline__ void write_split61 (float *split61, int matrix, int K, int k, int i, int j, float pv)
+{
+    const float hi = umma_to_tf32 (pv), lo = umma_to_tf32 (pv - hi);
+    float *img = split61 + ((size_t)matrix * K + k) * (2 * 64 * 64);
+    const unsigned off = (unsigned)((j >> 2) * (64 >> 3) * 128 + (i >> 3) * 128 + (i & 7) * 16 + (j & 3) * 4) / 4u;
+    img[off] = hi;
+    img[64 * 64 + off] = lo;
+}
+
 // K1 for large state counts (61-state codon): the same sum, organised for memory parallelism.
 // grid = (matrix updates, K, ceil(S/4)); one warp per ancestral state i: for each j the 32 lanes
 // read the S consecutive doubles c[i][j][.] (coalesced), multiply by exp(lambda_s t) from shared
@@ -103,7 +121,7 @@ tiprobs_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, const 
 // loop by O(1e-16) relative, invisible after the cast to float.)
 __global__ void __launch_bounds__(128)
 tiprobs_wide_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, const double *__restrict__ dvals,
-                     const DevMat *__restrict__ mats)
+                     const DevMat *__restrict__ mats, float *__restrict__ split61)
 {
     __shared__ double sExp[MB200_DEV_MAX_STATES];
     __shared__ int sEvalIdx;
@@ -133,7 +151,12 @@ tiprobs_wide_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, c
         {
         if (i < S)
             for (int j = lane; j < S; j += 32)
-                P[i*S + j] = (t < MB200_TIME_MIN) ? ((i == j) ? 1.0f : 0.0f) : (float) freqs[j];
+                {
+                const float pv = (t < MB200_TIME_MIN) ? ((i == j) ? 1.0f : 0.0f) : (float) freqs[j];
+                P[i*S + j] = pv;
+                if (split61 != nullptr)
+                    write_split61 (split61, mu.matrix, ctx.K, k, i, j, pv);
+                }
         return;
         }
     const size_t   partLen = 2*(size_t)S + (size_t)S*S*S;
@@ -145,17 +168,36 @@ tiprobs_wide_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, c
     if (i >= S)
         return;
     const double e0 = (lane < S) ? sExp[lane] : 0.0, e1 = (lane + 32 < S) ? sExp[lane + 32] : 0.0;
-    for (int j = 0; j < S; j++)
+    // four j at a time: the loads of a group are all in flight before the first reduction (one L2 round
+    // trip per group instead of one per j)
+    for (int j0 = 0; j0 < S; j0 += 4)
         {
-        const double *c = cij + ((size_t)i * S + j) * S;
-        double sum = 0.0;
-        if (lane < S)      sum  = c[lane] * e0;
-        if (lane + 32 < S) sum += c[lane + 32] * e1;
+        double sum[4];
+        #pragma unroll
+        for (int u = 0; u < 4; u++)
+            {
+            const int j = (j0 + u < S) ? j0 + u : S - 1;
+            const double *c = cij + ((size_t)i * S + j) * S;
+            double v = 0.0;
+            if (lane < S)      v  = c[lane] * e0;
+            if (lane + 32 < S) v += c[lane + 32] * e1;
+            sum[u] = v;
+            }
         #pragma unroll
         for (int off = 16; off > 0; off >>= 1)
-            sum += __shfl_xor_sync (0xffffffffu, sum, off);
-        if (lane == 0)
-            P[i*S + j] = (float) ((sum < 0.0) ? 0.0 : sum);
+            {
+            #pragma unroll
+            for (int u = 0; u < 4; u++)
+                sum[u] += __shfl_xor_sync (0xffffffffu, sum[u], off);
+            }
+        if (lane < 4 && j0 + lane < S)
+            {
+            const double sj = (lane == 0) ? sum[0] : (lane == 1) ? sum[1] : (lane == 2) ? sum[2] : sum[3];
+            const float  pv = (float) ((sj < 0.0) ? 0.0 : sj);
+            P[i*S + j0 + lane] = pv;
+            if (split61 != nullptr)              // the tensor-core kernel's operand image, no extra kernel
+                write_split61 (split61, mu.matrix, ctx.K, k, i, j0 + lane, pv);
+            }
         }
 }
 
