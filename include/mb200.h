@@ -37,6 +37,10 @@
  *   mb200_root_log_likelihood    Likelihood_NUC4* / Likelihood_Gen*
  *                                (src/likelihood.c:5764-6960) /
  *                                TreeLikelihood_Beagle (src/mbbeagle.c:1117)
+ *   mb200_set_pattern_states     m->nStates / tiIndex / bsIndex of STANDARD-data
+ *                                divisions (src/bayes.h:1329-1331); the *_Std
+ *                                kernel family (src/likelihood.c:1920, 4496,
+ *                                5547, 7359, 10066)
  *   mb200_evaluate               one whole LaunchLogLikeForDivision
  *                                (src/likelihood.c:7851-7973) per element,
  *                                any number of chains per call, ONE fused
@@ -89,6 +93,15 @@ extern "C" {
  * analyses, or the partitions of a large data set) keep the GPU busy together.  4-state path: one
  * CTA per evaluation walks all pattern tiles and rebuilds P(t) once instead of once per tile. */
 #define MB200_CONFIG_THROUGHPUT 1
+/* Variable-state division (STANDARD / morphological data; the reference's *_Std family:
+ * CondLikeDown_Std src/likelihood.c:1920, CondLikeRoot_Std :4496, CondLikeScaler_Std :5547,
+ * Likelihood_Std :7359, TiProbs_Std :10066).  Every site pattern has its own number of states
+ * (m->nStates[c] <= state_count) and its own transition matrices inside a branch's matrix block
+ * (m->tiIndex[c]); mb200_set_pattern_states supplies those tables.  P(t) is built by the engine for
+ * the equal-frequency Mk model (unordered characters, SYMPI_EQUAL: pNoChange / pChange per state
+ * count and category, src/likelihood.c:10135-10173); the root pass includes the correction for
+ * unobservable (dummy) patterns, Likelihood_Std's coding bias (src/likelihood.c:7401-7423, 7537). */
+#define MB200_CONFIG_VARIABLE_STATES 2
 
 /* evaluation flags */
 /* Root integration follows Likelihood_NUC4_{SSE,AVX,FMA}: when the site scaler is
@@ -116,7 +129,7 @@ typedef struct mb200_instance_config
     int weight_rows;      /* rows of numSitesOfPat (1, or numChains when reweighting)     */
     int device;           /* CUDA device ordinal                                          */
     int max_evaluations;  /* largest `count` ever passed to mb200_evaluate (>=1)          */
-    int flags;            /* MB200_CONFIG_THROUGHPUT | MB200_CONFIG_CIJK_PARTS(n), or 0                      */
+    int flags;            /* MB200_CONFIG_THROUGHPUT | MB200_CONFIG_VARIABLE_STATES | MB200_CONFIG_CIJK_PARTS(n), or 0 */
 } mb200_instance_config;
 
 /* One interior-node update: what CondLikeDown / CondLikeRoot + RemoveNodeScalers +
@@ -194,6 +207,22 @@ int mb200_finalize_instance (int instance);
  * replicated by the caller exactly as src/mcmc.c:6402-6411 does. */
 int mb200_set_tip_states      (int instance, int tip, const uint64_t *state_masks);
 int mb200_set_pattern_weights (int instance, int row, const float *weights);
+/* Variable-state instances only (MB200_CONFIG_VARIABLE_STATES), once, before the first evaluation:
+ *   state_counts[c]    m->nStates[c], 2 .. state_count                    (src/bayes.h:1331)
+ *   matrix_offsets[c]  m->tiIndex[c]: where pattern c's category-0 matrix starts inside a branch's
+ *                      block of matrix_length floats; category k follows at + k * nStates^2
+ *                      (src/likelihood.c:1958-1961)                        (src/bayes.h:1329)
+ *   freq_offsets[c]    m->bsIndex[c]: where pattern c's state frequencies start inside
+ *                      mb200_evaluation.state_freqs (freq_offsets[c] + nStates[c] <= 64)   (:1330)
+ *   matrix_length      m->tiProbLength: floats per branch (src/mcmc.c:5799-5828)
+ *   dummy_patterns     m->numDummyChars: leading all-constant patterns that only feed the
+ *                      unobservable-pattern correction (AddDummyChars, src/model.c:176-224)
+ *   uncompressed_sites m->numUncompressedChars: sites the correction applies to (:7537)
+ * Host layout of partials for these instances is the reference's ragged one: [k][c][nStates[c]]
+ * (src/likelihood.c:1941-1943); of a transition-matrix buffer: matrix_length floats. */
+int mb200_set_pattern_states (int instance, const int *state_counts, const int *matrix_offsets,
+                              const int *freq_offsets, int matrix_length, int dummy_patterns,
+                              int uncompressed_sites);
 
 /* ---- eigen systems ----------------------------------------------------------------- */
 /* block = [lambda_re(S), lambda_im(S), c_ijk(S*S*S)] exactly as m->cijks[idx] holds it
@@ -261,6 +290,17 @@ int mb200_synchronize      (int instance);
 int mb200_get_stream       (int instance, void **stream);
 /* kernels launched by the instance since creation (bench.py's gpu_launches) */
 int mb200_get_launch_count (int instance, long long *launches);
+/* the same count per kernel family, so a caller (or a test) can tell WHICH path served it: the
+ * 4-state shuffle kernel, the tcgen05 tensor-core kernel (20 / 61 states), the CUDA-core kernel for
+ * any other state count, the variable-state (Std) kernel, stand-alone P(t) builds, set-up kernels */
+#define MB200_KERNEL_NUC4     0
+#define MB200_KERNEL_TENSOR   1
+#define MB200_KERNEL_GENERIC  2
+#define MB200_KERNEL_STD      3
+#define MB200_KERNEL_TIPROBS  4
+#define MB200_KERNEL_SETUP    5
+#define MB200_KERNEL_KINDS    6
+int mb200_get_kernel_launches (int instance, int kind, long long *launches);
 /* Device-side timing of the dominant (fused pruning) kernel: when enabled, every launch of
  * it is bracketed by CUDA events on the instance's stream.  mb200_get_kernel_time
  * synchronises, returns the summed duration (ms) and the number of launches measured since

@@ -23,6 +23,8 @@ MAX_STATES = 64
 MAX_CATEGORIES = 20
 NONE = -1
 CONFIG_THROUGHPUT = 1        # mb200_instance_config.flags: favour throughput over single-call latency
+CONFIG_VARIABLE_STATES = 2   # STANDARD-data division: per-pattern state counts (the *_Std kernel family)
+KERNEL_NUC4, KERNEL_TENSOR, KERNEL_GENERIC, KERNEL_STD, KERNEL_TIPROBS, KERNEL_SETUP = range(6)
 EIGEN_INLINE = -2
 FLAG_NUC4_PINVAR_QUIRK = 1
 FLAG_TIP_SHORTCUTS = 2
@@ -111,6 +113,7 @@ class Library:
             "finalize_instance": [I],
             "set_tip_states": [I, I, P(C.c_uint64)],
             "set_pattern_weights": [I, I, P(C.c_float)],
+            "set_pattern_states": [I, P(I), P(I), P(I), I, I, I],
             "set_cijk": [I, I, P(D)],
             "set_eigen_decomposition": [I, I, P(D), P(D), P(D)],
             "evaluate": [I, P(Evaluation), I, P(D), P(I)],
@@ -133,6 +136,7 @@ class Library:
             "synchronize": [I],
             "get_stream": [I, P(C.c_void_p)],
             "get_launch_count": [I, P(C.c_longlong)],
+            "get_kernel_launches": [I, I, P(C.c_longlong)],
             "set_kernel_timing": [I, I],
             "get_kernel_time": [I, P(D), P(I)],
             "device_count": [],
@@ -246,6 +250,9 @@ class Instance:
         lib.check("create_instance", lib.fn("create_instance")(C.byref(self.cfg), C.byref(h)))
         self.handle = h.value
         self.S, self.K, self.C = state_count, category_count, pattern_count
+        self.variable_states = bool(flags & CONFIG_VARIABLE_STATES)
+        self.state_counts = None
+        self.matrix_length = None
 
     # -- lifetime --------------------------------------------------------------------
     def close(self):
@@ -278,6 +285,16 @@ class Instance:
         w = np.ascontiguousarray(w, np.float32)
         assert w.shape == (self.C,)
         self._call("set_pattern_weights", row, _ptr(w, C.c_float))
+
+    def set_pattern_states(self, state_counts, matrix_offsets, freq_offsets, matrix_length, dummy_patterns, uncompressed_sites):
+        """Variable-state divisions: m->nStates / tiIndex / bsIndex, tiProbLength, numDummyChars, numUncompressedChars."""
+        ns = np.ascontiguousarray(state_counts, np.int32)
+        ti = np.ascontiguousarray(matrix_offsets, np.int32)
+        bs = np.ascontiguousarray(freq_offsets, np.int32)
+        assert ns.shape == ti.shape == bs.shape == (self.C,)
+        self._call("set_pattern_states", _ptr(ns, C.c_int), _ptr(ti, C.c_int), _ptr(bs, C.c_int),
+                   int(matrix_length), int(dummy_patterns), int(uncompressed_sites))
+        self.state_counts, self.matrix_length = ns.copy(), int(matrix_length)
 
     def set_cijk(self, eigen: int, block):
         b = np.ascontiguousarray(block, np.float64)
@@ -346,6 +363,11 @@ class Instance:
         self._call("get_stream", C.byref(p))
         return p.value or 0
 
+    def kernel_launches(self, kind: int) -> int:
+        n = C.c_longlong(0)
+        self._call("get_kernel_launches", kind, C.byref(n))
+        return n.value
+
     def launch_count(self) -> int:
         n = C.c_longlong(0)
         self._call("get_launch_count", C.byref(n))
@@ -390,6 +412,10 @@ class Instance:
 
     # -- read-back ------------------------------------------------------------------------
     def get_partials(self, buffer: int) -> np.ndarray:
+        if self.variable_states:        # ragged reference layout [k][c][nStates[c]], returned flat per category
+            out = np.zeros((self.K, int(self.state_counts.sum())), np.float32)
+            self._call("get_partials", buffer, _ptr(out, C.c_float))
+            return out
         out = np.zeros((self.K, self.C, self.S), np.float32)
         self._call("get_partials", buffer, _ptr(out, C.c_float))
         return out
@@ -400,6 +426,10 @@ class Instance:
         self._call("set_partials", buffer, _ptr(a, C.c_float))
 
     def get_transition_matrix(self, matrix: int) -> np.ndarray:
+        if self.variable_states:
+            out = np.zeros(self.matrix_length, np.float32)
+            self._call("get_transition_matrix", matrix, _ptr(out, C.c_float))
+            return out
         out = np.zeros((self.K, self.S, self.S), np.float32)
         self._call("get_transition_matrix", matrix, _ptr(out, C.c_float))
         return out

@@ -7,6 +7,7 @@
 #include "mb200_device.cuh"
 #include "mb200_kernels.cuh"
 #include "mb200_kernels_tc.cuh"
+#include "mb200_kernels_std.cuh"
 
 #include <cuda_runtime.h>
 #include <float.h>
@@ -66,10 +67,12 @@ struct Instance
     int           cijkParts = 1;       // eigensystems per slot (one per category for NY98-type models)
     size_t        smemGen = 0;         // dynamic smem of eval_gen_kernel
     long long     launches = 0;
+    long long     launchKind[MB200_KERNEL_KINDS] = {0};   // per kernel family (mb200_get_kernel_launches)
     std::vector<int> tipPartAmbig;  // host copy (operand kinds of the 4-state records)
     int           tipEpoch = 0;
     int           writtenStamp = 0;
     int           pendingCount = 0;            // evaluations started by mb200_evaluate_begin, not yet collected
+    int           pendingSeq = 0;              // sequence number stamped by the launch begin() issued
     bool          pendingAllRoot = false;
     std::vector<char> pendingHasRoot;
     int           lastHostSum = 0, lastTiles = 1;   // how the last launch delivers its results
@@ -81,6 +84,16 @@ struct Instance
     std::vector<int> touched;          // scratch: matrices whose slotOf entry is set
     std::vector<int> dirtyOf;          // scratch: matrix index -> index in the evaluation's update list
     std::vector<DevChunk> chunkTmp; std::vector<DevMat> cmatTmp; std::vector<int> slotTmp, nChunkTmp, tipIdxTmp, writtenTmp;
+    // variable-state (STANDARD data) divisions
+    bool          std = false;         // MB200_CONFIG_VARIABLE_STATES
+    bool          stdReady = false;    // mb200_set_pattern_states done
+    bool          stdUniformMk = true; // every matrix the engine builds is an equal-frequency Mk matrix
+    StdCtx        sx;
+    int          *dStdTab = nullptr;   // nStates | tiIndex | bsIndex, [3][C]
+    int2         *dStdClasses = nullptr;
+    double       *dTilePartial2 = nullptr;
+    std::vector<int> hNStates, hTiIndex, hBsIndex;
+    std::vector<size_t> hClOff;        // ragged host layout: offset of pattern c inside a category's block
     bool          timing = false;      // bracket the fused kernel with events
     std::vector<cudaEvent_t> evA, evB; // ring of event pairs
     long long     evCount = 0;         // pairs recorded since the last read
@@ -193,8 +206,10 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     const int K = c.category_count, S = c.state_count;
     if (count < 1 || count > I->maxEval)
         return MB200_ERROR_OUT_OF_RANGE;
+    if (I->std && !I->stdReady)
+        return MB200_ERROR_UNSUPPORTED;                 // mb200_set_pattern_states first
 
-    const bool nuc4 = (S == 4 && K <= 8);
+    const bool nuc4 = (S == 4 && K <= 8 && !I->std);
     const int  ppbS = nuc4 ? nuc4PatternsPerBlock (K, true) : 1;
     const long ctas = (long)((c.pattern_count + ppbS - 1) / ppbS) * count;
     // fused P(t) rebuild (every CTA rebuilds the dirty matrices of its evaluation): small launches (latency-
@@ -233,7 +248,7 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
             {
             const mb200_matrix_update &u = ev.matrix_updates[i];
             const bool inl = (u.eigen == MB200_EIGEN_INLINE);
-            if (u.matrix < 0 || u.matrix >= c.matrix_count || (!inl && (u.eigen < 0 || u.eigen >= c.eigen_count)))
+            if (u.matrix < 0 || u.matrix >= c.matrix_count || (!inl && !I->std && (u.eigen < 0 || u.eigen >= c.eigen_count)))
                 { rcv = MB200_ERROR_OUT_OF_RANGE; break; }
             if (inl && (!ev.inline_eigen || S != 4))
                 { rcv = MB200_ERROR_UNSUPPORTED; break; }
@@ -517,7 +532,7 @@ int ensureInvMask (Instance *I)
     int C = I->cfg.pattern_count;
     invmask_kernel<<<(C + 255) / 256, 256, 0, I->stream>>> (I->dInvMask, I->dTip64, I->cfg.tip_count, C);
     CK (cudaGetLastError ());
-    I->launches++;
+    I->launches++; I->launchKind[MB200_KERNEL_SETUP]++;
     I->invMaskValid = true;
     return MB200_SUCCESS;
 }
@@ -629,7 +644,13 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
         int rc = ensureInvMask (I);
         if (rc != MB200_SUCCESS) return rc;
         }
-    if (b.nDirty > 0 && !b.fused)
+    if (b.nDirty > 0 && I->std)
+        {
+        tiprobs_std_kernel<<<b.nMat, 64, 0, I->stream>>> (ctx, I->sx, de, b.nEval, dd, du);
+        CK (cudaGetLastError ());
+        I->launches++; I->launchKind[MB200_KERNEL_TIPROBS]++;
+        }
+    else if (b.nDirty > 0 && !b.fused)
         {
         if (ctx.S > 32)
             {
@@ -642,12 +663,26 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
             tiprobs_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, b.nEval, dd, du);
             }
         CK (cudaGetLastError ());
-        I->launches++;
+        I->launches++; I->launchKind[MB200_KERNEL_TIPROBS]++;
         }
     const int evSlot = (int)(I->evCount % EV_RING);
     if (I->timing)
         CK (cudaEventRecord (I->evA[evSlot], I->stream));
-    if (ctx.S == 4 && ctx.K <= 8)
+    if (I->std)
+        {
+        const int NT = 128;
+        ctx.tilePatterns = NT / I->sx.lanes;
+        ctx.numTiles = (ctx.C + ctx.tilePatterns - 1) / ctx.tilePatterns;
+        dim3 grid (ctx.numTiles, b.nEval);
+        const int mk = I->stdUniformMk ? 1 : 0;
+        if (ctx.Sp <= 4)       eval_std_kernel<4, 128><<<grid, NT, 0, I->stream>>> (ctx, I->sx, de, dd, dops, res, seq, mk);
+        else if (ctx.Sp <= 8)  eval_std_kernel<8, 128><<<grid, NT, 0, I->stream>>> (ctx, I->sx, de, dd, dops, res, seq, mk);
+        else if (ctx.Sp <= 12) eval_std_kernel<12, 128><<<grid, NT, 0, I->stream>>> (ctx, I->sx, de, dd, dops, res, seq, mk);
+        else if (ctx.Sp <= 16) eval_std_kernel<16, 128><<<grid, NT, 0, I->stream>>> (ctx, I->sx, de, dd, dops, res, seq, mk);
+        else                   eval_std_kernel<24, 128><<<grid, NT, 0, I->stream>>> (ctx, I->sx, de, dd, dops, res, seq, mk);
+        I->launchKind[MB200_KERNEL_STD]++;
+        }
+    else if (ctx.S == 4 && ctx.K <= 8)
         {
         ctx.tilePatterns = nuc4PatternsPerBlock (ctx.K, b.fused);
         ctx.patternTiles = (ctx.C + ctx.tilePatterns - 1) / ctx.tilePatterns;
@@ -670,6 +705,7 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
         else
             rc = launchNuc4 (I, ctx, grid, de, dd, dc, dm, dops, res, seq, b.fused, b.jx);
         if (rc != MB200_SUCCESS) return rc;
+        I->launchKind[MB200_KERNEL_NUC4]++;
         }
     else if (I->tcS)
         {
@@ -681,7 +717,7 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
             if (I->tcS == 61) tc_split_kernel<61><<<sg, 128, 0, I->stream>>> (I->dMatrices, I->dSplit, du, 0, ctx.K);
             else              tc_split_kernel<20><<<sg, 128, 0, I->stream>>> (I->dMatrices, I->dSplit, du, 0, ctx.K);
             CK (cudaGetLastError ());
-            I->launches++;
+            I->launches++; I->launchKind[MB200_KERNEL_SETUP]++;
             }
         ctx.tilePatterns = 128;
         ctx.numTiles = (ctx.C + 127) / 128;
@@ -694,10 +730,12 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
             eval_tc_kernel<61, 1><<<grid, 128, tc_smem_bytes<61, 1> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
         else
             eval_tc_kernel<20, 1><<<grid, 128, tc_smem_bytes<20, 1> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
+        I->launchKind[MB200_KERNEL_TENSOR]++;
         }
     else
         {
         eval_gen_kernel<NT_GEN><<<dim3 (ctx.numTiles, b.nEval), NT_GEN, I->smemGen, I->stream>>> (ctx, de, dd, dops, res, seq);
+        I->launchKind[MB200_KERNEL_GENERIC]++;
         }
     CK (cudaGetLastError ());
     I->launches++;
@@ -712,7 +750,7 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
 // wait until the kernel has written `slots` results into the mapped host buffer
 int waitResults (Instance *I, Batch &b, int slots)
 {
-    const int seq = I->seq;
+    const int seq = I->pendingSeq;     // the launch begin() issued, whatever else ran on the instance since
     volatile DevResult *r = b.hRes;
     unsigned long long spins = 0;
     for (int e = 0; e < slots; e++)
@@ -739,6 +777,8 @@ int waitResults (Instance *I, Batch &b, int slots)
                 }
             }
         }
+    // the lnL / status words are ordinary loads: order them after the sequence-number polls
+    __atomic_thread_fence (__ATOMIC_ACQUIRE);
     return MB200_SUCCESS;
 }
 
@@ -774,7 +814,7 @@ int runBegin (Instance *I, const mb200_evaluation *evs, int count)
     rc = launch (I, b, b.hResDev, viaParams, allRoot && b.fused);
     MB200_HOST_T (tC);
     if (rc != MB200_SUCCESS) return rc;
-    I->pendingCount = count; I->pendingAllRoot = allRoot;
+    I->pendingCount = count; I->pendingAllRoot = allRoot; I->pendingSeq = I->seq;
 #ifdef MB200_PHASE_TIMING
     gHostPhase[0] += tB - tA; gHostPhase[1] += tC - tB; gHostPhase[3] += 1.0;
 #endif
@@ -849,6 +889,7 @@ void destroy (Instance *I)
     cudaFree (I->dTip8); cudaFree (I->dTip64); cudaFree (I->dTipPartAmbig); cudaFree (I->dSplit); cudaFree (I->dPartials); cudaFree (I->dMatrices);
     cudaFree (I->dScalers); cudaFree (I->dWeights); cudaFree (I->dEigen); cudaFree (I->dInvMask);
     cudaFree (I->dTilePartial); cudaFree (I->dTileAbort); cudaFree (I->dTicket); cudaFree (I->dDbg);
+    cudaFree (I->dStdTab); cudaFree (I->dStdClasses); cudaFree (I->dTilePartial2);
     if (I->hostStage) cudaFreeHost (I->hostStage);
     for (cudaEvent_t e : I->evA) cudaEventDestroy (e);
     for (cudaEvent_t e : I->evB) cudaEventDestroy (e);
@@ -932,14 +973,21 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     auto smemFor = [&] (int tp) { return sizeof(float) * ((size_t)S*S + (size_t)tp*(Sp+1) + (size_t)K*tp*S + 3*(size_t)tp); };
     while (TP > 1 && smemFor (TP) > 96*1024) TP >>= 1;
     I->smemGen = smemFor (TP);
-    const bool nuc4 = (S == 4 && K <= 8);
+    I->std = (cfg->flags & MB200_CONFIG_VARIABLE_STATES) != 0;
+    if (I->std && (S > MB200_STD_MAX_STATES || I->cijkParts != 1)) { delete I; return MB200_ERROR_UNSUPPORTED; }
+    const bool nuc4 = (S == 4 && K <= 8 && !I->std);
     if (nuc4 && (nInt * K * C >= (1ull << 32) || (size_t)cfg->tip_count * C >= (1ull << 32)))
         { delete I; return MB200_ERROR_OUT_OF_RANGE; }      // 4-state records carry 32-bit element offsets (64 GB of partials)
-    if (!getenv ("MB200_DISABLE_TC"))
+    if (!getenv ("MB200_DISABLE_TC") && !I->std)
         {
         if (S == 61 && K == 1) I->tcS = 61;      // 61-state codon, tcgen05 path
         if (S == 20 && K <= 4) I->tcS = 20;      // 20-state amino acids, tcgen05 path
         }
+    int stdLanes = 1;
+    while (stdLanes < K) stdLanes <<= 1;
+    if (I->std)
+        I->maxTiles = (C + 128 / stdLanes - 1) / (128 / stdLanes);
+    else
     I->maxTiles = I->tcS ? (C + 127) / 128 : nuc4 ? (C + nuc4MinPatternsPerBlock (K) - 1) / nuc4MinPatternsPerBlock (K) : (C + TP - 1) / TP;
 
 #define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc ((void **)&(ptr), (bytes)); if (e_ != cudaSuccess) { \
@@ -974,6 +1022,15 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     ALLOC (I->dTileAbort,   (size_t)I->maxEval * I->maxTiles * sizeof(int));
     ALLOC (I->dTicket,      (size_t)I->maxEval * sizeof(unsigned int));
     ALLOC (I->dDbg,         (size_t)I->maxEval * 64 * sizeof(unsigned long long));
+    if (I->std)
+        {
+        ALLOC (I->dStdTab,       (size_t)3 * C * sizeof(int));
+        ALLOC (I->dStdClasses,   (size_t)MB200_STD_MAX_STATES * sizeof(int2));
+        ALLOC (I->dTilePartial2, (size_t)I->maxEval * I->maxTiles * 2 * sizeof(double));
+        memset (&I->sx, 0, sizeof(I->sx));
+        I->sx.lanes = stdLanes;
+        I->sx.tilePartial2 = I->dTilePartial2;
+        }
 #undef ALLOC
     cudaMemsetAsync (I->dTip8, 0, (size_t)cfg->tip_count * C, I->stream);
     cudaMemsetAsync (I->dTip64, 0, (size_t)cfg->tip_count * C * sizeof(uint64_t), I->stream);
@@ -1069,6 +1126,54 @@ int mb200_set_pattern_weights (int instance, int row, const float *w)
     return MB200_SUCCESS;
 }
 
+int mb200_set_pattern_states (int instance, const int *ns, const int *ti, const int *bs, int matLen, int dummy, int uncompressed)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (!I->std) return MB200_ERROR_UNSUPPORTED;
+    const int C = I->cfg.pattern_count, K = I->cfg.category_count;
+    if (!ns || !ti || !bs || matLen < 1 || dummy < 0 || dummy > C) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    // state-count classes: (n, offset) pairs, every pattern of a class sharing the offset
+    std::vector<int2> classes;
+    for (int c = 0; c < C; c++)
+        {
+        if (ns[c] < 2 || ns[c] > I->cfg.state_count || ti[c] < 0 || (long) ti[c] + (long) K * ns[c] * ns[c] > (long) matLen ||
+            bs[c] < 0 || bs[c] + ns[c] > MB200_MAX_STATES)
+            return MB200_ERROR_OUT_OF_RANGE;
+        bool seen = false;
+        for (const int2 &q : classes)
+            if (q.x == ns[c] && q.y == ti[c]) { seen = true; break; }
+        if (!seen)
+            {
+            if ((int) classes.size () >= MB200_STD_MAX_STATES) return MB200_ERROR_UNSUPPORTED;
+            classes.push_back (make_int2 (ns[c], ti[c]));
+            }
+        }
+    I->hNStates.assign (ns, ns + C); I->hTiIndex.assign (ti, ti + C); I->hBsIndex.assign (bs, bs + C);
+    I->hClOff.assign (C + 1, 0);
+    for (int c = 0; c < C; c++) I->hClOff[c + 1] = I->hClOff[c] + (size_t) ns[c];
+    std::vector<int> tab (3 * (size_t)C);
+    memcpy (tab.data (), ns, (size_t)C * sizeof(int));
+    memcpy (tab.data () + C, ti, (size_t)C * sizeof(int));
+    memcpy (tab.data () + 2*(size_t)C, bs, (size_t)C * sizeof(int));
+    CK (cudaStreamSynchronize (I->stream));
+    // a branch's matrices are one block of matLen floats (m->tiProbLength)
+    cudaFree (I->dMatrices); I->dMatrices = nullptr;
+    CK (cudaMalloc ((void **)&I->dMatrices, (size_t)I->cfg.matrix_count * matLen * sizeof(float)));
+    CK (cudaMemsetAsync (I->dMatrices, 0, (size_t)I->cfg.matrix_count * matLen * sizeof(float), I->stream));
+    I->ctx.matrices = I->dMatrices;
+    CK (cudaMemcpyAsync (I->dStdTab, tab.data (), tab.size () * sizeof(int), cudaMemcpyHostToDevice, I->stream));
+    CK (cudaMemcpyAsync (I->dStdClasses, classes.data (), classes.size () * sizeof(int2), cudaMemcpyHostToDevice, I->stream));
+    CK (cudaStreamSynchronize (I->stream));
+    I->sx.nStates = I->dStdTab; I->sx.tiIndex = I->dStdTab + C; I->sx.bsIndex = I->dStdTab + 2*(size_t)C;
+    I->sx.classes = I->dStdClasses; I->sx.nClasses = (int) classes.size ();
+    I->sx.matLen = matLen; I->sx.dummy = dummy; I->sx.uncompressed = uncompressed;
+    I->stdUniformMk = true;
+    I->stdReady = true;
+    return MB200_SUCCESS;
+}
+
 int mb200_set_cijk (int instance, int eigen, const double *block)
 {
     Instance *I = get (instance);
@@ -1098,7 +1203,7 @@ int mb200_set_eigen_decomposition (int instance, int eigen, const double *V, con
     size_t n3 = n2 * S;
     int blocks = (int)((n3 + 255) / 256); if (blocks > 1024) blocks = 1024;
     cijk_kernel<<<blocks, 256, 0, I->stream>>> (I->dEigen + (size_t)eigen * I->eigenStride, tmp, tmp + n2, tmp + 2*n2, S);
-    I->launches++;
+    I->launches++; I->launchKind[MB200_KERNEL_SETUP]++;
     cudaError_t e = cudaStreamSynchronize (I->stream);
     cudaFree (tmp);
     CK (e);
@@ -1223,6 +1328,16 @@ int mb200_get_partials (int instance, int buffer, float *out)
     CK (cudaMemcpyAsync (tmp.data (), I->dPartials + (size_t)(buffer - I->cfg.tip_count) * n, n * sizeof(float),
                          cudaMemcpyDeviceToHost, I->stream));
     CK (cudaStreamSynchronize (I->stream));
+    if (I->std)
+        {
+        if (!I->stdReady) return MB200_ERROR_UNSUPPORTED;
+        const size_t numReps = I->hClOff[C];                // ragged [k][c][nStates[c]] (src/likelihood.c:1941-1943)
+        for (int k = 0; k < K; k++)
+            for (int c = 0; c < C; c++)
+                for (int s = 0; s < I->hNStates[c]; s++)
+                    out[(size_t)k * numReps + I->hClOff[c] + s] = tmp[((size_t)k * C + c) * Sp + s];
+        return MB200_SUCCESS;
+        }
     for (size_t r = 0; r < (size_t)K * C; r++)
         for (int s = 0; s < S; s++)
             out[r * S + s] = tmp[r * Sp + s];
@@ -1238,6 +1353,16 @@ int mb200_set_partials (int instance, int buffer, const float *in)
     const int S = I->cfg.state_count, K = I->cfg.category_count, C = I->cfg.pattern_count, Sp = I->ctx.Sp;
     const size_t n = (size_t)K * C * Sp;
     std::vector<float> tmp (n, 0.0f);
+    if (I->std)
+        {
+        if (!I->stdReady) return MB200_ERROR_UNSUPPORTED;
+        const size_t numReps = I->hClOff[C];
+        for (int k = 0; k < K; k++)
+            for (int c = 0; c < C; c++)
+                for (int s = 0; s < I->hNStates[c]; s++)
+                    tmp[((size_t)k * C + c) * Sp + s] = in[(size_t)k * numReps + I->hClOff[c] + s];
+        }
+    else
     for (size_t r = 0; r < (size_t)K * C; r++)
         for (int s = 0; s < S; s++)
             tmp[r * Sp + s] = in[r * S + s];
@@ -1253,7 +1378,8 @@ int mb200_get_transition_matrix (int instance, int matrix, float *out)
     if (!I) return MB200_ERROR_BAD_INSTANCE;
     if (matrix < 0 || matrix >= I->cfg.matrix_count || !out) return MB200_ERROR_OUT_OF_RANGE;
     int rc = use (I); if (rc) return rc;
-    const size_t n = (size_t)I->cfg.category_count * I->cfg.state_count * I->cfg.state_count;
+    if (I->std && !I->stdReady) return MB200_ERROR_UNSUPPORTED;
+    const size_t n = I->std ? (size_t) I->sx.matLen : (size_t)I->cfg.category_count * I->cfg.state_count * I->cfg.state_count;
     CK (cudaMemcpyAsync (out, I->dMatrices + (size_t)matrix * n, n * sizeof(float), cudaMemcpyDeviceToHost, I->stream));
     CK (cudaStreamSynchronize (I->stream));
     return MB200_SUCCESS;
@@ -1265,14 +1391,16 @@ int mb200_set_transition_matrix (int instance, int matrix, const float *in)
     if (!I) return MB200_ERROR_BAD_INSTANCE;
     if (matrix < 0 || matrix >= I->cfg.matrix_count || !in) return MB200_ERROR_OUT_OF_RANGE;
     int rc = use (I); if (rc) return rc;
-    const size_t n = (size_t)I->cfg.category_count * I->cfg.state_count * I->cfg.state_count;
+    if (I->std && !I->stdReady) return MB200_ERROR_UNSUPPORTED;
+    const size_t n = I->std ? (size_t) I->sx.matLen : (size_t)I->cfg.category_count * I->cfg.state_count * I->cfg.state_count;
+    if (I->std) I->stdUniformMk = false;        // a caller-supplied matrix need not have the Mk form: read every entry from now on
     CK (cudaMemcpyAsync (I->dMatrices + (size_t)matrix * n, in, n * sizeof(float), cudaMemcpyHostToDevice, I->stream));
     if (I->tcS)
         {
         dim3 sg (1, I->cfg.category_count);
         if (I->tcS == 61) tc_split_kernel<61><<<sg, 128, 0, I->stream>>> (I->dMatrices, I->dSplit, nullptr, matrix, I->cfg.category_count);
         else              tc_split_kernel<20><<<sg, 128, 0, I->stream>>> (I->dMatrices, I->dSplit, nullptr, matrix, I->cfg.category_count);
-        I->launches++;
+        I->launches++; I->launchKind[MB200_KERNEL_SETUP]++;
         }
     CK (cudaStreamSynchronize (I->stream));
     return MB200_SUCCESS;
@@ -1387,6 +1515,15 @@ int mb200_get_launch_count (int instance, long long *launches)
     Instance *I = get (instance);
     if (!I || !launches) return MB200_ERROR_BAD_INSTANCE;
     *launches = I->launches;
+    return MB200_SUCCESS;
+}
+
+int mb200_get_kernel_launches (int instance, int kind, long long *launches)
+{
+    Instance *I = get (instance);
+    if (!I || !launches) return MB200_ERROR_BAD_INSTANCE;
+    if (kind < 0 || kind >= MB200_KERNEL_KINDS) return MB200_ERROR_OUT_OF_RANGE;
+    *launches = I->launchKind[kind];
     return MB200_SUCCESS;
 }
 

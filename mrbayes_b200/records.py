@@ -28,6 +28,7 @@ class Division:
     cfg: dict
     tips: dict = field(default_factory=dict)        # tip -> uint64[C]
     weights: dict = field(default_factory=dict)     # row -> float32[C]
+    pattern_states: dict | None = None              # variable-state divisions: the 'PSTA' tables
 
 
 @dataclass
@@ -82,6 +83,11 @@ def load(path):
         elif tag == b"WGHT":
             d, row, C = struct.unpack_from("<3i", body, 0)
             divisions[d].weights[row] = np.frombuffer(body, "<f4", C, 12).copy()
+        elif tag == b"PSTA":
+            d, C, mat_len, dummy, uncompressed, freq_len = struct.unpack_from("<6i", body, 0)
+            tab = np.frombuffer(body, "<i4", 3 * C, 24).copy().reshape(3, C)
+            divisions[d].pattern_states = dict(state_counts=tab[0], matrix_offsets=tab[1], freq_offsets=tab[2],
+                                               matrix_length=mat_len, dummy_patterns=dummy, uncompressed_sites=uncompressed)
         elif tag == b"EIGN":
             d, eig, S = struct.unpack_from("<3i", body, 0)
             a = np.frombuffer(body, "<f8", S + 2 * S * S, 12).copy()
@@ -133,6 +139,8 @@ def make_instance(lib: abi.Library, div: Division, device: int = 0, max_evaluati
     c["device"] = device
     c["max_evaluations"] = max(max_evaluations, 1)
     inst = abi.Instance(lib, **c)
+    if div.pattern_states is not None:
+        inst.set_pattern_states(**div.pattern_states)
     for tip, m in div.tips.items():
         inst.set_tip_states(tip, m)
     for row, w in div.weights.items():

@@ -49,6 +49,9 @@ int UpDateCijk (int whichPart, int whichChain);
 typedef struct
     {
     int                  instance;          /* engine instance, -1 = none            */
+    mb200_instance_config cfg;              /* what the instance was created for     */
+    unsigned long long   tipStamp;          /* checksum of the tip data and pattern weights it holds */
+    const void          *parsPtr, *weightPtr; /* where that data lived on the host (cheap staleness test) */
     int                  capOps, capMats;
     mb200_operation     *ops;
     mb200_matrix_update *mats;
@@ -57,6 +60,7 @@ typedef struct
     double               eigenBlock[72];    /* [lambda_re(4), lambda_im(4), c_ijk(64)] */
     long long            clUpdates;         /* node*pattern*rate updates issued      */
     int                  pending;           /* launched by a deferred evaluation, result not yet collected */
+    int                  recording, recChain, recState;   /* function-pointer forms: evaluation being recorded */
     double               syncValue;         /* backend without begin/end: the result, kept until collected */
     int                  syncStatus, syncRc;
     } SeamDivision;
@@ -77,15 +81,16 @@ static int be_cijk (int i, int e, const double *b)                     { return 
 static int be_eval (int i, const mb200_evaluation *e, int n, double *l, int *s) { return mb200_evaluate (i, e, n, l, s); }
 static int be_begin (int i, const mb200_evaluation *e, int n)          { return mb200_evaluate_begin (i, e, n); }
 static int be_end (int i, double *l, int *s)                           { return mb200_evaluate_end (i, l, s); }
+static int be_pstates (int i, const int *n, const int *t, const int *b, int ml, int nd, int nu) { return mb200_set_pattern_states (i, n, t, b, ml, nd, nu); }
 
-static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end };
+static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates };
 static int seamDeferred = NO;   /* YES: TreeLikelihood_Beagle only launches; SeamCollect fetches the result */
 
 void MB200SeamSetBackend (const MB200SeamBackend *backend)
 {
     if (backend == NULL)
         {
-        MB200SeamBackend def = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end };
+        MB200SeamBackend def = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates };
         seamBackend = def;
         }
     else
@@ -224,6 +229,47 @@ static int SeamCategories (ModelInfo *m)
     return (SeamOmegaCategories (m) == YES) ? m->numOmegaCats : m->numRateCats;
 }
 
+/* STANDARD (morphological) data, the *_Std kernel family (SetLikeFunctions, src/mcmc.c:18300-18308).
+ * Covered: the equal-frequency Mk model (prset symdirihyperpr=fixed(infinity): SYMPI_EQUAL) on
+ * unordered characters with any number of gamma categories -- cynmix.nex's morphology partition.
+ * Ordered characters, unequal state frequencies (beta categories for binary characters, one
+ * eigensystem per multistate character, TiProbs_Std's second half src/likelihood.c:10410-10470) and
+ * state counts whose frequency table does not fit mb200_evaluation.state_freqs stay on the
+ * reference's own kernels. */
+static int SeamStdDivision (ModelInfo *m)
+{
+    int c, freqLen = 0;
+
+    if (m->dataType != STANDARD)
+        return NO;
+    if (getenv ("MB200_NO_STD") != NULL)
+        return NO;                              /* A/B switch: leave these divisions on the reference's kernels */
+    if (m->stateFreq == NULL || m->stateFreq->paramId != SYMPI_EQUAL || m->numBetaCats != 1)
+        return NO;
+    if (m->pInvar != NULL || m->switchRates != NULL || m->numOmegaCats != 1 || m->nStates == NULL ||
+        m->tiIndex == NULL || m->bsIndex == NULL || m->cType == NULL)
+        return NO;
+    for (c=0; c<m->numChars; c++)
+        {
+        if (m->cType[c] != UNORD || m->nStates[c] < 2 || m->nStates[c] > MB200_MAX_STATES)
+            return NO;
+        if (m->bsIndex[c] + m->nStates[c] > freqLen)
+            freqLen = m->bsIndex[c] + m->nStates[c];
+        }
+    if (freqLen > MB200_MAX_STATES)
+        return NO;
+    return YES;
+}
+
+static int SeamStdMaxStates (ModelInfo *m)
+{
+    int c, n = 2;
+    for (c=0; c<m->numChars; c++)
+        if (m->nStates[c] > n)
+            n = m->nStates[c];
+    return n;
+}
+
 /* Which divisions the engine takes; everything else stays on the reference's own
  * function pointers, the way the reference keeps BEAGLE away from models it does
  * not cover (src/mcmc.c:5741-5775). */
@@ -231,8 +277,16 @@ int MB200SeamDivisionSupported (ModelInfo *m)
 {
     if (m->parsModelId == YES)
         return NO;
+    if (m->dataType == STANDARD)
+        {
+        if (SeamStdDivision (m) == NO || m->gibbsGamma == YES || m->correlation != NULL || m->nParsIntsPerSite != 1 ||
+            m->numRateCats < 1 || m->numRateCats > MB200_MAX_CATEGORIES ||
+            m->printAncStates == YES || m->printSiteRates == YES)
+            return NO;
+        return YES;
+        }
     if (m->dataType != DNA && m->dataType != RNA && m->dataType != PROTEIN)
-        return NO;                              /* STANDARD / RESTRICTION / CONTINUOUS: next rows */
+        return NO;                              /* RESTRICTION / CONTINUOUS: outside the path */
     if (m->nCijkParts != 1 && MB200SeamClosedFormModel (m) == NO && SeamCategoryEigens (m) == NO)
         return NO;
     if (m->gibbsGamma == YES || m->correlation != NULL)
@@ -256,84 +310,201 @@ int MB200SeamDivisionSupported (ModelInfo *m)
     return YES;
 }
 
+/* Which GPU a division's buffers live on.  One process per GPU (MPI / torchrun style launch: the
+ * local rank picks the device, src/mcmc.c:18331 SetLocalChainsAndDataSplits gives the process its
+ * chains), or one process driving several GPUs with the partitions of every chain dealt out round
+ * robin (MB200_SHARD=partitions: lnL_chain = sum over divisions, src/mcmc.c:7441, so the divisions
+ * of a chain run concurrently on different devices); MB200_DEVICE pins everything to one ordinal. */
+int MB200SeamDeviceFor (int division)
+{
+    static int  nDev = -1;
+    const char *s;
+    int         r = 0;
+
+    if (nDev < 0)
+        {
+        nDev = mb200_device_count ();
+        if (nDev < 1)
+            nDev = 1;
+        }
+    if ((s = getenv ("MB200_DEVICE")) != NULL)
+        return atoi (s);
+    if ((s = getenv ("MB200_SHARD")) != NULL && strcmp (s, "partitions") == 0)
+        return division % nDev;
+    if ((s = getenv ("LOCAL_RANK")) != NULL || (s = getenv ("OMPI_COMM_WORLD_LOCAL_RANK")) != NULL ||
+        (s = getenv ("MV2_COMM_WORLD_LOCAL_RANK")) != NULL || (s = getenv ("SLURM_LOCALID")) != NULL)
+        r = atoi (s);
+#   if defined (MPI_ENABLED)
+    else
+        r = proc_id;
+#   endif
+    return (r >= 0) ? r % nDev : 0;
+}
+
+/* checksum (FNV-1a) of what InitBeagleInstance uploads: tip state sets and pattern weights */
+static unsigned long long SeamTipStamp (ModelInfo *m)
+{
+    unsigned long long  h = 1469598103934665603ULL;
+    const unsigned char *b;
+    size_t              i, n;
+    int                 t, r;
+
+    for (t=0; t<numLocalTaxa; t++)
+        {
+        b = (const unsigned char *) m->parsSets[t];
+        n = (size_t) m->numChars * m->nParsIntsPerSite * sizeof(BitsLong);
+        for (i=0; i<n; i++)
+            h = (h ^ b[i]) * 1099511628211ULL;
+        }
+    for (r=0; r<chainParams.numChains; r++)
+        {
+        b = (const unsigned char *) (numSitesOfPat + r*numCompressedChars + m->compCharStart);
+        n = (size_t) m->numChars * sizeof(CLFlt);
+        for (i=0; i<n; i++)
+            h = (h ^ b[i]) * 1099511628211ULL;
+        }
+    return h;
+}
+
+/* configuration of the engine instance a division needs right now */
+void MB200SeamDivisionConfig (ModelInfo *m, int division, mb200_instance_config *cfg)
+{
+    memset (cfg, 0, sizeof(*cfg));
+    cfg->tip_count       = numLocalTaxa;
+    cfg->partials_count  = m->numCondLikes;
+    cfg->state_count     = (m->dataType == STANDARD) ? SeamStdMaxStates (m) : m->numModelStates;
+    cfg->pattern_count   = m->numChars;
+    cfg->category_count  = SeamCategories (m);
+    cfg->flags           = (SeamCategoryEigens (m) == YES) ? MB200_CONFIG_CIJK_PARTS (m->nCijkParts) : 0;
+    if (m->dataType == STANDARD)
+        cfg->flags      |= MB200_CONFIG_VARIABLE_STATES;
+    cfg->matrix_count    = m->numTiProbs;
+    cfg->scaler_count    = m->numScalers;
+    cfg->eigen_count     = numLocalChains + 1;    /* unused (but harmless) for the inline-eigen models */
+    cfg->weight_rows     = chainParams.numChains;
+    cfg->device          = MB200SeamDeviceFor (division);
+    cfg->max_evaluations = (numLocalChains > 0) ? numLocalChains : 1;
+}
+
+/* release everything a division holds on the engine side */
+static void SeamDropDivision (int division)
+{
+    SeamDivision *sd = &seamDiv[division];
+
+    if (sd->instance >= 0)
+        seamBackend.finalize_instance (sd->instance);
+    free (sd->ops);
+    free (sd->mats);
+    memset (sd, 0, sizeof(SeamDivision));
+    sd->instance = -1;
+    memset (seamCijkSeen[division], 0, sizeof(seamCijkSeen[division]));
+}
+
 /* ---- InitBeagleInstance (src/mbbeagle.c:60): allocate device buffers, load tips ---- */
 int InitBeagleInstance (ModelInfo *m, int division)
 {
-    int                     i, c, b, nRep, rc;
-    uint64_t               *masks, obs, full;
+    int                     i, c, b, nRep, rc, inst = -1;
+    uint64_t               *masks = NULL, obs, full;
     mb200_instance_config   cfg;
     SeamDivision           *sd;
+    mb200_operation        *ops = NULL;
+    mb200_matrix_update    *mats = NULL;
 
     SeamInit ();
     if (division < 0 || division >= SEAM_MAX_DIVISIONS)
         return (ERROR);
     sd = &seamDiv[division];
-    if (sd->instance >= 0)
-        return (NO_ERROR);
     if (MB200SeamDivisionSupported (m) == NO)
         return (ERROR);
+    MB200SeamDivisionConfig (m, division, &cfg);
+    if (sd->instance >= 0)
+        {
+        /* a second mcmc in the same session after lset / charset / mcmcp changes: the cached instance
+           must match the model of THIS run, or it is rebuilt (the reference refuses a second run with
+           BEAGLE, src/mbbeagle.c:66-69; here it simply works) */
+        if (memcmp (&cfg, &sd->cfg, sizeof(cfg)) == 0 && sd->tipStamp == SeamTipStamp (m))
+            {
+            sd->parsPtr   = (const void *) m->parsSets;
+            sd->weightPtr = (const void *) numSitesOfPat;
+            return (NO_ERROR);
+            }
+        SeamDropDivision (division);
+        }
 
-    memset (&cfg, 0, sizeof(cfg));
-    cfg.tip_count       = numLocalTaxa;
-    cfg.partials_count  = m->numCondLikes;
-    cfg.state_count     = m->numModelStates;
-    cfg.pattern_count   = m->numChars;
-    cfg.category_count  = SeamCategories (m);
-    cfg.flags           = (SeamCategoryEigens (m) == YES) ? MB200_CONFIG_CIJK_PARTS (m->nCijkParts) : 0;
-    cfg.matrix_count    = m->numTiProbs;
-    cfg.scaler_count    = m->numScalers;
-    cfg.eigen_count     = numLocalChains + 1;    /* unused (but harmless) for the inline-eigen models */
-    cfg.weight_rows     = chainParams.numChains;
-    cfg.device          = 0;
-    cfg.max_evaluations = 1;
-    rc = seamBackend.create_instance (&cfg, &sd->instance);
+    /* everything that can fail on the host is allocated before the instance is published */
+    ops   = (mb200_operation *)     SafeCalloc ((size_t)m->numCondLikes, sizeof(mb200_operation));
+    mats  = (mb200_matrix_update *) SafeCalloc ((size_t)m->numTiProbs,  sizeof(mb200_matrix_update));
+    masks = (uint64_t *)            SafeMalloc ((size_t)m->numChars * sizeof(uint64_t));
+    if (!ops || !mats || !masks)
+        goto fail;
+
+    rc = seamBackend.create_instance (&cfg, &inst);
     if (rc != MB200_SUCCESS)
         {
         MrBayesPrint ("%s   B200 engine: cannot create instance for division %d (%s)\n", spacer, division+1, mb200_error_string (rc));
-        sd->instance = -1;
-        return (ERROR);
+        inst = -1;
+        goto fail;
+        }
+
+    if (m->dataType == STANDARD)
+        {
+        if (seamBackend.set_pattern_states == NULL ||
+            seamBackend.set_pattern_states (inst, m->nStates, m->tiIndex, m->bsIndex, m->tiProbLength,
+                                            m->numDummyChars, m->numUncompressedChars) != MB200_SUCCESS)
+            goto fail;
         }
 
     /* tip state sets: one bit per model state, hidden-state blocks replicated */
-    masks = (uint64_t *) SafeMalloc ((size_t)m->numChars * sizeof(uint64_t));
-    if (!masks)
-        return (ERROR);
-    nRep = m->numModelStates / m->numStates;
+    nRep = (m->dataType == STANDARD) ? 1 : m->numModelStates / m->numStates;
     full = (m->numStates == 64) ? ~(uint64_t)0 : (((uint64_t)1 << m->numStates) - 1);
     for (i=0; i<numLocalTaxa; i++)
         {
         for (c=0; c<m->numChars; c++)
             {
+            if (m->dataType == STANDARD)
+                full = ((uint64_t)1 << m->nStates[c]) - 1;      /* the pattern's own states (src/mcmc.c:6316-6322) */
             obs = (uint64_t) m->parsSets[i][c * m->nParsIntsPerSite] & full;
             masks[c] = 0;
             for (b=0; b<nRep; b++)
                 masks[c] |= obs << (b * m->numStates);
+            if (m->dataType == STANDARD)
+                masks[c] = obs;
             }
-        if (seamBackend.set_tip_states (sd->instance, i, masks) != MB200_SUCCESS)
-            {
-            free (masks);
-            return (ERROR);
-            }
+        if (seamBackend.set_tip_states (inst, i, masks) != MB200_SUCCESS)
+            goto fail;
         }
-    free (masks);
 
     /* pattern weights, one row per heat-ordered chain id (src/likelihood.c:5830) */
     for (i=0; i<chainParams.numChains; i++)
         {
-        if (seamBackend.set_pattern_weights (sd->instance, i, numSitesOfPat + i*numCompressedChars + m->compCharStart) != MB200_SUCCESS)
-            return (ERROR);
+        if (seamBackend.set_pattern_weights (inst, i, numSitesOfPat + i*numCompressedChars + m->compCharStart) != MB200_SUCCESS)
+            goto fail;
         }
+    free (masks);
 
-    sd->capOps  = m->numCondLikes;
-    sd->capMats = m->numTiProbs;
-    sd->ops  = (mb200_operation *)     SafeCalloc ((size_t)sd->capOps,  sizeof(mb200_operation));
-    sd->mats = (mb200_matrix_update *) SafeCalloc ((size_t)sd->capMats, sizeof(mb200_matrix_update));
-    if (!sd->ops || !sd->mats)
-        return (ERROR);
+    sd->instance = inst;
+    sd->cfg      = cfg;
+    sd->tipStamp = SeamTipStamp (m);
+    sd->parsPtr  = (const void *) m->parsSets;
+    sd->weightPtr = (const void *) numSitesOfPat;
+    sd->capOps   = m->numCondLikes;
+    sd->capMats  = m->numTiProbs;
+    sd->ops      = ops;
+    sd->mats     = mats;
+    memset (seamCijkSeen[division], 0, sizeof(seamCijkSeen[division]));
 
-    MrBayesPrint ("%s   Using B200 engine (%s) for division %d: %d patterns x %d rate cats x %d states\n",
-                  spacer, mb200_version_string (), division+1, m->numChars, m->numRateCats, m->numModelStates);
+    MrBayesPrint ("%s   Using B200 engine (%s) for division %d on device %d: %d patterns x %d categories x %d states\n",
+                  spacer, mb200_version_string (), division+1, cfg.device, m->numChars, SeamCategories (m), m->numModelStates);
     return (NO_ERROR);
+
+fail:
+    if (inst >= 0)
+        seamBackend.finalize_instance (inst);
+    free (ops);
+    free (mats);
+    free (masks);
+    sd->instance = -1;
+    return (ERROR);
 }
 
 void MB200SeamFinalize (void)
@@ -343,14 +514,8 @@ void MB200SeamFinalize (void)
         return;
     for (d=0; d<SEAM_MAX_DIVISIONS; d++)
         {
-        if (seamDiv[d].instance >= 0)
-            seamBackend.finalize_instance (seamDiv[d].instance);
-        free (seamDiv[d].ops);
-        free (seamDiv[d].mats);
-        memset (&seamDiv[d], 0, sizeof(SeamDivision));
-        seamDiv[d].instance = -1;
+        SeamDropDivision (d);
         }
-    memset (seamCijkSeen, 0, sizeof(seamCijkSeen));
 }
 
 /* branch length seen by the substitution model (src/likelihood.c:9471-9496) */
@@ -378,37 +543,16 @@ static void SeamQueueMatrix (SeamDivision *sd, ModelInfo *m, TreeNode *p, int ch
     FlipTiProbsSpace (m, chain, p->index);
     u = &sd->mats[sd->ev.matrix_update_count++];
     u->matrix = m->tiProbsIndex[chain][p->index];
-    u->eigen  = (sd->inlineEigen == YES) ? MB200_EIGEN_INLINE : m->cijkIndex[chain];
+    u->eigen  = (sd->inlineEigen == YES) ? MB200_EIGEN_INLINE : (m->dataType == STANDARD) ? MB200_NONE : m->cijkIndex[chain];
     u->length = SeamBranchLength (m, p, chain);
 }
 
-/* ---- TreeTiProbs_Beagle (src/mbbeagle.c:1368): which P(t) must be rebuilt ---------- */
-int TreeTiProbs_Beagle (Tree *t, int division, int chain)
+/* rate multipliers of TiProbs_Gen (src/likelihood.c:9432-9464): r_k = baseRate / (1 - pInvar) * catRate_k * corr */
+static void SeamCategoryRates (ModelInfo *m, SeamDivision *sd, int division, int chain)
 {
-    int             i, k;
-    MrBFlt          baseRate, corr, theRate, *catRate, pInvar;
-    TreeNode       *p;
-    ModelInfo      *m;
-    SeamDivision   *sd;
+    int     k;
+    MrBFlt  baseRate, corr, theRate, *catRate, pInvar;
 
-    m  = &modelSettings[division];
-    sd = &seamDiv[division];
-    sd->ev.matrix_update_count = 0;
-    sd->ev.matrix_updates      = sd->mats;
-
-    /* same visiting order and the same flips as src/likelihood.c:7892-7918 */
-    for (i=0; i<t->nIntNodes; i++)
-        {
-        p = t->intDownPass[i];
-        if (p->left->upDateTi == YES)
-            SeamQueueMatrix (sd, m, p->left, chain);
-        if (p->right->upDateTi == YES)
-            SeamQueueMatrix (sd, m, p->right, chain);
-        if (t->isRooted == NO && p->anc->anc == NULL)
-            SeamQueueMatrix (sd, m, p, chain);      /* interior root's branch: always rebuilt */
-        }
-
-    /* rate multipliers of TiProbs_Gen (src/likelihood.c:9432-9464) */
     corr = 1.0;
     if (m->dataType == DNA || m->dataType == RNA)
         {
@@ -436,6 +580,34 @@ int TreeTiProbs_Beagle (Tree *t, int division, int chain)
     if (SeamCategoryEigens (m) == YES)
         for (k=0; k<SeamCategories (m); k++)
             sd->ev.category_rates[k] = corr;    /* TiProbs_GenCov: t = length * correctionFactor, nothing else */
+}
+
+/* ---- TreeTiProbs_Beagle (src/mbbeagle.c:1368): which P(t) must be rebuilt ---------- */
+int TreeTiProbs_Beagle (Tree *t, int division, int chain)
+{
+    int             i;
+    TreeNode       *p;
+    ModelInfo      *m;
+    SeamDivision   *sd;
+
+    m  = &modelSettings[division];
+    sd = &seamDiv[division];
+    sd->ev.matrix_update_count = 0;
+    sd->ev.matrix_updates      = sd->mats;
+
+    /* same visiting order and the same flips as src/likelihood.c:7892-7918 */
+    for (i=0; i<t->nIntNodes; i++)
+        {
+        p = t->intDownPass[i];
+        if (p->left->upDateTi == YES)
+            SeamQueueMatrix (sd, m, p->left, chain);
+        if (p->right->upDateTi == YES)
+            SeamQueueMatrix (sd, m, p->right, chain);
+        if (t->isRooted == NO && p->anc->anc == NULL)
+            SeamQueueMatrix (sd, m, p, chain);      /* interior root's branch: always rebuilt */
+        }
+
+    SeamCategoryRates (m, sd, division, chain);
 
     return (NO_ERROR);
 }
@@ -516,9 +688,16 @@ int TreeCondLikes_Beagle_Rescale_All (Tree *t, int division, int chain)
 }
 
 static int SeamApplyResult (int division, int rc, double value, int status, MrBFlt *lnL);
+static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL, int whichSitePats);
 
 /* ---- TreeLikelihood_Beagle (src/mbbeagle.c:1117): root integration; launches ------- */
 int TreeLikelihood_Beagle (Tree *t, int division, int chain, MrBFlt *lnL, int whichSitePats)
+{
+    return SeamRootAndLaunch (division, chain, t->root->left->index, lnL, whichSitePats);
+}
+
+/* root integration parameters of Likelihood_* (src/likelihood.c:5764-7130), then the launch */
+static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL, int whichSitePats)
 {
     int             k, s, status, rc;
     MrBFlt          pInvar, freq, *bs;
@@ -529,7 +708,7 @@ int TreeLikelihood_Beagle (Tree *t, int division, int chain, MrBFlt *lnL, int wh
     m  = &modelSettings[division];
     sd = &seamDiv[division];
 
-    sd->ev.root_buffer = m->condLikeIndex[chain][t->root->left->index];
+    sd->ev.root_buffer = m->condLikeIndex[chain][rootNode];
     sd->ev.weights_row = whichSitePats;
     sd->ev.flags       = 0;
     sd->ev.inline_eigen = (sd->inlineEigen == YES) ? sd->eigenBlock : NULL;
@@ -544,7 +723,9 @@ int TreeLikelihood_Beagle (Tree *t, int division, int chain, MrBFlt *lnL, int wh
     sd->ev.p_invar = pInvar;
     /* which reference kernel family this division would run (SetLikeFunctions,
        src/mcmc.c:17995-18010 vs 18109-18243) decides two rounding-level details */
-    if (m->numModelStates == 4 && (m->dataType == DNA || m->dataType == RNA))
+    if (m->dataType == STANDARD)
+        sd->ev.flags = 0;                               /* *_Std family: dense tips, no pInvar */
+    else if (m->numModelStates == 4 && (m->dataType == DNA || m->dataType == RNA))
         sd->ev.flags |= MB200_FLAG_NUC4_PINVAR_QUIRK;   /* Likelihood_NUC4_* family */
     else
         sd->ev.flags |= MB200_FLAG_TIP_SHORTCUTS;       /* *_Gen_SSE family */
@@ -564,9 +745,23 @@ int TreeLikelihood_Beagle (Tree *t, int division, int chain, MrBFlt *lnL, int wh
             sd->ev.category_weights[k] = omegaCatFreq[k];
         }
 
-    bs = GetParamSubVals (m->stateFreq, chain, state[chain]);
-    for (s=0; s<m->numModelStates; s++)
-        sd->ev.state_freqs[s] = bs[s];
+    if (m->dataType == STANDARD)
+        {
+        /* Likelihood_Std: bs = GetParamStdStateFreqs (...) + m->bsIndex[c] (src/likelihood.c:7387, 7409) */
+        int c, freqLen = 0;
+        for (c=0; c<m->numChars; c++)
+            if (m->bsIndex[c] + m->nStates[c] > freqLen)
+                freqLen = m->bsIndex[c] + m->nStates[c];
+        bs = GetParamStdStateFreqs (m->stateFreq, chain, state[chain]);
+        for (s=0; s<freqLen && s<MB200_MAX_STATES; s++)
+            sd->ev.state_freqs[s] = bs[s];
+        }
+    else
+        {
+        bs = GetParamSubVals (m->stateFreq, chain, state[chain]);
+        for (s=0; s<m->numModelStates; s++)
+            sd->ev.state_freqs[s] = bs[s];
+        }
     if (m->switchRates != NULL)
         {
         /* covarion: stationary frequencies of the on / off copies of every state, on-states first
@@ -632,12 +827,28 @@ void LaunchBEAGLELogLikeForDivision (int chain, int d, ModelInfo *m, Tree *tree,
     TreeLikelihood_Beagle (tree, d, chain, lnL, chainId[chain] % chainParams.numChains);
 }
 
+/* the engine's copy of the chain's eigensystem follows the host's: upload after UpDateCijk, and the
+   first time a slot is read that the device has never seen */
+static int SeamSyncCijk (ModelInfo *m, SeamDivision *sd, int d, int chain)
+{
+    int idx = m->cijkIndex[chain];
+
+    if (idx < 0 || idx > MAX_CHAINS)
+        return (ERROR);
+    if (m->upDateCijk == YES || (seamCijkSeen[d][idx >> 3] & (1 << (idx & 7))) == 0)
+        {
+        if (seamBackend.set_cijk (sd->instance, idx, m->cijks[idx]) != MB200_SUCCESS)
+            return (ERROR);
+        seamCijkSeen[d][idx >> 3] |= (unsigned char)(1 << (idx & 7));
+        }
+    return (NO_ERROR);
+}
+
 /* ---- replacement for LaunchLogLikeForDivision (src/likelihood.c:7851) -------------- */
 /* Returns NO when the division is not handled by the engine (caller keeps the
    reference's own function-pointer path for it). */
 int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
 {
-    int         idx;
     ModelInfo  *m;
     Tree       *tree;
     SeamDivision *sd;
@@ -647,6 +858,18 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
     if (MB200SeamDivisionSupported (m) == NO)
         return (NO);
     sd = &seamDiv[d];
+    if (sd->instance >= 0 &&
+        (sd->parsPtr != (const void *) m->parsSets || sd->weightPtr != (const void *) numSitesOfPat ||
+         sd->cfg.pattern_count != m->numChars || sd->cfg.category_count != SeamCategories (m) ||
+         sd->cfg.partials_count != m->numCondLikes || sd->cfg.matrix_count != m->numTiProbs ||
+         sd->cfg.scaler_count != m->numScalers || (m->dataType != STANDARD && sd->cfg.state_count != m->numModelStates) ||
+         sd->cfg.weight_rows != chainParams.numChains || sd->cfg.eigen_count != numLocalChains + 1))
+        {
+        /* another mcmc run in the same session (new model, character set or chain count): the cached
+           instance is checked against the current model and rebuilt when it no longer matches */
+        if (InitBeagleInstance (m, d) == ERROR)
+            return (NO);
+        }
     if (sd->instance < 0 && InitBeagleInstance (m, d) == ERROR)
         return (NO);
 
@@ -670,6 +893,30 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
         }
     sd->inlineEigen = NO;
 
+    if (m->dataType == STANDARD)
+        {
+        /* equal-frequency Mk: no eigensystem (cijkLength == 0); the reference's driver would still call
+           UpDateCijk when flagged (src/likelihood.c:7864), which is a no-op for these models */
+        if (m->upDateCijk == YES)
+            {
+            if (UpDateCijk (d, chain) == ERROR)
+                {
+                (*lnL) = MRBFLT_NEG_MAX;
+                return (YES);
+                }
+            m->upDateAll = YES;
+            }
+        LaunchBEAGLELogLikeForDivision (chain, d, m, tree, lnL);
+        return (YES);
+        }
+
+    /* every reason to hand the division back to the reference's own path comes BEFORE UpDateCijk:
+       that call flips the cijk space, and a second UpDateCijk by the fallback path would overwrite
+       the slot ResetFlips needs to restore a rejected move (src/mcmc.c:15695) */
+    if (m->cijkIndex[chain] < 0 || m->cijkIndex[chain] > MAX_CHAINS ||
+        m->cijkScratchIndex < 0 || m->cijkScratchIndex > MAX_CHAINS)
+        return (NO);
+
     if (m->upDateCijk == YES)
         {
         if (UpDateCijk (d, chain) == ERROR)
@@ -679,19 +926,11 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
             }
         m->upDateAll = YES;
         }
-    /* the engine's copy of the eigensystem follows the host's */
-    idx = m->cijkIndex[chain];
-    if (idx < 0 || idx > MAX_CHAINS)
-        return (NO);
-    if (m->upDateCijk == YES || (seamCijkSeen[d][idx >> 3] & (1 << (idx & 7))) == 0)
+    if (SeamSyncCijk (m, sd, d, chain) == ERROR)
         {
-        if (seamBackend.set_cijk (sd->instance, idx, m->cijks[idx]) != MB200_SUCCESS)
-            {
-            (*lnL) = MRBFLT_NEG_MAX;
-            abortMove = YES;
-            return (YES);
-            }
-        seamCijkSeen[d][idx >> 3] |= (unsigned char)(1 << (idx & 7));
+        (*lnL) = MRBFLT_NEG_MAX;
+        abortMove = YES;
+        return (YES);
         }
 
     LaunchBEAGLELogLikeForDivision (chain, d, m, tree, lnL);
@@ -791,4 +1030,208 @@ void LaunchBEAGLELogLikeMultiPartition (int *divisions, int divisionCount, int c
         }
     if (abortMove == YES)
         (*lnL) = MRBFLT_NEG_MAX;
+}
+
+
+/* ======================================================================================
+ * Node-granular function-pointer forms (typedefs src/bayes.h:960-965; installed per division by
+ * SetLikeFunctions, src/mcmc.c:17918-18327; called by the reference's own per-node loop,
+ * src/likelihood.c:7892-7971).
+ *
+ * With these installed in ModelInfo (m->TiProbs, m->CondLikeDown, m->CondLikeRoot,
+ * m->CondLikeScaler, m->Likelihood) the UNMODIFIED LaunchLogLikeForDivision drives the engine: every
+ * call below records one piece of the evaluation exactly where the reference's CPU kernel would have
+ * done the arithmetic -- TiProbs_* queue a P(t) rebuild, CondLikeDown_* / CondLikeRoot_* flip the
+ * conditional-likelihood space like their CPU namesakes (src/likelihood.c:795) and queue a node update,
+ * CondLikeScaler_* marks that node as rescaled -- and Likelihood_* closes the record and runs it as ONE
+ * fused launch, returning lnL with the reference's conventions.  The driver's own FlipTiProbsSpace /
+ * FlipNodeScalerSpace / FlipSiteScalerSpace calls are the index bookkeeping; its RemoveNodeScalers /
+ * Copy / ResetSiteScalers calls touch only the (unused) host scaler arrays, the device does the same
+ * work from scale_remove / site_scaler_src.
+ * ====================================================================================== */
+static void SeamOpenRecord (SeamDivision *sd, ModelInfo *m, int chain)
+{
+    if (sd->recording == YES && sd->recChain == chain && sd->recState == state[chain])
+        return;
+    sd->recording = YES;
+    sd->recChain  = chain;
+    sd->recState  = state[chain];
+    sd->ev.matrix_update_count = 0;
+    sd->ev.matrix_updates      = sd->mats;
+    sd->ev.operation_count     = 0;
+    sd->ev.operations          = sd->ops;
+    sd->inlineEigen = MB200SeamClosedFormModel (m);
+}
+
+int TiProbs_B200 (TreeNode *p, int division, int chain)
+{
+    ModelInfo           *m  = &modelSettings[division];
+    SeamDivision        *sd = &seamDiv[division];
+    mb200_matrix_update *u;
+
+    if (sd->instance < 0)
+        return (ERROR);
+    SeamOpenRecord (sd, m, chain);
+    if (sd->ev.matrix_update_count >= sd->capMats)
+        return (ERROR);
+    /* the caller has flipped the branch's slot already (src/likelihood.c:7899) */
+    u = &sd->mats[sd->ev.matrix_update_count++];
+    u->matrix = m->tiProbsIndex[chain][p->index];
+    u->eigen  = (sd->inlineEigen == YES) ? MB200_EIGEN_INLINE : (m->dataType == STANDARD) ? MB200_NONE : m->cijkIndex[chain];
+    u->length = SeamBranchLength (m, p, chain);
+    return (NO_ERROR);
+}
+
+static int SeamRecordNode (TreeNode *p, int division, int chain, int isRoot)
+{
+    ModelInfo       *m  = &modelSettings[division];
+    SeamDivision    *sd = &seamDiv[division];
+    mb200_operation *op;
+
+    if (sd->instance < 0)
+        return (ERROR);
+    SeamOpenRecord (sd, m, chain);
+    if (sd->ev.operation_count >= sd->capOps)
+        return (ERROR);
+    op = &sd->ops[sd->ev.operation_count++];
+    FlipCondLikeSpace (m, chain, p->index);
+    op->dest    = m->condLikeIndex[chain][p->index];
+    op->child1  = m->condLikeIndex[chain][p->left->index];
+    op->matrix1 = m->tiProbsIndex [chain][p->left->index];
+    op->child2  = m->condLikeIndex[chain][p->right->index];
+    op->matrix2 = m->tiProbsIndex [chain][p->right->index];
+    op->child3  = (isRoot == YES) ? m->condLikeIndex[chain][p->anc->index] : MB200_NONE;
+    op->matrix3 = (isRoot == YES) ? m->tiProbsIndex [chain][p->index]      : MB200_NONE;
+    /* the caller removes the node's old scaler right after this call when this holds
+       (src/likelihood.c:7938) and flips the node-scaler space after that (:7959) */
+    op->scale_remove = (m->unscaledNodes[chain][p->index] == 0 && m->upDateAll == NO)
+                     ? m->nodeScalerIndex[chain][p->index] : MB200_NONE;
+    op->scale_write  = MB200_NONE;
+    sd->clUpdates += (long long) m->numChars * SeamCategories (m);
+    return (NO_ERROR);
+}
+
+int CondLikeDown_B200 (TreeNode *p, int division, int chain)
+{
+    return SeamRecordNode (p, division, chain, NO);
+}
+
+int CondLikeRoot_B200 (TreeNode *p, int division, int chain)
+{
+    return SeamRecordNode (p, division, chain, YES);
+}
+
+int CondLikeScaler_B200 (TreeNode *p, int division, int chain)
+{
+    int              i;
+    ModelInfo       *m  = &modelSettings[division];
+    SeamDivision    *sd = &seamDiv[division];
+
+    if (sd->instance < 0 || sd->recording == NO)
+        return (ERROR);
+    /* the node just recorded (the caller rescales right after computing, src/likelihood.c:7962-7965) */
+    for (i=sd->ev.operation_count-1; i>=0; i--)
+        if (sd->ops[i].dest == m->condLikeIndex[chain][p->index])
+            break;
+    if (i < 0)
+        return (ERROR);
+    sd->ops[i].scale_write = m->nodeScalerIndex[chain][p->index];    /* after the caller's FlipNodeScalerSpace */
+    m->unscaledNodes[chain][p->index] = 0;                           /* CondLikeScaler_* (src/likelihood.c:4985) */
+    return (NO_ERROR);
+}
+
+int Likelihood_B200 (TreeNode *p, int division, int chain, MrBFlt *lnL, int whichSitePats)
+{
+    ModelInfo       *m  = &modelSettings[division];
+    SeamDivision    *sd = &seamDiv[division];
+
+    if (sd->instance < 0)
+        return (ERROR);
+    SeamOpenRecord (sd, m, chain);          /* nothing dirty: root integration alone */
+    sd->recording = NO;
+    /* the caller has flipped the site-scaler space and reset or copied it (src/likelihood.c:7885-7889) */
+    sd->ev.site_scaler_dst = m->siteScalerIndex[chain];
+    sd->ev.site_scaler_src = (m->upDateAll == YES) ? MB200_NONE : m->siteScalerScratchIndex;
+    if (sd->inlineEigen == YES)
+        {
+        if (SeamClosedFormEigen (m, chain, sd->eigenBlock) == ERROR)
+            { (*lnL) = MRBFLT_NEG_MAX; abortMove = YES; return (ERROR); }
+        }
+    else if (m->dataType != STANDARD && SeamSyncCijk (m, sd, division, chain) == ERROR)
+        { (*lnL) = MRBFLT_NEG_MAX; abortMove = YES; return (ERROR); }
+    SeamCategoryRates (m, sd, division, chain);
+    return SeamRootAndLaunch (division, chain, p->index, lnL, whichSitePats);
+}
+
+/* What SetLikeFunctions (src/mcmc.c:17918) does for a division the engine covers: create the
+ * instance and point the five hot-path function pointers at the forms above.  Call it after
+ * SetLikeFunctions and InitChainCondLikes; returns ERROR (pointers untouched) for divisions
+ * outside the engine's coverage. */
+int MB200InstallLikeFunctions (int division)
+{
+    ModelInfo *m;
+
+    SeamInit ();
+    if (division < 0 || division >= numCurrentDivisions || division >= SEAM_MAX_DIVISIONS)
+        return (ERROR);
+    m = &modelSettings[division];
+    if (MB200SeamDivisionSupported (m) == NO || InitBeagleInstance (m, division) == ERROR)
+        return (ERROR);
+    m->TiProbs        = &TiProbs_B200;
+    m->CondLikeDown   = &CondLikeDown_B200;
+    m->CondLikeRoot   = &CondLikeRoot_B200;
+    m->CondLikeScaler = &CondLikeScaler_B200;
+    m->Likelihood     = &Likelihood_B200;
+    return (NO_ERROR);
+}
+
+/* ---- InitBeagleMultiPartitionInstance (src/mbbeagle.h:28, src/mbbeagle.c:1500): one instance per
+ *      division; unlike BEAGLE's single multi-partition instance the divisions need not share their
+ *      dimensions (src/mbbeagle.c:1522-1546), and they may live on different GPUs ------------- */
+int InitBeagleMultiPartitionInstance (void)
+{
+    int d, nOk = 0;
+
+    for (d=0; d<numCurrentDivisions; d++)
+        if (MB200SeamDivisionSupported (&modelSettings[d]) == YES)
+            {
+            if (InitBeagleInstance (&modelSettings[d], d) == ERROR)
+                return (ERROR);
+            nOk++;
+            }
+    return (nOk > 0) ? NO_ERROR : ERROR;
+}
+
+/* ---- recalculateScalers (src/mbbeagle.h:16, src/mbbeagle.c:541): rebuild every scaler of a chain's
+ *      current state.  The engine rescales every node (the built-in path's policy), so this is one
+ *      full evaluation of each division with the site scalers reset: all interior nodes recomputed
+ *      into their scratch slots and flipped in, like TreeCondLikes_Beagle_Rescale_All. ------------ */
+void recalculateScalers (int chain)
+{
+    int         d, i;
+    ModelInfo  *m;
+    Tree       *tree;
+    TreeNode   *p;
+    MrBFlt      lnL;
+    int         savedAll, savedCl, savedAbort = abortMove;
+
+    for (d=0; d<numCurrentDivisions; d++)
+        {
+        m = &modelSettings[d];
+        if (MB200SeamDivisionSupported (m) == NO || d >= SEAM_MAX_DIVISIONS || seamDiv[d].instance < 0)
+            continue;
+        tree = GetTree (m->brlens, chain, state[chain]);
+        savedAll = m->upDateAll;
+        savedCl  = m->upDateCl;
+        for (i=0; i<tree->nIntNodes; i++)
+            {
+            p = tree->intDownPass[i];
+            p->upDateCl = YES;
+            }
+        m->upDateAll = YES;                 /* ResetSiteScalers instead of CopySiteScalers */
+        MB200LaunchLogLikeForDivision (chain, d, &lnL);
+        m->upDateAll = savedAll;
+        m->upDateCl  = savedCl;
+        }
+    abortMove = savedAbort;
 }

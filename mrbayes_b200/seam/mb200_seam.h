@@ -25,6 +25,22 @@ int       MB200SeamClosedFormModel (ModelInfo *m);     /* nst = 1, 2 4x4 models:
  * abortMove = YES on a numerical failure, like the reference). */
 MrBFlt    MB200LogLike (int chain, void (*cpuPath) (int chain, int d, MrBFlt *lnL));
 void      MB200SeamFinalize (void);
+/* CUDA device a division's buffers live on (local rank, MB200_DEVICE, MB200_SHARD=partitions) */
+int       MB200SeamDeviceFor (int division);
+/* the engine instance a division needs (what InitBeagleInstance creates) */
+void      MB200SeamDivisionConfig (ModelInfo *m, int division, mb200_instance_config *cfg);
+
+/* Node-granular function-pointer forms (typedefs src/bayes.h:960-965): same signatures as the
+ * reference's TiProbs_*, CondLikeDown_*, CondLikeRoot_*, CondLikeScaler_*, Likelihood_* families
+ * (src/likelihood.h:43-162), installable by SetLikeFunctions (src/mcmc.c:17918).  They record the
+ * evaluation while the reference's own LaunchLogLikeForDivision loop runs and launch it as one fused
+ * pass from Likelihood_B200.  MB200InstallLikeFunctions points a division's ModelInfo at them. */
+int       TiProbs_B200        (TreeNode *p, int division, int chain);
+int       CondLikeDown_B200   (TreeNode *p, int division, int chain);
+int       CondLikeRoot_B200   (TreeNode *p, int division, int chain);
+int       CondLikeScaler_B200 (TreeNode *p, int division, int chain);
+int       Likelihood_B200     (TreeNode *p, int division, int chain, MrBFlt *lnL, int whichSitePats);
+int       MB200InstallLikeFunctions (int division);
 long long MB200SeamUpdateCount (int division);   /* node*pattern*rate CL updates issued  */
 int       MB200SeamInstance (int division);      /* engine instance of a division, or -1 */
 
@@ -42,6 +58,10 @@ typedef struct
     /* optional (may be NULL: the seam then evaluates synchronously) */
     int (*evaluate_begin)      (int instance, const mb200_evaluation *evaluations, int count);
     int (*evaluate_end)        (int instance, double *lnL, int *status);
+    /* variable-state (STANDARD data) divisions; NULL: those divisions stay on the reference's kernels */
+    int (*set_pattern_states)  (int instance, const int *state_counts, const int *matrix_offsets,
+                                const int *freq_offsets, int matrix_length, int dummy_patterns,
+                                int uncompressed_sites);
     } MB200SeamBackend;
 
 void      MB200SeamSetBackend (const MB200SeamBackend *backend);   /* NULL = the engine  */

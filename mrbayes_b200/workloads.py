@@ -365,3 +365,82 @@ def make_problem(S: int, K: int, C: int, n_tips: int, n_chains: int, seed: int, 
     pr = Problem(S, K, C, n_chains, trees, masks, weights, pi, V, Vinv, lam, rates, p_invar, flags=flags)
     pr.allocate()
     return pr
+
+
+# ----------------------------------------------------------------------------- variable-state (STANDARD data) divisions
+@dataclass
+class StdProblem(Problem):
+    """Morphology-like division: every pattern has its own number of states (m->nStates), the
+    equal-frequency Mk model, K gamma categories; tables as MrBayes lays them out for SYMPI_EQUAL
+    (one [K][n][n] run of matrices per state count that occurs, in increasing n: tiIndex; one
+    frequency vector per state count: bsIndex), `dummy` leading unobservable patterns
+    (AddDummyChars, reference src/model.c:176-224) and the coding-bias correction at the root."""
+    state_counts: np.ndarray = None
+    matrix_offsets: np.ndarray = None
+    freq_offsets: np.ndarray = None
+    matrix_length: int = 0
+    dummy: int = 0
+    uncompressed: int = 0
+
+    def config(self, max_evaluations=None):
+        c = super().config(max_evaluations)
+        c["flags"] = abi.CONFIG_VARIABLE_STATES
+        return c
+
+    def create(self, lib: abi.Library, device=0, max_evaluations=None, flags=0) -> abi.Instance:
+        cfg = self.config(max_evaluations)
+        cfg["flags"] |= flags
+        inst = abi.Instance(lib, device=device, **cfg)
+        inst.set_pattern_states(self.state_counts, self.matrix_offsets, self.freq_offsets, self.matrix_length,
+                                self.dummy, self.uncompressed)
+        for t in range(self.n_tips):
+            inst.set_tip_states(t, self.masks[t])
+        inst.set_pattern_weights(0, self.weights)
+        return inst
+
+    def _spec(self, ch, dirty_branches, dirty_nodes, full):
+        sp = super()._spec(ch, dirty_branches, dirty_nodes, full)
+        if len(sp.mats):
+            sp.mats["eigen"] = abi.NONE
+        return sp
+
+
+def make_std_problem(C: int, K: int, n_tips: int, n_chains: int, seed: int, max_states=6, dummy=2,
+                     alpha=0.8, p_missing=0.05, same_tree=False) -> StdProblem:
+    rng = np.random.default_rng(seed)
+    ns = rng.choice(np.arange(2, max_states + 1), size=C, p=None).astype(np.int32)
+    ns[:dummy] = 2
+    if C > dummy:
+        ns[dummy] = max_states                       # make sure the largest class occurs
+    classes = sorted(set(int(n) for n in ns))
+    ti_of, bs_of, ti, bs = {}, {}, 0, 0
+    for n in classes:
+        ti_of[n], bs_of[n] = ti, bs
+        ti += n * n * K
+        bs += n
+    freqs = np.concatenate([np.full(n, 1.0 / n) for n in classes])
+    masks = np.zeros((n_tips, C), np.uint64)
+    base = rng.integers(0, 1 << 30, size=C)
+    for t in range(n_tips):
+        mut = rng.random(C) < 0.3
+        st = np.where(mut, rng.integers(0, 1 << 30, size=C), base) % ns
+        m = np.uint64(1) << st.astype(np.uint64)
+        miss = rng.random(C) < p_missing
+        m = np.where(miss, (np.uint64(1) << ns.astype(np.uint64)) - np.uint64(1), m)
+        masks[t] = m
+    # unobservable (dummy) patterns: all taxa in state 0, all taxa in state 1, ... (coding=variable)
+    for d in range(dummy):
+        masks[:, d] = np.uint64(1) << np.uint64(d % 2)
+    weights = rng.integers(1, 4, size=C).astype(np.float32)
+    weights[:dummy] = 0.0
+    t0 = random_tree(n_tips, rng)
+    trees = [t0 if same_tree else random_tree(n_tips, rng) for _ in range(n_chains)]
+    rates = discrete_gamma_rates(alpha, K) * rng.uniform(0.5, 2.0)
+    S = int(max(classes))
+    pr = StdProblem(S, K, C, n_chains, trees, masks, weights, freqs, np.zeros((S, S)), np.zeros((S, S)), np.zeros(S),
+                    rates, 0.0, flags=0,
+                    state_counts=ns, matrix_offsets=np.array([ti_of[int(n)] for n in ns], np.int32),
+                    freq_offsets=np.array([bs_of[int(n)] for n in ns], np.int32), matrix_length=ti,
+                    dummy=dummy, uncompressed=int(weights.sum()))
+    pr.allocate()
+    return pr

@@ -35,6 +35,11 @@ typedef struct
     float      *weights;     /* [row][C]                                             */
     float      *tmp[3];      /* per-child matvec results [K][C][S]                   */
     long long   updates;
+    /* variable-state (STANDARD data) divisions: the *_Std family */
+    int         std;         /* MB200_CONFIG_VARIABLE_STATES                          */
+    int        *nStates, *tiIndex, *bsIndex;    /* [C] m->nStates, m->tiIndex, m->bsIndex */
+    size_t     *clOff;       /* [C+1] offset of pattern c inside one category's block  */
+    int         matLen, dummy, uncompressed;
     } OrcInst;
 
 static OrcInst *orcTab[ORC_MAX_INST];
@@ -78,6 +83,7 @@ int orc_create_instance (const mb200_instance_config *c, int *instance)
     o->weights      = (float *)    calloc ((size_t)c->weight_rows * C, sizeof(float));
     for (i=0; i<3; i++)
         o->tmp[i]   = (float *)    calloc (K * C * S, sizeof(float));
+    o->std = (c->flags & MB200_CONFIG_VARIABLE_STATES) ? 1 : 0;
     orcTab[id] = o;
     *instance = id;
     return MB200_SUCCESS;
@@ -90,6 +96,7 @@ int orc_finalize_instance (int instance)
     if (!o) return MB200_ERROR_BAD_INSTANCE;
     free (o->tips); free (o->tipPartAmbig); free (o->partials); free (o->matrices);
     free (o->scalers); free (o->eigen); free (o->weights);
+    free (o->nStates); free (o->tiIndex); free (o->bsIndex); free (o->clOff);
     for (i=0; i<3; i++) free (o->tmp[i]);
     free (o);
     orcTab[instance] = NULL;
@@ -447,6 +454,201 @@ static int RootLikelihood (OrcInst *o, const mb200_evaluation *ev, const float *
     return MB200_EVAL_OK;
 }
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Variable-state (STANDARD data) divisions: the reference's *_Std family.  Conditional likelihoods
+ * are ragged, [k][c][nStates[c]] (src/likelihood.c:1941-1943); a branch's transition matrices are
+ * one block of tiProbLength floats in which pattern c's category-k matrix sits at
+ * tiIndex[c] + k*nStates^2 (src/likelihood.c:1958-1961).  numBetaCats == 1 only.
+ * --------------------------------------------------------------------------------------------- */
+#define ORC_BRLENS_MIN ((double)0.00000001f)   /* src/bayes.h:318 */
+#define ORC_BRLENS_MAX ((double)100.0f)        /* src/bayes.h:319 */
+
+int orc_set_pattern_states (int instance, const int *ns, const int *ti, const int *bs, int matLen, int dummy, int uncompressed)
+{
+    int c, C;
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    if (!o->std) return MB200_ERROR_UNSUPPORTED;
+    if (!ns || !ti || !bs || matLen < 1 || dummy < 0 || dummy > o->cfg.pattern_count) return MB200_ERROR_OUT_OF_RANGE;
+    C = o->cfg.pattern_count;
+    for (c=0; c<C; c++)
+        if (ns[c] < 2 || ns[c] > o->cfg.state_count || ti[c] < 0 || ti[c] + o->cfg.category_count * ns[c] * ns[c] > matLen ||
+            bs[c] < 0 || bs[c] + ns[c] > MB200_MAX_STATES)
+            return MB200_ERROR_OUT_OF_RANGE;
+    free (o->nStates); free (o->tiIndex); free (o->bsIndex); free (o->clOff);
+    o->nStates = (int *) malloc ((size_t)C * sizeof(int));
+    o->tiIndex = (int *) malloc ((size_t)C * sizeof(int));
+    o->bsIndex = (int *) malloc ((size_t)C * sizeof(int));
+    o->clOff   = (size_t *) malloc ((size_t)(C + 1) * sizeof(size_t));
+    memcpy (o->nStates, ns, (size_t)C * sizeof(int));
+    memcpy (o->tiIndex, ti, (size_t)C * sizeof(int));
+    memcpy (o->bsIndex, bs, (size_t)C * sizeof(int));
+    o->clOff[0] = 0;
+    for (c=0; c<C; c++)
+        o->clOff[c+1] = o->clOff[c] + (size_t)ns[c];
+    o->matLen = matLen; o->dummy = dummy; o->uncompressed = uncompressed;
+    free (o->matrices);
+    o->matrices = (float *) calloc ((size_t)o->cfg.matrix_count * (size_t)matLen, sizeof(float));
+    return MB200_SUCCESS;
+}
+
+/* TiProbs_Std, equal state frequencies, unordered characters (src/likelihood.c:10066-10173): one
+ * [K][n][n] run per state count n that occurs, in increasing n, which is where tiIndex points */
+static void StdTiProbs (OrcInst *o, const mb200_matrix_update *mu, const mb200_evaluation *ev)
+{
+    int     K = o->cfg.category_count, C = o->cfg.pattern_count, c, n, k, i, j, index, found;
+    double  length = mu->length, v, eV1;
+    float   pNoChange, pChange, *tiP = o->matrices + (size_t)mu->matrix * o->matLen;
+
+    if (length > ORC_BRLENS_MAX)
+        length = ORC_BRLENS_MAX;
+    else if (length < ORC_BRLENS_MIN)
+        length = ORC_BRLENS_MIN;
+    for (n=2; n<=o->cfg.state_count; n++)
+        {
+        found = -1;
+        for (c=0; c<C && found < 0; c++)
+            if (o->nStates[c] == n)
+                found = o->tiIndex[c];
+        if (found < 0)
+            continue;                                   /* isTiNeeded[n-2] == NO */
+        index = found;
+        for (k=0; k<K; k++)
+            {
+            v = length * ev->category_rates[k];
+            eV1 = exp (-((double)n / ((double)n - 1.0)) * v);
+            pChange   = (float) ((1.0 / n) - ((1.0 / n) * eV1));
+            pNoChange = (float) ((1.0 / n) + (((double)n - 1.0) / n) * eV1);
+            if (pChange < 0.0)
+                pChange = 0.0f;
+            for (i=0; i<n; i++)
+                for (j=0; j<n; j++)
+                    tiP[index++] = (i == j) ? pNoChange : pChange;
+            }
+        }
+}
+
+/* one child's factor, CondLikeDown_Std / CondLikeRoot_Std inner loops (src/likelihood.c:1966-1976,
+ * 4547-4559): like = sum_i P[a][i] * cl[i], accumulated from 0 with separate multiply and add */
+static void StdChildTerm (OrcInst *o, int child, int matrix, float *out)
+{
+    int     K = o->cfg.category_count, C = o->cfg.pattern_count, c, k, a, i, n;
+    size_t  numReps = o->clOff[C];
+    const float *P = o->matrices + (size_t)matrix * o->matLen, *ti, *cl;
+    float   x[MB200_MAX_STATES], like;
+    uint64_t m;
+
+    for (k=0; k<K; k++)
+        for (c=0; c<C; c++)
+            {
+            n = o->nStates[c];
+            if (child < o->cfg.tip_count)
+                {
+                /* tip conditional likelihoods: 1.0 for every state in the observed set (src/mcmc.c:6302-6330) */
+                m = o->tips[(size_t)child*C + c];
+                for (i=0; i<n; i++) x[i] = ((m >> i) & 1) ? 1.0f : 0.0f;
+                cl = x;
+                }
+            else
+                cl = o->partials + (size_t)(child - o->cfg.tip_count) * K * numReps + (size_t)k * numReps + o->clOff[c];
+            ti = P + o->tiIndex[c] + k*n*n;
+            for (a=0; a<n; a++)
+                {
+                like = 0.0f;
+                for (i=0; i<n; i++)
+                    like = like + (*ti++) * cl[i];
+                out[(size_t)k * numReps + o->clOff[c] + a] = like;
+                }
+            }
+}
+
+static void StdOperation (OrcInst *o, const mb200_operation *op, float *lnScaler)
+{
+    int     K = o->cfg.category_count, C = o->cfg.pattern_count, c, k, s, n;
+    size_t  numReps = o->clOff[C], tot = (size_t)K * numReps, idx;
+    float  *dst = o->partials + (size_t)(op->dest - o->cfg.tip_count) * tot;
+    float   scaler, *scP;
+
+    StdChildTerm (o, op->child1, op->matrix1, o->tmp[0]);
+    StdChildTerm (o, op->child2, op->matrix2, o->tmp[1]);
+    if (op->child3 != MB200_NONE)
+        {
+        StdChildTerm (o, op->child3, op->matrix3, o->tmp[2]);
+        for (idx=0; idx<tot; idx++)
+            dst[idx] = o->tmp[0][idx] * o->tmp[1][idx] * o->tmp[2][idx];    /* likeL * likeR * likeA (:4559) */
+        }
+    else
+        for (idx=0; idx<tot; idx++)
+            dst[idx] = o->tmp[0][idx] * o->tmp[1][idx];                      /* likeL * likeR (:1974) */
+    o->updates += (long long) K * C;
+
+    if (op->scale_remove != MB200_NONE && lnScaler)      /* RemoveNodeScalers (src/likelihood.c:7981-8002) */
+        {
+        scP = o->scalers + (size_t)op->scale_remove * C;
+        for (c=0; c<C; c++)
+            lnScaler[c] -= scP[c];
+        }
+    if (op->scale_write != MB200_NONE)                   /* CondLikeScaler_Std (src/likelihood.c:5547-5610) */
+        {
+        scP = o->scalers + (size_t)op->scale_write * C;
+        for (c=0; c<C; c++)
+            {
+            n = o->nStates[c];
+            scaler = 0.0f;
+            for (k=0; k<K; k++)
+                for (s=0; s<n; s++)
+                    if (dst[(size_t)k*numReps + o->clOff[c] + s] > scaler)
+                        scaler = dst[(size_t)k*numReps + o->clOff[c] + s];
+            for (k=0; k<K; k++)
+                for (s=0; s<n; s++)
+                    dst[(size_t)k*numReps + o->clOff[c] + s] /= scaler;
+            scP[c] = (float) log (scaler);
+            if (lnScaler)
+                lnScaler[c] += scP[c];
+            }
+        }
+}
+
+/* Likelihood_Std, numBetaCats == 1 (src/likelihood.c:7401-7455, 7537) */
+static int StdRootLikelihood (OrcInst *o, const mb200_evaluation *ev, const float *lnScaler, double *lnL)
+{
+    int     K = o->cfg.category_count, C = o->cfg.pattern_count, c, k, j, n;
+    size_t  numReps = o->clOff[C];
+    const float *cl = o->partials + (size_t)(ev->root_buffer - o->cfg.tip_count) * K * numReps;
+    const float *w = o->weights + (size_t)ev->weights_row * C;
+    const double *bs;
+    double  catFreq = 1.0 / K, like, catLike, pUnobserved = 0.0, pObserved, sum = 0.0;
+
+    for (c=0; c<C; c++)
+        {
+        n = o->nStates[c];
+        bs = ev->state_freqs + o->bsIndex[c];
+        like = 0.0;
+        for (k=0; k<K; k++)
+            {
+            catLike = 0.0;
+            for (j=0; j<n; j++)
+                catLike += cl[(size_t)k*numReps + o->clOff[c] + j] * bs[j];
+            like += catLike * catFreq;
+            }
+        if (c < o->dummy)
+            {
+            pUnobserved += like * exp (lnScaler[c]);
+            continue;
+            }
+        if (like < ORC_LIKE_EPSILON)
+            { *lnL = -DBL_MAX; return MB200_EVAL_UNDERFLOW; }
+        sum += (lnScaler[c] + log (like)) * w[c];
+        }
+    pObserved = 1.0 - pUnobserved;
+    if (pObserved < ORC_LIKE_EPSILON)
+        pObserved = ORC_LIKE_EPSILON;
+    sum -= log (pObserved) * (o->uncompressed);
+    *lnL = sum;
+    return MB200_EVAL_OK;
+}
+
 /* LaunchLogLikeForDivision (src/likelihood.c:7851-7973), one call per evaluation */
 int orc_evaluate (int instance, const mb200_evaluation *evs, int count, double *lnL, int *status)
 {
@@ -458,8 +660,13 @@ int orc_evaluate (int instance, const mb200_evaluation *evs, int count, double *
     for (e=0; e<count; e++)
         {
         const mb200_evaluation *ev = &evs[e];
+        if (o->std && !o->nStates)
+            return MB200_ERROR_UNSUPPORTED;             /* orc_set_pattern_states first */
         for (i=0; i<ev->matrix_update_count; i++)
-            TiProbs (o, &ev->matrix_updates[i], ev);
+            {
+            if (o->std) StdTiProbs (o, &ev->matrix_updates[i], ev);
+            else        TiProbs (o, &ev->matrix_updates[i], ev);
+            }
         /* FlipSiteScalerSpace + ResetSiteScalers | CopySiteScalers (src/likelihood.c:7885-7889) */
         if (ev->site_scaler_dst != MB200_NONE)
             {
@@ -477,10 +684,13 @@ int orc_evaluate (int instance, const mb200_evaluation *evs, int count, double *
             lnScaler = zero;
             }
         for (i=0; i<ev->operation_count; i++)
-            Operation (o, &ev->operations[i], ev, lnScaler);
+            {
+            if (o->std) StdOperation (o, &ev->operations[i], lnScaler);
+            else        Operation (o, &ev->operations[i], ev, lnScaler);
+            }
         if (ev->root_buffer != MB200_NONE)
             {
-            int st = RootLikelihood (o, ev, lnScaler, &lnL[e]);
+            int st = o->std ? StdRootLikelihood (o, ev, lnScaler, &lnL[e]) : RootLikelihood (o, ev, lnScaler, &lnL[e]);
             if (status) status[e] = st;
             }
         else
@@ -499,7 +709,7 @@ int orc_get_partials (int instance, int buffer, float *out)
     OrcInst *o = Get (instance);
     if (!o) return MB200_ERROR_BAD_INSTANCE;
     if (buffer < o->cfg.tip_count || buffer >= o->cfg.partials_count) return MB200_ERROR_OUT_OF_RANGE;
-    n = (size_t)o->cfg.category_count * o->cfg.pattern_count * o->cfg.state_count;
+    n = (size_t)o->cfg.category_count * (o->std ? o->clOff[o->cfg.pattern_count] : (size_t)o->cfg.pattern_count * o->cfg.state_count);
     memcpy (out, o->partials + (size_t)(buffer - o->cfg.tip_count) * n, n * sizeof(float));
     return MB200_SUCCESS;
 }
@@ -510,7 +720,7 @@ int orc_set_partials (int instance, int buffer, const float *in)
     OrcInst *o = Get (instance);
     if (!o) return MB200_ERROR_BAD_INSTANCE;
     if (buffer < o->cfg.tip_count || buffer >= o->cfg.partials_count) return MB200_ERROR_OUT_OF_RANGE;
-    n = (size_t)o->cfg.category_count * o->cfg.pattern_count * o->cfg.state_count;
+    n = (size_t)o->cfg.category_count * (o->std ? o->clOff[o->cfg.pattern_count] : (size_t)o->cfg.pattern_count * o->cfg.state_count);
     memcpy (o->partials + (size_t)(buffer - o->cfg.tip_count) * n, in, n * sizeof(float));
     return MB200_SUCCESS;
 }
@@ -521,7 +731,7 @@ int orc_get_transition_matrix (int instance, int matrix, float *out)
     OrcInst *o = Get (instance);
     if (!o) return MB200_ERROR_BAD_INSTANCE;
     if (matrix < 0 || matrix >= o->cfg.matrix_count) return MB200_ERROR_OUT_OF_RANGE;
-    n = (size_t)o->cfg.category_count * o->cfg.state_count * o->cfg.state_count;
+    n = o->std ? (size_t)o->matLen : (size_t)o->cfg.category_count * o->cfg.state_count * o->cfg.state_count;
     memcpy (out, o->matrices + (size_t)matrix * n, n * sizeof(float));
     return MB200_SUCCESS;
 }

@@ -28,6 +28,9 @@ int orc_finalize_instance (int instance);
 int orc_set_arith         (int instance, int arith);
 int orc_set_tip_states      (int instance, int tip, const uint64_t *state_masks);
 int orc_set_pattern_weights (int instance, int row, const float *weights);
+int orc_set_pattern_states  (int instance, const int *state_counts, const int *matrix_offsets,
+                             const int *freq_offsets, int matrix_length, int dummy_patterns,
+                             int uncompressed_sites);
 int orc_set_cijk (int instance, int eigen, const double *block);
 int orc_set_eigen_decomposition (int instance, int eigen, const double *eigvecs,
                                  const double *inverse_eigvecs, const double *eigvals);

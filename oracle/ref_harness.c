@@ -18,11 +18,17 @@
  *   MB200_DUMP_MAX    stop recording after this many evaluations (default: all)
  *   MB200_TOL         shadow-mode relative tolerance (default 1e-6)
  *   MB200_REPORT      file the JSON summary is appended to (default: stderr)
+ *   MB200_VIA         "fnptr": every mode reaches the engine through the node-granular function-pointer
+ *                     forms installed in ModelInfo (what SetLikeFunctions would do), with the reference's
+ *                     own LaunchLogLikeForDivision loop driving them; default: the seam's own loop
  *
  * Golden file: "MB200GLD" u32 version=1, then chunks {u32 tag, u32 bytes, payload}:
  *   'INST' i32 division, 12 x i32 mb200_instance_config
  *   'TIPS' i32 division, i32 tip, i32 C, C x u64
  *   'WGHT' i32 division, i32 row, i32 C, C x f32
+ *   'PSTA' i32 division, i32 C, i32 matrix_length, i32 dummy_patterns, i32 uncompressed_sites, i32 freq_length,
+ *          C x i32 nStates, C x i32 tiIndex, C x i32 bsIndex     (variable-state divisions; EVAL's S field
+ *          is then freq_length, the number of state frequencies recorded)
  *   'EIGN' i32 division, i32 eigen, i32 S, f64 lambda[S], V[S*S], Vinv[S*S]
  *   'CIJK' i32 division, i32 eigen, i32 S, f64 block[2S+S^3]   (when V/Vinv unavailable; eigen = -2:
  *          the block travels inline with the NEXT 'EVAL' record)
@@ -50,6 +56,9 @@ enum { MODE_CPU, MODE_DUMP, MODE_SHADOW, MODE_GPU };
 
 static int        hMode = -1;
 static int        hMultiPart = 1;    /* gpu mode: all divisions of a chain in flight together (MB200LogLike) */
+static int        hViaFn = 0;        /* MB200_VIA=fnptr: reach the engine through the node-granular function pointers
+                                        (TiProbs_B200 ... Likelihood_B200 installed in ModelInfo) driven by the
+                                        reference's own LaunchLogLikeForDivision loop, instead of the seam's own loop */
 static FILE      *hDump = NULL;
 static long       hDumpMax = -1, hDumped = 0;
 static double     hTol = 1e-6;
@@ -57,6 +66,15 @@ static double     hSecCpu = 0.0, hSecGpu = 0.0;
 static long long  hCalls = 0, hUpdates = 0, hNodeUpdates = 0, hAborts = 0, hUnsupported = 0;
 static double     hMaxRel = 0.0, hSumRel = 0.0;
 static long long  hCompared = 0, hFailed = 0;
+static unsigned long long hLnlHash = 1469598103934665603ULL;   /* FNV-1a over every lnL handed back to the chain */
+
+static void HashLnl (double v)
+{
+    const unsigned char *b = (const unsigned char *) &v;
+    int i;
+    for (i=0; i<8; i++)
+        hLnlHash = (hLnlHash ^ b[i]) * 1099511628211ULL;
+}
 
 /* last eigensystem seen by CalcCijk */
 static int        hEigDim = 0;
@@ -81,6 +99,7 @@ static struct
 static int hInstDivision[4096];     /* recorder instance id -> division */
 static int hInstReal[4096];         /* recorder instance id -> engine instance (shadow) */
 static mb200_instance_config hInstCfg[4096];
+static int hInstFreqLen[4096];     /* variable-state instances: entries of state_freqs in use */
 static int hNumInst = 0;
 
 static double Now (void)
@@ -146,6 +165,26 @@ static int rec_weights (int inst, int row, const float *w)
     Chunk ("WGHT", hdr, sizeof(hdr), w, (size_t)hdr[2] * sizeof(float));
     if (hMode == MODE_SHADOW)
         return mb200_set_pattern_weights (hInstReal[inst], row, w);
+    return MB200_SUCCESS;
+}
+
+static int rec_pstates (int inst, const int *ns, const int *ti, const int *bs, int matLen, int dummy, int uncompressed)
+{
+    int hdr[6], c, nPat = hInstCfg[inst].pattern_count, freqLen = 0, *body;
+
+    for (c=0; c<nPat; c++)
+        if (bs[c] + ns[c] > freqLen)
+            freqLen = bs[c] + ns[c];
+    hInstFreqLen[inst] = freqLen;
+    hdr[0] = hInstDivision[inst]; hdr[1] = nPat; hdr[2] = matLen; hdr[3] = dummy; hdr[4] = uncompressed; hdr[5] = freqLen;
+    body = (int *) malloc ((size_t)3 * nPat * sizeof(int));
+    memcpy (body, ns, (size_t)nPat * sizeof(int));
+    memcpy (body + nPat, ti, (size_t)nPat * sizeof(int));
+    memcpy (body + 2*nPat, bs, (size_t)nPat * sizeof(int));
+    Chunk ("PSTA", hdr, sizeof(hdr), body, (size_t)3 * nPat * sizeof(int));
+    free (body);
+    if (hMode == MODE_SHADOW)
+        return mb200_set_pattern_states (hInstReal[inst], ns, ti, bs, matLen, dummy, uncompressed);
     return MB200_SUCCESS;
 }
 
@@ -285,6 +324,8 @@ static void WriteEval (int division, int chain, double lnLRef, int aborted)
         }
     hdr[0] = division; hdr[1] = chain; hdr[2] = e->matrix_update_count; hdr[3] = e->operation_count;
     hdr[4] = e->site_scaler_dst; hdr[5] = e->site_scaler_src; hdr[6] = e->root_buffer; hdr[7] = e->weights_row;
+    if (hInstCfg[hLast.instance].flags & MB200_CONFIG_VARIABLE_STATES)
+        S = hInstFreqLen[hLast.instance];           /* how many state frequencies the division uses */
     hdr[8] = e->flags; hdr[9] = e->has_p_invar; hdr[10] = K; hdr[11] = S;
     nb = sizeof(double) * (size_t)(1 + 2*K + S) + (size_t)e->matrix_update_count * 16 + (size_t)e->operation_count * 36 + 16;
     buf = q = (char *) malloc (nb);
@@ -319,9 +360,11 @@ static void Report (void)
     if (!f) f = stderr;
     fprintf (f, "{\"mb200_harness\": \"%s\", \"calls\": %lld, \"node_updates\": %lld, \"cl_updates\": %lld, "
                 "\"sec_cpu\": %.6f, \"sec_gpu\": %.6f, \"aborts\": %lld, \"unsupported_calls\": %lld, "
-                "\"compared\": %lld, \"failed\": %lld, \"max_rel\": %.3e, \"mean_rel\": %.3e, \"tol\": %.1e, \"dumped\": %ld}\n",
+                "\"compared\": %lld, \"failed\": %lld, \"max_rel\": %.3e, \"mean_rel\": %.3e, \"tol\": %.1e, \"dumped\": %ld, "
+                "\"via\": \"%s\", \"lnl_hash\": \"%016llx\"}\n",
              names[hMode], hCalls, hNodeUpdates, hUpdates, hSecCpu, hSecGpu, hAborts, hUnsupported,
-             hCompared, hFailed, hMaxRel, hCompared ? hSumRel / hCompared : 0.0, hTol, hDumped);
+             hCompared, hFailed, hMaxRel, hCompared ? hSumRel / hCompared : 0.0, hTol, hDumped,
+             hViaFn ? "fnptr" : "seam", hLnlHash);
     if (f != stderr) fclose (f);
     if (hDump) { fclose (hDump); hDump = NULL; }
     if (hMode == MODE_SHADOW || hMode == MODE_GPU)
@@ -337,6 +380,7 @@ static void Setup (void)
     if (s && !strcmp (s, "gpu"))    hMode = MODE_GPU;
     if ((s = getenv ("MB200_TOL")) != NULL)      hTol = atof (s);
     if ((s = getenv ("MB200_MULTIPART")) != NULL) hMultiPart = atoi (s);
+    if ((s = getenv ("MB200_VIA")) != NULL && !strcmp (s, "fnptr")) { hViaFn = 1; hMultiPart = 0; }
     if ((s = getenv ("MB200_DUMP_MAX")) != NULL) hDumpMax = atol (s);
     memset (&hLast, 0, sizeof(hLast));
     if (hMode == MODE_DUMP)
@@ -350,7 +394,7 @@ static void Setup (void)
         }
     if (hMode == MODE_DUMP || hMode == MODE_SHADOW)
         {
-        MB200SeamBackend be = { rec_create, rec_finalize, rec_tips, rec_weights, rec_cijk, rec_eval };
+        MB200SeamBackend be = { rec_create, rec_finalize, rec_tips, rec_weights, rec_cijk, rec_eval, NULL, NULL, rec_pstates };
         MB200SeamSetBackend (&be);
         }
     atexit (Report);
@@ -493,13 +537,21 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
     if (hMode == MODE_GPU)
         {
         t0 = Now ();
-        if (MB200LaunchLogLikeForDivision (chain, d, lnL) == NO)
+        if (hViaFn)
+            {
+            /* SetLikeFunctions runs again for every mcmc command: (re)install when the pointer is not ours */
+            if (m->Likelihood != &Likelihood_B200 && MB200InstallLikeFunctions (d) == ERROR)
+                hUnsupported++;
+            __real_LaunchLogLikeForDivision (chain, d, lnL);
+            }
+        else if (MB200LaunchLogLikeForDivision (chain, d, lnL) == NO)
             {
             hUnsupported++;
             __real_LaunchLogLikeForDivision (chain, d, lnL);
             }
         hSecGpu += Now () - t0;
         if (abortMove == YES) hAborts++;
+        HashLnl (*lnL);
         return;
         }
 
@@ -526,17 +578,8 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
         hdr[0] = d;
         {
         mb200_instance_config c;
-        memset (&c, 0, sizeof(c));
-        c.tip_count = numLocalTaxa; c.partials_count = m->numCondLikes; c.state_count = m->numModelStates;
-        c.pattern_count = m->numChars; c.matrix_count = m->numTiProbs;
-        c.category_count = (m->numOmegaCats > 1) ? m->numOmegaCats : m->numRateCats;     /* as InitBeagleInstance in the seam */
-        c.scaler_count = m->numScalers;
-        {
-        extern int numLocalChains;
-        c.eigen_count = numLocalChains + 1;
-        }
-        c.weight_rows = chainParams.numChains; c.device = 0; c.max_evaluations = 1;
-        c.flags = (m->nCijkParts > 1) ? MB200_CONFIG_CIJK_PARTS (m->nCijkParts) : 0;            /* NY98, covarion + gamma */
+        MB200SeamDivisionConfig (m, d, &c);     /* as InitBeagleInstance in the seam ... */
+        c.device = 0; c.max_evaluations = 1;    /* ... minus what depends on the machine or the run */
         memcpy (hdr + 1, &c, 12 * sizeof(int));
         }
         Chunk ("INST", hdr, sizeof(hdr), NULL, 0);
@@ -545,7 +588,20 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
 
     SnapTake (&snap, m, chain, tree->nNodes);
     hLast.valid = 0;
-    handled = MB200LaunchLogLikeForDivision (chain, d, &lnLSeam);   /* runs UpDateCijk for real */
+    if (hViaFn)
+        {
+        TiProbFxn       fT = m->TiProbs;
+        LikeDownFxn     fD = m->CondLikeDown;
+        LikeRootFxn     fR = m->CondLikeRoot;
+        LikeScalerFxn   fS = m->CondLikeScaler;
+        LikeFxn         fL = m->Likelihood;
+        handled = (MB200InstallLikeFunctions (d) == NO_ERROR) ? YES : NO;
+        if (handled == YES)
+            __real_LaunchLogLikeForDivision (chain, d, &lnLSeam);   /* the reference's loop over OUR pointers */
+        m->TiProbs = fT; m->CondLikeDown = fD; m->CondLikeRoot = fR; m->CondLikeScaler = fS; m->Likelihood = fL;
+        }
+    else
+        handled = MB200LaunchLogLikeForDivision (chain, d, &lnLSeam);   /* runs UpDateCijk for real */
     SnapRestore (&snap, m, chain);
     abortMove = savedAbort;
 

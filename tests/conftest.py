@@ -20,6 +20,7 @@ GOLDEN_FILES = [
     ("primates_f81_i_fma", 1),       # nst=1 + pInvar
     ("replicase_ny98_sse", 0),       # codon NY98: one eigensystem per omega category (TiProbs_GenCov, *_NY98)
     ("cynmix_part_fma", 1),          # cynmix, 4 unlinked GTR+I+G4 DNA partitions (32 taxa), interleaved evaluations
+    ("cynmix_full_fma", 1),          # cynmix, all 5 partitions: morphology Mk+G4 (variable-state *_Std family) + the 4 DNA ones
 ]
 
 

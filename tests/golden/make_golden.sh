@@ -24,7 +24,8 @@ run ovomucoids_wag_g4_sse mb_b200    100  80 ovomucoids_wag_g4
 run replicase_m0_sse      mb_b200    100  40 replicase_m0
 run primates_hky_g4_fma   mb_b200    100 200 primates_hky_g4
 run primates_f81_i_fma    mb_b200    100 150 primates_f81_i
-run cynmix_part_fma       mb_b200     40 160 cynmix_part
+MB200_NO_STD=1 run cynmix_part_fma       mb_b200     40 160 cynmix_part    # DNA partitions only (morphology left on the CPU)
 run replicase_ny98_sse    mb_b200     60  40 replicase_ny98
+run cynmix_full_fma       mb_b200     40 200 cynmix_full
 rm -rf $TMP
 ls -la $OUT/*.gold.gz

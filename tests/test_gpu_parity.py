@@ -375,3 +375,91 @@ def test_api_edge_cases(engine_lib, oracle_lib):
         # the instance is still usable afterwards
         again, st = e.evaluate(pr_e.full_evaluation(0))
         assert not st.any() and np.isfinite(again).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# variable-state (STANDARD data) divisions: the *_Std kernel family
+# ---------------------------------------------------------------------------------------------
+STD_CASES = [
+    # C, K, tips, max states, dummy patterns
+    (162, 4, 32, 8, 2),       # cynmix's morphology partition: size and shape
+    (1, 4, 4, 2, 0),
+    (33, 1, 5, 3, 2),
+    (70, 5, 6, 10, 2),        # L = 8 lanes per pattern
+    (129, 2, 7, 4, 4),
+    (40, 10, 5, 6, 0),        # L = 16
+    (37, 4, 6, 16, 2),
+    (25, 3, 5, 24, 2),        # MAX_STD_STATES
+]
+
+
+@pytest.mark.parametrize("C,K,tips,smax,dummy", STD_CASES)
+def test_variable_state_engine_matches_oracle(engine_lib, oracle_lib, C, K, tips, smax, dummy):
+    """Mk + gamma on patterns with their own state counts: P(t), every written conditional-likelihood
+    buffer (ragged host layout), node and site scalers, and lnL with the coding-bias correction."""
+    nch = 2
+    pr = workloads.make_std_problem(C, K, tips, nch, seed=900 + C + K + smax, max_states=smax, dummy=dummy)
+    rng = np.random.default_rng(11)
+    with pr.create(engine_lib) as e, pr.create(oracle_lib) as o:
+        for ch in range(nch):
+            sp = pr.full_evaluation(ch)
+            (le,), (se,) = e.evaluate(sp)
+            (lo,), (so,) = o.evaluate(sp)
+            assert se == so == abi.EVAL_OK
+            assert rel(le, lo) < 1e-9
+            for m in sp.mats["matrix"][:5]:
+                assert np.allclose(e.get_transition_matrix(int(m)), o.get_transition_matrix(int(m)), rtol=2.5e-7, atol=1e-30)
+            _compare_state(e, o, sp, smax)
+        for it in range(12):
+            ch = it % nch
+            old = pr.tree[ch].length.copy()
+            sp = pr.random_branch_update(ch, rng)
+            (le,), _ = e.evaluate(sp)
+            (lo,), _ = o.evaluate(sp)
+            assert rel(le, lo) < 1e-9, f"iteration {it}"
+            _compare_state(e, o, sp, smax)
+            if it % 3 == 2:
+                pr.reject(ch, sp, old)
+        assert e.kernel_launches(abi.KERNEL_STD) == nch + 12        # the variable-state kernel served every call
+        # all chains of a generation in one launch == one call per chain
+        sps = [pr.random_branch_update(ch, rng) for ch in range(nch)]
+        lb, _ = e.evaluate(sps)
+        lo2 = np.array([o.evaluate(sp)[0][0] for sp in sps])
+        assert np.allclose(lb, lo2, rtol=1e-9)
+
+
+def test_variable_state_general_matrices(engine_lib, oracle_lib):
+    """Caller-supplied transition matrices (mb200_set_transition_matrix) need not have the Mk form:
+    the kernel then reads every entry."""
+    pr = workloads.make_std_problem(60, 2, 5, 1, seed=77, max_states=5, dummy=2)
+    rng = np.random.default_rng(3)
+    with pr.create(engine_lib) as e, pr.create(oracle_lib) as o:
+        sp = pr.full_evaluation(0)
+        (l0,), _ = e.evaluate(sp)
+        (o0,), _ = o.evaluate(sp)
+        assert rel(l0, o0) < 1e-9
+        # re-load one matrix unchanged: same lnL through the general path
+        m = int(sp.mats["matrix"][0])
+        e.lib.check("set_transition_matrix", e.lib.fn("set_transition_matrix")(
+            e.handle, m, e.get_transition_matrix(m).ctypes.data_as(abi.C.POINTER(abi.C.c_float))))
+        sp2 = abi.EvalSpec(ops=sp.ops[-1:].copy(), site_dst=sp.site_dst, site_src=sp.site_dst, root=sp.root, rates=sp.rates,
+                           cat_weights=sp.cat_weights, freqs=sp.freqs)
+        sp2.ops["scale_remove"] = abi.NONE
+        (l1,), _ = e.evaluate(sp2)
+        (o1,), _ = o.evaluate(sp2)
+        assert rel(l1, o1) < 1e-9
+
+
+def test_tensor_core_kernel_serves_20_and_61_states(engine_lib):
+    """S = 20 and S = 61 must run on the tcgen05 kernel, not on the CUDA-core correctness path
+    (which would pass the same parity tolerance)."""
+    for S, K in ((20, 4), (61, 1)):
+        pr = workloads.make_problem(S, K, 300, 8, 1, seed=3)
+        with pr.create(engine_lib) as e:
+            e.evaluate(pr.full_evaluation(0))
+            assert e.kernel_launches(abi.KERNEL_TENSOR) == 1
+            assert e.kernel_launches(abi.KERNEL_GENERIC) == 0
+    pr = workloads.make_problem(4, 4, 300, 8, 1, seed=3)
+    with pr.create(engine_lib) as e:
+        e.evaluate(pr.full_evaluation(0))
+        assert e.kernel_launches(abi.KERNEL_NUC4) == 1 and e.kernel_launches(abi.KERNEL_TENSOR) == 0
