@@ -283,6 +283,11 @@ int mb200_pack_evaluations (int instance, const mb200_evaluation *evaluations, i
                             int *batch);
 int mb200_replay           (int instance, int batch);
 int mb200_replay_results   (int instance, int batch, double *lnL, int *status);
+/* the same launch with the results delivered like mb200_evaluate_begin / _end delivers them (16-byte
+ * records written by the kernel into pinned host memory, the caller polls): resident descriptors in,
+ * lnL on the host out, no copy and no stream synchronisation.  One launch in flight per instance. */
+int mb200_replay_begin     (int instance, int batch);
+int mb200_replay_end       (int instance, double *lnL, int *status);
 int mb200_free_batch       (int instance, int batch);
 int mb200_synchronize      (int instance);
 /* the CUDA stream (cudaStream_t as void*) all work of the instance is issued on, so a

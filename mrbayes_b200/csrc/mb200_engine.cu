@@ -40,6 +40,8 @@ struct Batch                       // packed evaluations (device job format)
     bool    used = false;
     int     tipEpoch = 0;          // Instance::tipEpoch at pack time (4-state records embed tip kinds)
     JobIndex jx;                   // 4-state latency path: where each evaluation's first chunk lives
+    std::vector<char> hasRoot;     // [nEval] the evaluation ends in a root integration
+    bool    allRoot = false;
 };
 
 struct Instance
@@ -73,8 +75,7 @@ struct Instance
     int           writtenStamp = 0;
     int           pendingCount = 0;            // evaluations started by mb200_evaluate_begin, not yet collected
     int           pendingSeq = 0;              // sequence number stamped by the launch begin() issued
-    bool          pendingAllRoot = false;
-    std::vector<char> pendingHasRoot;
+    Batch        *pendingBatch = nullptr;      // whose result buffer the pending launch writes
     int           lastHostSum = 0, lastTiles = 1;   // how the last launch delivers its results
     Batch         scratch;             // used by the synchronous entry points
     std::vector<Batch *> batches;      // resident batches (mb200_pack_evaluations)
@@ -210,6 +211,8 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         return MB200_ERROR_UNSUPPORTED;                 // mb200_set_pattern_states first
 
     const bool nuc4 = (S == 4 && K <= 8 && !I->std);
+    // state frequencies per evaluation: S, or the whole table for variable-state divisions (one vector per state count)
+    const int  nFreq = I->std ? MB200_MAX_STATES : S;
     const int  ppbS = nuc4 ? nuc4PatternsPerBlock (K, true) : 1;
     const long ctas = (long)((c.pattern_count + ppbS - 1) / ppbS) * count;
     // fused P(t) rebuild (every CTA rebuilds the dirty matrices of its evaluation): small launches (latency-
@@ -349,7 +352,7 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     // eigensystem, the cijk block [2S + S^3]
     int nDbl = 0;
     for (int e = 0; e < count; e++)
-        nDbl += 2*K + S + (evs[e].inline_eigen ? 2*S + S*S*S : 0);
+        nDbl += 2*K + nFreq + (evs[e].inline_eigen ? 2*S + S*S*S : 0);
     nDbl = (nDbl + 1) & ~1;
     size_t offEval  = mb200_align16 (sizeof(DevBatchHeader));
     size_t offDbl   = mb200_align16 (offEval + sizeof(DevEval) * (size_t)count);
@@ -388,7 +391,7 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
         d.flags = ev.flags;              d.hasPInvar = ev.has_p_invar ? 1 : 0;
         d.pInvar = ev.p_invar;
         d.dOff = dblPos;
-        dblPos += 2*K + S + (ev.inline_eigen ? 2*S + S*S*S : 0);
+        dblPos += 2*K + nFreq + (ev.inline_eigen ? 2*S + S*S*S : 0);
         d.fuseP = fused ? 1 : 0;
         d.eigen0 = (ev.matrix_update_count > 0) ? ev.matrix_updates[0].eigen : 0;
         d.nChunk = nChunkOf[e];
@@ -416,7 +419,7 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
             if (ev.category_weights[k] != ev.category_weights[0]) eq = false;
             }
         d.equalWeights = eq ? 1 : 0;
-        for (int s = 0; s < S; s++)
+        for (int s = 0; s < nFreq; s++)
             dv[2*K + s] = ev.state_freqs[s];
         if (ev.inline_eigen)
             {
@@ -516,6 +519,13 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
             }
         mOff += fused ? 0 : ev.matrix_update_count;
         oOff += ev.operation_count;
+        }
+    b.hasRoot.resize (count);
+    b.allRoot = true;
+    for (int e = 0; e < count; e++)
+        {
+        b.hasRoot[e] = (evs[e].root_buffer != MB200_NONE);
+        if (!b.hasRoot[e]) b.allRoot = false;
         }
     b.bytes = bytes; b.nEval = count; b.nMat = nUpd; b.nOp = nOp; b.nDbl = nDbl;
     b.nDirty = nMat; b.fused = fused; b.tipEpoch = I->tipEpoch;
@@ -803,18 +813,11 @@ int runBegin (Instance *I, const mb200_evaluation *evs, int count)
     const bool viaParams = paramEligible (I, b);
     if (!viaParams)
         CK (cudaMemcpyAsync (b.dBlob, b.hBlob, b.bytes, cudaMemcpyHostToDevice, I->stream));
-    bool allRoot = true;
-    if ((int) I->pendingHasRoot.size () < count) I->pendingHasRoot.resize (count);
-    for (int e = 0; e < count; e++)
-        {
-        I->pendingHasRoot[e] = (evs[e].root_buffer != MB200_NONE);
-        if (!I->pendingHasRoot[e]) allRoot = false;
-        }
     I->lastHostSum = 0; I->lastTiles = 1;
-    rc = launch (I, b, b.hResDev, viaParams, allRoot && b.fused);
+    rc = launch (I, b, b.hResDev, viaParams, b.allRoot && b.fused);
     MB200_HOST_T (tC);
     if (rc != MB200_SUCCESS) return rc;
-    I->pendingCount = count; I->pendingAllRoot = allRoot; I->pendingSeq = I->seq;
+    I->pendingCount = count; I->pendingBatch = &b; I->pendingSeq = I->seq;
 #ifdef MB200_PHASE_TIMING
     gHostPhase[0] += tB - tA; gHostPhase[1] += tC - tB; gHostPhase[3] += 1.0;
 #endif
@@ -828,9 +831,9 @@ int runEnd (Instance *I, double *lnL, int *status)
     if (count <= 0)
         return MB200_ERROR_OUT_OF_RANGE;
     I->pendingCount = 0;
-    Batch &b = I->scratch;
+    Batch &b = *I->pendingBatch;
     MB200_HOST_T (tC);
-    if (I->pendingAllRoot)
+    if (b.allRoot)
         {
         // results land in pinned host memory; no D2H copy, no stream synchronisation
         int rc = waitResults (I, b, I->lastHostSum ? count * I->lastTiles : count);
@@ -843,7 +846,7 @@ int runEnd (Instance *I, double *lnL, int *status)
 #endif
     for (int e = 0; e < count; e++)
         {
-        if (I->pendingHasRoot[e])
+        if (b.hasRoot[e])
             {
             if (I->lastHostSum)
                 {
@@ -1461,6 +1464,32 @@ int mb200_replay (int instance, int batch)
     if (rb.tipEpoch != I->tipEpoch)
         return MB200_ERROR_OUT_OF_RANGE;           // tip states changed since mb200_pack_evaluations: pack again
     return launch (I, rb, rb.dRes, false);
+}
+
+int mb200_replay_begin (int instance, int batch)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (batch < 0 || batch >= (int) I->batches.size () || !I->batches[batch]) return MB200_ERROR_OUT_OF_RANGE;
+    if (I->pendingCount > 0) return MB200_ERROR_OUT_OF_RANGE;       // one evaluation in flight per instance
+    int rc = use (I); if (rc) return rc;
+    Batch &rb = *I->batches[batch];
+    if (rb.tipEpoch != I->tipEpoch)
+        return MB200_ERROR_OUT_OF_RANGE;
+    I->lastHostSum = 0; I->lastTiles = 1;
+    rc = launch (I, rb, rb.hResDev, false, rb.allRoot && rb.fused);
+    if (rc != MB200_SUCCESS) return rc;
+    I->pendingCount = rb.nEval; I->pendingBatch = &rb; I->pendingSeq = I->seq;
+    return MB200_SUCCESS;
+}
+
+int mb200_replay_end (int instance, double *lnL, int *status)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (!lnL || !status) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    return runEnd (I, lnL, status);
 }
 
 int mb200_replay_results (int instance, int batch, double *lnL, int *status)

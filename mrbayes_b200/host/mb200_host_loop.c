@@ -151,3 +151,123 @@ double mb200_host_replay_loop (const int *instances, int replicas, const int *ba
     free (streams); free (done); free (start); free (stop);
     return (rc == 0) ? total : (double) rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * MC^3 generation loop of ONE analysis on this process' GPU (the structure of the reference's RunChain,
+ * src/mcmc.c:16704-16958, for the chains SetLocalChainsAndDataSplits gave this process): every
+ * generation all local chains are evaluated in ONE launch per data partition (the partitions of a chain
+ * in flight together), accepted or rejected, and every swap generation the coordinator
+ * (include/mb200_mc3.h) exchanges {lnL, lnPrior} and decides the swaps.  The exchange of generation g
+ * is in flight while generation g+1's likelihoods run: a swap changes heats, not states, so only the
+ * accept step of g+1 has to wait for it.
+ *
+ *   parts            engine instances of this process, one per data partition
+ *   steps            mode 0: steps[p * cycle + i] -> mb200_evaluation[n_local] (host structs, the C-ABI call)
+ *   batches          mode 1: batches[p * cycle + i] = packed batch handle (descriptors resident in HBM)
+ *   accept           accept[i * n_local + c]: the proposal of local chain c in cycle step i is accepted
+ *   lnprior          lnprior[i * n_local + c]: log prior of that proposal
+ *   cur_lnl/cur_lnpr in: state before the first generation; out: state after the last
+ *   sums             out: [2] wall-clock seconds, device milliseconds (events on the first partition's stream)
+ * Returns 0 or a negative error code.
+ */
+#include "mb200_mc3.h"
+
+int mb200_host_mc3_loop (mb200_mc3 *mc, const int *parts, int n_parts, int n_local, int mode,
+                         const mb200_evaluation *const *steps, const int *batches, int cycle,
+                         const unsigned char *accept, const double *lnprior, const int *order, int n_generations,
+                         int swap_freq, double *cur_lnl, double *cur_lnpr, double *sums, long long *swaps_accepted)
+{
+    struct timespec t0, t1;
+    cudaEvent_t evA = NULL, evB = NULL;
+    cudaStream_t s0 = NULL;
+    double *lnl_p, *lnl_new;
+    int    *status, g, p, c, rc = 0, swap_pending = 0, acc = 0;
+    long long n_acc = 0;
+    void   *sv = NULL;
+    float   ms = 0.0f;
+
+    if (!mc || !parts || n_parts < 1 || n_local < 1 || !order || !accept || !lnprior || !cur_lnl || !cur_lnpr)
+        return -1;
+    lnl_p   = (double *) malloc ((size_t) n_local * sizeof(double));
+    lnl_new = (double *) malloc ((size_t) n_local * sizeof(double));
+    status  = (int *)    malloc ((size_t) n_local * sizeof(int));
+    if (!lnl_p || !lnl_new || !status)
+        return -1;
+    if (mb200_get_stream (parts[0], &sv) != MB200_SUCCESS)
+        return -2;
+    s0 = (cudaStream_t) sv;
+    if (cudaEventCreate (&evA) != cudaSuccess || cudaEventCreate (&evB) != cudaSuccess)
+        return -3;
+    for (p = 0; p < n_parts; p++)
+        mb200_synchronize (parts[p]);
+    clock_gettime (CLOCK_MONOTONIC, &t0);
+    cudaEventRecord (evA, s0);
+    for (g = 0; g < n_generations && rc == 0; g++)
+        {
+        const int i = order[g];
+        /* launch: all local chains of every partition */
+        for (p = 0; p < n_parts && rc == 0; p++)
+            {
+            if (mode == 0)
+                rc = mb200_evaluate_begin (parts[p], steps[(size_t) p * cycle + i], n_local);
+            else
+                rc = mb200_replay_begin (parts[p], batches[(size_t) p * cycle + i]);
+            }
+        if (rc != 0) break;
+        /* the previous generation's exchange has been travelling meanwhile: heats are needed from here on */
+        if (swap_pending)
+            {
+            if ((rc = mb200_mc3_exchange_end (mc)) != 0) break;
+            if ((rc = mb200_mc3_attempt_swaps (mc, &acc)) != 0) break;
+            n_acc += acc;
+            swap_pending = 0;
+            }
+        /* collect: lnL of a chain = sum over its partitions (src/mcmc.c:7441) */
+        for (c = 0; c < n_local; c++) lnl_new[c] = 0.0;
+        for (p = 0; p < n_parts && rc == 0; p++)
+            {
+            if (mode == 0)
+                rc = mb200_evaluate_end (parts[p], lnl_p, status);
+            else
+                rc = mb200_replay_end (parts[p], lnl_p, status);
+            for (c = 0; c < n_local; c++)
+                lnl_new[c] += lnl_p[c];
+            }
+        if (rc != 0) break;
+        /* accept / reject (the reference: r = exp (T * (lnL' - lnL) + T * (lnPr' - lnPr) + proposal ratio),
+           src/mcmc.c:16865-16890; here the outcome is part of the pre-generated proposal cycle, because a
+           rejected proposal's index flips are baked into the next step's evaluation) */
+        for (c = 0; c < n_local; c++)
+            if (accept[(size_t) i * n_local + c])
+                {
+                cur_lnl[c]  = lnl_new[c];
+                cur_lnpr[c] = lnprior[(size_t) i * n_local + c];
+                }
+        if (swap_freq > 0 && (g + 1) % swap_freq == 0)
+            {
+            if ((rc = mb200_mc3_exchange_begin (mc, cur_lnl, cur_lnpr)) != 0) break;
+            swap_pending = 1;
+            }
+        }
+    if (rc == 0 && swap_pending)
+        {
+        rc = mb200_mc3_exchange_end (mc);
+        if (rc == 0) rc = mb200_mc3_attempt_swaps (mc, &acc);
+        n_acc += acc;
+        }
+    cudaEventRecord (evB, s0);
+    for (p = 0; p < n_parts; p++)
+        mb200_synchronize (parts[p]);
+    cudaEventSynchronize (evB);
+    clock_gettime (CLOCK_MONOTONIC, &t1);
+    cudaEventElapsedTime (&ms, evA, evB);
+    cudaEventDestroy (evA); cudaEventDestroy (evB);
+    if (sums)
+        {
+        sums[0] = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+        sums[1] = (double) ms;
+        }
+    if (swaps_accepted) *swaps_accepted = n_acc;
+    free (lnl_p); free (lnl_new); free (status);
+    return rc;
+}

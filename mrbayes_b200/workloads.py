@@ -408,7 +408,11 @@ class StdProblem(Problem):
 def make_std_problem(C: int, K: int, n_tips: int, n_chains: int, seed: int, max_states=6, dummy=2,
                      alpha=0.8, p_missing=0.05, same_tree=False) -> StdProblem:
     rng = np.random.default_rng(seed)
-    ns = rng.choice(np.arange(2, max_states + 1), size=C, p=None).astype(np.int32)
+    # a handful of state counts (the frequency table, one vector per count, must fit 64 entries)
+    pool = sorted(set([2, 3, min(4, max_states), max(2, max_states // 2), max_states]))
+    while sum(pool) > 64:
+        pool.pop(-2)
+    ns = rng.choice(np.array(pool), size=C).astype(np.int32)
     ns[:dummy] = 2
     if C > dummy:
         ns[dummy] = max_states                       # make sure the largest class occurs

@@ -363,7 +363,8 @@ static void Report (void)
                 "\"compared\": %lld, \"failed\": %lld, \"max_rel\": %.3e, \"mean_rel\": %.3e, \"tol\": %.1e, \"dumped\": %ld, "
                 "\"via\": \"%s\", \"lnl_hash\": \"%016llx\"}\n",
              names[hMode], hCalls, hNodeUpdates, hUpdates, hSecCpu, hSecGpu, hAborts, hUnsupported,
-             hCompared, hFailed, hMaxRel, hCompared ? hSumRel / hCompared : 0.0, hTol, hDumped,
+             hCompared, hFailed, (hMaxRel == hMaxRel && hMaxRel < 1e300) ? hMaxRel : 9.999e99,
+             (hCompared && hSumRel == hSumRel && hSumRel < 1e300) ? hSumRel / hCompared : (hCompared ? 9.999e99 : 0.0), hTol, hDumped,
              hViaFn ? "fnptr" : "seam", hLnlHash);
     if (f != stderr) fclose (f);
     if (hDump) { fclose (hDump); hDump = NULL; }
@@ -627,7 +628,7 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
                 rel = fabs (hLast.lnLGpu - lnLRef) / fabs (lnLRef);
             hCompared++;
             hSumRel += rel;
-            if (rel > hMaxRel) hMaxRel = rel;
+            if (rel > hMaxRel || rel != rel) hMaxRel = rel;
             if (!(rel <= hTol))
                 {
                 hFailed++;
