@@ -1,9 +1,11 @@
-"""N > 1 path of bench.py on CPU: two processes over gloo (the GPU run uses the same code over NCCL).
+"""N > 1 path of bench.py on CPU: two processes over gloo (the GPU run moves the same rows with NCCL).
 
-Every rank drives its own independent analyses (weak scaling, no data-path collective); what crosses
-ranks is (1) the bench contract's reduction -- times MAX over ranks, work SUM over ranks -- and
-(2) one all-reduce of per-run lnL sums (the marginal-likelihood reduce of the reference's MPI
-build, src/mcmc.c:17246).  The likelihoods here come from the CPU oracle (test infrastructure)."""
+ONE run of primates (nruns=1, nchains=8) whose heated chains are dealt out over the processes in
+contiguous blocks (the reference's chain -> process map, src/mcmc.c:18331): every generation each
+process evaluates its own chains (CPU oracle here: test infrastructure), then {lnL, lnPrior, chainId}
+of all chains is all-gathered and every process attempts the same swaps.  The swap decisions and the
+final heats must be what ONE process holding all eight chains gets from the same seed -- a chain's
+trajectory and the swap generator do not depend on the number of processes."""
 import os
 import socket
 import sys
@@ -15,6 +17,8 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
+GENS = 24
+
 
 def _free_port():
     with socket.socket() as s:
@@ -22,59 +26,61 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _single_process_answer():
+    import bench
+    from mrbayes_b200 import abi, mc3
+    w = bench.WORKLOADS["primates-sharded"]
+    job = bench.Job("primates-sharded", 0, 1, abi.oracle_library(), 0, 16)
+    with mc3.Coordinator(num_runs=job.runs, chains_per_run=job.chains, num_swaps=w["swaps"], chain_temp=0.1, swap_seed=12345) as mc:
+        cur = bench.python_mc3_loop(job, mc, GENS)
+        out = (mc.decision_hash(), [mc.chain_id(g) for g in range(job.runs * job.chains)], cur.copy(), int(mc.swap_info().sum()))
+    job.close()
+    return out
+
+
 def _worker(rank: int, world: int, port: int, out_dir: str):
     import torch
     import torch.distributed as dist
     import bench
-    from mrbayes_b200 import abi
+    from mrbayes_b200 import abi, mc3
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        # disjoint replicas per rank
-        seeds = bench.replica_seeds(rank, 2)
-        gathered = [None] * world
-        dist.all_gather_object(gathered, seeds)
-        flat = [s for per_rank in gathered for s in per_rank]
-        assert len(set(flat)) == len(flat)
+        w = bench.WORKLOADS["primates-sharded"]
+        job = bench.Job("primates-sharded", rank, world, abi.oracle_library(), 0, 16)
+        assert job.n_local == 4 and job.globals == list(range(4 * rank, 4 * rank + 4))
+        mc = mc3.Coordinator(rank=rank, world=world, num_runs=job.runs, chains_per_run=job.chains, num_swaps=w["swaps"],
+                             chain_temp=0.1, swap_seed=12345, backend=mc3.LOOPBACK)
 
-        # each rank evaluates one generation of its own analyses (oracle), 8 chains each
-        lib = abi.oracle_library()
-        lnl_sum, updates = 0.0, 0
-        for prob_seed, cycle_seed in seeds:
-            pr = bench.primates_problem(8, seed=prob_seed)
-            with pr.create(lib, max_evaluations=8) as inst:
-                steps = bench.make_cycle(pr, inst, 4, seed=cycle_seed)
-                for sp in steps:
-                    lnl, st = inst.evaluate(sp)
-                    assert not st.any() and np.isfinite(lnl).all()
-                    updates += bench.updates_of(sp, pr.C, pr.K)
-                lnl_sum += float(lnl.sum())
+        def gather(rows):
+            mine = torch.from_numpy(rows)
+            parts = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            return torch.cat(parts).numpy()
 
-        # (2) the one data-independent collective: sum of per-run lnL over ranks
-        t = torch.tensor([lnl_sum], dtype=torch.float64)
+        cur = bench.python_mc3_loop(job, mc, GENS, gather)
+        # end of run: one double per run summed over the processes (MPI_Reduce, src/mcmc.c:17246)
+        t = torch.tensor([float(cur.sum())], dtype=torch.float64)
         dist.all_reduce(t)
-        all_sums = [None] * world
-        dist.all_gather_object(all_sums, lnl_sum)
-        assert abs(t.item() - sum(all_sums)) <= 1e-9 * abs(sum(all_sums))
-
-        # (1) the bench contract: MAX of times, SUM of work
-        my_ms = 10.0 + 5.0 * rank
-        ms_value, ms_warm, ms_e2e, all_updates, all_launches = bench.reduce_over_ranks(
-            torch, dist, "cpu", my_ms, my_ms + 1.0, my_ms + 2.0, updates, 3 + rank)
-        all_upd = [None] * world
-        dist.all_gather_object(all_upd, updates)
-        assert ms_value == 10.0 + 5.0 * (world - 1) and ms_warm == ms_value + 1.0 and ms_e2e == ms_value + 2.0
-        assert all_updates == float(sum(all_upd)) and all_launches == sum(3 + r for r in range(world))
-        Path(out_dir, f"ok{rank}").write_text("ok")
+        ids = [mc.chain_id(g) for g in range(job.runs * job.chains)]
+        np.save(Path(out_dir, f"r{rank}.npy"), np.array([mc.decision_hash() & 0xffffffff, mc.decision_hash() >> 32, *ids, t.item(), *cur]))
+        mc.close(); job.close()
     finally:
         dist.destroy_process_group()
 
 
-def test_two_ranks_over_gloo(tmp_path):
-    torch = pytest.importorskip("torch")
+def test_one_run_sharded_over_two_ranks_matches_single_process(tmp_path):
+    pytest.importorskip("torch")
     import torch.multiprocessing as mp
     world, port = 2, _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
-    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+    r = [np.load(tmp_path / f"r{k}.npy") for k in range(world)]
+    h1, ids1, cur1, nswap = _single_process_answer()
+    assert nswap > GENS                                   # swaps were attempted (2 per generation) and some accepted
+    for k in range(world):
+        assert (int(r[k][0]) | (int(r[k][1]) << 32)) == h1, "swap decisions differ from the single-process run"
+        assert [int(x) for x in r[k][2:10]] == ids1
+        assert r[k][10] == pytest.approx(float(cur1.sum()), rel=1e-12)
+        assert np.array_equal(r[k][11:], cur1[4 * k:4 * k + 4])       # a chain's trajectory does not depend on its owner
