@@ -164,7 +164,11 @@ class Job:
         self.globals = list(range(self.first, self.first + self.n_local))
         # one tree per GLOBAL chain, seeded by the chain, so that a chain's trajectory does not depend on
         # which process owns it; the partitions of a chain share its tree (linked branch lengths)
-        trees = [workloads.random_tree(w["tips"], np.random.default_rng([seed, g]), mean_len=0.08) for g in self.globals]
+        # the chains of a run start from the run's common tree (like a real run after burn-in they sit at
+        # comparable likelihoods, so that heat swaps are actually accepted) and then go their own way
+        import copy
+        trees = [copy.deepcopy(workloads.random_tree(w["tips"], np.random.default_rng([seed, g // self.chains]), mean_len=0.08))
+                 for g in self.globals]
         if name.startswith("primates"):
             self.parts = [primates_partition(self.n_local, trees)]
         elif name == "cynmix":

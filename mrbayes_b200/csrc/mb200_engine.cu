@@ -58,6 +58,7 @@ struct Instance
     size_t        smemTc = 0;
     float        *dPartials = nullptr, *dMatrices = nullptr, *dScalers = nullptr, *dWeights = nullptr;
     double       *dEigen = nullptr;
+    double       *dFactor = nullptr;    // large state counts: rank-one factors (U, W) of every eigensystem's c_ijk slices
     uint64_t     *dInvMask = nullptr;
     double       *dTilePartial = nullptr;
     int          *dTileAbort = nullptr;
@@ -636,6 +637,38 @@ bool paramEligible (const Instance *I, const Batch &b)
     return b.fused && b.bytes <= (size_t) PARAM_BIG;
 }
 
+// Rows (site patterns) per tile of the tensor-core kernel: the MMA is 128 rows tall, but a CTA is latency-bound
+// (load + split -> MMA -> TMEM read-out -> store, back to back), so what matters is how many CTAs an SM holds at
+// once (two: shared memory and registers) and that the grid fills those slots in whole waves.  Pick the number
+// of waves w that minimises  w * (fixed cost per node + cost per row * rows per tile).
+const int TC_MIN_ROWS = 32;
+int tcRowsPerTile (const Instance *I, int nEval)
+{
+    static const int forced = getenv ("MB200_TC_ROWS") ? atoi (getenv ("MB200_TC_ROWS")) : 0;
+    if (forced >= TC_MIN_ROWS && forced <= 128)
+        return forced & ~7;
+    const size_t smem = (I->tcS == 61) ? tc_smem_bytes<61, 1> () : tc_smem_bytes<20, 1> ();
+    const long perSM = (2 * smem + 4096 <= 227 * 1024) ? 2 : 1;
+    const long slots = (long) I->numSMs * perSM;             // co-resident CTAs per wave
+    const long C = I->cfg.pattern_count;
+    double best = 1e300; int bestRows = 128;
+    for (int w = 1; w <= 64; w++)
+        {
+        long tilesPerEval = (slots * w) / (nEval > 0 ? nEval : 1);
+        if (tilesPerEval < 1) tilesPerEval = 1;
+        long rows = (C + tilesPerEval - 1) / tilesPerEval;
+        rows = (rows + 7) & ~7L;
+        if (rows > 128) continue;
+        if (rows < TC_MIN_ROWS) rows = TC_MIN_ROWS;
+        const long tiles = ((C + rows - 1) / rows) * (nEval > 0 ? nEval : 1);
+        const long waves = (tiles + slots - 1) / slots;
+        const double cost = (double) waves * (48.0 + (double) rows);     // fixed part ~ 48 rows' worth (measured)
+        if (cost < best) { best = cost; bestRows = (int) rows; }
+        if (rows == TC_MIN_ROWS) break;
+        }
+    return bestRows;
+}
+
 // launch the fused pass for a packed batch; fromHost: the job lives in b.hBlob only and is
 // delivered through the parameter block when it fits (otherwise the caller has copied it to dBlob)
 int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum = false)
@@ -662,7 +695,15 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
         }
     else if (b.nDirty > 0 && !b.fused)
         {
-        if (ctx.S > 32)
+        static const bool wideOld = getenv ("MB200_TIPROBS_WIDE") != nullptr;      // A/B switch: the c_ijk-streaming kernel
+        if (ctx.S > 32 && I->dFactor && !wideOld)
+            {
+            dim3 grid (b.nMat, ctx.K);
+            const int LD = (ctx.S + 3) & ~3;
+            tiprobs_mm_kernel<<<grid, 256, (size_t)2 * ctx.S * LD * sizeof(double), I->stream>>> (ctx, de, b.nEval, dd, du, I->dFactor,
+                                                                                                   (I->tcS == 61) ? I->dSplit : nullptr);
+            }
+        else if (ctx.S > 32)
             {
             dim3 grid (b.nMat, ctx.K, (ctx.S + 3) / 4);
             tiprobs_wide_kernel<<<grid, 128, 0, I->stream>>> (ctx, de, b.nEval, dd, du, (I->tcS == 61) ? I->dSplit : nullptr);
@@ -729,12 +770,12 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
             CK (cudaGetLastError ());
             I->launches++; I->launchKind[MB200_KERNEL_SETUP]++;
             }
-        ctx.tilePatterns = 128;
-        ctx.numTiles = (ctx.C + 127) / 128;
+        ctx.tilePatterns = tcRowsPerTile (I, b.nEval);
+        ctx.numTiles = (ctx.C + ctx.tilePatterns - 1) / ctx.tilePatterns;
         dim3 grid (ctx.numTiles, b.nEval);
         // 61 states: two children in flight per CTA when the grid is at most one CTA per SM anyway
         static const bool oneSlot = getenv ("MB200_TC_ONE_SLOT") != nullptr;      // A/B switch for measurements
-        if (I->tcS == 61 && !oneSlot && (long) grid.x * grid.y <= (long) I->numSMs)
+        if (I->tcS == 61 && !oneSlot && (long) grid.x * grid.y <= (long) I->numSMs && ctx.tilePatterns == 128)
             eval_tc_kernel<61, 2><<<grid, 128, tc_smem_bytes<61, 2> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
         else if (I->tcS == 61)
             eval_tc_kernel<61, 1><<<grid, 128, tc_smem_bytes<61, 1> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
@@ -890,7 +931,7 @@ void destroy (Instance *I)
     freeBatch (I->scratch);
     for (Batch *b : I->batches) if (b) { freeBatch (*b); delete b; }
     cudaFree (I->dTip8); cudaFree (I->dTip64); cudaFree (I->dTipPartAmbig); cudaFree (I->dSplit); cudaFree (I->dPartials); cudaFree (I->dMatrices);
-    cudaFree (I->dScalers); cudaFree (I->dWeights); cudaFree (I->dEigen); cudaFree (I->dInvMask);
+    cudaFree (I->dScalers); cudaFree (I->dWeights); cudaFree (I->dEigen); cudaFree (I->dFactor); cudaFree (I->dInvMask);
     cudaFree (I->dTilePartial); cudaFree (I->dTileAbort); cudaFree (I->dTicket); cudaFree (I->dDbg);
     cudaFree (I->dStdTab); cudaFree (I->dStdClasses); cudaFree (I->dTilePartial2);
     if (I->hostStage) cudaFreeHost (I->hostStage);
@@ -991,7 +1032,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     if (I->std)
         I->maxTiles = (C + 128 / stdLanes - 1) / (128 / stdLanes);
     else
-    I->maxTiles = I->tcS ? (C + 127) / 128 : nuc4 ? (C + nuc4MinPatternsPerBlock (K) - 1) / nuc4MinPatternsPerBlock (K) : (C + TP - 1) / TP;
+    I->maxTiles = I->tcS ? (C + TC_MIN_ROWS - 1) / TC_MIN_ROWS + 1 : nuc4 ? (C + nuc4MinPatternsPerBlock (K) - 1) / nuc4MinPatternsPerBlock (K) : (C + TP - 1) / TP;
 
 #define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc ((void **)&(ptr), (bytes)); if (e_ != cudaSuccess) { \
         cudaGetLastError (); destroy (I); return (e_ == cudaErrorMemoryAllocation) ? MB200_ERROR_OUT_OF_MEMORY : MB200_ERROR_CUDA; } } while (0)
@@ -1004,6 +1045,13 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     ALLOC (I->dScalers,  (size_t)cfg->scaler_count * C * sizeof(float));
     ALLOC (I->dWeights,  (size_t)cfg->weight_rows * C * sizeof(float));
     ALLOC (I->dEigen,    (size_t)cfg->eigen_count * I->eigenStride * sizeof(double));
+    if (S > 32)
+        {
+        ALLOC (I->dFactor, (size_t)cfg->eigen_count * I->cijkParts * 2 * S * S * sizeof(double));
+        const int LD = (S + 3) & ~3;
+        if (cudaFuncSetAttribute (tiprobs_mm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * S * LD * sizeof(double))) != cudaSuccess)
+            { destroy (I); return MB200_ERROR_CUDA; }
+        }
     if (I->tcS)
         {
         const size_t fl = (I->tcS == 61) ? tc_split_floats<61> () : tc_split_floats<20> ();
@@ -1185,6 +1233,14 @@ int mb200_set_cijk (int instance, int eigen, const double *block)
     int rc = use (I); if (rc) return rc;
     CK (cudaMemcpyAsync (I->dEigen + (size_t)eigen * I->eigenStride, block, I->eigenStride * sizeof(double),
                          cudaMemcpyHostToDevice, I->stream));
+    if (I->dFactor)
+        {
+        const int S = I->cfg.state_count;
+        cijk_factor_kernel<<<dim3 (S, I->cijkParts), 256, 0, I->stream>>> (I->dEigen + (size_t)eigen * I->eigenStride,
+                                                                            I->dFactor + (size_t)eigen * I->cijkParts * 2 * S * S, S);
+        CK (cudaGetLastError ());
+        I->launches++; I->launchKind[MB200_KERNEL_SETUP]++;
+        }
     CK (cudaStreamSynchronize (I->stream));
     return MB200_SUCCESS;
 }
@@ -1207,6 +1263,11 @@ int mb200_set_eigen_decomposition (int instance, int eigen, const double *V, con
     int blocks = (int)((n3 + 255) / 256); if (blocks > 1024) blocks = 1024;
     cijk_kernel<<<blocks, 256, 0, I->stream>>> (I->dEigen + (size_t)eigen * I->eigenStride, tmp, tmp + n2, tmp + 2*n2, S);
     I->launches++; I->launchKind[MB200_KERNEL_SETUP]++;
+    if (I->dFactor)         // the factors are the caller's V and V^-1 themselves
+        {
+        cudaMemcpyAsync (I->dFactor + (size_t)eigen * 2 * n2, tmp, n2 * sizeof(double), cudaMemcpyDeviceToDevice, I->stream);
+        cudaMemcpyAsync (I->dFactor + (size_t)eigen * 2 * n2 + n2, tmp + n2, n2 * sizeof(double), cudaMemcpyDeviceToDevice, I->stream);
+        }
     cudaError_t e = cudaStreamSynchronize (I->stream);
     cudaFree (tmp);
     CK (e);

@@ -201,6 +201,143 @@ tiprobs_wide_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, c
         }
 }
 
+// ---------------------------------------------------------------------------------------
+// K1 for large state counts as a batched contraction.  MrBayes hands over c[i][j][s] = V[i][s] * Vinv[s][j]
+// (CalcCijk, src/utils.c:9734-9746): for every s the S x S slice is a rank-one matrix, so it factors again into a
+// column u_s and a row w_s (any scaling: u_s[i] = c[i][j0][s], w_s[j] = c[i0][j][s] / c[i0][j0][s] with (i0, j0)
+// the slice's largest entry).  With U[i][s], W[s][j] in hand
+//     P_k = (U diag(e^{lambda t r_k})) W                                   (TiProbs_Gen, src/likelihood.c:9499-9542)
+// is an S x S x S matrix product per branch and category: 2 S^2 doubles of operands instead of the S^3 doubles of
+// the c_ijk block (1.8 MB at S = 61), both staged in shared memory, 4 x 4 outputs per thread.
+// Rounding: (U e) W instead of (U W) e, same summation order over s: <= 1 ulp of double per term, i.e. the
+// float-rounded P(t) agrees with the reference's except where the double sum sits on a float rounding boundary.
+// ---------------------------------------------------------------------------------------
+// grid = (S, eigen parts), block = 256: factor one slice
+__global__ void __launch_bounds__(256)
+cijk_factor_kernel (const double *__restrict__ block, double *__restrict__ factor, int S)
+{
+    __shared__ double sMax[256];
+    __shared__ int    sArg[256];
+    const int s = blockIdx.x, part = blockIdx.y;
+    const size_t partLen = 2*(size_t)S + (size_t)S*S*S;
+    const double *c = block + (size_t)part * partLen + 2*S;
+    double *U = factor + (size_t)part * 2 * S * S, *W = U + (size_t)S * S;
+    double best = -1.0; int arg = 0;
+    for (int e = threadIdx.x; e < S*S; e += 256)
+        {
+        const double a = fabs (c[(size_t)e * S + s]);
+        if (a > best) { best = a; arg = e; }
+        }
+    sMax[threadIdx.x] = best; sArg[threadIdx.x] = arg;
+    __syncthreads ();
+    for (int off = 128; off > 0; off >>= 1)
+        {
+        if (threadIdx.x < off && (sMax[threadIdx.x + off] > sMax[threadIdx.x] ||
+                                  (sMax[threadIdx.x + off] == sMax[threadIdx.x] && sArg[threadIdx.x + off] < sArg[threadIdx.x])))
+            { sMax[threadIdx.x] = sMax[threadIdx.x + off]; sArg[threadIdx.x] = sArg[threadIdx.x + off]; }
+        __syncthreads ();
+        }
+    const int i0 = sArg[0] / S, j0 = sArg[0] % S;
+    const double piv = c[((size_t)i0 * S + j0) * S + s];
+    for (int e = threadIdx.x; e < S; e += 256)
+        {
+        U[(size_t)e * S + s] = c[((size_t)e * S + j0) * S + s];                                  // u_s[i]
+        W[(size_t)s * S + e] = (piv != 0.0) ? c[((size_t)i0 * S + e) * S + s] / piv : 0.0;      // w_s[j]
+        }
+}
+
+// grid = (matrix updates, K), block = 256, dynamic shared memory = 2 * S * LD doubles (LD = S rounded up to 4)
+__global__ void __launch_bounds__(256)
+tiprobs_mm_kernel (DevCtx ctx, const DevEval *__restrict__ evals, int nEval, const double *__restrict__ dvals,
+                   const DevMat *__restrict__ mats, const double *__restrict__ factor, float *__restrict__ split61)
+{
+    extern __shared__ __align__(16) double mmS[];
+    __shared__ double sExp[MB200_DEV_MAX_STATES];
+    __shared__ int sEvalIdx;
+    const DevMat   mu = mats[blockIdx.x];
+    const int      k  = blockIdx.y;
+    const int      S  = ctx.S, LD = (S + 3) & ~3;
+    double *sUt = mmS;                      // [s][i]  (U e, transposed: a thread's four rows are contiguous)
+    double *sW  = mmS + (size_t)S * LD;     // [s][j]
+    if (threadIdx.x == 0)
+        {
+        int e = 0;
+        while (e + 1 < nEval && (int) blockIdx.x >= evals[e + 1].matOff)
+            e++;
+        while (e > 0 && evals[e].nMat == 0)
+            e--;
+        sEvalIdx = e;
+        }
+    __syncthreads ();
+    const DevEval *ev = evals + sEvalIdx;
+    if (ev->fuseP)
+        return;
+    const double  *rates = dvals + ev->dOff;
+    const double  *freqs = rates + 2*ctx.K;
+    const double   t  = mu.length * rates[k];
+    float         *P  = ctx.matrices + ((size_t)mu.matrix * ctx.K + k) * S * S;
+    if (t < MB200_TIME_MIN || t > MB200_TIME_MAX)
+        {
+        for (int idx = threadIdx.x; idx < S*S; idx += blockDim.x)
+            {
+            const int i = idx / S, j = idx % S;
+            const float pv = (t < MB200_TIME_MIN) ? ((i == j) ? 1.0f : 0.0f) : (float) freqs[j];
+            P[idx] = pv;
+            if (split61 != nullptr)
+                write_split61 (split61, mu.matrix, ctx.K, k, i, j, pv);
+            }
+        return;
+        }
+    const int     part = (ctx.cijkParts > 1) ? k : 0;
+    const size_t  partLen = 2*(size_t)S + (size_t)S*S*S;
+    const double *lam = ctx.eigen + ((size_t)mu.eigen * ctx.cijkParts + part) * partLen;
+    const double *U = factor + ((size_t)mu.eigen * ctx.cijkParts + part) * 2 * S * S, *W = U + (size_t)S * S;
+    if (threadIdx.x < S)
+        sExp[threadIdx.x] = exp (lam[threadIdx.x] * t);
+    for (int idx = threadIdx.x; idx < S * LD; idx += blockDim.x)
+        { sUt[idx] = 0.0; sW[idx] = 0.0; }
+    __syncthreads ();
+    for (int idx = threadIdx.x; idx < S*S; idx += blockDim.x)
+        {
+        const int a = idx / S, b = idx % S;
+        sUt[(size_t)b * LD + a] = U[idx] * sExp[b];          // U[i = a][s = b] e_s  ->  [s][i]
+        sW [(size_t)a * LD + b] = W[idx];                    // W[s = a][j = b]
+        }
+    __syncthreads ();
+    const int nt = LD / 4;                                   // 4 x 4 micro-tiles per side
+    for (int tile = threadIdx.x; tile < nt * nt; tile += blockDim.x)
+        {
+        const int i4 = (tile / nt) * 4, j4 = (tile % nt) * 4;
+        double acc[4][4];
+        #pragma unroll
+        for (int a = 0; a < 4; a++)
+            #pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+        for (int s = 0; s < S; s++)
+            {
+            const double2 u01 = *reinterpret_cast<const double2 *>(sUt + (size_t)s * LD + i4), u23 = *reinterpret_cast<const double2 *>(sUt + (size_t)s * LD + i4 + 2);
+            const double2 w01 = *reinterpret_cast<const double2 *>(sW + (size_t)s * LD + j4),  w23 = *reinterpret_cast<const double2 *>(sW + (size_t)s * LD + j4 + 2);
+            const double u[4] = { u01.x, u01.y, u23.x, u23.y }, w[4] = { w01.x, w01.y, w23.x, w23.y };
+            #pragma unroll
+            for (int a = 0; a < 4; a++)
+                #pragma unroll
+                for (int b = 0; b < 4; b++)
+                    acc[a][b] = fma (u[a], w[b], acc[a][b]);
+            }
+        #pragma unroll
+        for (int a = 0; a < 4; a++)
+            #pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (i4 + a < S && j4 + b < S)
+                    {
+                    const float pv = (float) ((acc[a][b] < 0.0) ? 0.0 : acc[a][b]);
+                    P[(i4 + a) * S + j4 + b] = pv;
+                    if (split61 != nullptr)
+                        write_split61 (split61, mu.matrix, ctx.K, k, i4 + a, j4 + b, pv);
+                    }
+        }
+}
+
 // c_ijk = V[i][k] * Vinv[k][j]  (CalcCijk, src/utils.c:9734-9746)
 __global__ void cijk_kernel (double *block, const double *V, const double *Vinv, const double *lambda, int S)
 {

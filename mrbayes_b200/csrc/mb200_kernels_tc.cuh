@@ -118,8 +118,10 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
     uint32_t parB = 0, parM = 0;
 
     const double *catW = dvals + sEv.dOff + K, *freqs = dvals + sEv.dOff + 2*K;
-    const int   c0 = blockIdx.x * TM;
-    const int   np = min (TM, C - c0);
+    // a tile may hold fewer than the MMA's 128 rows (ctx.tilePatterns, a multiple of 8): more, smaller CTAs
+    // co-resident per SM overlap each other's load / MMA / read-out phases; the unused rows are zero padding
+    const int   c0 = blockIdx.x * ctx.tilePatterns;
+    const int   np = min (ctx.tilePatterns, C - c0);
     const int   c  = c0 + tid;                                 // this thread's pattern (epilogue role)
     const bool  active = tid < np;
     const size_t bufStride = (size_t)K * C * Sp;

@@ -1,0 +1,50 @@
+"""GPU probe (not a test): whole-evaluation time of the tensor-core path as a function of the rows per tile.
+usage: python tests/tc_rows_probe.py [aa50k|codon20k ...]   (spawns one process per setting: MB200_TC_ROWS is read once)"""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def one(name):
+    import torch
+    import bench
+    from mrbayes_b200 import abi, workloads
+    S, K, Cn, tips = bench.SYNTH[name]
+    pr = workloads.make_problem(S, K, Cn, tips, 1, seed=2026)
+    lib = abi.engine_library()
+    with pr.create(lib) as inst:
+        inst.evaluate(pr.full_evaluation(0))
+        batch = inst.pack([pr.full_evaluation(0)])
+        stream = torch.cuda.ExternalStream(inst.stream())
+        for _ in range(3):
+            inst.replay(batch)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(10):
+            inst.replay(batch)
+        b.record(stream)
+        inst.synchronize()
+        ms = a.elapsed_time(b) / 10
+        upd = pr.n_int * pr.C * pr.K
+        print(json.dumps({"workload": name, "rows": os.environ.get("MB200_TC_ROWS", "auto"), "ms": ms,
+                          "frac": upd * bench.bytes_per_update(S, K) / (ms * 1e-3) / 1e9 / 6569.6}), flush=True)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--one":
+        one(sys.argv[2])
+    else:
+        names = sys.argv[1:] or ["codon20k", "aa50k"]
+        for n in names:
+            for rows in ("auto", "128", "96", "88", "72", "64", "48", "40", "32"):
+                env = dict(os.environ)
+                if rows != "auto":
+                    env["MB200_TC_ROWS"] = rows
+                else:
+                    env.pop("MB200_TC_ROWS", None)
+                subprocess.run([sys.executable, __file__, "--one", n], env=env, check=False)
