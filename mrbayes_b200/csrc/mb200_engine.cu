@@ -27,7 +27,8 @@ struct Batch                       // packed evaluations (device job format)
     size_t  cap    = 0;            // bytes allocated
     size_t  bytes  = 0;            // bytes used
     int     nEval = 0, nMat = 0, nOp = 0, nDbl = 0;
-    size_t  offEval = 0, offDbl = 0, offUpd = 0, offChunk = 0, offCmat = 0, offOp = 0;
+    size_t  offEval = 0, offDbl = 0, offUpd = 0, offChunk = 0, offCmat = 0, offOp = 0, offOrd = 0;
+    int     maxOps = 0;            // most operations of any evaluation (tensor-core path: work-queue geometry)
     DevResult *dRes = nullptr;     // [capEval] results in HBM (device-resident replay)
     DevResult *hRes = nullptr;     // [capEval] pinned + mapped: kernels of the host-call path write
                                    // results straight into host memory, the caller polls `seq`
@@ -58,6 +59,11 @@ struct Instance
     size_t        smemTc = 0;
     float        *dPartials = nullptr, *dMatrices = nullptr, *dScalers = nullptr, *dWeights = nullptr;
     double       *dEigen = nullptr;
+    unsigned int *dTcCounter = nullptr;  // tensor-core path: ticket counter of the node-parallel work queue (monotone)
+    unsigned int  tcBase = 0;            // its value before the next launch's first ticket
+    int          *dTcFlags = nullptr;    // [maxEval][maxTiles][tcFlagStride] node-done flags (== launch sequence number)
+    int          *dTcError = nullptr;
+    int           tcFlagStride = 0, tcGrid = 0;
     double       *dFactor = nullptr;    // large state counts: rank-one factors (U, W) of every eigensystem's c_ijk slices
     uint64_t     *dInvMask = nullptr;
     double       *dTilePartial = nullptr;
@@ -361,7 +367,8 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     size_t offChunk = mb200_align16 (offUpd + sizeof(DevMat) * (size_t)nUpd);
     size_t offCmat  = mb200_align16 (offChunk + sizeof(DevChunk) * (size_t)nExtraChunks);
     size_t offOp    = mb200_align16 (offCmat + sizeof(DevMat) * cmats.size ());
-    size_t bytes    = mb200_align16 (offOp + sizeof(DevOp) * (size_t)nOp);
+    size_t offOrd   = mb200_align16 (offOp + sizeof(DevOp) * (size_t)nOp);      // tensor-core path: level order of the operations
+    size_t bytes    = mb200_align16 (offOrd + (I->tcS ? sizeof(int) * (size_t)nOp : 0));
     int rc = reserveBatch (b, bytes, count);
     if (rc != MB200_SUCCESS)
         return rc;
@@ -373,6 +380,8 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     DevChunk *dc = (DevChunk *)(b.hBlob + offChunk);
     DevMat   *dm = (DevMat   *)(b.hBlob + offCmat);
     DevOp    *dops = (DevOp  *)(b.hBlob + offOp);
+    int      *dord = (int    *)(b.hBlob + offOrd);
+    b.maxOps = 0;
     if (!cmats.empty ())
         memcpy (dm, cmats.data (), sizeof(DevMat) * cmats.size ());
 
@@ -508,15 +517,49 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
             d.rootOff = (ev.root_buffer != MB200_NONE) ? (unsigned)(ev.root_buffer - c.tip_count) * bufStride : 0u;
             }
         else
-        for (int i = 0; i < ev.operation_count; i++)
             {
-            const mb200_operation &op = ev.operations[i];
-            DevOp &o = dops[oOff + i];
-            o.dest = op.dest; o.c1 = op.child1; o.m1 = op.matrix1; o.c2 = op.child2; o.m2 = op.matrix2;
-            o.c3 = op.child3; o.m3 = (op.child3 == MB200_NONE) ? MB200_NONE : op.matrix3;
-            o.sw = op.scale_write; o.sr = op.scale_remove;
-            o.s1 = slots[slotPos]; o.s2 = slots[slotPos + 1]; o.s3 = slots[slotPos + 2];
-            slotPos += 3;
+            for (int i = 0; i < ev.operation_count; i++)
+                {
+                const mb200_operation &op = ev.operations[i];
+                DevOp &o = dops[oOff + i];
+                o.dest = op.dest; o.c1 = op.child1; o.m1 = op.matrix1; o.c2 = op.child2; o.m2 = op.matrix2;
+                o.c3 = op.child3; o.m3 = (op.child3 == MB200_NONE) ? MB200_NONE : op.matrix3;
+                o.sw = op.scale_write; o.sr = op.scale_remove;
+                o.s1 = slots[slotPos]; o.s2 = slots[slotPos + 1]; o.s3 = slots[slotPos + 2];
+                slotPos += 3;
+                }
+            if (I->tcS)
+                {
+                // tensor-core path: the nodes of an evaluation are work items of a device-side queue; an item waits for
+                // the items that produce its operands.  s1/s2/s3 = producing operation (index within the evaluation)
+                // or -1 (tip, or a buffer this evaluation does not write); the queue hands the nodes out level by
+                // level (height above the clean operands) so that dependent items sit far apart in it
+                std::vector<int> &producer = I->writtenTmp;      // [buffer] -> operation index + 1 (0: none), stamped per evaluation
+                if ((int) producer.size () < c.partials_count) producer.assign (c.partials_count, 0);
+                std::vector<int> level (ev.operation_count, 0);
+                for (int i = 0; i < ev.operation_count; i++)
+                    {
+                    DevOp &o = dops[oOff + i];
+                    const int ch[3] = { o.c1, o.c2, o.c3 };
+                    int pr[3], lv = 0;
+                    for (int j = 0; j < 3; j++)
+                        {
+                        pr[j] = (ch[j] >= c.tip_count && producer[ch[j]] > 0) ? producer[ch[j]] - 1 : -1;
+                        if (pr[j] >= 0 && level[pr[j]] + 1 > lv) lv = level[pr[j]] + 1;
+                        }
+                    o.s1 = pr[0]; o.s2 = pr[1]; o.s3 = pr[2];
+                    level[i] = lv;
+                    producer[o.dest] = i + 1;
+                    }
+                for (int i = 0; i < ev.operation_count; i++)
+                    producer[dops[oOff + i].dest] = 0;
+                int pos = 0;
+                for (int lv = 0; pos < ev.operation_count; lv++)
+                    for (int i = 0; i < ev.operation_count; i++)
+                        if (level[i] == lv)
+                            dord[oOff + pos++] = i;
+                if (ev.operation_count > b.maxOps) b.maxOps = ev.operation_count;
+                }
             }
         mOff += fused ? 0 : ev.matrix_update_count;
         oOff += ev.operation_count;
@@ -532,7 +575,7 @@ int pack (Instance *I, Batch &b, const mb200_evaluation *evs, int count)
     b.nDirty = nMat; b.fused = fused; b.tipEpoch = I->tipEpoch;
     b.singleChunk = true;
     for (int e = 0; e < count; e++) if (nChunkOf[e] != 1) b.singleChunk = false;
-    b.offEval = offEval; b.offDbl = offDbl; b.offUpd = offUpd; b.offChunk = offChunk; b.offCmat = offCmat; b.offOp = offOp;
+    b.offEval = offEval; b.offDbl = offDbl; b.offUpd = offUpd; b.offChunk = offChunk; b.offCmat = offCmat; b.offOp = offOp; b.offOrd = offOrd;
     return MB200_SUCCESS;
 }
 
@@ -669,6 +712,21 @@ int tcRowsPerTile (const Instance *I, int nEval)
     return bestRows;
 }
 
+// node-parallel kernel: full 128-row tiles as soon as the queue holds a few items per resident CTA; smaller tiles
+// (more items) for small problems
+int tcqRowsPerTile (const Instance *I, int nEval)
+{
+    static const int forced = getenv ("MB200_TC_ROWS") ? atoi (getenv ("MB200_TC_ROWS")) : 0;
+    if (forced >= TC_MIN_ROWS && forced <= 128)
+        return forced & ~7;
+    const long want = (long) I->tcGrid / 4 + 1;                 // tiles (over all evaluations) we would like to have at least
+    long rows = ((long) I->cfg.pattern_count * (nEval > 0 ? nEval : 1) + want - 1) / want;
+    rows = (rows + 7) & ~7L;
+    if (rows > 128) rows = 128;
+    if (rows < TC_MIN_ROWS) rows = TC_MIN_ROWS;
+    return (int) rows;
+}
+
 // launch the fused pass for a packed batch; fromHost: the job lives in b.hBlob only and is
 // delivered through the parameter block when it fits (otherwise the caller has copied it to dBlob)
 int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum = false)
@@ -770,6 +828,25 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
             CK (cudaGetLastError ());
             I->launches++; I->launchKind[MB200_KERNEL_SETUP]++;
             }
+        static const bool serialWalk = getenv ("MB200_TC_SERIAL") != nullptr;     // A/B switch: one CTA walks a tile's whole operation list
+        if (!serialWalk)
+            {
+            // node-parallel: (node, tile) work items on a device-side queue, persistent grid
+            ctx.tilePatterns = tcqRowsPerTile (I, b.nEval);
+            ctx.numTiles = (ctx.C + ctx.tilePatterns - 1) / ctx.tilePatterns;
+            TcQueue Q;
+            Q.counter = I->dTcCounter; Q.base = I->tcBase; Q.flags = I->dTcFlags; Q.flagStride = I->tcFlagStride;
+            Q.maxOps = b.maxOps; Q.nEval = b.nEval; Q.error = I->dTcError; Q.order = (const int *)(b.dBlob + b.offOrd);
+            const long total = (long)(b.maxOps + 1) * b.nEval * ctx.numTiles;
+            const int  g = (int)((total < (long) I->tcGrid) ? total : (long) I->tcGrid);
+            I->tcBase += (unsigned int)(total + g);                  // every CTA draws exactly one ticket past the end
+            if (I->tcS == 61)
+                eval_tcq_kernel<61><<<g, 128, tc_smem_bytes<61, 1> (), I->stream>>> (ctx, Q, de, dd, dops, I->dSplit, res, seq);
+            else
+                eval_tcq_kernel<20><<<g, 128, tc_smem_bytes<20, 1> (), I->stream>>> (ctx, Q, de, dd, dops, I->dSplit, res, seq);
+            }
+        else
+            {
         ctx.tilePatterns = tcRowsPerTile (I, b.nEval);
         ctx.numTiles = (ctx.C + ctx.tilePatterns - 1) / ctx.tilePatterns;
         dim3 grid (ctx.numTiles, b.nEval);
@@ -781,6 +858,7 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
             eval_tc_kernel<61, 1><<<grid, 128, tc_smem_bytes<61, 1> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
         else
             eval_tc_kernel<20, 1><<<grid, 128, tc_smem_bytes<20, 1> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
+            }
         I->launchKind[MB200_KERNEL_TENSOR]++;
         }
     else
@@ -934,6 +1012,7 @@ void destroy (Instance *I)
     cudaFree (I->dScalers); cudaFree (I->dWeights); cudaFree (I->dEigen); cudaFree (I->dFactor); cudaFree (I->dInvMask);
     cudaFree (I->dTilePartial); cudaFree (I->dTileAbort); cudaFree (I->dTicket); cudaFree (I->dDbg);
     cudaFree (I->dStdTab); cudaFree (I->dStdClasses); cudaFree (I->dTilePartial2);
+    cudaFree (I->dTcCounter); cudaFree (I->dTcFlags); cudaFree (I->dTcError);
     if (I->hostStage) cudaFreeHost (I->hostStage);
     for (cudaEvent_t e : I->evA) cudaEventDestroy (e);
     for (cudaEvent_t e : I->evB) cudaEventDestroy (e);
@@ -1067,6 +1146,29 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
         else
             ea = cudaFuncSetAttribute (eval_tc_kernel<20, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc_smem_bytes<20, 1> ());
         if (ea != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
+        // node-parallel work queue
+        int occ = 0;
+        if (I->tcS == 61)
+            {
+            ea = cudaFuncSetAttribute (eval_tcq_kernel<61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc_smem_bytes<61, 1> ());
+            if (ea == cudaSuccess) ea = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, eval_tcq_kernel<61>, 128, tc_smem_bytes<61, 1> ());
+            }
+        else
+            {
+            ea = cudaFuncSetAttribute (eval_tcq_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc_smem_bytes<20, 1> ());
+            if (ea == cudaSuccess) ea = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, eval_tcq_kernel<20>, 128, tc_smem_bytes<20, 1> ());
+            }
+        if (ea != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
+        if (occ < 1) occ = 1;
+        I->tcGrid = I->numSMs * occ;
+        I->tcFlagStride = (int) nInt + 1;
+        const size_t nFlags = (size_t) I->maxEval * ((size_t)(C + TC_MIN_ROWS - 1) / TC_MIN_ROWS + 1) * I->tcFlagStride;
+        ALLOC (I->dTcCounter, sizeof(unsigned int));
+        ALLOC (I->dTcError, sizeof(int));
+        ALLOC (I->dTcFlags, nFlags * sizeof(int));
+        cudaMemsetAsync (I->dTcCounter, 0, sizeof(unsigned int), I->stream);
+        cudaMemsetAsync (I->dTcError, 0, sizeof(int), I->stream);
+        cudaMemsetAsync (I->dTcFlags, 0, nFlags * sizeof(int), I->stream);
         }
     ALLOC (I->dInvMask,  (size_t)C * sizeof(uint64_t));
     ALLOC (I->dTilePartial, (size_t)I->maxEval * I->maxTiles * sizeof(double));
