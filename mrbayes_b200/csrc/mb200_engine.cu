@@ -7,6 +7,7 @@
 #include "mb200_device.cuh"
 #include "mb200_kernels.cuh"
 #include "mb200_kernels_tc.cuh"
+#include "mb200_kernels_tcp.cuh"
 #include "mb200_kernels_std.cuh"
 
 #include <cuda_runtime.h>
@@ -64,6 +65,8 @@ struct Instance
     int          *dTcFlags = nullptr;    // [maxEval][maxTiles][tcFlagStride] node-done flags (== launch sequence number)
     int          *dTcError = nullptr;
     int           tcFlagStride = 0, tcGrid = 0;
+    int           tcpStages = 0;         // pipelined tensor-core kernel: operand-ring stages that fit (0: kernel not usable)
+    size_t        tcpSmem = 0;
     double       *dFactor = nullptr;    // large state counts: rank-one factors (U, W) of every eigensystem's c_ijk slices
     uint64_t     *dInvMask = nullptr;
     double       *dTilePartial = nullptr;
@@ -828,7 +831,28 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
             CK (cudaGetLastError ());
             I->launches++; I->launchKind[MB200_KERNEL_SETUP]++;
             }
-        static const bool serialWalk = getenv ("MB200_TC_SERIAL") != nullptr;     // A/B switch: one CTA walks a tile's whole operation list
+        static const bool serialEnv = getenv ("MB200_TC_SERIAL") != nullptr;       // A/B switch: one CTA walks a tile's whole operation list
+        static const bool queueEnv  = getenv ("MB200_TC_QUEUE") != nullptr;        // A/B switch: node-parallel queue, one item at a time per CTA
+        const bool kFits = ctx.K <= ((I->tcS == 61) ? TcGeom<61>::KMAX : TcGeom<20>::KMAX);
+        const bool pipelined = I->tcpStages > 0 && !((serialEnv || queueEnv) && kFits);
+        const bool serialWalk = serialEnv;
+        if (pipelined)
+            {
+            // warp-specialised pipeline over the node-parallel queue: one persistent CTA per SM
+            ctx.tilePatterns = 128;
+            ctx.numTiles = (ctx.C + 127) / 128;
+            TcQueue Q;
+            Q.counter = I->dTcCounter; Q.base = I->tcBase; Q.flags = I->dTcFlags; Q.flagStride = I->tcFlagStride;
+            Q.maxOps = b.maxOps; Q.nEval = b.nEval; Q.error = I->dTcError; Q.order = (const int *)(b.dBlob + b.offOrd);
+            const long total = (long)(b.maxOps + 1) * b.nEval * ctx.numTiles;
+            const int  g = (int)((total < (long) I->numSMs) ? total : (long) I->numSMs);
+            I->tcBase += (unsigned int)(total + g);                  // every CTA draws exactly one ticket past the end
+            if (I->tcS == 61)
+                eval_tcp_kernel<61><<<g, TCP_THREADS, I->tcpSmem, I->stream>>> (ctx, Q, I->tcpStages, de, dd, dops, I->dSplit, res, seq);
+            else
+                eval_tcp_kernel<20><<<g, TCP_THREADS, I->tcpSmem, I->stream>>> (ctx, Q, I->tcpStages, de, dd, dops, I->dSplit, res, seq);
+            }
+        else
         if (!serialWalk)
             {
             // node-parallel: (node, tile) work items on a device-side queue, persistent grid
@@ -1103,7 +1127,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
         { delete I; return MB200_ERROR_OUT_OF_RANGE; }      // 4-state records carry 32-bit element offsets (64 GB of partials)
     if (!getenv ("MB200_DISABLE_TC") && !I->std)
         {
-        if (S == 61 && K == 1) I->tcS = 61;      // 61-state codon, tcgen05 path
+        if (S == 61 && K <= 3) I->tcS = 61;      // 61-state codon (K > 1: omega categories, NY98 / M3), tcgen05 path
         if (S == 20 && K <= 4) I->tcS = 20;      // 20-state amino acids, tcgen05 path
         }
     int stdLanes = 1;
@@ -1161,6 +1185,26 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
         if (ea != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
         if (occ < 1) occ = 1;
         I->tcGrid = I->numSMs * occ;
+        // warp-specialised pipelined kernel: one CTA per SM, as many operand-ring stages as fit beside the staging area
+        {
+        int optin = 0;
+        cudaDeviceGetAttribute (&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, I->cfg.device);
+        cudaFuncAttributes fa;
+        ea = (I->tcS == 61) ? cudaFuncGetAttributes (&fa, eval_tcp_kernel<61>) : cudaFuncGetAttributes (&fa, eval_tcp_kernel<20>);
+        const size_t staticBytes = (ea == cudaSuccess) ? fa.sharedSizeBytes : 4096;    // barriers, item ring, row maxima
+        const size_t limit = ((size_t) optin > staticBytes + 1024) ? (size_t) optin - staticBytes : 0;
+        I->tcpStages = (I->tcS == 61) ? tcp_stages<61> (K, limit) : tcp_stages<20> (K, limit);
+        if (I->tcpStages > 0)
+            {
+            I->tcpSmem = (I->tcS == 61) ? I->tcpStages * tcp_stage_bytes<61> () + tcp_staging_bytes<61> (K) + tcp_tipring_bytes<61> (I->tcpStages)
+                                        : I->tcpStages * tcp_stage_bytes<20> () + tcp_staging_bytes<20> (K) + tcp_tipring_bytes<20> (I->tcpStages);
+            ea = (I->tcS == 61) ? cudaFuncSetAttribute (eval_tcp_kernel<61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) I->tcpSmem)
+                                : cudaFuncSetAttribute (eval_tcp_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) I->tcpSmem);
+            if (ea != cudaSuccess) { cudaGetLastError (); I->tcpStages = 0; }
+            }
+        if (I->tcpStages == 0 && K > ((I->tcS == 61) ? TcGeom<61>::KMAX : TcGeom<20>::KMAX))
+            { destroy (I); return MB200_ERROR_UNSUPPORTED; }
+        }
         I->tcFlagStride = (int) nInt + 1;
         const size_t nFlags = (size_t) I->maxEval * ((size_t)(C + TC_MIN_ROWS - 1) / TC_MIN_ROWS + 1) * I->tcFlagStride;
         ALLOC (I->dTcCounter, sizeof(unsigned int));
@@ -1174,7 +1218,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     ALLOC (I->dTilePartial, (size_t)I->maxEval * I->maxTiles * sizeof(double));
     ALLOC (I->dTileAbort,   (size_t)I->maxEval * I->maxTiles * sizeof(int));
     ALLOC (I->dTicket,      (size_t)I->maxEval * sizeof(unsigned int));
-    ALLOC (I->dDbg,         (size_t)I->maxEval * 64 * sizeof(unsigned long long));
+    ALLOC (I->dDbg,         ((size_t)I->maxEval * 64 + 4096) * sizeof(unsigned long long));
     if (I->std)
         {
         ALLOC (I->dStdTab,       (size_t)3 * C * sizeof(int));
@@ -1733,6 +1777,19 @@ int mb200_debug_read_stamps (int instance, unsigned long long *out, int evaluati
     CK (cudaStreamSynchronize (I->stream));
     CK (cudaMemcpy (out, I->dDbg, (size_t)evaluations * 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     CK (cudaMemset (I->dDbg, 0, (size_t)I->maxEval * 64 * sizeof(unsigned long long)));
+    return MB200_SUCCESS;
+}
+
+// pipeline trace of the tensor-core kernel's first CTA (debug builds only): 16 stamps per work item
+int mb200_debug_read_trace (int instance, unsigned long long *out, int count)
+{
+    Instance *I = get (instance);
+    if (!I || !out) return MB200_ERROR_BAD_INSTANCE;
+    if (count < 1 || count > 4096) return MB200_ERROR_OUT_OF_RANGE;
+    int rc = use (I); if (rc) return rc;
+    CK (cudaStreamSynchronize (I->stream));
+    CK (cudaMemcpy (out, I->dDbg, (size_t)count * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK (cudaMemset (I->dDbg, 0, ((size_t)I->maxEval * 64 + 4096) * sizeof(unsigned long long)));
     return MB200_SUCCESS;
 }
 

@@ -104,14 +104,15 @@ __device__ __forceinline__ float umma_to_tf32 (float x)      // round-to-nearest
 }
 
 // 61-state tensor-core path: entry (i, j) of a P(t) matrix -> the pre-split operand image of tc kernel B
-// (canonical K-major layout of a 64-row tile, hi image then lo image: umma_common.cuh canon_off; mb200_kernels_tc.cuh)
+// (canonical K-major layout, umma_common.cuh canon_off; mb200_kernels_tc.cuh)
 __device__ __forceinline__ void write_split61 (float *split61, int matrix, int K, int k, int i, int j, float pv)
 {
     const float hi = umma_to_tf32 (pv), lo = umma_to_tf32 (pv - hi);
     float *img = split61 + ((size_t)matrix * K + k) * (2 * 64 * 64);
-    const unsigned off = (unsigned)((j >> 2) * (64 >> 3) * 128 + (i >> 3) * 128 + (i & 7) * 16 + (j & 3) * 4) / 4u;
-    img[off] = hi;
-    img[64 * 64 + off] = lo;
+    // one canonical image of 128 rows: rows 0..63 hi, rows 64..127 lo (tc_write_split_entry, mb200_kernels_tc.cuh)
+    const unsigned offHi = (unsigned)((j >> 2) * (128 >> 3) * 128 + (i >> 3) * 128 + (i & 7) * 16 + (j & 3) * 4) / 4u;
+    img[offHi] = hi;
+    img[offHi + (64 >> 3) * 128 / 4] = lo;
 }
 
 // K1 for large state counts (61-state codon): the same sum, organised for memory parallelism.

@@ -40,18 +40,19 @@ template <int S, int SLOTS> __host__ __device__ constexpr size_t tc_smem_bytes (
     return (size_t) SLOTS * TcGeom<S>::KMAX * (2 * 128 * TcGeom<S>::KP + 2 * TcGeom<S>::NP * TcGeom<S>::KP) * sizeof(float);
 }
 
-// floats per pre-split matrix image: hi then lo, each NP x KP in canonical layout
+// floats per pre-split matrix image: ONE canonical-layout operand of 2 NP rows x KP -- rows [0, NP) hold the hi
+// parts, rows [NP, 2 NP) the lo parts, so that  A x [B_hi | B_lo]^T  is a single N = 2 NP MMA chain (the pipelined
+// kernel) and B_hi / B_lo alone are the same image addressed with N = NP (row offset 0 / NP)
 template <int S> __host__ __device__ constexpr int tc_split_floats () { return 2 * TcGeom<S>::NP * TcGeom<S>::KP; }
 
-// P(t) [S][S] row-major (row = ancestral state i) -> hi/lo images of B[n = i][k = j] in canonical layout
+// P(t) [S][S] row-major (row = ancestral state i) -> hi/lo rows of B[n = i][k = j] in canonical layout
 template <int S>
 __device__ __forceinline__ void tc_write_split_entry (float *img, int i, int j, float p)
 {
-    constexpr int NP = TcGeom<S>::NP, KP = TcGeom<S>::KP;
+    constexpr int NP = TcGeom<S>::NP;
     const float hi = umma::to_tf32 (p), lo = umma::to_tf32 (p - hi);
-    const uint32_t off = umma::canon_off (i, j, NP) / 4;
-    img[off] = hi;
-    img[NP * KP + off] = lo;
+    img[umma::canon_off (i, j, 2 * NP) / 4] = hi;
+    img[umma::canon_off (NP + i, j, 2 * NP) / 4] = lo;
 }
 
 // split images of matrices already present in the matrix buffer (set_transition_matrix, or a
@@ -81,7 +82,7 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
     constexpr int TM = 128;                                   // patterns per tile = MMA M
     constexpr int ACC_COLS = 2 * NP * KMAX;                   // TMEM columns of one child's accumulators
     constexpr int TMEM_COLS = (SLOTS * ACC_COLS <= 64) ? 64 : (SLOTS * ACC_COLS <= 128) ? 128 : (SLOTS * ACC_COLS <= 256) ? 256 : 512;
-    constexpr uint32_t LBO_A = (TM / 8) * 128, LBO_B = (NP / 8) * 128, SBO = 128;
+    constexpr uint32_t LBO_A = (TM / 8) * 128, LBO_B = (2 * NP / 8) * 128, SBO = 128;
     constexpr int A_FLOATS = TM * KP;                         // one hi (or lo) image
     constexpr int B_FLOATS = 2 * NP * KP;                     // hi + lo image of one P(t)
     constexpr int NQ = (S + 3) / 4;                           // 16-byte chunks per stored row
@@ -136,7 +137,7 @@ eval_tc_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__r
     const uint64_t dA0 = make_desc (smem_u32 (sA), LBO_A, SBO);      // hi image of slot 0, category 0
     const uint64_t dB0 = make_desc (smem_u32 (sB), LBO_B, SBO);
     constexpr uint64_t A_LO = (A_FLOATS * 4) >> 4, A_K = (2 * A_FLOATS * 4) >> 4, A_KS = (2 * LBO_A) >> 4, A_SL = ((uint64_t) A_SLOT * 4) >> 4;
-    constexpr uint64_t B_LO = (NP * KP * 4) >> 4, B_K = (B_FLOATS * 4) >> 4, B_KS = (2 * LBO_B) >> 4, B_SL = ((uint64_t) B_SLOT * 4) >> 4;
+    constexpr uint64_t B_LO = ((NP / 8) * 128) >> 4, B_K = (B_FLOATS * 4) >> 4, B_KS = (2 * LBO_B) >> 4, B_SL = ((uint64_t) B_SLOT * 4) >> 4;
 
     int preloaded = -1;          // partials buffer whose hi/lo images already sit in A slot 0 (previous node's result)
 
@@ -512,7 +513,7 @@ eval_tcq_kernel (DevCtx ctx, TcQueue Q, const DevEval *__restrict__ evals, const
     constexpr int TM = 128;
     constexpr int ACC_COLS = 2 * NP * KMAX;
     constexpr int TMEM_COLS = (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
-    constexpr uint32_t LBO_A = (TM / 8) * 128, LBO_B = (NP / 8) * 128, SBO = 128;
+    constexpr uint32_t LBO_A = (TM / 8) * 128, LBO_B = (2 * NP / 8) * 128, SBO = 128;
     constexpr int A_FLOATS = TM * KP;
     constexpr int B_FLOATS = 2 * NP * KP;
     constexpr int NQ = (S + 3) / 4;
@@ -548,7 +549,7 @@ eval_tcq_kernel (DevCtx ctx, TcQueue Q, const DevEval *__restrict__ evals, const
     const uint64_t dA0 = make_desc (smem_u32 (sA), LBO_A, SBO);
     const uint64_t dB0 = make_desc (smem_u32 (sB), LBO_B, SBO);
     constexpr uint64_t A_LO = (A_FLOATS * 4) >> 4, A_K = (2 * A_FLOATS * 4) >> 4, A_KS = (2 * LBO_A) >> 4;
-    constexpr uint64_t B_LO = (NP * KP * 4) >> 4, B_K = (B_FLOATS * 4) >> 4, B_KS = (2 * LBO_B) >> 4;
+    constexpr uint64_t B_LO = ((NP / 8) * 128) >> 4, B_K = (B_FLOATS * 4) >> 4, B_KS = (2 * LBO_B) >> 4;
     const int rows = ctx.tilePatterns, numTiles = ctx.numTiles;
     const int perSlot = Q.nEval * numTiles;
     const int total = (Q.maxOps + 1) * perSlot;

@@ -57,7 +57,27 @@ typedef struct
     mb200_matrix_update *mats;
     mb200_evaluation     ev;                /* evaluation being assembled            */
     int                  inlineEigen;       /* nst = 1, 2: eigensystem derived per evaluation */
-    double               eigenBlock[72];    /* [lambda_re(4), lambda_im(4), c_ijk(64)] */
+    double              *eigenBlock;        /* [lambda_re(4), lambda_im(4), c_ijk(64)] of the evaluation being assembled */
+    /* chain-batched generations (MB200Batch*, mb200_seam.h): one queue slot per local chain, so that the
+       evaluations of all chains of a generation go to the device in ONE call */
+    int                  nSlots, nQueued;
+    mb200_operation     *opsArena;          /* [nSlots][capOps]  */
+    mb200_matrix_update *matsArena;         /* [nSlots][capMats] */
+    double              *eigArena;          /* [nSlots][72]      */
+    mb200_evaluation    *qEv;               /* [nSlots] evaluations queued this generation */
+    int                 *qChain, *qStatus;  /* [nSlots] */
+    double              *qLnL;              /* [nSlots] */
+    int                  qRc, qLaunched;
+    /* per-chain scratch sets: the reference keeps ONE scratch slot per node, shared by all chains
+       (src/mcmc.c:5940-5949), which is fine while a chain is accepted or rejected before the next one is
+       touched; with the accept step deferred every chain needs its own.  Chain 0 keeps the reference's. */
+    int                  nScratchChains, scratchNodes;
+    int                **scrCl, **scrTi, **scrNs, **scrUn;  /* [chain][node]; [0] unused */
+    int                 *scrSite, *scrCijk;                  /* [chain] */
+    int                 *origCl, *origTi, *origNs, *origUn; /* the reference's arrays while a chain's set is installed */
+    int                  origSite, origCijk, installed;     /* installed: chain whose set is in place, or -1 */
+    int                  extraCl, extraTi, extraNs, extraEig;  /* buffers beyond the reference's own counts */
+    MrBFlt             **extraCijks;        /* host eigensystem blocks appended to m->cijks for the extra slots */
     long long            clUpdates;         /* node*pattern*rate updates issued      */
     int                  pending;           /* launched by a deferred evaluation, result not yet collected */
     int                  recording, recChain, recState;   /* function-pointer forms: evaluation being recorded */
@@ -70,7 +90,7 @@ static int          seamInitialized = NO;
 /* cijk slots the device has a copy of (bit per slot).  An evaluation that reads a slot
    the device has never seen uploads it first: chains whose first evaluation ran on the
    reference's own path, or an instance that was re-created. */
-static unsigned char seamCijkSeen[SEAM_MAX_DIVISIONS][(MAX_CHAINS + 8) / 8 + 1];
+static unsigned char seamCijkSeen[SEAM_MAX_DIVISIONS][(2 * MAX_CHAINS + 8) / 8 + 1];
 
 /* ---- backend indirection: lets the oracle harness record or shadow every call ---- */
 static int be_create (const mb200_instance_config *c, int *i)          { return mb200_create_instance (c, i); }
@@ -85,6 +105,10 @@ static int be_pstates (int i, const int *n, const int *t, const int *b, int ml, 
 
 static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates };
 static int seamDeferred = NO;   /* YES: TreeLikelihood_Beagle only launches; SeamCollect fetches the result */
+static int seamBatchWanted = NO;    /* MB200BatchEnable: instances are created with per-chain scratch buffers */
+static int seamBatchQueue = NO;     /* YES while MB200BatchQueueLogLike assembles: evaluations are queued, not launched */
+static void SeamScratchCounts (ModelInfo *m, int *nCl, int *nTi, int *nNs);
+static void SeamDropDivision (int division);
 
 void MB200SeamSetBackend (const MB200SeamBackend *backend)
 {
@@ -106,6 +130,7 @@ static void SeamInit (void)
         {
         memset (&seamDiv[d], 0, sizeof(SeamDivision));
         seamDiv[d].instance = -1;
+        seamDiv[d].installed = -1;
         }
     seamInitialized = YES;
 }
@@ -366,6 +391,22 @@ static unsigned long long SeamTipStamp (ModelInfo *m)
     return h;
 }
 
+/* how many scratch slots the reference keeps per kind (entries >= 0 of its scratch index arrays) */
+static void SeamScratchCounts (ModelInfo *m, int *nCl, int *nTi, int *nNs)
+{
+    int   i, nNodes;
+    Tree *t = GetTree (m->brlens, 0, state[0]);
+
+    nNodes = t->nNodes;
+    *nCl = *nTi = *nNs = 0;
+    for (i=0; i<nNodes; i++)
+        {
+        if (m->condLikeScratchIndex   != NULL && m->condLikeScratchIndex[i]   >= 0) (*nCl)++;
+        if (m->tiProbsScratchIndex    != NULL && m->tiProbsScratchIndex[i]    >= 0) (*nTi)++;
+        if (m->nodeScalerScratchIndex != NULL && m->nodeScalerScratchIndex[i] >= 0) (*nNs)++;
+        }
+}
+
 /* configuration of the engine instance a division needs right now */
 void MB200SeamDivisionConfig (ModelInfo *m, int division, mb200_instance_config *cfg)
 {
@@ -384,31 +425,170 @@ void MB200SeamDivisionConfig (ModelInfo *m, int division, mb200_instance_config 
     cfg->weight_rows     = chainParams.numChains;
     cfg->device          = MB200SeamDeviceFor (division);
     cfg->max_evaluations = (numLocalChains > 0) ? numLocalChains : 1;
+    if (seamBatchWanted == YES && numLocalChains > 1)
+        {
+        /* chain-batched generations: every chain but the first gets scratch buffers of its own */
+        int extraCl, extraTi, extraNs;
+        SeamScratchCounts (m, &extraCl, &extraTi, &extraNs);
+        cfg->partials_count += (numLocalChains - 1) * extraCl;
+        cfg->matrix_count   += (numLocalChains - 1) * extraTi;
+        cfg->scaler_count   += (numLocalChains - 1) * (extraNs + 1);   /* + the site-scaler scratch */
+        cfg->eigen_count    += (numLocalChains - 1);
+        }
+}
+
+/* ---- per-chain scratch sets (chain-batched generations) ------------------------------------------
+ * Flip*Space (src/likelihood.c:5614-5682) swaps a chain's index with the division's ONE scratch entry;
+ * installing a chain's own scratch arrays in ModelInfo before its proposal, evaluation or ResetFlips and
+ * putting the reference's arrays back afterwards gives every chain a private double buffer without touching
+ * any of the reference's code. */
+static void SeamInstallScratch (ModelInfo *m, SeamDivision *sd, int chain)
+{
+    if (chain < 1 || chain >= sd->nScratchChains || sd->installed >= 0)
+        return;
+    sd->origCl = m->condLikeScratchIndex;    sd->origTi = m->tiProbsScratchIndex;
+    sd->origNs = m->nodeScalerScratchIndex;  sd->origUn = m->unscaledNodesScratch;
+    sd->origSite = m->siteScalerScratchIndex; sd->origCijk = m->cijkScratchIndex;
+    m->condLikeScratchIndex   = sd->scrCl[chain];
+    m->tiProbsScratchIndex    = sd->scrTi[chain];
+    m->nodeScalerScratchIndex = sd->scrNs[chain];
+    m->unscaledNodesScratch   = sd->scrUn[chain];
+    m->siteScalerScratchIndex = sd->scrSite[chain];
+    if (sd->scrCijk[chain] >= 0)
+        m->cijkScratchIndex   = sd->scrCijk[chain];
+    sd->installed = chain;
+}
+
+static void SeamRestoreScratch (ModelInfo *m, SeamDivision *sd)
+{
+    int chain = sd->installed;
+
+    if (chain < 0)
+        return;
+    sd->scrSite[chain] = m->siteScalerScratchIndex;      /* scalars travel by value; the arrays were flipped in place */
+    if (sd->scrCijk[chain] >= 0)
+        sd->scrCijk[chain] = m->cijkScratchIndex;
+    m->condLikeScratchIndex   = sd->origCl;
+    m->tiProbsScratchIndex    = sd->origTi;
+    m->nodeScalerScratchIndex = sd->origNs;
+    m->unscaledNodesScratch   = sd->origUn;
+    m->siteScalerScratchIndex = sd->origSite;
+    m->cijkScratchIndex       = sd->origCijk;
+    sd->installed = -1;
+}
+
+/* build the scratch sets of chains 1 .. n-1: new buffer indices beyond the reference's own counts, laid out
+   like the reference's scratch arrays (src/mcmc.c:5940-5949, 6139-6150, 6026-6046) */
+static int SeamBuildScratchSets (ModelInfo *m, SeamDivision *sd)
+{
+    int   c, i, n = numLocalChains, nNodes, nextCl, nextTi, nextNs, nextEig;
+    Tree *t = GetTree (m->brlens, 0, state[0]);
+
+    nNodes = t->nNodes;
+    sd->scratchNodes = nNodes;
+    sd->nScratchChains = n;
+    sd->scrCl   = (int **) SafeCalloc ((size_t)n, sizeof(int *));
+    sd->scrTi   = (int **) SafeCalloc ((size_t)n, sizeof(int *));
+    sd->scrNs   = (int **) SafeCalloc ((size_t)n, sizeof(int *));
+    sd->scrUn   = (int **) SafeCalloc ((size_t)n, sizeof(int *));
+    sd->scrSite = (int *)  SafeCalloc ((size_t)n, sizeof(int));
+    sd->scrCijk = (int *)  SafeCalloc ((size_t)n, sizeof(int));
+    sd->extraCijks = (MrBFlt **) SafeCalloc ((size_t)n, sizeof(MrBFlt *));
+    if (!sd->scrCl || !sd->scrTi || !sd->scrNs || !sd->scrUn || !sd->scrSite || !sd->scrCijk || !sd->extraCijks)
+        return (ERROR);
+    nextCl  = m->numCondLikes;
+    nextTi  = m->numTiProbs;
+    nextNs  = m->numScalers;
+    nextEig = numLocalChains + 1;
+    if (m->cijks != NULL && m->nCijkParts > 0 && m->cijkLength > 0)
+        {
+        /* the host computes eigensystems into m->cijks[index] (UpDateCijk): the extra slots need host blocks too */
+        MrBFlt **grown = (MrBFlt **) SafeRealloc ((void *) m->cijks, (size_t)(numLocalChains + n) * sizeof(MrBFlt *));
+        if (!grown)
+            return (ERROR);
+        m->cijks = grown;
+        }
+    for (c=1; c<n; c++)
+        {
+        sd->scrCl[c] = (int *) SafeMalloc ((size_t)nNodes * sizeof(int));
+        sd->scrTi[c] = (int *) SafeMalloc ((size_t)nNodes * sizeof(int));
+        sd->scrNs[c] = (int *) SafeMalloc ((size_t)nNodes * sizeof(int));
+        sd->scrUn[c] = (int *) SafeMalloc ((size_t)nNodes * sizeof(int));
+        if (!sd->scrCl[c] || !sd->scrTi[c] || !sd->scrNs[c] || !sd->scrUn[c])
+            return (ERROR);
+        for (i=0; i<nNodes; i++)
+            {
+            sd->scrCl[c][i] = (m->condLikeScratchIndex[i]   >= 0) ? nextCl++ : -1;
+            sd->scrTi[c][i] = (m->tiProbsScratchIndex[i]    >= 0) ? nextTi++ : -1;
+            sd->scrNs[c][i] = (m->nodeScalerScratchIndex[i] >= 0) ? nextNs++ : -1;
+            sd->scrUn[c][i] = m->unscaledNodesScratch[i];
+            }
+        sd->scrSite[c] = nextNs++;
+        sd->scrCijk[c] = -1;
+        if (m->cijks != NULL && m->nCijkParts > 0 && m->cijkLength > 0)
+            {
+            sd->extraCijks[c] = (MrBFlt *) SafeMalloc ((size_t)m->cijkLength * sizeof(MrBFlt));
+            if (!sd->extraCijks[c])
+                return (ERROR);
+            m->cijks[nextEig] = sd->extraCijks[c];
+            sd->scrCijk[c] = nextEig++;
+            }
+        }
+    return (NO_ERROR);
 }
 
 /* release everything a division holds on the engine side */
 static void SeamDropDivision (int division)
 {
     SeamDivision *sd = &seamDiv[division];
+    int           c;
 
+    if (sd->installed >= 0)
+        SeamRestoreScratch (&modelSettings[division], sd);
     if (sd->instance >= 0)
         seamBackend.finalize_instance (sd->instance);
-    free (sd->ops);
-    free (sd->mats);
+    free (sd->opsArena);
+    free (sd->matsArena);
+    free (sd->eigArena);
+    free (sd->qEv); free (sd->qChain); free (sd->qStatus); free (sd->qLnL);
+    for (c=1; c<sd->nScratchChains; c++)
+        {
+        if (sd->scrCl) free (sd->scrCl[c]);
+        if (sd->scrTi) free (sd->scrTi[c]);
+        if (sd->scrNs) free (sd->scrNs[c]);
+        if (sd->scrUn) free (sd->scrUn[c]);
+        if (sd->extraCijks) free (sd->extraCijks[c]);
+        }
+    free (sd->scrCl); free (sd->scrTi); free (sd->scrNs); free (sd->scrUn); free (sd->scrSite); free (sd->scrCijk);
+    free (sd->extraCijks);
     memset (sd, 0, sizeof(SeamDivision));
+    sd->installed = -1;
     sd->instance = -1;
     memset (seamCijkSeen[division], 0, sizeof(seamCijkSeen[division]));
+}
+
+/* the evaluation being assembled writes into queue slot q */
+static void SeamSelectSlot (SeamDivision *sd, int q)
+{
+    if (q < 0 || q >= sd->nSlots)
+        q = 0;
+    sd->ops        = sd->opsArena  + (size_t)q * sd->capOps;
+    sd->mats       = sd->matsArena + (size_t)q * sd->capMats;
+    sd->eigenBlock = sd->eigArena  + (size_t)q * 72;
 }
 
 /* ---- InitBeagleInstance (src/mbbeagle.c:60): allocate device buffers, load tips ---- */
 int InitBeagleInstance (ModelInfo *m, int division)
 {
-    int                     i, c, b, nRep, rc, inst = -1;
+    int                     i, c, b, nRep, rc, inst = -1, nSlots = 1;
     uint64_t               *masks = NULL, obs, full;
     mb200_instance_config   cfg;
     SeamDivision           *sd;
     mb200_operation        *ops = NULL;
     mb200_matrix_update    *mats = NULL;
+    double                 *eigs = NULL, *qLnL = NULL;
+    mb200_evaluation       *qEv = NULL;
+    int                    *qChain = NULL, *qStatus = NULL;
 
     SeamInit ();
     if (division < 0 || division >= SEAM_MAX_DIVISIONS)
@@ -431,11 +611,18 @@ int InitBeagleInstance (ModelInfo *m, int division)
         SeamDropDivision (division);
         }
 
-    /* everything that can fail on the host is allocated before the instance is published */
-    ops   = (mb200_operation *)     SafeCalloc ((size_t)m->numCondLikes, sizeof(mb200_operation));
-    mats  = (mb200_matrix_update *) SafeCalloc ((size_t)m->numTiProbs,  sizeof(mb200_matrix_update));
+    /* everything that can fail on the host is allocated before the instance is published: one queue slot
+       (operation list, matrix list, inline eigensystem) per local chain */
+    nSlots = (numLocalChains > 0) ? numLocalChains : 1;
+    ops   = (mb200_operation *)     SafeCalloc ((size_t)nSlots * m->numCondLikes, sizeof(mb200_operation));
+    mats  = (mb200_matrix_update *) SafeCalloc ((size_t)nSlots * m->numTiProbs,  sizeof(mb200_matrix_update));
+    eigs  = (double *)              SafeCalloc ((size_t)nSlots * 72, sizeof(double));
+    qEv   = (mb200_evaluation *)    SafeCalloc ((size_t)nSlots, sizeof(mb200_evaluation));
+    qChain  = (int *)               SafeCalloc ((size_t)nSlots, sizeof(int));
+    qStatus = (int *)               SafeCalloc ((size_t)nSlots, sizeof(int));
+    qLnL  = (double *)              SafeCalloc ((size_t)nSlots, sizeof(double));
     masks = (uint64_t *)            SafeMalloc ((size_t)m->numChars * sizeof(uint64_t));
-    if (!ops || !mats || !masks)
+    if (!ops || !mats || !eigs || !qEv || !qChain || !qStatus || !qLnL || !masks)
         goto fail;
 
     rc = seamBackend.create_instance (&cfg, &inst);
@@ -489,9 +676,22 @@ int InitBeagleInstance (ModelInfo *m, int division)
     sd->weightPtr = (const void *) numSitesOfPat;
     sd->capOps   = m->numCondLikes;
     sd->capMats  = m->numTiProbs;
-    sd->ops      = ops;
-    sd->mats     = mats;
+    sd->nSlots   = nSlots;
+    sd->opsArena = ops;   sd->matsArena = mats;  sd->eigArena = eigs;
+    sd->qEv = qEv; sd->qChain = qChain; sd->qStatus = qStatus; sd->qLnL = qLnL;
+    sd->nQueued  = 0;
+    SeamSelectSlot (sd, 0);
     memset (seamCijkSeen[division], 0, sizeof(seamCijkSeen[division]));
+    sd->extraCl = cfg.partials_count - m->numCondLikes;
+    sd->extraTi = cfg.matrix_count - m->numTiProbs;
+    sd->extraNs = cfg.scaler_count - m->numScalers;
+    sd->extraEig = cfg.eigen_count - (numLocalChains + 1);
+    if (seamBatchWanted == YES && numLocalChains > 1 && SeamBuildScratchSets (m, sd) == ERROR)
+        {
+        MrBayesPrint ("%s   B200 engine: cannot build the per-chain scratch sets of division %d\n", spacer, division+1);
+        SeamDropDivision (division);
+        return (ERROR);
+        }
 
     MrBayesPrint ("%s   Using B200 engine (%s) for division %d on device %d: %d patterns x %d categories x %d states\n",
                   spacer, mb200_version_string (), division+1, cfg.device, m->numChars, SeamCategories (m), m->numModelStates);
@@ -502,6 +702,7 @@ fail:
         seamBackend.finalize_instance (inst);
     free (ops);
     free (mats);
+    free (eigs); free (qEv); free (qChain); free (qStatus); free (qLnL);
     free (masks);
     sd->instance = -1;
     return (ERROR);
@@ -776,6 +977,23 @@ static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL
             }
         }
 
+    if (seamBatchQueue == YES)
+        {
+        /* chain-batched generation: the evaluation waits in the division's queue until MB200BatchFlush
+           sends every chain's evaluation to the device in one call */
+        int q = sd->nQueued;
+        if (q >= sd->nSlots)
+            {
+            (*lnL) = MRBFLT_NEG_MAX;
+            abortMove = YES;
+            return (ERROR);
+            }
+        sd->qEv[q]    = sd->ev;
+        sd->qChain[q] = chain;
+        sd->nQueued   = q + 1;
+        SeamSelectSlot (sd, q + 1);
+        return (NO_ERROR);
+        }
     if (seamDeferred == YES)
         {
         /* partition-batched evaluation: launch only, MB200LogLike collects */
@@ -833,7 +1051,7 @@ static int SeamSyncCijk (ModelInfo *m, SeamDivision *sd, int d, int chain)
 {
     int idx = m->cijkIndex[chain];
 
-    if (idx < 0 || idx > MAX_CHAINS)
+    if (idx < 0 || idx > 2 * MAX_CHAINS)
         return (ERROR);
     if (m->upDateCijk == YES || (seamCijkSeen[d][idx >> 3] & (1 << (idx & 7))) == 0)
         {
@@ -861,9 +1079,9 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
     if (sd->instance >= 0 &&
         (sd->parsPtr != (const void *) m->parsSets || sd->weightPtr != (const void *) numSitesOfPat ||
          sd->cfg.pattern_count != m->numChars || sd->cfg.category_count != SeamCategories (m) ||
-         sd->cfg.partials_count != m->numCondLikes || sd->cfg.matrix_count != m->numTiProbs ||
-         sd->cfg.scaler_count != m->numScalers || (m->dataType != STANDARD && sd->cfg.state_count != m->numModelStates) ||
-         sd->cfg.weight_rows != chainParams.numChains || sd->cfg.eigen_count != numLocalChains + 1))
+         sd->cfg.partials_count != m->numCondLikes + sd->extraCl || sd->cfg.matrix_count != m->numTiProbs + sd->extraTi ||
+         sd->cfg.scaler_count != m->numScalers + sd->extraNs || (m->dataType != STANDARD && sd->cfg.state_count != m->numModelStates) ||
+         sd->cfg.weight_rows != chainParams.numChains || sd->cfg.eigen_count != numLocalChains + 1 + sd->extraEig))
         {
         /* another mcmc run in the same session (new model, character set or chain count): the cached
            instance is checked against the current model and rebuilt when it no longer matches */
@@ -913,8 +1131,8 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
     /* every reason to hand the division back to the reference's own path comes BEFORE UpDateCijk:
        that call flips the cijk space, and a second UpDateCijk by the fallback path would overwrite
        the slot ResetFlips needs to restore a rejected move (src/mcmc.c:15695) */
-    if (m->cijkIndex[chain] < 0 || m->cijkIndex[chain] > MAX_CHAINS ||
-        m->cijkScratchIndex < 0 || m->cijkScratchIndex > MAX_CHAINS)
+    if (m->cijkIndex[chain] < 0 || m->cijkIndex[chain] > 2 * MAX_CHAINS ||
+        m->cijkScratchIndex < 0 || m->cijkScratchIndex > 2 * MAX_CHAINS)
         return (NO);
 
     if (m->upDateCijk == YES)
@@ -989,6 +1207,172 @@ MrBFlt MB200LogLike (int chain, void (*cpuPath) (int chain, int d, MrBFlt *lnL))
         return MRBFLT_NEG_MAX;
     for (d=0; d<numCurrentDivisions; d++)
         chainLnLike += modelSettings[d].lnLike[2*chain + state[chain]];
+    return chainLnLike;
+}
+
+/* ======================================================================================
+ * Chain-batched generations (RunChain's chain loop, src/mcmc.c:16718-16938).
+ *
+ * The reference proposes, evaluates and accepts or rejects one chain at a time.  Nothing in a generation couples
+ * the chains except the random-number stream, so the loop can be cut in two around LogLike: phase A proposes a
+ * move for EVERY local chain and queues its likelihood evaluation (all host-side work happens here, in the
+ * reference's order: parameter reads, UpDateCijk, every Flip*Space), draws the chain's acceptance variate at the
+ * very position of the stream where the serial loop draws it (LogLike consumes no random numbers), ONE device
+ * call evaluates the generation's queue per division, and phase B applies the results chain by chain with the
+ * reference's accept / reject code.  What the serial loop shares between chains and a deferred accept cannot
+ * share is given per chain: the scratch index sets (SeamInstallScratch) and the division update flags that
+ * ResetFlips reads (src/mcmc.c:15695-15760).
+ *
+ *   MB200BatchEnable (YES)            before the instances are created (they get the extra scratch buffers)
+ *   MB200BatchBegin ()                start of a generation: YES when every division can be batched
+ *   MB200BatchEnterChain (c, phase) / MB200BatchLeaveChain (c, phase)      bracket everything chain c does
+ *   MB200BatchQueueLogLike (c)        phase A, where the serial loop calls LogLike
+ *   MB200BatchFlush ()                between the phases
+ *   MB200BatchFinishLogLike (c)       phase B: the chain's lnL (abortMove / MRBFLT_NEG_MAX like LogLike)
+ * ====================================================================================== */
+static unsigned char seamFlagCl[MAX_CHAINS][SEAM_MAX_DIVISIONS / 8], seamFlagCijk[MAX_CHAINS][SEAM_MAX_DIVISIONS / 8],
+                     seamFlagAll[MAX_CHAINS][SEAM_MAX_DIVISIONS / 8];
+
+void MB200BatchEnable (int enable)
+{
+    seamBatchWanted = (enable == YES) ? YES : NO;
+}
+
+int MB200BatchBegin (void)
+{
+    int           d;
+    ModelInfo    *m;
+    SeamDivision *sd;
+
+    SeamInit ();
+    if (seamBatchWanted == NO || numLocalChains < 2 || numLocalChains > MAX_CHAINS || numCurrentDivisions > SEAM_MAX_DIVISIONS ||
+        chainParams.runWithData == NO)
+        return (NO);
+    for (d=0; d<numCurrentDivisions; d++)
+        {
+        m  = &modelSettings[d];
+        sd = &seamDiv[d];
+        /* a division on the reference's own kernels shares ITS scratch buffers between the chains: no deferral */
+        if (MB200SeamDivisionSupported (m) == NO)
+            return (NO);
+        if (sd->instance < 0 && InitBeagleInstance (m, d) == ERROR)
+            return (NO);
+        if (sd->nScratchChains != numLocalChains)
+            return (NO);
+        sd->nQueued = 0;
+        sd->qLaunched = NO;
+        SeamSelectSlot (sd, 0);
+        }
+    return (YES);
+}
+
+void MB200BatchEnterChain (int chain, int phase)
+{
+    int d;
+
+    for (d=0; d<numCurrentDivisions; d++)
+        {
+        ModelInfo *m = &modelSettings[d];
+        SeamInstallScratch (m, &seamDiv[d], chain);
+        if (phase == 1)
+            {
+            /* the division flags as this chain's move left them (ResetFlips reads them) */
+            m->upDateCl   = (seamFlagCl  [chain][d >> 3] >> (d & 7)) & 1 ? YES : NO;
+            m->upDateCijk = (seamFlagCijk[chain][d >> 3] >> (d & 7)) & 1 ? YES : NO;
+            m->upDateAll  = (seamFlagAll [chain][d >> 3] >> (d & 7)) & 1 ? YES : NO;
+            }
+        }
+}
+
+void MB200BatchLeaveChain (int chain, int phase)
+{
+    int d;
+
+    for (d=0; d<numCurrentDivisions; d++)
+        {
+        ModelInfo *m = &modelSettings[d];
+        if (phase == 0)
+            {
+            unsigned char bit = (unsigned char)(1 << (d & 7));
+            if (m->upDateCl   == YES) seamFlagCl  [chain][d >> 3] |= bit; else seamFlagCl  [chain][d >> 3] &= (unsigned char) ~bit;
+            if (m->upDateCijk == YES) seamFlagCijk[chain][d >> 3] |= bit; else seamFlagCijk[chain][d >> 3] &= (unsigned char) ~bit;
+            if (m->upDateAll  == YES) seamFlagAll [chain][d >> 3] |= bit; else seamFlagAll [chain][d >> 3] &= (unsigned char) ~bit;
+            }
+        SeamRestoreScratch (m, &seamDiv[d]);
+        }
+}
+
+/* phase A: what LogLike's division loop does (src/mcmc.c:7421-7441), minus the arithmetic */
+void MB200BatchQueueLogLike (int chain)
+{
+    int         d;
+    ModelInfo  *m;
+
+    seamBatchQueue = YES;
+    for (d=0; d<numCurrentDivisions; d++)
+        {
+        m = &modelSettings[d];
+        if (m->upDateCl != YES)
+            continue;
+        if (MB200LaunchLogLikeForDivision (chain, d, &(m->lnLike[2*chain + state[chain]])) == NO)
+            {
+            m->lnLike[2*chain + state[chain]] = MRBFLT_NEG_MAX;       /* cannot happen after MB200BatchBegin's check */
+            abortMove = YES;
+            }
+        if (abortMove == YES)
+            break;
+        }
+    seamBatchQueue = NO;
+}
+
+/* one device call per division for the whole generation; the divisions overlap on the device */
+void MB200BatchFlush (void)
+{
+    int           d;
+    SeamDivision *sd;
+    const int     split = (seamBackend.evaluate_begin != NULL && seamBackend.evaluate_end != NULL) ? YES : NO;
+
+    for (d=0; d<numCurrentDivisions; d++)
+        {
+        sd = &seamDiv[d];
+        if (sd->nQueued == 0)
+            continue;
+        if (split == YES)
+            sd->qRc = seamBackend.evaluate_begin (sd->instance, sd->qEv, sd->nQueued);
+        else
+            sd->qRc = seamBackend.evaluate (sd->instance, sd->qEv, sd->nQueued, sd->qLnL, sd->qStatus);
+        sd->qLaunched = YES;
+        }
+    if (split == YES)
+        for (d=0; d<numCurrentDivisions; d++)
+            {
+            sd = &seamDiv[d];
+            if (sd->nQueued > 0 && sd->qRc == MB200_SUCCESS)
+                sd->qRc = seamBackend.evaluate_end (sd->instance, sd->qLnL, sd->qStatus);
+            }
+}
+
+/* phase B: the chain's log likelihood, with LogLike's conventions */
+MrBFlt MB200BatchFinishLogLike (int chain)
+{
+    int           d, q;
+    ModelInfo    *m;
+    SeamDivision *sd;
+    MrBFlt        chainLnLike = 0.0;
+
+    for (d=0; d<numCurrentDivisions; d++)
+        {
+        m  = &modelSettings[d];
+        sd = &seamDiv[d];
+        for (q=0; q<sd->nQueued; q++)
+            if (sd->qChain[q] == chain)
+                break;
+        if (q < sd->nQueued && sd->qLaunched == YES)
+            SeamApplyResult (d, sd->qRc, sd->qLnL[q], sd->qStatus[q], &(m->lnLike[2*chain + state[chain]]));
+        if (abortMove == YES)
+            return MRBFLT_NEG_MAX;
+        chainLnLike += m->lnLike[2*chain + state[chain]];
+        }
     return chainLnLike;
 }
 

@@ -24,6 +24,15 @@ int       MB200SeamClosedFormModel (ModelInfo *m);     /* nst = 1, 2 4x4 models:
  * own LaunchLogLikeForDivision body).  Returns the chain's log likelihood (MRBFLT_NEG_MAX and
  * abortMove = YES on a numerical failure, like the reference). */
 MrBFlt    MB200LogLike (int chain, void (*cpuPath) (int chain, int d, MrBFlt *lnL));
+/* Chain-batched generations (RunChain's chain loop cut in two around LogLike, src/mcmc.c:16718-16938; see
+ * mb200_seam.c and INTEGRATION.md): all local chains' evaluations of a generation in ONE device call. */
+void      MB200BatchEnable (int enable);
+int       MB200BatchBegin (void);
+void      MB200BatchEnterChain (int chain, int phase);
+void      MB200BatchLeaveChain (int chain, int phase);
+void      MB200BatchQueueLogLike (int chain);
+void      MB200BatchFlush (void);
+MrBFlt    MB200BatchFinishLogLike (int chain);
 void      MB200SeamFinalize (void);
 /* CUDA device a division's buffers live on (local rank, MB200_DEVICE, MB200_SHARD=partitions) */
 int       MB200SeamDeviceFor (int division);

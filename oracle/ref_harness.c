@@ -13,11 +13,18 @@
  *   shadow  reference path drives the chain; the same calls also run on the GPU
  *           engine and |lnL_gpu - lnL_cpu| / |lnL_cpu| is checked per evaluation
  *   gpu     the GPU engine alone drives the chain (the drop-in), timed
+ *   oracle  like gpu, but the seam talks to the CPU oracle (oracle/liboracle.so, loaded at run time) instead of
+ *           the engine: the whole host side -- seam, flip protocol, chain batching -- runs where there is no GPU,
+ *           and must reproduce the reference's own trajectory (the oracle is bit-exact on the FMA build)
  * Other environment variables:
  *   MB200_DUMP_FILE   output of dump mode (default mb200_golden.bin)
  *   MB200_DUMP_MAX    stop recording after this many evaluations (default: all)
  *   MB200_TOL         shadow-mode relative tolerance (default 1e-6)
  *   MB200_REPORT      file the JSON summary is appended to (default: stderr)
+ *   MB200_BATCH       chain-batched generations (binaries linked with the patched RunChain, oracle/patch_runchain.py:
+ *                     mb_b200_batched): 1 (default in gpu / oracle mode) = all local chains of a generation in one
+ *                     engine call; 0 = evaluate at queue time (reproduces the serial binary bit for bit)
+ *   MB200_ORACLE_LIB  oracle mode: path of liboracle.so (default: next to this binary's parent directory)
  *   MB200_VIA         "fnptr": every mode reaches the engine through the node-granular function-pointer
  *                     forms installed in ModelInfo (what SetLikeFunctions would do), with the reference's
  *                     own LaunchLogLikeForDivision loop driving them; default: the seam's own loop
@@ -47,18 +54,25 @@
 #include "mb200_seam.h"
 
 #include <time.h>
+#include <dlfcn.h>
+#include <unistd.h>
 
 void __real_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL);
 MrBFlt __real_LogLike (int chain);
 void __real_CalcCijk (int dim, MrBFlt *c_ijk, MrBFlt **u, MrBFlt **v);
 
-enum { MODE_CPU, MODE_DUMP, MODE_SHADOW, MODE_GPU };
+enum { MODE_CPU, MODE_DUMP, MODE_SHADOW, MODE_GPU, MODE_ORACLE };
+#define ENGINE_DRIVES(mode) ((mode) == MODE_GPU || (mode) == MODE_ORACLE)
 
 static int        hMode = -1;
 static int        hMultiPart = 1;    /* gpu mode: all divisions of a chain in flight together (MB200LogLike) */
 static int        hViaFn = 0;        /* MB200_VIA=fnptr: reach the engine through the node-granular function pointers
                                         (TiProbs_B200 ... Likelihood_B200 installed in ModelInfo) driven by the
                                         reference's own LaunchLogLikeForDivision loop, instead of the seam's own loop */
+extern int MB200RC_patched __attribute__((weak));   /* defined by the patched RunChain only */
+static int        hBatch = 1;        /* MB200_BATCH */
+static int        hBatchActive = NO; /* this generation runs chain-batched */
+static long long  hFlushes = 0, hBatchedGens = 0;
 static FILE      *hDump = NULL;
 static long       hDumpMax = -1, hDumped = 0;
 static double     hTol = 1e-6;
@@ -355,21 +369,76 @@ static void WriteEval (int division, int chain, double lnLRef, int aborted)
 static void Report (void)
 {
     const char *path = getenv ("MB200_REPORT");
-    const char *names[] = { "cpu", "dump", "shadow", "gpu" };
+    const char *names[] = { "cpu", "dump", "shadow", "gpu", "oracle" };
     FILE *f = path ? fopen (path, "a") : stderr;
     if (!f) f = stderr;
     fprintf (f, "{\"mb200_harness\": \"%s\", \"calls\": %lld, \"node_updates\": %lld, \"cl_updates\": %lld, "
                 "\"sec_cpu\": %.6f, \"sec_gpu\": %.6f, \"aborts\": %lld, \"unsupported_calls\": %lld, "
                 "\"compared\": %lld, \"failed\": %lld, \"max_rel\": %.3e, \"mean_rel\": %.3e, \"tol\": %.1e, \"dumped\": %ld, "
-                "\"via\": \"%s\", \"lnl_hash\": \"%016llx\"}\n",
+                "\"via\": \"%s\", \"lnl_hash\": \"%016llx\", \"batched_generations\": %lld, \"flushes\": %lld}\n",
              names[hMode], hCalls, hNodeUpdates, hUpdates, hSecCpu, hSecGpu, hAborts, hUnsupported,
              hCompared, hFailed, (hMaxRel == hMaxRel && hMaxRel < 1e300) ? hMaxRel : 9.999e99,
              (hCompared && hSumRel == hSumRel && hSumRel < 1e300) ? hSumRel / hCompared : (hCompared ? 9.999e99 : 0.0), hTol, hDumped,
-             hViaFn ? "fnptr" : "seam", hLnlHash);
+             hViaFn ? "fnptr" : "seam", hLnlHash, hBatchedGens, hFlushes);
     if (f != stderr) fclose (f);
     if (hDump) { fclose (hDump); hDump = NULL; }
-    if (hMode == MODE_SHADOW || hMode == MODE_GPU)
+    if (hMode == MODE_SHADOW || ENGINE_DRIVES (hMode))
         MB200SeamFinalize ();
+}
+
+/* ---- oracle backend: the seam's calls go to the CPU restatement (same C-ABI, orc_ prefix) --------- */
+static struct
+    {
+    void *lib;
+    int (*create) (const mb200_instance_config *, int *);
+    int (*finalize) (int);
+    int (*arith) (int, int);
+    int (*tips) (int, int, const uint64_t *);
+    int (*weights) (int, int, const float *);
+    int (*cijk) (int, int, const double *);
+    int (*eval) (int, const mb200_evaluation *, int, double *, int *);
+    int (*pstates) (int, const int *, const int *, const int *, int, int, int);
+    } hOrc;
+
+static int orc_create (const mb200_instance_config *c, int *inst)
+{
+    int rc = hOrc.create (c, inst);
+#   if defined (HAVE_FMA3) || defined (FMA_ENABLED)
+    if (rc == MB200_SUCCESS) hOrc.arith (*inst, 1);     /* ORC_ARITH_FMA: this binary's reference objects use the FMA kernels */
+#   else
+    if (rc == MB200_SUCCESS) hOrc.arith (*inst, 0);
+#   endif
+    return rc;
+}
+
+static void LoadOracle (void)
+{
+    const char *path = getenv ("MB200_ORACLE_LIB");
+    char        buf[4096];
+
+    if (!path)
+        {
+        ssize_t n = readlink ("/proc/self/exe", buf, sizeof(buf) - 64);
+        char   *slash;
+        if (n <= 0) { fprintf (stderr, "oracle mode: cannot locate the binary\n"); exit (2); }
+        buf[n] = 0;
+        slash = strrchr (buf, '/');  if (slash) *slash = 0;      /* .../oracle/_ref */
+        slash = strrchr (buf, '/');  if (slash) *slash = 0;      /* .../oracle */
+        strcat (buf, "/liboracle.so");
+        path = buf;
+        }
+    hOrc.lib = dlopen (path, RTLD_NOW);
+    if (!hOrc.lib) { fprintf (stderr, "oracle mode: %s\n", dlerror ()); exit (2); }
+    hOrc.create   = (int (*) (const mb200_instance_config *, int *)) dlsym (hOrc.lib, "orc_create_instance");
+    hOrc.finalize = (int (*) (int)) dlsym (hOrc.lib, "orc_finalize_instance");
+    hOrc.arith    = (int (*) (int, int)) dlsym (hOrc.lib, "orc_set_arith");
+    hOrc.tips     = (int (*) (int, int, const uint64_t *)) dlsym (hOrc.lib, "orc_set_tip_states");
+    hOrc.weights  = (int (*) (int, int, const float *)) dlsym (hOrc.lib, "orc_set_pattern_weights");
+    hOrc.cijk     = (int (*) (int, int, const double *)) dlsym (hOrc.lib, "orc_set_cijk");
+    hOrc.eval     = (int (*) (int, const mb200_evaluation *, int, double *, int *)) dlsym (hOrc.lib, "orc_evaluate");
+    hOrc.pstates  = (int (*) (int, const int *, const int *, const int *, int, int, int)) dlsym (hOrc.lib, "orc_set_pattern_states");
+    if (!hOrc.create || !hOrc.finalize || !hOrc.arith || !hOrc.tips || !hOrc.weights || !hOrc.cijk || !hOrc.eval || !hOrc.pstates)
+        { fprintf (stderr, "oracle mode: %s lacks part of the orc_ API\n", path); exit (2); }
 }
 
 static void Setup (void)
@@ -379,6 +448,8 @@ static void Setup (void)
     if (s && !strcmp (s, "dump"))   hMode = MODE_DUMP;
     if (s && !strcmp (s, "shadow")) hMode = MODE_SHADOW;
     if (s && !strcmp (s, "gpu"))    hMode = MODE_GPU;
+    if (s && !strcmp (s, "oracle")) hMode = MODE_ORACLE;
+    if ((s = getenv ("MB200_BATCH")) != NULL) hBatch = atoi (s);
     if ((s = getenv ("MB200_TOL")) != NULL)      hTol = atof (s);
     if ((s = getenv ("MB200_MULTIPART")) != NULL) hMultiPart = atoi (s);
     if ((s = getenv ("MB200_VIA")) != NULL && !strcmp (s, "fnptr")) { hViaFn = 1; hMultiPart = 0; }
@@ -398,6 +469,19 @@ static void Setup (void)
         MB200SeamBackend be = { rec_create, rec_finalize, rec_tips, rec_weights, rec_cijk, rec_eval, NULL, NULL, rec_pstates };
         MB200SeamSetBackend (&be);
         }
+    if (hMode == MODE_ORACLE)
+        {
+        MB200SeamBackend be;
+        LoadOracle ();
+        be.create_instance = orc_create;       be.finalize_instance = hOrc.finalize;
+        be.set_tip_states = hOrc.tips;         be.set_pattern_weights = hOrc.weights;
+        be.set_cijk = hOrc.cijk;               be.evaluate = hOrc.eval;
+        be.evaluate_begin = NULL;              be.evaluate_end = NULL;
+        be.set_pattern_states = hOrc.pstates;
+        MB200SeamSetBackend (&be);
+        }
+    if (ENGINE_DRIVES (hMode) && hBatch && &MB200RC_patched != NULL)
+        MB200BatchEnable (YES);                 /* before the first instance is created */
     atexit (Report);
 }
 
@@ -491,8 +575,12 @@ MrBFlt __wrap_LogLike (int chain)
 
     if (hMode < 0)
         Setup ();
-    if (hMode != MODE_GPU || hMultiPart == 0 || chainParams.runWithData == NO)
-        return __real_LogLike (chain);
+    if (!ENGINE_DRIVES (hMode) || hMultiPart == 0 || chainParams.runWithData == NO)
+        {
+        v = __real_LogLike (chain);
+        HashLnl (v);
+        return v;
+        }
     for (d=0; d<numCurrentDivisions; d++)
         {
         ModelInfo *m = &modelSettings[d];
@@ -508,6 +596,78 @@ MrBFlt __wrap_LogLike (int chain)
     v = MB200LogLike (chain, CpuPathTimed);
     hSecGpu += Now () - t0;
     if (abortMove == YES) hAborts++;
+    HashLnl (v);
+    return v;
+}
+
+/* ---- hooks of the patched RunChain (oracle/patch_runchain.py; binaries mb_b200_batched*) ----------
+ * A generation that cannot be batched (MB200RC_Begin returns NO) runs the original serial loop body. */
+int MB200RC_Begin (void)
+{
+    if (hMode < 0)
+        Setup ();
+    hBatchActive = (hBatch && ENGINE_DRIVES (hMode) && !hViaFn) ? MB200BatchBegin () : NO;
+    if (hBatchActive == YES)
+        hBatchedGens++;
+    return hBatchActive;
+}
+
+void MB200RC_Enter (int chain, int phase)
+{
+    if (hBatchActive == YES)
+        MB200BatchEnterChain (chain, phase);
+}
+
+void MB200RC_Leave (int chain, int phase)
+{
+    if (hBatchActive == YES)
+        MB200BatchLeaveChain (chain, phase);
+}
+
+void MB200RC_Queue (int chain)
+{
+    int    d;
+    double t0;
+
+    if (hBatchActive == NO)
+        return;
+    for (d=0; d<numCurrentDivisions; d++)
+        {
+        ModelInfo *m = &modelSettings[d];
+        if (m->upDateCl == YES)
+            {
+            long long dirty = CountDirty (GetTree (m->brlens, chain, state[chain]));
+            hCalls++;
+            hNodeUpdates += dirty;
+            hUpdates += dirty * m->numChars * m->numRateCats * m->numOmegaCats;
+            }
+        }
+    t0 = Now ();
+    MB200BatchQueueLogLike (chain);
+    hSecGpu += Now () - t0;
+}
+
+void MB200RC_Flush (void)
+{
+    double t0;
+
+    if (hBatchActive == NO)
+        return;
+    t0 = Now ();
+    MB200BatchFlush ();
+    hSecGpu += Now () - t0;
+    hFlushes++;
+}
+
+MrBFlt MB200RC_Finish (int chain)
+{
+    MrBFlt v;
+
+    if (hBatchActive == NO)
+        return MRBFLT_NEG_MAX;
+    v = MB200BatchFinishLogLike (chain);
+    if (abortMove == YES) hAborts++;
+    HashLnl (v);
     return v;
 }
 
@@ -535,7 +695,7 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
         return;
         }
 
-    if (hMode == MODE_GPU)
+    if (ENGINE_DRIVES (hMode))
         {
         t0 = Now ();
         if (hViaFn)
@@ -552,7 +712,6 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
             }
         hSecGpu += Now () - t0;
         if (abortMove == YES) hAborts++;
-        HashLnl (*lnL);
         return;
         }
 

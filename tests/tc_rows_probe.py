@@ -31,7 +31,7 @@ def one(name):
         inst.synchronize()
         ms = a.elapsed_time(b) / 10
         upd = pr.n_int * pr.C * pr.K
-        print(json.dumps({"workload": name, "rows": os.environ.get("MB200_TC_ROWS", "auto"), "serial_walk": os.environ.get("MB200_TC_SERIAL", "0"), "ms": ms,
+        print(json.dumps({"workload": name, "rows": os.environ.get("MB200_TC_ROWS", "auto"), "kernel": "serial" if os.environ.get("MB200_TC_SERIAL") else "queue" if os.environ.get("MB200_TC_QUEUE") else "pipelined", "ms": ms,
                           "frac": upd * bench.bytes_per_update(S, K) / (ms * 1e-3) / 1e9 / 6569.6}), flush=True)
 
 
@@ -41,12 +41,14 @@ if __name__ == "__main__":
     else:
         names = sys.argv[1:] or ["codon20k", "aa50k"]
         for n in names:
-            for serial in ("0", "1"):
-                for rows in ("auto", "128", "96", "64") if serial == "0" else ("auto",):
+            for serial in ("0", "queue", "1"):
+                for rows in ("auto",):
                     env = dict(os.environ)
-                    env.pop("MB200_TC_ROWS", None); env.pop("MB200_TC_SERIAL", None)
+                    env.pop("MB200_TC_ROWS", None); env.pop("MB200_TC_SERIAL", None); env.pop("MB200_TC_QUEUE", None)
                     if rows != "auto":
                         env["MB200_TC_ROWS"] = rows
                     if serial == "1":
                         env["MB200_TC_SERIAL"] = "1"
+                    if serial == "queue":
+                        env["MB200_TC_QUEUE"] = "1"
                     subprocess.run(["timeout", "120", sys.executable, __file__, "--one", n], env=env, check=False)
