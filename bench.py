@@ -561,7 +561,7 @@ def kernel_roofline(torch, job, flush, peaks, device, max_launches=1024):
     avg_s = ms * 1e-3 / max(cnt, 1)
     ach = (tot_bytes / max(cnt, 1)) / avg_s / 1e9
     kind = "eval_nuc4_kernel<K=4,NT=256,FUSE> (4-state shuffle kernel)" if pr.S == 4 else \
-           f"eval_tc_kernel<{pr.S}> (tcgen05)" if pr.S in (20, 61) else "eval_gen_kernel"
+           f"eval_tcp_kernel<{pr.S}> (tcgen05, warp-specialised pipeline)" if pr.S in (20, 61) else "eval_gen_kernel"
     if len(job.parts) > 1:
         kind += f" of partition {pi + 1} of {len(job.parts)} (the largest)"
     return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],

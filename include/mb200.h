@@ -115,6 +115,12 @@ extern "C" {
  * sum_j P[i][j] (which is 1 only up to rounding).  The 4-state SSE/AVX/FMA kernels treat
  * tips as dense vectors and do not take the shortcut (src/likelihood.c:1121-1250). */
 #define MB200_FLAG_TIP_SHORTCUTS      2
+/* Float-range guard for callers that rescale sparsely (scale_write on a subset of the nodes: the dynamic scheme of
+ * src/mbbeagle.c:429-534).  With the flag set, a rescaler maximum or an unscaled root likelihood below 1e-24 --
+ * values whose smaller siblings are on their way out of the float range -- ends the evaluation with
+ * MB200_EVAL_UNDERFLOW, so that the caller can repeat it with every node rescaled before precision is lost
+ * (without the flag only a dead likelihood, < 1e-300 like the reference, does).  4-state instances. */
+#define MB200_FLAG_RANGE_GUARD        4
 
 typedef struct mb200_instance_config
 {

@@ -683,52 +683,7 @@ bool paramEligible (const Instance *I, const Batch &b)
     return b.fused && b.bytes <= (size_t) PARAM_BIG;
 }
 
-// Rows (site patterns) per tile of the tensor-core kernel: the MMA is 128 rows tall, but a CTA is latency-bound
-// (load + split -> MMA -> TMEM read-out -> store, back to back), so what matters is how many CTAs an SM holds at
-// once (two: shared memory and registers) and that the grid fills those slots in whole waves.  Pick the number
-// of waves w that minimises  w * (fixed cost per node + cost per row * rows per tile).
-const int TC_MIN_ROWS = 32;
-int tcRowsPerTile (const Instance *I, int nEval)
-{
-    static const int forced = getenv ("MB200_TC_ROWS") ? atoi (getenv ("MB200_TC_ROWS")) : 0;
-    if (forced >= TC_MIN_ROWS && forced <= 128)
-        return forced & ~7;
-    const size_t smem = (I->tcS == 61) ? tc_smem_bytes<61, 1> () : tc_smem_bytes<20, 1> ();
-    const long perSM = (2 * smem + 4096 <= 227 * 1024) ? 2 : 1;
-    const long slots = (long) I->numSMs * perSM;             // co-resident CTAs per wave
-    const long C = I->cfg.pattern_count;
-    double best = 1e300; int bestRows = 128;
-    for (int w = 1; w <= 64; w++)
-        {
-        long tilesPerEval = (slots * w) / (nEval > 0 ? nEval : 1);
-        if (tilesPerEval < 1) tilesPerEval = 1;
-        long rows = (C + tilesPerEval - 1) / tilesPerEval;
-        rows = (rows + 7) & ~7L;
-        if (rows > 128) continue;
-        if (rows < TC_MIN_ROWS) rows = TC_MIN_ROWS;
-        const long tiles = ((C + rows - 1) / rows) * (nEval > 0 ? nEval : 1);
-        const long waves = (tiles + slots - 1) / slots;
-        const double cost = (double) waves * (48.0 + (double) rows);     // fixed part ~ 48 rows' worth (measured)
-        if (cost < best) { best = cost; bestRows = (int) rows; }
-        if (rows == TC_MIN_ROWS) break;
-        }
-    return bestRows;
-}
-
-// node-parallel kernel: full 128-row tiles as soon as the queue holds a few items per resident CTA; smaller tiles
-// (more items) for small problems
-int tcqRowsPerTile (const Instance *I, int nEval)
-{
-    static const int forced = getenv ("MB200_TC_ROWS") ? atoi (getenv ("MB200_TC_ROWS")) : 0;
-    if (forced >= TC_MIN_ROWS && forced <= 128)
-        return forced & ~7;
-    const long want = (long) I->tcGrid / 4 + 1;                 // tiles (over all evaluations) we would like to have at least
-    long rows = ((long) I->cfg.pattern_count * (nEval > 0 ? nEval : 1) + want - 1) / want;
-    rows = (rows + 7) & ~7L;
-    if (rows > 128) rows = 128;
-    if (rows < TC_MIN_ROWS) rows = TC_MIN_ROWS;
-    return (int) rows;
-}
+const int TC_MIN_ROWS = 128;    // rows (site patterns) per tile of the tensor-core kernel = the MMA's M
 
 // launch the fused pass for a packed batch; fromHost: the job lives in b.hBlob only and is
 // delivered through the parameter block when it fits (otherwise the caller has copied it to dBlob)
@@ -831,58 +786,21 @@ int launch (Instance *I, Batch &b, DevResult *res, bool viaParams, bool hostSum 
             CK (cudaGetLastError ());
             I->launches++; I->launchKind[MB200_KERNEL_SETUP]++;
             }
-        static const bool serialEnv = getenv ("MB200_TC_SERIAL") != nullptr;       // A/B switch: one CTA walks a tile's whole operation list
-        static const bool queueEnv  = getenv ("MB200_TC_QUEUE") != nullptr;        // A/B switch: node-parallel queue, one item at a time per CTA
-        const bool kFits = ctx.K <= ((I->tcS == 61) ? TcGeom<61>::KMAX : TcGeom<20>::KMAX);
-        const bool pipelined = I->tcpStages > 0 && !((serialEnv || queueEnv) && kFits);
-        const bool serialWalk = serialEnv;
-        if (pipelined)
-            {
-            // warp-specialised pipeline over the node-parallel queue: one persistent CTA per SM
-            ctx.tilePatterns = 128;
-            ctx.numTiles = (ctx.C + 127) / 128;
-            TcQueue Q;
-            Q.counter = I->dTcCounter; Q.base = I->tcBase; Q.flags = I->dTcFlags; Q.flagStride = I->tcFlagStride;
-            Q.maxOps = b.maxOps; Q.nEval = b.nEval; Q.error = I->dTcError; Q.order = (const int *)(b.dBlob + b.offOrd);
-            const long total = (long)(b.maxOps + 1) * b.nEval * ctx.numTiles;
-            const int  g = (int)((total < (long) I->numSMs) ? total : (long) I->numSMs);
-            I->tcBase += (unsigned int)(total + g);                  // every CTA draws exactly one ticket past the end
-            if (I->tcS == 61)
-                eval_tcp_kernel<61><<<g, TCP_THREADS, I->tcpSmem, I->stream>>> (ctx, Q, I->tcpStages, de, dd, dops, I->dSplit, res, seq);
-            else
-                eval_tcp_kernel<20><<<g, TCP_THREADS, I->tcpSmem, I->stream>>> (ctx, Q, I->tcpStages, de, dd, dops, I->dSplit, res, seq);
-            }
+        {
+        // warp-specialised pipeline over the node-parallel queue: one persistent CTA per SM
+        ctx.tilePatterns = 128;
+        ctx.numTiles = (ctx.C + 127) / 128;
+        TcQueue Q;
+        Q.counter = I->dTcCounter; Q.base = I->tcBase; Q.flags = I->dTcFlags; Q.flagStride = I->tcFlagStride;
+        Q.maxOps = b.maxOps; Q.nEval = b.nEval; Q.error = I->dTcError; Q.order = (const int *)(b.dBlob + b.offOrd);
+        const long total = (long)(b.maxOps + 1) * b.nEval * ctx.numTiles;
+        const int  g = (int)((total < (long) I->numSMs) ? total : (long) I->numSMs);
+        I->tcBase += (unsigned int)(total + g);                  // every CTA draws exactly one ticket past the end
+        if (I->tcS == 61)
+            eval_tcp_kernel<61><<<g, TCP_THREADS, I->tcpSmem, I->stream>>> (ctx, Q, I->tcpStages, de, dd, dops, I->dSplit, res, seq);
         else
-        if (!serialWalk)
-            {
-            // node-parallel: (node, tile) work items on a device-side queue, persistent grid
-            ctx.tilePatterns = tcqRowsPerTile (I, b.nEval);
-            ctx.numTiles = (ctx.C + ctx.tilePatterns - 1) / ctx.tilePatterns;
-            TcQueue Q;
-            Q.counter = I->dTcCounter; Q.base = I->tcBase; Q.flags = I->dTcFlags; Q.flagStride = I->tcFlagStride;
-            Q.maxOps = b.maxOps; Q.nEval = b.nEval; Q.error = I->dTcError; Q.order = (const int *)(b.dBlob + b.offOrd);
-            const long total = (long)(b.maxOps + 1) * b.nEval * ctx.numTiles;
-            const int  g = (int)((total < (long) I->tcGrid) ? total : (long) I->tcGrid);
-            I->tcBase += (unsigned int)(total + g);                  // every CTA draws exactly one ticket past the end
-            if (I->tcS == 61)
-                eval_tcq_kernel<61><<<g, 128, tc_smem_bytes<61, 1> (), I->stream>>> (ctx, Q, de, dd, dops, I->dSplit, res, seq);
-            else
-                eval_tcq_kernel<20><<<g, 128, tc_smem_bytes<20, 1> (), I->stream>>> (ctx, Q, de, dd, dops, I->dSplit, res, seq);
-            }
-        else
-            {
-        ctx.tilePatterns = tcRowsPerTile (I, b.nEval);
-        ctx.numTiles = (ctx.C + ctx.tilePatterns - 1) / ctx.tilePatterns;
-        dim3 grid (ctx.numTiles, b.nEval);
-        // 61 states: two children in flight per CTA when the grid is at most one CTA per SM anyway
-        static const bool oneSlot = getenv ("MB200_TC_ONE_SLOT") != nullptr;      // A/B switch for measurements
-        if (I->tcS == 61 && !oneSlot && (long) grid.x * grid.y <= (long) I->numSMs && ctx.tilePatterns == 128)
-            eval_tc_kernel<61, 2><<<grid, 128, tc_smem_bytes<61, 2> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
-        else if (I->tcS == 61)
-            eval_tc_kernel<61, 1><<<grid, 128, tc_smem_bytes<61, 1> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
-        else
-            eval_tc_kernel<20, 1><<<grid, 128, tc_smem_bytes<20, 1> (), I->stream>>> (ctx, de, dd, dops, I->dSplit, res, seq);
-            }
+            eval_tcp_kernel<20><<<g, TCP_THREADS, I->tcpSmem, I->stream>>> (ctx, Q, I->tcpStages, de, dd, dops, I->dSplit, res, seq);
+        }
         I->launchKind[MB200_KERNEL_TENSOR]++;
         }
     else
@@ -1161,31 +1079,15 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
         ALLOC (I->dSplit, (size_t)cfg->matrix_count * K * fl * sizeof(float));
         cudaMemsetAsync (I->dSplit, 0, (size_t)cfg->matrix_count * K * fl * sizeof(float), I->stream);
         cudaError_t ea;
-        if (I->tcS == 61)
-            {
-            ea = cudaFuncSetAttribute (eval_tc_kernel<61, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc_smem_bytes<61, 1> ());
-            if (ea == cudaSuccess)
-                ea = cudaFuncSetAttribute (eval_tc_kernel<61, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc_smem_bytes<61, 2> ());
-            }
-        else
-            ea = cudaFuncSetAttribute (eval_tc_kernel<20, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc_smem_bytes<20, 1> ());
-        if (ea != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
-        // node-parallel work queue
-        int occ = 0;
-        if (I->tcS == 61)
-            {
-            ea = cudaFuncSetAttribute (eval_tcq_kernel<61>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc_smem_bytes<61, 1> ());
-            if (ea == cudaSuccess) ea = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, eval_tcq_kernel<61>, 128, tc_smem_bytes<61, 1> ());
-            }
-        else
-            {
-            ea = cudaFuncSetAttribute (eval_tcq_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tc_smem_bytes<20, 1> ());
-            if (ea == cudaSuccess) ea = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&occ, eval_tcq_kernel<20>, 128, tc_smem_bytes<20, 1> ());
-            }
-        if (ea != cudaSuccess) { destroy (I); return MB200_ERROR_CUDA; }
-        if (occ < 1) occ = 1;
-        I->tcGrid = I->numSMs * occ;
-        // warp-specialised pipelined kernel: one CTA per SM, as many operand-ring stages as fit beside the staging area
+        I->tcFlagStride = (int) nInt + 1;
+        const size_t nFlags = (size_t) I->maxEval * ((size_t)(C + TC_MIN_ROWS - 1) / TC_MIN_ROWS + 1) * I->tcFlagStride;
+        ALLOC (I->dTcCounter, sizeof(unsigned int));
+        ALLOC (I->dTcError, sizeof(int));
+        ALLOC (I->dTcFlags, nFlags * sizeof(int));
+        cudaMemsetAsync (I->dTcCounter, 0, sizeof(unsigned int), I->stream);
+        cudaMemsetAsync (I->dTcError, 0, sizeof(int), I->stream);
+        cudaMemsetAsync (I->dTcFlags, 0, nFlags * sizeof(int), I->stream);
+        // warp-specialised pipelined kernel: one CTA per SM, as many operand-ring stages as fit
         {
         int optin = 0;
         cudaDeviceGetAttribute (&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, I->cfg.device);
@@ -1202,17 +1104,9 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
                                 : cudaFuncSetAttribute (eval_tcp_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) I->tcpSmem);
             if (ea != cudaSuccess) { cudaGetLastError (); I->tcpStages = 0; }
             }
-        if (I->tcpStages == 0 && K > ((I->tcS == 61) ? TcGeom<61>::KMAX : TcGeom<20>::KMAX))
-            { destroy (I); return MB200_ERROR_UNSUPPORTED; }
+        if (I->tcpStages == 0)
+            { destroy (I); return MB200_ERROR_UNSUPPORTED; }     // cannot happen for K <= 4 on a 227 KB part
         }
-        I->tcFlagStride = (int) nInt + 1;
-        const size_t nFlags = (size_t) I->maxEval * ((size_t)(C + TC_MIN_ROWS - 1) / TC_MIN_ROWS + 1) * I->tcFlagStride;
-        ALLOC (I->dTcCounter, sizeof(unsigned int));
-        ALLOC (I->dTcError, sizeof(int));
-        ALLOC (I->dTcFlags, nFlags * sizeof(int));
-        cudaMemsetAsync (I->dTcCounter, 0, sizeof(unsigned int), I->stream);
-        cudaMemsetAsync (I->dTcError, 0, sizeof(int), I->stream);
-        cudaMemsetAsync (I->dTcFlags, 0, nFlags * sizeof(int), I->stream);
         }
     ALLOC (I->dInvMask,  (size_t)C * sizeof(uint64_t));
     ALLOC (I->dTilePartial, (size_t)I->maxEval * I->maxTiles * sizeof(double));

@@ -27,6 +27,9 @@
 #define MB200_LIKE_EPSILON 1.0e-300         /* src/likelihood.c:44                           */
 #define MB200_QUIRK_FLAG 1
 #define MB200_SHORTCUT_FLAG 2                /* MB200_FLAG_TIP_SHORTCUTS */
+#define MB200_GUARD_FLAG 4                   /* MB200_FLAG_RANGE_GUARD */
+#define MB200_GUARD_MIN  1.0e-24f            /* rescaler maxima / unscaled root likelihoods below this trip the guard */
+#define MB200_GUARD_LN   (-55.262f)          /* log (MB200_GUARD_MIN) */
 
 #ifdef MB200_PHASE_TIMING
 __device__ __forceinline__ unsigned long long mb200_now () { unsigned long long t; asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -1065,6 +1068,8 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
                     // but rare last-bit cases
                     sc = log_of_max (sNewT[oo * PPB]);
                     ctx.scalers[(size_t)sw * C + c] = sc;
+                    if ((sEv.flags & MB200_GUARD_FLAG) && sc < MB200_GUARD_LN)
+                        abortAcc = 1;                   // sparse rescaling ran this subtree too close to the float range
                     }
                 if (sr >= 0)
                     old = ctx.scalers[(size_t)sr * C + c];
@@ -1140,8 +1145,12 @@ nuc4_body (const DevCtx &ctx, const DevEval *__restrict__ evals, const double *_
         int    abortFlag = 0;
         double term = 0.0;
         if (active && lk == 0)
+            {
             term = site_term ((double) likeF, likeI, sEv.hasPInvar, sEv.flags & MB200_QUIRK_FLAG, lnScaler,
                               ctx.weights[(size_t)sEv.weightsRow * C + c], abortFlag);
+            if ((sEv.flags & MB200_GUARD_FLAG) && likeF < MB200_GUARD_MIN)
+                abortFlag = 1;
+            }
         termAcc += term; abortAcc |= abortFlag;
         }
         }   // tiles of this CTA

@@ -3,26 +3,28 @@
 // reference src/likelihood.c:204, 1575, 2152, 4010, 4939, 5413, 5764, 6975).
 //
 // Work = (node, 128-pattern tile) items of the device-side queue of mb200_kernels_tc.cuh (level order, acquire /
-// release flags between the CTAs of a persistent grid), but inside the CTA the phases of an item no longer run back
-// to back: one CTA per SM, 14 warps with fixed roles, mbarrier rings between them.
+// release flags between the CTAs of a persistent grid).  Inside the CTA the phases of an item do not run back to
+// back: one CTA per SM, 20 warps with fixed roles, mbarrier rings between them.
 //
 //   scheduler (1 warp)    draws tickets, decodes (slot, evaluation, tile), waits for the item's producers (flag
 //                         acquire), publishes the item in a 4-deep shared-memory ring
-//   loaders   (2 x 4)     one *unit* = one (rate category, child) operand of an item.  The two groups take alternate
-//                         units, so two units' loads are in flight per SM: child rows HBM/L2 -> registers (512-byte
-//                         coalesced LDG.128) -> hi/lo TF32 split -> canonical K-major core-matrix images in an
-//                         operand-ring stage; the branch's pre-split P(t) image [hi | lo] arrives in the same stage by
+//   loaders   (8 warps)   one *unit* = one (rate category, child) operand of an item.  Groups of warps take the units
+//                         round-robin, so several units' loads are in flight per SM: child rows HBM/L2 -> registers
+//                         (512-byte coalesced LDG.128) -> hi/lo TF32 split -> canonical K-major core-matrix images in
+//                         an operand-ring stage; the branch's pre-split P(t) image [hi | lo] arrives in the same stage by
 //                         one bulk async copy (TMA engine, complete_tx on the stage's full barrier)
 //   MMA       (1 warp)    per unit: [main | corr] = A_hi x [B_hi | B_lo]^T  (ONE tcgen05.mma chain, N = 2 NP) and
 //                         corr += A_lo x B_hi^T (N = NP) into one slot of a TMEM accumulator ring; tcgen05.commit
 //                         frees the operand stage and hands the accumulators to the epilogue
-//   epilogue  (4 warps)   thread = pattern row = TMEM lane: tcgen05.ld, main + corr, product over the children, row
-//                         maximum; unscaled rows staged in shared memory, then coalesced 16-byte stores of
-//                         row * (1 / max) -- the same two roundings as the serial kernels, so results are bit-identical
-//                         to eval_tc_kernel / eval_tcq_kernel; node scaler, flag release; the evaluation's closing
-//                         item (site scalers, root integration, lnL tile sums) also runs here
+//   epilogue  (2 x 4)     two halves share an item: thread = pattern row = TMEM lane, the 16-column strips of a row
+//                         alternate between the halves: tcgen05.ld, main + corr, product over the children, row maximum;
+//                         unscaled rows staged in shared memory, then coalesced 16-byte stores of row * (1 / max) -- the
+//                         two roundings of the reference's rescaler; node scaler; the evaluation's closing item (site
+//                         scalers, root integration, lnL tile sums) runs here too
+//   publisher (1 warp)    release-stores the node-done flags (the memory barrier of a release does not stall a warp that
+//                         has accumulators waiting)
 //
-// 3xTF32 as before (x = hi + lo, lo x lo dropped); the large term and the two correction terms still land in separate
+// 3xTF32 as before (x = hi + lo, lo x lo dropped); the large term and the two correction terms land in separate
 // accumulators and are added in FP32 in the epilogue.
 #pragma once
 #include "mb200_kernels_tc.cuh"
@@ -33,7 +35,7 @@ template <int S> struct TcpGeom;
 template <> struct TcpGeom<61> { static constexpr int NA = 4, LG = 2; };
 template <> struct TcpGeom<20> { static constexpr int NA = 8, LG = 4; };
 
-constexpr int TCP_THREADS   = 608;     // 8 epilogue warps, 8 loader warps, MMA issuer, scheduler, publisher
+constexpr int TCP_THREADS   = 608;     // 2 x 4 epilogue warps, 8 loader warps, MMA issuer, scheduler, publisher
 constexpr int TCP_NPUB      = 4;       // flag-publication ring (epilogue -> publisher warp)
 constexpr int TCP_NS_MAX    = 8;       // operand-ring stages (as many as fit beside the staging area)
 constexpr int TCP_NI        = 4;       // item ring
@@ -53,7 +55,7 @@ template <int S> __host__ __device__ constexpr size_t tcp_stage_bytes ()
 }
 template <int S> __host__ __device__ constexpr size_t tcp_staging_bytes (int K)
 {
-    return (size_t) K * ((S + 3) / 4) * 129 * sizeof(float4);
+    return (size_t) K * ((S + 3) / 4) * 129 * sizeof(float4);   // one item's result rows, [k][16-byte chunk][row + pad]
 }
 // "this row's tip is fully ambiguous" bytes, one 128-byte record per unit in flight (loader -> epilogue)
 template <int S> __host__ __device__ constexpr size_t tcp_tipring_bytes (int NS) { return (size_t)(TcpGeom<S>::NA + NS) * 128; }
@@ -93,8 +95,13 @@ __device__ __forceinline__ void tcp_wait (uint64_t *bar, uint32_t parity)
             }
         }
 }
-__device__ __forceinline__ void tcp_bar_epilogue () { asm volatile ("bar.sync 1, 256;\n" ::: "memory"); }      // both epilogue halves
-__device__ __forceinline__ void tcp_bar_half0 ()    { asm volatile ("bar.sync 2, 128;\n" ::: "memory"); }      // warps 0-3
+__device__ __forceinline__ void tcp_bar_epilogue () { asm volatile ("bar.sync 3, 256;\n" ::: "memory"); }      // both epilogue halves
+// barrier of one epilogue half (warps 0-3: id 1, warps 4-7: id 2)
+__device__ __forceinline__ void tcp_bar_group (int grp)
+{
+    if (grp == 0) asm volatile ("bar.sync 1, 128;\n" ::: "memory");
+    else          asm volatile ("bar.sync 2, 128;\n" ::: "memory");
+}
 
 // debug builds (-DMB200_PHASE_TIMING): CTA 0 stamps the pipeline events of its first items, 16 slots per item
 #ifdef MB200_PHASE_TIMING
@@ -126,15 +133,15 @@ eval_tcp_kernel (DevCtx ctx, TcQueue Q, int NS, const DevEval *__restrict__ eval
     __shared__ uint64_t barFull[TCP_NS_MAX], barEmpty[TCP_NS_MAX], barAccFull[NA], barAccEmpty[NA], barInfoFull[TCP_NI], barInfoEmpty[TCP_NI];
     __shared__ TcpItem sInfo[TCP_NI];
     __shared__ uint32_t tmemBase;
-    __shared__ float  sMax[2][TM];     // row maxima found by the two epilogue halves
     __shared__ uint64_t barPubFull[TCP_NPUB], barPubEmpty[TCP_NPUB];
     __shared__ int   *sPub[TCP_NPUB];  // flags to release, in order (nullptr: stop)
-    __shared__ double qSum[4];
-    __shared__ int    qAb[4];
+    __shared__ float  sMax[2][TM];     // row maxima found by the two epilogue halves
+    __shared__ double qSum[2][4];
+    __shared__ int    qAb[2][4];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Sp = ctx.Sp, K = ctx.K, C = ctx.C;
-    float4 *sStage = reinterpret_cast<float4 *>(tcp_smem + (size_t) NS * STAGE);     // [k][q][TM+1]
+    float4 *sStage = reinterpret_cast<float4 *>(tcp_smem + (size_t) NS * STAGE);     // [group][buffer][chunk][TM+1]
     const int TIPRING = NA + NS;
     unsigned char *sTipFull = tcp_smem + (size_t) NS * STAGE + tcp_staging_bytes<S> (K);   // [unit % TIPRING][row]
 
@@ -412,7 +419,8 @@ eval_tcp_kernel (DevCtx ctx, TcQueue Q, int NS, const DevEval *__restrict__ eval
         }
     else if (warp == 18)
         {
-        // =================================================================== publisher: releases the node-done flags
+        // =================================================================== publisher: release-stores the node-done flags,
+        // so that no epilogue warp sits in a memory barrier
         int slot = 0; uint32_t ph = 0;
         for (;;)
             {
@@ -432,14 +440,18 @@ eval_tcp_kernel (DevCtx ctx, TcQueue Q, int NS, const DevEval *__restrict__ eval
         }
     else
         {
-        // =================================================================== epilogue: two halves (warps 0-3, 4-7) share an
-        // item: thread = pattern row = TMEM lane in both, the 16-column strips of a row alternate between them
-        const int half = warp >> 2, row = tid & (TM - 1);
+        // =================================================================== epilogue: two halves of four warps share every
+        // item -- thread = pattern row = TMEM lane in both, the 16-column strips of a row alternate between them; the
+        // products are staged UNSCALED in shared memory ([k][chunk][row]: conflict-free for thread = row), the halves
+        // exchange their row maxima, and all 256 threads copy the rows out with coalesced 16-byte stores of
+        // row * (1 / max) -- the two roundings of CondLikeScaler_Gen (src/likelihood.c:4939-4990).
+        const int grp = warp >> 2, gtid = tid & (TM - 1), row = gtid;
         const uint32_t laneSel = (uint32_t)((warp & 3) * 32) << 16;
         int islot = 0; uint32_t iph = 0;
         int pslot = 0; uint32_t pph = 0;
         unsigned u = 0;
         unsigned nItem = 0;
+        unsigned accPar = 0;                                    // parity of the next phase of barAccFull[slot], one bit per slot
         for (;; nItem++)
             {
             tcp_wait (&barInfoFull[islot], iph);
@@ -476,12 +488,15 @@ eval_tcp_kernel (DevCtx ctx, TcQueue Q, int NS, const DevEval *__restrict__ eval
                 for (int k = 0; k < K; k++)
                     {
                     // the accumulators of all children of (item, k) sit in consecutive slots of the TMEM ring: wait for
-                    // the last one (commits complete in issue order), then combine 16 columns at a time -- registers
-                    // hold one 16-column strip of the product, not the whole row
+                    // the last one (commits complete in issue order), then combine 16 columns at a time
                     for (int ch = 0; ch < it.nChild; ch++)
-                        tcp_wait (&barAccFull[(int)((u + ch) % (unsigned) NA)], ((u + ch) / (unsigned) NA) & 1u);
+                        {
+                        const int a = (int)((u + ch) % (unsigned) NA);
+                        tcp_wait (&barAccFull[a], (accPar >> a) & 1u);
+                        accPar ^= 1u << a;
+                        }
                     fence_after_sync ();
-                    if (tid == 0 && k == K - 1) TCP_T (nItem, 12);
+                    if (gtid == 0 && k == K - 1) TCP_T (nItem, 12);
                     unsigned tipFull = 0;
                     if (tipKids)
                         {
@@ -496,7 +511,7 @@ eval_tcp_kernel (DevCtx ctx, TcQueue Q, int NS, const DevEval *__restrict__ eval
                     for (int cb = 0; cb < NP; cb += 16)
                         {
                         if (cb >= S) break;
-                        if ((((cb >> 4) + k) & 1) != half) continue;
+                        if ((((cb >> 4) + k) & 1) != grp) continue;     // the other half's strip
                         float prod[16];
                         {
                         // the first two children's strips are read together: four TMEM loads in flight, one wait
@@ -552,50 +567,52 @@ eval_tcp_kernel (DevCtx ctx, TcQueue Q, int NS, const DevEval *__restrict__ eval
                             mbar_arrive (&barAccEmpty[(int)((u + ch) % (unsigned) NA)]);
                     u += (unsigned) it.nChild;
                     }
-                // rescale (CondLikeScaler_Gen, src/likelihood.c:4939-4990): one IEEE reciprocal of the row maximum, then
-                // multiplies on the way out; the site-scaler bookkeeping is the closing item's
-                sMax[half][row] = mx;
                 if (tid == 0) TCP_T (nItem, 13);
+                // the halves meet: row maxima, then the copy-out
+                sMax[grp][row] = mx;
                 tcp_bar_epilogue ();
-#ifdef TCP_TRACE_EPI
-                if (tid == 0) TCP_T (nItem, 4);
-                if (tid == 128) TCP_T (nItem, 5);
-#endif
                 const bool doScale = it.sw >= 0;
                 {
                 float *dstBase = ctx.partials + (size_t)(it.dest - ctx.tipCount) * bufStride;
-                constexpr int nq = SPC / 4;
+                constexpr int nq = SPC / 4, NCP = (nq + 1) / 2;
+                // the reciprocals of the rows this thread copies, all of them first (straight-line code below: the
+                // shared-memory loads of the copy are then in flight together)
+                float fr[NCP];
+                #pragma unroll
+                for (int n = 0; n < NCP; n++)
+                    {
+                    const int idx = n * 256 + tid;
+                    const int r = (idx < nq * TM) ? idx / nq : 0;
+                    fr[n] = doScale ? __frcp_rn (fmaxf (sMax[0][r], sMax[1][r])) : 1.0f;      // = 1.0f / max, IEEE
+                    }
                 for (int k = 0; k < K; k++)
                     {
                     float4 *dst = reinterpret_cast<float4 *>(dstBase + ((size_t)k * C + c0) * SPC);
+                    float4 v[NCP];
                     #pragma unroll
-                    for (int n = 0; n < (nq + 1) / 2; n++)
+                    for (int n = 0; n < NCP; n++)
                         {
                         const int idx = n * 256 + tid;
-                        const int r = idx / nq, q = idx % nq;
+                        const int r = (idx < nq * TM) ? idx / nq : 0, q = idx % nq;
+                        v[n] = sStage[((size_t)k * NQ + ((q < NQ) ? q : 0)) * (TM + 1) + r];
+                        if (q >= NQ) v[n] = make_float4 (0.f, 0.f, 0.f, 0.f);
+                        }
+                    #pragma unroll
+                    for (int n = 0; n < NCP; n++)
+                        {
+                        const int idx = n * 256 + tid;
+                        const int r = idx / nq;
+                        v[n].x *= fr[n]; v[n].y *= fr[n]; v[n].z *= fr[n]; v[n].w *= fr[n];
                         if (r < np && idx < nq * TM)
-                            {
-                            float4 v = make_float4 (0.f, 0.f, 0.f, 0.f);
-                            if (q < NQ)
-                                {
-                                v = sStage[((size_t)k * NQ + q) * (TM + 1) + r];
-                                const float f = doScale ? __frcp_rn (fmaxf (sMax[0][r], sMax[1][r])) : 1.0f;   // = 1.0f / max, IEEE
-                                v.x *= f; v.y *= f; v.z *= f; v.w *= f;
-                                }
-                            dst[idx] = v;
-                            }
+                            dst[idx] = v[n];
                         }
                     }
                 }
-#ifdef TCP_TRACE_EPI
-                if (tid == 0) TCP_T (nItem, 6);
-                if (tid == 128) TCP_T (nItem, 7);
-#endif
-                if (doScale && half == 0 && active)             // node scaler (CondLikeScaler_Gen_SSE, src/likelihood.c:5055), after the stores are on their way
+                if (doScale && grp == 0 && active)              // node scaler (CondLikeScaler_Gen_SSE: log in double, cast to float, src/likelihood.c:5055)
                     ctx.scalers[(size_t)it.sw * C + c] = log_of_max (fmaxf (sMax[0][row], sMax[1][row]));
-                // publish: the barrier orders every epilogue thread's stores before thread 0's hand-over; the publisher
-                // warp acquires it and release-stores the flag (cumulative at GPU scope), so no epilogue warp sits in a
-                // memory barrier while the next item's accumulators are waiting
+                // publish: the barrier orders every epilogue thread's stores before thread 0's hand-over; the publisher warp
+                // acquires it and release-stores the flag (cumulative at GPU scope), so no epilogue warp sits in a memory
+                // barrier while the next item's accumulators are waiting
                 if (tid == 0) TCP_T (nItem, 14);
                 tcp_bar_epilogue ();
                 if (tid == 0)
@@ -610,7 +627,7 @@ eval_tcp_kernel (DevCtx ctx, TcQueue Q, int NS, const DevEval *__restrict__ eval
                 }
 
             // ---------------------------------------------------------------- closing item of (e, t): warps 0-3
-            if (half != 0)
+            if (grp != 0)
                 continue;
             const int nOp = ev->nOp;
             float site = 0.0f;
@@ -668,12 +685,12 @@ eval_tcp_kernel (DevCtx ctx, TcQueue Q, int NS, const DevEval *__restrict__ eval
                 term      += __shfl_xor_sync (0xffffffffu, term, off);
                 abortFlag |= __shfl_xor_sync (0xffffffffu, abortFlag, off);
                 }
-            if (lane == 0) { qSum[warp] = term; qAb[warp] = abortFlag; }
-            tcp_bar_half0 ();
-            if (tid == 0)
+            if (lane == 0) { qSum[grp][warp & 3] = term; qAb[grp][warp & 3] = abortFlag; }
+            tcp_bar_group (grp);
+            if (gtid == 0)
                 {
-                const double s = qSum[0] + qSum[1] + qSum[2] + qSum[3];
-                const int    a = qAb[0] | qAb[1] | qAb[2] | qAb[3];
+                const double s = qSum[grp][0] + qSum[grp][1] + qSum[grp][2] + qSum[grp][3];
+                const int    a = qAb[grp][0] | qAb[grp][1] | qAb[grp][2] | qAb[grp][3];
                 ctx.tilePartial[(size_t)it.e * numTiles + it.t] = s;
                 ctx.tileAbort  [(size_t)it.e * numTiles + it.t] = a;
                 __threadfence ();
@@ -695,7 +712,7 @@ eval_tcp_kernel (DevCtx ctx, TcQueue Q, int NS, const DevEval *__restrict__ eval
                     ctx.ticket[it.e] = 0u;
                     }
                 }
-            tcp_bar_half0 ();                               // qSum / qAb free for the next closing item
+            tcp_bar_group (grp);                               // qSum / qAb free for the group's next closing item
             }
         }
 

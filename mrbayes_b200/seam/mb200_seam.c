@@ -78,6 +78,12 @@ typedef struct
     int                  origSite, origCijk, installed;     /* installed: chain whose set is in place, or -1 */
     int                  extraCl, extraTi, extraNs, extraEig;  /* buffers beyond the reference's own counts */
     MrBFlt             **extraCijks;        /* host eigensystem blocks appended to m->cijks for the extra slots */
+    /* dynamic rescaling (MB200_RESCALE=dynamic): per chain, the rescale frequency and the run of clean evaluations */
+    int                 *dynFreq, *dynRun;
+    int                 *extraFlip, *nExtraFlip, *queuedState;  /* [chain][capOps] nodes the retry flipped beyond the move's own;
+                                                                   [chain] how many; [chain] state[] when the chain was queued */
+    int                  guard;             /* the evaluation being assembled was built with a rescale frequency > 1 */
+    long long            dynRetries;
     long long            clUpdates;         /* node*pattern*rate updates issued      */
     int                  pending;           /* launched by a deferred evaluation, result not yet collected */
     int                  recording, recChain, recState;   /* function-pointer forms: evaluation being recorded */
@@ -133,6 +139,17 @@ static void SeamInit (void)
         seamDiv[d].installed = -1;
         }
     seamInitialized = YES;
+}
+
+/* dynamic rescaling: evaluations repeated with every node rescaled after an underflow (all divisions) */
+long long MB200SeamRescaleRetries (void)
+{
+    long long n = 0;
+    int       d;
+    if (seamInitialized == YES)
+        for (d=0; d<SEAM_MAX_DIVISIONS; d++)
+            n += seamDiv[d].dynRetries;
+    return n;
 }
 
 long long MB200SeamUpdateCount (int division)
@@ -551,6 +568,7 @@ static void SeamDropDivision (int division)
     free (sd->matsArena);
     free (sd->eigArena);
     free (sd->qEv); free (sd->qChain); free (sd->qStatus); free (sd->qLnL);
+    free (sd->dynFreq); free (sd->dynRun); free (sd->extraFlip); free (sd->nExtraFlip); free (sd->queuedState);
     for (c=1; c<sd->nScratchChains; c++)
         {
         if (sd->scrCl) free (sd->scrCl[c]);
@@ -588,7 +606,7 @@ int InitBeagleInstance (ModelInfo *m, int division)
     mb200_matrix_update    *mats = NULL;
     double                 *eigs = NULL, *qLnL = NULL;
     mb200_evaluation       *qEv = NULL;
-    int                    *qChain = NULL, *qStatus = NULL;
+    int                    *qChain = NULL, *qStatus = NULL, *dynF = NULL, *dynR = NULL, *xFlip = NULL, *nXFlip = NULL, *qState = NULL;
 
     SeamInit ();
     if (division < 0 || division >= SEAM_MAX_DIVISIONS)
@@ -621,9 +639,16 @@ int InitBeagleInstance (ModelInfo *m, int division)
     qChain  = (int *)               SafeCalloc ((size_t)nSlots, sizeof(int));
     qStatus = (int *)               SafeCalloc ((size_t)nSlots, sizeof(int));
     qLnL  = (double *)              SafeCalloc ((size_t)nSlots, sizeof(double));
+    dynF  = (int *)                 SafeCalloc ((size_t)nSlots, sizeof(int));
+    dynR  = (int *)                 SafeCalloc ((size_t)nSlots, sizeof(int));
+    xFlip = (int *)                 SafeCalloc ((size_t)nSlots * m->numCondLikes, sizeof(int));
+    nXFlip = (int *)                SafeCalloc ((size_t)nSlots, sizeof(int));
+    qState = (int *)                SafeCalloc ((size_t)nSlots, sizeof(int));
     masks = (uint64_t *)            SafeMalloc ((size_t)m->numChars * sizeof(uint64_t));
-    if (!ops || !mats || !eigs || !qEv || !qChain || !qStatus || !qLnL || !masks)
+    if (!ops || !mats || !eigs || !qEv || !qChain || !qStatus || !qLnL || !dynF || !dynR || !xFlip || !nXFlip || !qState || !masks)
         goto fail;
+    for (i=0; i<nSlots; i++)
+        dynF[i] = 1;
 
     rc = seamBackend.create_instance (&cfg, &inst);
     if (rc != MB200_SUCCESS)
@@ -679,6 +704,7 @@ int InitBeagleInstance (ModelInfo *m, int division)
     sd->nSlots   = nSlots;
     sd->opsArena = ops;   sd->matsArena = mats;  sd->eigArena = eigs;
     sd->qEv = qEv; sd->qChain = qChain; sd->qStatus = qStatus; sd->qLnL = qLnL;
+    sd->dynFreq = dynF; sd->dynRun = dynR; sd->extraFlip = xFlip; sd->nExtraFlip = nXFlip; sd->queuedState = qState;
     sd->nQueued  = 0;
     SeamSelectSlot (sd, 0);
     memset (seamCijkSeen[division], 0, sizeof(seamCijkSeen[division]));
@@ -702,7 +728,7 @@ fail:
         seamBackend.finalize_instance (inst);
     free (ops);
     free (mats);
-    free (eigs); free (qEv); free (qChain); free (qStatus); free (qLnL);
+    free (eigs); free (qEv); free (qChain); free (qStatus); free (qLnL); free (dynF); free (dynR); free (xFlip); free (nXFlip); free (qState);
     free (masks);
     sd->instance = -1;
     return (ERROR);
@@ -813,8 +839,19 @@ int TreeTiProbs_Beagle (Tree *t, int division, int chain)
     return (NO_ERROR);
 }
 
-/* ---- TreeCondLikes_Beagle_Always_Rescale (src/mbbeagle.c:995): the op list --------- */
-int TreeCondLikes_Beagle_Always_Rescale (Tree *t, int division, int chain)
+/* ---- the op list: TreeCondLikes_Beagle_Always_Rescale / _No_Rescale / _Rescale_All (src/mbbeagle.c:995, 783, 884) ----
+ * SEAM_OPS_POLICY   the built-in path's bookkeeping (src/likelihood.c:7938-7965): an updated node is rescaled when
+ *                   unscaledNodes reaches m->rescaleFreq[chain] -- every node with the reference's rescaleFreq of 1
+ *                   (src/mcmc.c:6157-6164), every few levels under the dynamic scheme below;
+ * SEAM_OPS_NONE     the same updates, no node is rescaled (the first attempt of BEAGLE's dynamic scheme);
+ * SEAM_OPS_ALL      EVERY interior node is recomputed and the site scalers are rebuilt from nothing (the retry after a
+ *                   numerical failure).  Nodes the failed attempt has already flipped keep their slots; the others are
+ *                   flipped now and RECORDED (not flagged: the tree's update flags are shared by every division that
+ *                   uses it, and ResetFlips, src/mcmc.c:15695, reads them for all of them): should the move be rejected,
+ *                   MB200BatchLeaveChain flips them back. */
+enum { SEAM_OPS_POLICY, SEAM_OPS_NONE, SEAM_OPS_ALL };
+
+static int SeamBuildOps (Tree *t, int division, int chain, int mode)
 {
     int                 i;
     TreeNode           *p;
@@ -830,14 +867,26 @@ int TreeCondLikes_Beagle_Always_Rescale (Tree *t, int division, int chain)
     for (i=0; i<t->nIntNodes; i++)
         {
         p = t->intDownPass[i];
-        if (p->upDateCl != YES)
+        if (p->upDateCl != YES && mode != SEAM_OPS_ALL)
             continue;
 
         op = &sd->ops[sd->ev.operation_count++];
 
-        /* CondLikeDown_* / CondLikeRoot_* flip first, then read the child indices
-           (src/likelihood.c:795-804) */
-        FlipCondLikeSpace (m, chain, p->index);
+        if (mode == SEAM_OPS_ALL)
+            {
+            if (p->upDateCl != YES)
+                {
+                FlipCondLikeSpace (m, chain, p->index);
+                FlipNodeScalerSpace (m, chain, p->index);
+                sd->extraFlip[(size_t)chain * sd->capOps + sd->nExtraFlip[chain]++] = p->index;
+                }
+            }
+        else
+            {
+            /* CondLikeDown_* / CondLikeRoot_* flip first, then read the child indices
+               (src/likelihood.c:795-804) */
+            FlipCondLikeSpace (m, chain, p->index);
+            }
         op->dest    = m->condLikeIndex[chain][p->index];
         op->child1  = m->condLikeIndex[chain][p->left->index];
         op->matrix1 = m->tiProbsIndex [chain][p->left->index];
@@ -854,15 +903,20 @@ int TreeCondLikes_Beagle_Always_Rescale (Tree *t, int division, int chain)
             op->matrix3 = MB200_NONE;
             }
 
-        /* scaler bookkeeping of src/likelihood.c:7938-7965 */
-        if (m->unscaledNodes[chain][p->index] == 0 && m->upDateAll == NO)
-            op->scale_remove = m->nodeScalerIndex[chain][p->index];
+        if (mode == SEAM_OPS_ALL)
+            op->scale_remove = MB200_NONE;              /* the site scalers start from zero */
         else
-            op->scale_remove = MB200_NONE;
-        FlipNodeScalerSpace (m, chain, p->index);
+            {
+            /* scaler bookkeeping of src/likelihood.c:7938-7965 */
+            if (m->unscaledNodes[chain][p->index] == 0 && m->upDateAll == NO)
+                op->scale_remove = m->nodeScalerIndex[chain][p->index];
+            else
+                op->scale_remove = MB200_NONE;
+            FlipNodeScalerSpace (m, chain, p->index);
+            }
         m->unscaledNodes[chain][p->index] = 1 + m->unscaledNodes[chain][p->left->index]
                                               + m->unscaledNodes[chain][p->right->index];
-        if (m->unscaledNodes[chain][p->index] >= m->rescaleFreq[chain] && p->anc->anc != NULL)
+        if (mode != SEAM_OPS_NONE && m->unscaledNodes[chain][p->index] >= m->rescaleFreq[chain] && p->anc->anc != NULL)
             {
             op->scale_write = m->nodeScalerIndex[chain][p->index];
             m->unscaledNodes[chain][p->index] = 0;
@@ -876,19 +930,47 @@ int TreeCondLikes_Beagle_Always_Rescale (Tree *t, int division, int chain)
     return (NO_ERROR);
 }
 
-/* the reference has these two for the dynamic-rescaling scheme; the engine always
-   rescales (the built-in path's policy), so both map onto the same op list */
+int TreeCondLikes_Beagle_Always_Rescale (Tree *t, int division, int chain)
+{
+    return SeamBuildOps (t, division, chain, SEAM_OPS_POLICY);
+}
+
 int TreeCondLikes_Beagle_No_Rescale (Tree *t, int division, int chain)
 {
-    return TreeCondLikes_Beagle_Always_Rescale (t, division, chain);
+    return SeamBuildOps (t, division, chain, SEAM_OPS_NONE);
 }
 
 int TreeCondLikes_Beagle_Rescale_All (Tree *t, int division, int chain)
 {
-    return TreeCondLikes_Beagle_Always_Rescale (t, division, chain);
+    return SeamBuildOps (t, division, chain, SEAM_OPS_ALL);
 }
 
-static int SeamApplyResult (int division, int rc, double value, int status, MrBFlt *lnL);
+/* ---- dynamic rescaling (the reference's BEAGLE path has it as MB_BEAGLE_SCALE_DYNAMIC, src/mbbeagle.c:429-534,
+ *      TODO:19-33 "rescaling takes a surprisingly large amount of time") -- opt-in: MB200_RESCALE=dynamic.
+ * The built-in path rescales every updated node; most of those divisions and logarithms are not needed to stay inside
+ * the float range.  Under the dynamic scheme a chain's nodes are rescaled when unscaledNodes reaches the chain's
+ * rescale frequency f (>= 1): f grows by one after a run of clean evaluations and is halved when an evaluation
+ * underflows, in which case the evaluation is REPEATED at once with every interior node recomputed and rescaled
+ * (SEAM_OPS_ALL at f = 1) before the chain sees a result -- a move is never rejected because of sparse rescaling.
+ * lnL then agrees with the always-rescale arithmetic to rounding (fewer divisions by the maximum; bar: 1e-6 relative),
+ * which is why the default stays the reference's policy (bit-level parity). */
+static int seamDynMaxFreq = 8;      /* MB200_RESCALE_MAXFREQ */
+static int seamDynRun     = 200;    /* MB200_RESCALE_RUN: clean evaluations before the frequency grows */
+
+static int SeamDynamicRescaling (void)
+{
+    static int mode = -1;
+    if (mode < 0)
+        {
+        const char *s = getenv ("MB200_RESCALE");
+        mode = (s != NULL && strcmp (s, "dynamic") == 0) ? YES : NO;
+        if ((s = getenv ("MB200_RESCALE_MAXFREQ")) != NULL && atoi (s) >= 1) seamDynMaxFreq = atoi (s);
+        if ((s = getenv ("MB200_RESCALE_RUN")) != NULL && atoi (s) >= 1)     seamDynRun = atoi (s);
+        }
+    return mode;
+}
+
+static int SeamApplyResult (int division, int chain, int rc, double value, int status, MrBFlt *lnL);
 static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL, int whichSitePats);
 
 /* ---- TreeLikelihood_Beagle (src/mbbeagle.c:1117): root integration; launches ------- */
@@ -927,7 +1009,11 @@ static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL
     if (m->dataType == STANDARD)
         sd->ev.flags = 0;                               /* *_Std family: dense tips, no pInvar */
     else if (m->numModelStates == 4 && (m->dataType == DNA || m->dataType == RNA))
+        {
         sd->ev.flags |= MB200_FLAG_NUC4_PINVAR_QUIRK;   /* Likelihood_NUC4_* family */
+        if (sd->guard == YES)
+            sd->ev.flags |= MB200_FLAG_RANGE_GUARD;     /* sparsely rescaled evaluation (dynamic scheme) */
+        }
     else
         sd->ev.flags |= MB200_FLAG_TIP_SHORTCUTS;       /* *_Gen_SSE family */
 
@@ -990,6 +1076,8 @@ static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL
             }
         sd->qEv[q]    = sd->ev;
         sd->qChain[q] = chain;
+        sd->queuedState[chain] = state[chain];
+        sd->nExtraFlip[chain]  = 0;
         sd->nQueued   = q + 1;
         SeamSelectSlot (sd, q + 1);
         return (NO_ERROR);
@@ -1005,12 +1093,74 @@ static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL
         return (NO_ERROR);
         }
     rc = seamBackend.evaluate (sd->instance, &sd->ev, 1, &value, &status);
-    return SeamApplyResult (division, rc, value, status, lnL);
+    return SeamApplyResult (division, chain, rc, value, status, lnL);
+}
+
+/* dynamic rescaling, the retry: the evaluation underflowed with sparse rescaling -> every interior node of the chain's
+   tree again, rescaled at every node, site scalers from zero (the P(t) of this evaluation are on the device already) */
+static int SeamRetryRescaleAll (int division, int chain, double *value, int *status)
+{
+    ModelInfo    *m  = &modelSettings[division];
+    SeamDivision *sd = &seamDiv[division];
+    Tree         *t  = GetTree (m->brlens, chain, state[chain]);
+    const mb200_evaluation failed = sd->ev;     /* root, weights row, rates, frequencies, pInvar: unchanged */
+    int           rc, savedFreq = m->rescaleFreq[chain];
+
+    if (sd->nQueued > 0 && sd->qLaunched == YES)
+        {
+        /* chain-batched generation: the failed evaluation is the chain's queue entry */
+        int q;
+        for (q=0; q<sd->nQueued; q++)
+            if (sd->qChain[q] == chain)
+                break;
+        if (q == sd->nQueued)
+            return (ERROR);
+        sd->ev = sd->qEv[q];
+        SeamSelectSlot (sd, q);
+        }
+    (void) failed;
+    m->rescaleFreq[chain] = 1;
+    SeamBuildOps (t, division, chain, SEAM_OPS_ALL);
+    m->rescaleFreq[chain] = savedFreq;
+    sd->ev.matrix_update_count = 0;
+    sd->ev.site_scaler_dst = m->siteScalerIndex[chain];
+    sd->ev.site_scaler_src = MB200_NONE;
+    sd->ev.flags &= ~MB200_FLAG_RANGE_GUARD;            /* every node rescaled: only a dead likelihood fails now */
+    sd->dynRetries++;
+    rc = seamBackend.evaluate (sd->instance, &sd->ev, 1, value, status);
+    return (rc == MB200_SUCCESS) ? NO_ERROR : ERROR;
 }
 
 /* result of an evaluation -> the reference's conventions */
-static int SeamApplyResult (int division, int rc, double value, int status, MrBFlt *lnL)
+static int SeamApplyResult (int division, int chain, int rc, double value, int status, MrBFlt *lnL)
 {
+    SeamDivision *sd = &seamDiv[division];
+
+    if (rc == MB200_SUCCESS && SeamDynamicRescaling () == YES && chain >= 0 && chain < sd->nSlots)
+        {
+        static int forceRetry = -1;             /* MB200_RESCALE_FORCE_RETRY=1 (tests): every evaluation takes the retry path */
+        if (forceRetry < 0)
+            forceRetry = (getenv ("MB200_RESCALE_FORCE_RETRY") != NULL) ? YES : NO;
+        if (sd->qLaunched == YES && sd->nQueued > 0 &&
+            ((status == MB200_EVAL_UNDERFLOW && sd->dynFreq[chain] > 1) || (forceRetry == YES && status == MB200_EVAL_OK)))
+            {
+            const double failedValue = value;
+            const int    failedFreq = sd->dynFreq[chain];
+            sd->dynFreq[chain] = (sd->dynFreq[chain] + 1) / 2;
+            sd->dynRun[chain]  = 0;
+            if (SeamRetryRescaleAll (division, chain, &value, &status) == ERROR)
+                rc = MB200_ERROR_GENERAL;
+            if (getenv ("MB200_RESCALE_DEBUG") != NULL)
+                fprintf (stderr, "mb200 rescale retry: division %d chain %d freq %d: first attempt %.10g -> %.10g (status %d)\n",
+                         division + 1, chain, failedFreq, failedValue, value, status);
+            }
+        else if (status == MB200_EVAL_OK && modelSettings[division].numModelStates == 4 && ++sd->dynRun[chain] >= seamDynRun)
+            {
+            sd->dynRun[chain] = 0;
+            if (sd->dynFreq[chain] < seamDynMaxFreq)
+                sd->dynFreq[chain]++;
+            }
+        }
     if (rc != MB200_SUCCESS)
         {
         MrBayesPrint ("%s   B200 engine: evaluation failed for division %d (%s)\n", spacer, division+1, mb200_error_string (rc));
@@ -1041,7 +1191,22 @@ void LaunchBEAGLELogLikeForDivision (int chain, int d, ModelInfo *m, Tree *tree,
     sd->ev.site_scaler_src = (m->upDateAll == YES) ? MB200_NONE : m->siteScalerScratchIndex;
 
     TreeTiProbs_Beagle (tree, d, chain);
-    TreeCondLikes_Beagle_Always_Rescale (tree, d, chain);
+    sd->guard = NO;
+    /* (only inside chain-batched generations: their hooks are what can undo a retry's extra flips after a rejection) */
+    if (SeamDynamicRescaling () == YES && seamBatchQueue == YES && chain < sd->nSlots && m->numModelStates == 4 &&
+        (m->dataType == DNA || m->dataType == RNA) && sd->dynFreq[chain] > 1)
+        {
+        /* 4-state divisions only (the kernels that carry the float-range guard, MB200_FLAG_RANGE_GUARD).
+           The chain's own rescale frequency steers the reference's bookkeeping fields (m->rescaleFreq is 1 in builds
+           without BEAGLE, src/mcmc.c:6157-6164) for the duration of the call */
+        const int savedFreq = m->rescaleFreq[chain];
+        m->rescaleFreq[chain] = sd->dynFreq[chain];
+        TreeCondLikes_Beagle_Always_Rescale (tree, d, chain);
+        m->rescaleFreq[chain] = savedFreq;
+        sd->guard = YES;
+        }
+    else
+        TreeCondLikes_Beagle_Always_Rescale (tree, d, chain);
     TreeLikelihood_Beagle (tree, d, chain, lnL, chainId[chain] % chainParams.numChains);
 }
 
@@ -1156,7 +1321,7 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
 }
 
 /* collect the result of a deferred evaluation of division d */
-static int SeamCollect (int d, MrBFlt *lnL)
+static int SeamCollect (int d, int chain, MrBFlt *lnL)
 {
     SeamDivision *sd = &seamDiv[d];
     double        value = 0.0;
@@ -1170,7 +1335,7 @@ static int SeamCollect (int d, MrBFlt *lnL)
         }
     else
         { value = sd->syncValue; status = sd->syncStatus; }
-    return SeamApplyResult (d, rc, value, status, lnL);
+    return SeamApplyResult (d, chain, rc, value, status, lnL);
 }
 
 /* ---- replacement for the division loop of LogLike (src/mcmc.c:7421-7441) ------------ */
@@ -1201,7 +1366,7 @@ MrBFlt MB200LogLike (int chain, void (*cpuPath) (int chain, int d, MrBFlt *lnL))
         {
         m = &modelSettings[d];
         if (d < SEAM_MAX_DIVISIONS && seamDiv[d].pending == YES)
-            SeamCollect (d, &(m->lnLike[2*chain + state[chain]]));
+            SeamCollect (d, chain, &(m->lnLike[2*chain + state[chain]]));
         }
     if (abortMove == YES)
         return MRBFLT_NEG_MAX;
@@ -1298,6 +1463,21 @@ void MB200BatchLeaveChain (int chain, int phase)
             if (m->upDateCijk == YES) seamFlagCijk[chain][d >> 3] |= bit; else seamFlagCijk[chain][d >> 3] &= (unsigned char) ~bit;
             if (m->upDateAll  == YES) seamFlagAll [chain][d >> 3] |= bit; else seamFlagAll [chain][d >> 3] &= (unsigned char) ~bit;
             }
+        if (phase == 1 && chain < seamDiv[d].nSlots && seamDiv[d].nExtraFlip != NULL && seamDiv[d].nExtraFlip[chain] > 0)
+            {
+            /* a retry (dynamic rescaling) flipped nodes the move had not touched; ResetFlips knows nothing of them:
+               the move was rejected (state[chain] is back at its pre-proposal value) -> flip them back here */
+            SeamDivision *sd = &seamDiv[d];
+            int           i;
+            if (state[chain] != sd->queuedState[chain])
+                for (i=0; i<sd->nExtraFlip[chain]; i++)
+                    {
+                    const int node = sd->extraFlip[(size_t)chain * sd->capOps + i];
+                    FlipCondLikeSpace (m, chain, node);
+                    FlipNodeScalerSpace (m, chain, node);
+                    }
+            sd->nExtraFlip[chain] = 0;
+            }
         SeamRestoreScratch (m, &seamDiv[d]);
         }
 }
@@ -1368,7 +1548,7 @@ MrBFlt MB200BatchFinishLogLike (int chain)
             if (sd->qChain[q] == chain)
                 break;
         if (q < sd->nQueued && sd->qLaunched == YES)
-            SeamApplyResult (d, sd->qRc, sd->qLnL[q], sd->qStatus[q], &(m->lnLike[2*chain + state[chain]]));
+            SeamApplyResult (d, chain, sd->qRc, sd->qLnL[q], sd->qStatus[q], &(m->lnLike[2*chain + state[chain]]));
         if (abortMove == YES)
             return MRBFLT_NEG_MAX;
         chainLnLike += m->lnLike[2*chain + state[chain]];
@@ -1409,7 +1589,7 @@ void LaunchBEAGLELogLikeMultiPartition (int *divisions, int divisionCount, int c
         d = divisions[i];
         m = &modelSettings[d];
         if (d < SEAM_MAX_DIVISIONS && seamDiv[d].pending == YES)
-            SeamCollect (d, &(m->lnLike[2*chain + state[chain]]));
+            SeamCollect (d, chain, &(m->lnLike[2*chain + state[chain]]));
         (*lnL) += m->lnLike[2*chain + state[chain]];
         }
     if (abortMove == YES)

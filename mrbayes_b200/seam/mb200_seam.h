@@ -51,6 +51,7 @@ int       CondLikeScaler_B200 (TreeNode *p, int division, int chain);
 int       Likelihood_B200     (TreeNode *p, int division, int chain, MrBFlt *lnL, int whichSitePats);
 int       MB200InstallLikeFunctions (int division);
 long long MB200SeamUpdateCount (int division);   /* node*pattern*rate CL updates issued  */
+long long MB200SeamRescaleRetries (void);        /* MB200_RESCALE=dynamic: evaluations repeated after an underflow */
 int       MB200SeamInstance (int division);      /* engine instance of a division, or -1 */
 
 /* Every engine call the seam makes goes through this table, so a test harness can

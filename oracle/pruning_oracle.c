@@ -35,6 +35,7 @@ typedef struct
     float      *weights;     /* [row][C]                                             */
     float      *tmp[3];      /* per-child matvec results [K][C][S]                   */
     long long   updates;
+    int         guardHit;       /* MB200_FLAG_RANGE_GUARD tripped during the evaluation in progress */
     /* variable-state (STANDARD data) divisions: the *_Std family */
     int         std;         /* MB200_CONFIG_VARIABLE_STATES                          */
     int        *nStates, *tiIndex, *bsIndex;    /* [C] m->nStates, m->tiIndex, m->bsIndex */
@@ -340,6 +341,8 @@ static void Operation (OrcInst *o, const mb200_operation *op, const mb200_evalua
                 scP[c] = (float) log (scaler);       /* _Gen_SSE :5055, _NUC4_SSE :5328 */
             if (lnScaler)
                 lnScaler[c] += scP[c];
+            if ((ev->flags & MB200_FLAG_RANGE_GUARD) && scaler < 1.0e-24f)
+                o->guardHit = 1;                     /* MB200_FLAG_RANGE_GUARD (include/mb200.h) */
             }
         }
 }
@@ -387,6 +390,8 @@ static int RootLikelihood (OrcInst *o, const mb200_evaluation *ev, const float *
                 }
             }
         like = (double) likeF;
+        if ((ev->flags & MB200_FLAG_RANGE_GUARD) && likeF < 1.0e-24f)
+            o->guardHit = 1;
         likeI = 0.0;
         if (ev->has_p_invar)
             {
@@ -683,6 +688,7 @@ int orc_evaluate (int instance, const mb200_evaluation *evs, int count, double *
                 memcpy (zero, o->scalers + (size_t)ev->site_scaler_src * C, (size_t)C * sizeof(float));
             lnScaler = zero;
             }
+        o->guardHit = 0;
         for (i=0; i<ev->operation_count; i++)
             {
             if (o->std) StdOperation (o, &ev->operations[i], lnScaler);
@@ -691,6 +697,8 @@ int orc_evaluate (int instance, const mb200_evaluation *evs, int count, double *
         if (ev->root_buffer != MB200_NONE)
             {
             int st = o->std ? StdRootLikelihood (o, ev, lnScaler, &lnL[e]) : RootLikelihood (o, ev, lnScaler, &lnL[e]);
+            if (o->guardHit && st == MB200_EVAL_OK)
+                { st = MB200_EVAL_UNDERFLOW; lnL[e] = -DBL_MAX; }
             if (status) status[e] = st;
             }
         else

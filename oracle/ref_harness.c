@@ -134,6 +134,20 @@ static void Chunk (const char *tag, const void *hdr, size_t hdrBytes, const void
     if (bodyBytes) fwrite (body, 1, bodyBytes, hDump);
 }
 
+/* ---- what shadow mode runs beside the reference: the engine, or (MB200_SHADOW_BACKEND=oracle) the CPU oracle -- the
+ *      latter lets the seam's policies (dynamic rescaling, its retry) be checked per evaluation where there is no GPU */
+static struct
+    {
+    int (*create) (const mb200_instance_config *, int *);
+    int (*finalize) (int);
+    int (*tips) (int, int, const uint64_t *);
+    int (*weights) (int, int, const float *);
+    int (*cijk) (int, int, const double *);
+    int (*eval) (int, const mb200_evaluation *, int, double *, int *);
+    int (*pstates) (int, const int *, const int *, const int *, int, int, int);
+    } hSh = { mb200_create_instance, mb200_finalize_instance, mb200_set_tip_states, mb200_set_pattern_weights, mb200_set_cijk,
+              mb200_evaluate, mb200_set_pattern_states };
+
 /* ---- recording backend ------------------------------------------------------------- */
 static int rec_create (const mb200_instance_config *c, int *inst)
 {
@@ -145,7 +159,7 @@ static int rec_create (const mb200_instance_config *c, int *inst)
     *inst = id;
     if (hMode == MODE_SHADOW)
         {
-        int rc = mb200_create_instance (c, &hInstReal[id]);
+        int rc = hSh.create (c, &hInstReal[id]);
         if (rc != MB200_SUCCESS)
             return rc;
         }
@@ -158,7 +172,7 @@ static int rec_create (const mb200_instance_config *c, int *inst)
 static int rec_finalize (int inst)
 {
     if (hMode == MODE_SHADOW && hInstReal[inst] >= 0)
-        return mb200_finalize_instance (hInstReal[inst]);
+        return hSh.finalize (hInstReal[inst]);
     return MB200_SUCCESS;
 }
 
@@ -168,7 +182,7 @@ static int rec_tips (int inst, int tip, const uint64_t *masks)
     hdr[0] = hInstDivision[inst]; hdr[1] = tip; hdr[2] = hInstCfg[inst].pattern_count;
     Chunk ("TIPS", hdr, sizeof(hdr), masks, (size_t)hdr[2] * sizeof(uint64_t));
     if (hMode == MODE_SHADOW)
-        return mb200_set_tip_states (hInstReal[inst], tip, masks);
+        return hSh.tips (hInstReal[inst], tip, masks);
     return MB200_SUCCESS;
 }
 
@@ -178,7 +192,7 @@ static int rec_weights (int inst, int row, const float *w)
     hdr[0] = hInstDivision[inst]; hdr[1] = row; hdr[2] = hInstCfg[inst].pattern_count;
     Chunk ("WGHT", hdr, sizeof(hdr), w, (size_t)hdr[2] * sizeof(float));
     if (hMode == MODE_SHADOW)
-        return mb200_set_pattern_weights (hInstReal[inst], row, w);
+        return hSh.weights (hInstReal[inst], row, w);
     return MB200_SUCCESS;
 }
 
@@ -198,7 +212,7 @@ static int rec_pstates (int inst, const int *ns, const int *ti, const int *bs, i
     Chunk ("PSTA", hdr, sizeof(hdr), body, (size_t)3 * nPat * sizeof(int));
     free (body);
     if (hMode == MODE_SHADOW)
-        return mb200_set_pattern_states (hInstReal[inst], ns, ti, bs, matLen, dummy, uncompressed);
+        return hSh.pstates (hInstReal[inst], ns, ti, bs, matLen, dummy, uncompressed);
     return MB200_SUCCESS;
 }
 
@@ -272,7 +286,7 @@ static int rec_cijk (int inst, int eigen, const double *block)
             Chunk ("CIJK", hdr, sizeof(hdr), block, (2*(size_t)S + n3) * sizeof(double));
         }
     if (hMode == MODE_SHADOW)
-        return mb200_set_cijk (hInstReal[inst], eigen, block);
+        return hSh.cijk (hInstReal[inst], eigen, block);
     return MB200_SUCCESS;
 }
 
@@ -311,7 +325,7 @@ static int rec_eval (int inst, const mb200_evaluation *e, int n, double *lnL, in
     if (hMode == MODE_SHADOW)
         {
         double t0 = Now ();
-        int rc = mb200_evaluate (hInstReal[inst], e, 1, lnL, status);
+        int rc = hSh.eval (hInstReal[inst], e, 1, lnL, status);
         hSecGpu += Now () - t0;
         hLast.lnLGpu = lnL[0];
         hLast.statusGpu = status[0];
@@ -375,11 +389,11 @@ static void Report (void)
     fprintf (f, "{\"mb200_harness\": \"%s\", \"calls\": %lld, \"node_updates\": %lld, \"cl_updates\": %lld, "
                 "\"sec_cpu\": %.6f, \"sec_gpu\": %.6f, \"aborts\": %lld, \"unsupported_calls\": %lld, "
                 "\"compared\": %lld, \"failed\": %lld, \"max_rel\": %.3e, \"mean_rel\": %.3e, \"tol\": %.1e, \"dumped\": %ld, "
-                "\"via\": \"%s\", \"lnl_hash\": \"%016llx\", \"batched_generations\": %lld, \"flushes\": %lld}\n",
+                "\"via\": \"%s\", \"lnl_hash\": \"%016llx\", \"batched_generations\": %lld, \"flushes\": %lld, \"rescale_retries\": %lld}\n",
              names[hMode], hCalls, hNodeUpdates, hUpdates, hSecCpu, hSecGpu, hAborts, hUnsupported,
              hCompared, hFailed, (hMaxRel == hMaxRel && hMaxRel < 1e300) ? hMaxRel : 9.999e99,
              (hCompared && hSumRel == hSumRel && hSumRel < 1e300) ? hSumRel / hCompared : (hCompared ? 9.999e99 : 0.0), hTol, hDumped,
-             hViaFn ? "fnptr" : "seam", hLnlHash, hBatchedGens, hFlushes);
+             hViaFn ? "fnptr" : "seam", hLnlHash, hBatchedGens, hFlushes, MB200SeamRescaleRetries ());
     if (f != stderr) fclose (f);
     if (hDump) { fclose (hDump); hDump = NULL; }
     if (hMode == MODE_SHADOW || ENGINE_DRIVES (hMode))
@@ -463,6 +477,12 @@ static void Setup (void)
         if (!hDump) { perror ("MB200_DUMP_FILE"); exit (2); }
         fwrite ("MB200GLD", 1, 8, hDump);
         fwrite (&ver, 4, 1, hDump);
+        }
+    if (hMode == MODE_SHADOW && (s = getenv ("MB200_SHADOW_BACKEND")) != NULL && !strcmp (s, "oracle"))
+        {
+        LoadOracle ();
+        hSh.create = orc_create;   hSh.finalize = hOrc.finalize; hSh.tips = hOrc.tips; hSh.weights = hOrc.weights;
+        hSh.cijk = hOrc.cijk;      hSh.eval = hOrc.eval;         hSh.pstates = hOrc.pstates;
         }
     if (hMode == MODE_DUMP || hMode == MODE_SHADOW)
         {

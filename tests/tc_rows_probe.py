@@ -15,11 +15,12 @@ def one(name):
     import bench
     from mrbayes_b200 import abi, workloads
     S, K, Cn, tips = bench.SYNTH[name]
-    pr = workloads.make_problem(S, K, Cn, tips, 1, seed=2026)
+    nch = int(os.environ.get("PROBE_CHAINS", "1"))
+    pr = workloads.make_problem(S, K, Cn, tips, nch, seed=2026)
     lib = abi.engine_library()
     with pr.create(lib) as inst:
         inst.evaluate(pr.full_evaluation(0))
-        batch = inst.pack([pr.full_evaluation(0)])
+        batch = inst.pack([pr.full_evaluation(c) for c in range(nch)])
         stream = torch.cuda.ExternalStream(inst.stream())
         for _ in range(3):
             inst.replay(batch)
@@ -30,8 +31,8 @@ def one(name):
         b.record(stream)
         inst.synchronize()
         ms = a.elapsed_time(b) / 10
-        upd = pr.n_int * pr.C * pr.K
-        print(json.dumps({"workload": name, "rows": os.environ.get("MB200_TC_ROWS", "auto"), "kernel": "serial" if os.environ.get("MB200_TC_SERIAL") else "queue" if os.environ.get("MB200_TC_QUEUE") else "pipelined", "ms": ms,
+        upd = pr.n_int * pr.C * pr.K * nch
+        print(json.dumps({"workload": name, "chains": nch, "rows": os.environ.get("MB200_TC_ROWS", "auto"), "kernel": "serial" if os.environ.get("MB200_TC_SERIAL") else "queue" if os.environ.get("MB200_TC_QUEUE") else "pipelined", "ms": ms,
                           "frac": upd * bench.bytes_per_update(S, K) / (ms * 1e-3) / 1e9 / 6569.6}), flush=True)
 
 
@@ -41,7 +42,7 @@ if __name__ == "__main__":
     else:
         names = sys.argv[1:] or ["codon20k", "aa50k"]
         for n in names:
-            for serial in ("0", "queue", "1"):
+            for serial in ("0", "1"):
                 for rows in ("auto",):
                     env = dict(os.environ)
                     env.pop("MB200_TC_ROWS", None); env.pop("MB200_TC_SERIAL", None); env.pop("MB200_TC_QUEUE", None)

@@ -25,23 +25,29 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 BIN = ROOT / "oracle" / "_ref" / "mb_b200"
+BIN_BATCHED = ROOT / "oracle" / "_ref" / "mb_b200_batched"     # the same objects with the patched RunChain (oracle/patch_runchain.py)
 CMD = ROOT / "tests" / "golden" / "cmd"
 
 needs_harness = pytest.mark.skipif(not BIN.exists(), reason="oracle/_ref/mb_b200 not built (needs /root/reference at build time)")
 
 
-def run_harness(tmp_path: Path, stem: str, ngen: int, mode: str, via: str = "seam", extra_env=None, timeout=900):
-    nex = tmp_path / f"{stem}.{mode}.{via}.nex"
-    text = (CMD / f"{stem}.nex").read_text().replace("NGEN", str(ngen)).replace("OUTPREFIX", str(tmp_path / f"out_{stem}_{mode}_{via}"))
+def run_harness(tmp_path: Path, stem: str, ngen: int, mode: str, via: str = "seam", extra_env=None, timeout=900, binary: Path = BIN, tag: str = ""):
+    key = f"{stem}.{mode}.{via}" if not tag else "r" + tag.replace(".", "_")     # MrBayes limits file name lengths to 100 characters
+    nex = tmp_path / f"{key}.nex"
+    prefix = tmp_path / (f"out_{stem}_{mode}_{via}" if not tag else "o" + tag.replace(".", "_"))
+    text = (CMD / f"{stem}.nex").read_text().replace("NGEN", str(ngen)).replace("OUTPREFIX", str(prefix))
     nex.write_text(text)
-    report = tmp_path / f"{stem}.{mode}.{via}.json"
+    report = tmp_path / f"{key}.json"
     env = dict(os.environ, MB200_MODE=mode, MB200_REPORT=str(report), MB200_VIA=via)
     env.update(extra_env or {})
-    p = subprocess.run([str(BIN), str(nex)], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    p = subprocess.run([str(binary), str(nex)], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert report.exists(), p.stdout[-2000:] + p.stderr[-2000:]
     rep = json.loads(report.read_text().strip().splitlines()[-1])
     rep["stderr"] = p.stderr[-2000:]
+    # what the run sampled (parameter and tree files), minus the random [ID: ...] stamp MrBayes puts in each file
+    rep["samples"] = {f.name.replace(prefix.name, ""): "\n".join(l for l in f.read_text().splitlines() if "ID:" not in l)
+                      for f in sorted(tmp_path.glob(prefix.name + "*")) if f.suffix in (".p", ".t")}
     return rep
 
 
@@ -70,7 +76,84 @@ def test_function_pointer_forms_record_the_same_evaluations(tmp_path, stem, ngen
         assert files["seam"] == committed, f"seam no longer reproduces tests/golden/{golden}.gold.gz"
 
 
+# Chain-batched generations.  oracle/patch_runchain.py cuts RunChain's chain loop in two around LogLike; the
+# seam queues every local chain's evaluation and sends one call per division and generation.  Here the seam's
+# backend is the CPU oracle (harness mode "oracle"), which is bit-exact on the FMA build -- so the batched run must
+# sample exactly what the unmodified reference samples: same accept / reject decisions, same trees, same lnL, every
+# generation.  (The reference's seed, proposals and acceptance draws are untouched: the acceptance variate is drawn
+# at the same position of the random stream.)
+needs_batched = pytest.mark.skipif(not BIN_BATCHED.exists(), reason="oracle/_ref/mb_b200_batched not built (needs /root/reference at build time)")
+
+
+@needs_harness
+@needs_batched
+@pytest.mark.parametrize("stem,ngen", [("primates_gtr_g4", 400), ("primates_hky_g4", 200), ("primates_gtr_ig4", 200), ("cynmix_full", 60)])
+def test_chain_batched_generations_reproduce_the_serial_reference(tmp_path, stem, ngen):
+    ref = run_harness(tmp_path, stem, ngen, "cpu", tag=".ref")                                  # the unmodified reference
+    ser = run_harness(tmp_path, stem, ngen, "cpu", binary=BIN_BATCHED, tag=".patched")          # patched loop, serial path
+    bat = run_harness(tmp_path, stem, ngen, "oracle", binary=BIN_BATCHED, tag=".batched")      # one call per generation
+    assert ref["samples"] and ref["samples"] == ser["samples"], "the patched RunChain changed the serial trajectory"
+    assert bat["batched_generations"] == ngen and bat["flushes"] == ngen and bat["unsupported_calls"] == 0, bat
+    assert bat["calls"] == ref["calls"] and bat["aborts"] == ref["aborts"]
+    assert bat["samples"] == ref["samples"], "chain-batched generations sample differently from the serial reference"
+
+
+# Dynamic rescaling (opt-in MB200_RESCALE=dynamic): nodes are rescaled every few levels instead of at every
+# node; an evaluation that trips the float-range guard is repeated at once with every node rescaled.  lnL then differs from
+# the always-rescale arithmetic by rounding only -- a run follows the reference run's decisions and stays within the
+# north-star tolerance of its lnL, generation by generation (CPU oracle as the seam's backend).
+def _lnl_columns(rep_stdout):
+    import re
+    return [[float(x) for x in re.findall(r"-\d+\.\d+", l)] for l in rep_stdout.splitlines() if re.match(r"^\s+\d+ -- ", l)]
+
+
+def _run_printing(tmp_path, stem, ngen, env, tag):
+    nex = tmp_path / f"r{tag}.nex"
+    text = (CMD / f"{stem}.nex").read_text().replace("NGEN", str(ngen)).replace("OUTPREFIX", str(tmp_path / f"o{tag}")) \
+                                          .replace("printfreq=100000", "printfreq=1")
+    nex.write_text(text)
+    report = tmp_path / f"r{tag}.json"
+    e = dict(os.environ, MB200_MODE="oracle", MB200_BATCH="1", MB200_REPORT=str(report))
+    e.update(env)
+    p = subprocess.run([str(BIN_BATCHED), str(nex)], cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return json.loads(report.read_text().strip().splitlines()[-1]), _lnl_columns(p.stdout)
+
+
+@needs_harness
+@needs_batched
+@pytest.mark.parametrize("env,min_retries", [
+    ({"MB200_RESCALE": "dynamic", "MB200_RESCALE_RUN": "3", "MB200_RESCALE_MAXFREQ": "8"}, 0),           # sparse rescaling
+    ({"MB200_RESCALE": "dynamic", "MB200_RESCALE_RUN": "4", "MB200_RESCALE_MAXFREQ": "1000"}, 1),        # ... until the guard trips
+    ({"MB200_RESCALE": "dynamic", "MB200_RESCALE_RUN": "4", "MB200_RESCALE_MAXFREQ": "6", "MB200_RESCALE_FORCE_RETRY": "1"}, 500),
+])
+def test_dynamic_rescaling_follows_the_always_rescale_run(tmp_path, env, min_retries):
+    ngen = 120
+    base, a = _run_printing(tmp_path, "cynmix_part", ngen, {}, "a")
+    dyn, b = _run_printing(tmp_path, "cynmix_part", ngen, env, "d")
+    assert base["rescale_retries"] == 0 and dyn["rescale_retries"] >= min_retries, dyn
+    assert dyn["aborts"] == base["aborts"] and dyn["calls"] == base["calls"] and dyn["batched_generations"] == ngen
+    assert len(a) == len(b) and len(a) >= ngen
+    worst = max(abs(u - v) / abs(u) for x, y in zip(a, b) for u, v in zip(sorted(x), sorted(y)))
+    assert worst < 1e-6, worst          # printed lnL of every chain, every generation (3 decimals of ~3e4: resolves 3e-8)
+
+
 # ---------------------------------------------------------------------------------------- GPU
+@needs_harness
+@needs_batched
+@pytest.mark.gpu
+@pytest.mark.parametrize("stem,ngen", [("primates_gtr_g4", 2000), ("cynmix_full", 200)])
+def test_chain_batched_generations_on_the_engine(tmp_path, engine_lib, stem, ngen):
+    """The engine driving the chain: all local chains of a generation in ONE launch per division == one launch per chain
+    (bit-identical lnL streams, hence identical samples), and both stay within the north-star tolerance of the
+    reference's own trajectory for as long as the two runs make the same decisions."""
+    one = run_harness(tmp_path, stem, ngen, "gpu", binary=BIN_BATCHED, extra_env={"MB200_BATCH": "0"}, tag=".serial")
+    bat = run_harness(tmp_path, stem, ngen, "gpu", binary=BIN_BATCHED, extra_env={"MB200_BATCH": "1"}, tag=".batched")
+    assert bat["batched_generations"] == ngen and bat["unsupported_calls"] == 0 and one["batched_generations"] == 0, (one, bat)
+    assert bat["calls"] == one["calls"] and bat["aborts"] == one["aborts"]
+    assert bat["samples"] and bat["samples"] == one["samples"], "chain-batched launches sample differently from per-chain launches"
+
+
 SHADOW_CASES = [
     # stem, generations, expected unsupported calls (None = any), min evaluations
     ("primates_gtr_g4", 2000, 0, 16000),
