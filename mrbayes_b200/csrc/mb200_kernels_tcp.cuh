@@ -73,6 +73,9 @@ template <int S> inline int tcp_stages (int K, size_t limit)
     return (int) n;
 }
 
+#ifndef TCP_BACKOFF_NS
+#define TCP_BACKOFF_NS 32
+#endif
 // mbarrier wait that cannot hang the device: a CTA whose pipeline stalls for two seconds traps (the launch fails
 // with an error instead of sitting on the GPU until somebody's watchdog fires)
 __device__ __forceinline__ void tcp_wait (uint64_t *bar, uint32_t parity)
@@ -86,6 +89,9 @@ __device__ __forceinline__ void tcp_wait (uint64_t *bar, uint32_t parity)
                       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                       "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(a), "r"(parity) : "memory");
         if (done) return;
+#ifndef TCP_NO_BACKOFF
+        __nanosleep (TCP_BACKOFF_NS);          // a waiting warp must not compete for issue slots with the working ones
+#endif
         if ((it & 0xfffu) == 0xfffu)
             {
             unsigned long long now;

@@ -73,6 +73,8 @@ extern int MB200RC_patched __attribute__((weak));   /* defined by the patched Ru
 static int        hBatch = 1;        /* MB200_BATCH */
 static int        hBatchActive = NO; /* this generation runs chain-batched */
 static long long  hFlushes = 0, hBatchedGens = 0;
+static double     hSecQueue = 0.0, hSecFlush = 0.0, hSecFinish = 0.0;   /* chain-batched generations: where sec_gpu goes */
+static double     hSecInit = 0.0;    /* calls that created an engine instance (CUDA context, buffers, tip upload): not in sec_gpu */
 static FILE      *hDump = NULL;
 static long       hDumpMax = -1, hDumped = 0;
 static double     hTol = 1e-6;
@@ -389,11 +391,11 @@ static void Report (void)
     fprintf (f, "{\"mb200_harness\": \"%s\", \"calls\": %lld, \"node_updates\": %lld, \"cl_updates\": %lld, "
                 "\"sec_cpu\": %.6f, \"sec_gpu\": %.6f, \"aborts\": %lld, \"unsupported_calls\": %lld, "
                 "\"compared\": %lld, \"failed\": %lld, \"max_rel\": %.3e, \"mean_rel\": %.3e, \"tol\": %.1e, \"dumped\": %ld, "
-                "\"via\": \"%s\", \"lnl_hash\": \"%016llx\", \"batched_generations\": %lld, \"flushes\": %lld, \"rescale_retries\": %lld}\n",
+                "\"via\": \"%s\", \"lnl_hash\": \"%016llx\", \"batched_generations\": %lld, \"flushes\": %lld, \"rescale_retries\": %lld, \"sec_queue\": %.6f, \"sec_flush\": %.6f, \"sec_finish\": %.6f, \"sec_init\": %.6f}\n",
              names[hMode], hCalls, hNodeUpdates, hUpdates, hSecCpu, hSecGpu, hAborts, hUnsupported,
              hCompared, hFailed, (hMaxRel == hMaxRel && hMaxRel < 1e300) ? hMaxRel : 9.999e99,
              (hCompared && hSumRel == hSumRel && hSumRel < 1e300) ? hSumRel / hCompared : (hCompared ? 9.999e99 : 0.0), hTol, hDumped,
-             hViaFn ? "fnptr" : "seam", hLnlHash, hBatchedGens, hFlushes, MB200SeamRescaleRetries ());
+             hViaFn ? "fnptr" : "seam", hLnlHash, hBatchedGens, hFlushes, MB200SeamRescaleRetries (), hSecQueue, hSecFlush, hSecFinish, hSecInit);
     if (f != stderr) fclose (f);
     if (hDump) { fclose (hDump); hDump = NULL; }
     if (hMode == MODE_SHADOW || ENGINE_DRIVES (hMode))
@@ -664,6 +666,7 @@ void MB200RC_Queue (int chain)
         }
     t0 = Now ();
     MB200BatchQueueLogLike (chain);
+    hSecQueue += Now () - t0;
     hSecGpu += Now () - t0;
 }
 
@@ -675,6 +678,7 @@ void MB200RC_Flush (void)
         return;
     t0 = Now ();
     MB200BatchFlush ();
+    hSecFlush += Now () - t0;
     hSecGpu += Now () - t0;
     hFlushes++;
 }
@@ -685,7 +689,12 @@ MrBFlt MB200RC_Finish (int chain)
 
     if (hBatchActive == NO)
         return MRBFLT_NEG_MAX;
+    {
+    double t0 = Now ();
     v = MB200BatchFinishLogLike (chain);
+    hSecFinish += Now () - t0;
+    hSecGpu += Now () - t0;
+    }
     if (abortMove == YES) hAborts++;
     HashLnl (v);
     return v;
@@ -717,6 +726,7 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
 
     if (ENGINE_DRIVES (hMode))
         {
+        const int fresh = (MB200SeamInstance (d) < 0);
         t0 = Now ();
         if (hViaFn)
             {
@@ -730,7 +740,8 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
             hUnsupported++;
             __real_LaunchLogLikeForDivision (chain, d, lnL);
             }
-        hSecGpu += Now () - t0;
+        if (fresh) hSecInit += Now () - t0;
+        else       hSecGpu += Now () - t0;
         if (abortMove == YES) hAborts++;
         return;
         }

@@ -17,7 +17,7 @@ def one(name):
     S, K, Cn, tips = bench.SYNTH[name]
     nch = int(os.environ.get("PROBE_CHAINS", "1"))
     pr = workloads.make_problem(S, K, Cn, tips, nch, seed=2026)
-    lib = abi.engine_library()
+    lib = abi.engine_library() if not os.environ.get("MB200_PROBE_LIB") else abi.Library(str(ROOT / "mrbayes_b200" / "lib" / os.environ["MB200_PROBE_LIB"]), "mb200_")
     with pr.create(lib) as inst:
         inst.evaluate(pr.full_evaluation(0))
         batch = inst.pack([pr.full_evaluation(c) for c in range(nch)])
