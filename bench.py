@@ -167,8 +167,13 @@ class Job:
         # the chains of a run start from the run's common tree (like a real run after burn-in they sit at
         # comparable likelihoods, so that heat swaps are actually accepted) and then go their own way
         import copy
-        trees = [copy.deepcopy(workloads.random_tree(w["tips"], np.random.default_rng([seed, g // self.chains]), mean_len=0.08))
-                 for g in self.globals]
+        # weak-scaling workloads (whole runs per GPU): every GPU gets the SAME two runs' trees and proposals (seeded by the
+        # chain's index within its process), so that the work per GPU is exactly equal and value(N) / (N value(1)) measures
+        # the machine, not the luck of the proposal draw; sharded workloads seed by the global chain (a chain's trajectory
+        # must not depend on which process owns it)
+        self.seed_ids = [(g - self.first) if w["scaling"] == "weak" else g for g in self.globals]
+        trees = [copy.deepcopy(workloads.random_tree(w["tips"], np.random.default_rng([seed, s // self.chains]), mean_len=0.08))
+                 for s in self.seed_ids]
         if name.startswith("primates"):
             self.parts = [primates_partition(self.n_local, trees)]
         elif name == "cynmix":
@@ -197,7 +202,7 @@ class Job:
         self.lnl0 = lnl0
         self.lnpr0 = np.array([self._lnprior(ch) for ch in range(nl)])
         snaps = [workloads.snapshot(pr) for pr in parts]
-        rngs = [np.random.default_rng([self.seed, 1, g]) for g in self.globals]
+        rngs = [np.random.default_rng([self.seed, 1, s]) for s in self.seed_ids]
         steps = [[None] * self.cycle_len for _ in parts]        # [part][step] -> list of specs (local chains)
         accept = np.zeros((self.cycle_len, nl), np.uint8)
         lnprior = np.zeros((self.cycle_len, nl))
@@ -802,7 +807,8 @@ def bench_engine(args):
                        "swaps_per_run_and_generation": w["swaps"],
                        "l2": "flushed before every timed step (256 MB memset); within a step the working set stays where a real run keeps it",
                        "sharding": ("whole runs per GPU (reference chain->process map): swap pairs co-resident, no data-path collective; "
-                                    "end-of-run ncclReduce of per-run lnL sums in the timed region" if w["scaling"] == "weak" else
+                                    "end-of-run ncclReduce of per-run lnL sums in the timed region; every GPU's runs replay the same "
+                                    "proposal cycle, so the work per GPU is exactly equal" if w["scaling"] == "weak" else
                                     "one run's heated chains dealt out over the GPUs in contiguous blocks; per swap generation one ncclAllGather of "
                                     "{lnL, lnPrior, chainId} per chain (24 B), overlapped with the next generation's launches; end-of-run ncclReduce")},
             "timed_region_ms": ms_value, "wall_ms_of_value_leg": ms_wall_value,

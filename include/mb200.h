@@ -102,6 +102,11 @@ extern "C" {
  * count and category, src/likelihood.c:10135-10173); the root pass includes the correction for
  * unobservable (dummy) patterns, Likelihood_Std's coding bias (src/likelihood.c:7401-7423, 7537). */
 #define MB200_CONFIG_VARIABLE_STATES 2
+/* Hint: the reference runs this division on its scalar kernels (SetLikeFunctions picks CondLikeDown_NUC4 / _Gen
+ * instead of the SIMD variants when ancestral states or site rates are reported, src/mcmc.c:17971-17992).  The
+ * engine's operation order does not depend on it (lnL agrees to rounding either way); a CPU restatement that
+ * reproduces the reference bit for bit (oracle/) follows the scalar kernels' order when it is set. */
+#define MB200_CONFIG_SCALAR_KERNELS 4
 
 /* evaluation flags */
 /* Root integration follows Likelihood_NUC4_{SSE,AVX,FMA}: when the site scaler is

@@ -78,6 +78,15 @@ typedef struct
     int                  origSite, origCijk, installed;     /* installed: chain whose set is in place, or -1 */
     int                  extraCl, extraTi, extraNs, extraEig;  /* buffers beyond the reference's own counts */
     MrBFlt             **extraCijks;        /* host eigensystem blocks appended to m->cijks for the extra slots */
+    /* host readers (MB200InstallReaders): the reference's own function pointers, what the host arrays currently mirror,
+       host buffers appended to m->condLikes / m->tiProbs / m->scalers for the chain-batching scratch sets */
+    LikeUpFxn            refCondLikeUp;
+    PrintAncStFxn        refPrintAncStates;
+    PrintSiteRateFxn     refPrintSiteRates;
+    long long            evalStamp, syncedStamp;
+    int                  syncedChain, syncedState, readers;
+    CLFlt              **hostExtra;         /* the appended host buffers (freed by the seam) */
+    int                  nHostExtra;
     /* dynamic rescaling (MB200_RESCALE=dynamic): per chain, the rescale frequency and the run of clean evaluations */
     int                 *dynFreq, *dynRun;
     int                 *extraFlip, *nExtraFlip, *queuedState;  /* [chain][capOps] nodes the retry flipped beyond the move's own;
@@ -108,19 +117,23 @@ static int be_eval (int i, const mb200_evaluation *e, int n, double *l, int *s) 
 static int be_begin (int i, const mb200_evaluation *e, int n)          { return mb200_evaluate_begin (i, e, n); }
 static int be_end (int i, double *l, int *s)                           { return mb200_evaluate_end (i, l, s); }
 static int be_pstates (int i, const int *n, const int *t, const int *b, int ml, int nd, int nu) { return mb200_set_pattern_states (i, n, t, b, ml, nd, nu); }
+static int be_getp (int i, int b, float *o)                            { return mb200_get_partials (i, b, o); }
+static int be_getm (int i, int m, float *o)                            { return mb200_get_transition_matrix (i, m, o); }
+static int be_gets (int i, int s, float *o)                            { return mb200_get_scalers (i, s, o); }
 
-static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates };
+static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates, be_getp, be_getm, be_gets };
 static int seamDeferred = NO;   /* YES: TreeLikelihood_Beagle only launches; SeamCollect fetches the result */
 static int seamBatchWanted = NO;    /* MB200BatchEnable: instances are created with per-chain scratch buffers */
 static int seamBatchQueue = NO;     /* YES while MB200BatchQueueLogLike assembles: evaluations are queued, not launched */
 static void SeamScratchCounts (ModelInfo *m, int *nCl, int *nTi, int *nNs);
+static int  SeamReadersWanted (ModelInfo *m);
 static void SeamDropDivision (int division);
 
 void MB200SeamSetBackend (const MB200SeamBackend *backend)
 {
     if (backend == NULL)
         {
-        MB200SeamBackend def = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates };
+        MB200SeamBackend def = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates, be_getp, be_getm, be_gets };
         seamBackend = def;
         }
     else
@@ -312,6 +325,12 @@ static int SeamStdMaxStates (ModelInfo *m)
     return n;
 }
 
+/* ancestral states or site rates requested for the division (its CL buffers are then read on the host at sample time) */
+static int SeamReadersWanted (ModelInfo *m)
+{
+    return (m->printAncStates == YES || m->printSiteRates == YES) ? YES : NO;
+}
+
 /* Which divisions the engine takes; everything else stays on the reference's own
  * function pointers, the way the reference keeps BEAGLE away from models it does
  * not cover (src/mcmc.c:5741-5775). */
@@ -324,7 +343,7 @@ int MB200SeamDivisionSupported (ModelInfo *m)
         if (SeamStdDivision (m) == NO || m->gibbsGamma == YES || m->correlation != NULL || m->nParsIntsPerSite != 1 ||
             m->numRateCats < 1 || m->numRateCats > MB200_MAX_CATEGORIES ||
             m->printAncStates == YES || m->printSiteRates == YES)
-            return NO;
+            return NO;                          /* (readers of the ragged Std buffers: not covered) */
         return YES;
         }
     if (m->dataType != DNA && m->dataType != RNA && m->dataType != PROTEIN)
@@ -347,8 +366,12 @@ int MB200SeamDivisionSupported (ModelInfo *m)
         return NO;
     if (m->nParsIntsPerSite != 1)
         return NO;
-    if (m->printAncStates == YES || m->printSiteRates == YES || m->printPosSel == YES || m->printSiteOmegas == YES)
-        return NO;                              /* host readers of CL buffers (src/mcmc.c:5761-5772) */
+    if (m->printPosSel == YES || m->printSiteOmegas == YES)
+        return NO;                              /* PosSelProbs / SiteOmegas read the CL buffers on the host (src/mcmc.c:5761-5772) */
+    if (SeamReadersWanted (m) == YES &&
+        (seamBackend.get_partials == NULL || seamBackend.get_transition_matrix == NULL || seamBackend.get_scalers == NULL ||
+         m->numOmegaCats != 1 || getenv ("MB200_NO_READERS") != NULL))
+        return NO;                              /* ancestral states / site rates without a read-back path */
     return YES;
 }
 
@@ -436,6 +459,8 @@ void MB200SeamDivisionConfig (ModelInfo *m, int division, mb200_instance_config 
     cfg->flags           = (SeamCategoryEigens (m) == YES) ? MB200_CONFIG_CIJK_PARTS (m->nCijkParts) : 0;
     if (m->dataType == STANDARD)
         cfg->flags      |= MB200_CONFIG_VARIABLE_STATES;
+    if (SeamReadersWanted (m) == YES && getenv ("MB200_DEBUG_NOSCALAR") == NULL)
+        cfg->flags      |= MB200_CONFIG_SCALAR_KERNELS;     /* the reference's scalar kernel family (src/mcmc.c:17971-17992) */
     cfg->matrix_count    = m->numTiProbs;
     cfg->scaler_count    = m->numScalers;
     cfg->eigen_count     = numLocalChains + 1;    /* unused (but harmless) for the inline-eigen models */
@@ -568,6 +593,9 @@ static void SeamDropDivision (int division)
     free (sd->matsArena);
     free (sd->eigArena);
     free (sd->qEv); free (sd->qChain); free (sd->qStatus); free (sd->qLnL);
+    for (c=0; c<sd->nHostExtra; c++)
+        free (sd->hostExtra[c]);
+    free (sd->hostExtra);
     free (sd->dynFreq); free (sd->dynRun); free (sd->extraFlip); free (sd->nExtraFlip); free (sd->queuedState);
     for (c=1; c<sd->nScratchChains; c++)
         {
@@ -579,7 +607,15 @@ static void SeamDropDivision (int division)
         }
     free (sd->scrCl); free (sd->scrTi); free (sd->scrNs); free (sd->scrUn); free (sd->scrSite); free (sd->scrCijk);
     free (sd->extraCijks);
+    {
+    /* the reference's reader pointers outlive the instance (the wrappers stay installed in ModelInfo) */
+    const LikeUpFxn        up = sd->refCondLikeUp;
+    const PrintAncStFxn    an = sd->refPrintAncStates;
+    const PrintSiteRateFxn sr = sd->refPrintSiteRates;
     memset (sd, 0, sizeof(SeamDivision));
+    sd->refCondLikeUp = up; sd->refPrintAncStates = an; sd->refPrintSiteRates = sr;
+    }
+    sd->syncedStamp = -1;
     sd->installed = -1;
     sd->instance = -1;
     memset (seamCijkSeen[division], 0, sizeof(seamCijkSeen[division]));
@@ -991,6 +1027,7 @@ static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL
     m  = &modelSettings[division];
     sd = &seamDiv[division];
 
+    sd->evalStamp++;
     sd->ev.root_buffer = m->condLikeIndex[chain][rootNode];
     sd->ev.weights_row = whichSitePats;
     sd->ev.flags       = 0;
@@ -1011,6 +1048,8 @@ static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL
     else if (m->numModelStates == 4 && (m->dataType == DNA || m->dataType == RNA))
         {
         sd->ev.flags |= MB200_FLAG_NUC4_PINVAR_QUIRK;   /* Likelihood_NUC4_* family */
+        if (SeamReadersWanted (m) == YES && getenv ("MB200_DEBUG_NOSHORT") == NULL)
+            sd->ev.flags |= MB200_FLAG_TIP_SHORTCUTS;   /* scalar CondLikeDown_NUC4: preLike shortcuts (src/likelihood.c:816-832) */
         if (sd->guard == YES)
             sd->ev.flags |= MB200_FLAG_RANGE_GUARD;     /* sparsely rescaled evaluation (dynamic scheme) */
         }
@@ -1063,6 +1102,23 @@ static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL
             }
         }
 
+    if (getenv ("MB200_SEAM_DEBUG") != NULL)
+        {
+        int i;
+        fprintf (stderr, "seam eval: div %d chain %d nMat %d nOp %d root %d wrow %d flags %d pinv %d %.17g dst %d src %d stamp %llx\n rates",
+                 division, chain, sd->ev.matrix_update_count, sd->ev.operation_count, sd->ev.root_buffer, sd->ev.weights_row, sd->ev.flags,
+                 sd->ev.has_p_invar, sd->ev.p_invar, sd->ev.site_scaler_dst, sd->ev.site_scaler_src, sd->tipStamp);
+        for (i=0; i<m->numRateCats; i++) fprintf (stderr, " %.17g", sd->ev.category_rates[i]);
+        fprintf (stderr, "\n w");
+        for (i=0; i<m->numRateCats; i++) fprintf (stderr, " %.17g", sd->ev.category_weights[i]);
+        fprintf (stderr, "\n f");
+        for (i=0; i<m->numModelStates; i++) fprintf (stderr, " %.17g", sd->ev.state_freqs[i]);
+        fprintf (stderr, "\n");
+        for (i=0; i<sd->ev.matrix_update_count; i++) fprintf (stderr, " m%d e%d %.17g", sd->mats[i].matrix, sd->mats[i].eigen, sd->mats[i].length);
+        fprintf (stderr, "\n");
+        for (i=0; i<sd->ev.operation_count; i++) fprintf (stderr, " [%d<-%d.%d %d.%d %d.%d w%d r%d]", sd->ops[i].dest, sd->ops[i].child1, sd->ops[i].matrix1, sd->ops[i].child2, sd->ops[i].matrix2, sd->ops[i].child3, sd->ops[i].matrix3, sd->ops[i].scale_write, sd->ops[i].scale_remove);
+        fprintf (stderr, "\n");
+        }
     if (seamBatchQueue == YES)
         {
         /* chain-batched generation: the evaluation waits in the division's queue until MB200BatchFlush
@@ -1746,6 +1802,142 @@ int MB200InstallLikeFunctions (int division)
     m->CondLikeRoot   = &CondLikeRoot_B200;
     m->CondLikeScaler = &CondLikeScaler_B200;
     m->Likelihood     = &Likelihood_B200;
+    return (NO_ERROR);
+}
+
+/* ======================================================================================
+ * Host readers of conditional-likelihood buffers.  CondLikeUp_* (src/likelihood.c:4574-4925),
+ * PrintAncStates_* (src/mcmc.c:10713, 10902) and PrintSiteRates_Gen (src/mcmc.c:12212) work on the host arrays
+ * m->condLikes / m->tiProbs / m->scalers of the cold chain at sample time (src/mcmc.c:13029, 13134-13153), through
+ * function pointers.  The engine owns those buffers, so the three pointers are wrapped: the first reader call after an
+ * evaluation copies the chain's CURRENT buffers (every interior node's conditional likelihoods, every branch's P(t), the
+ * site scalers) from the device into the host arrays, in the reference's scalar layout [k][c][s] -- which is the
+ * engine's own order -- and then the reference's reader runs unchanged.  The readers' scratch writes (the final-pass
+ * vectors go to the scratch slots, src/likelihood.c:4870-4873) stay on the host.
+ * ====================================================================================== */
+static int SeamHostBuffersFor (ModelInfo *m, SeamDivision *sd)
+{
+    /* chain batching gave the chains buffer indices beyond the reference's own counts: the host tables need entries
+       for them too (the reference frees its own numCondLikes / numTiProbs / numScalers entries and the table; the
+       appended buffers are the seam's) */
+    int     i, n = sd->extraCl + sd->extraTi + sd->extraNs;
+    CLFlt **tab;
+
+    if (n == 0 || sd->hostExtra != NULL)
+        return (NO_ERROR);
+    sd->hostExtra = (CLFlt **) SafeCalloc ((size_t)n, sizeof(CLFlt *));
+    if (!sd->hostExtra)
+        return (ERROR);
+    if (sd->extraCl > 0)
+        {
+        tab = (CLFlt **) SafeRealloc ((void *) m->condLikes, (size_t)(m->numCondLikes + sd->extraCl) * sizeof(CLFlt *));
+        if (!tab) return (ERROR);
+        m->condLikes = tab;
+        for (i=0; i<sd->extraCl; i++)
+            if ((tab[m->numCondLikes + i] = sd->hostExtra[sd->nHostExtra++] = (CLFlt *) SafeCalloc ((size_t)m->condLikeLength, sizeof(CLFlt))) == NULL)
+                return (ERROR);
+        }
+    if (sd->extraTi > 0)
+        {
+        tab = (CLFlt **) SafeRealloc ((void *) m->tiProbs, (size_t)(m->numTiProbs + sd->extraTi) * sizeof(CLFlt *));
+        if (!tab) return (ERROR);
+        m->tiProbs = tab;
+        for (i=0; i<sd->extraTi; i++)
+            if ((tab[m->numTiProbs + i] = sd->hostExtra[sd->nHostExtra++] = (CLFlt *) SafeCalloc ((size_t)m->tiProbLength, sizeof(CLFlt))) == NULL)
+                return (ERROR);
+        }
+    if (sd->extraNs > 0)
+        {
+        tab = (CLFlt **) SafeRealloc ((void *) m->scalers, (size_t)(m->numScalers + sd->extraNs) * sizeof(CLFlt *));
+        if (!tab) return (ERROR);
+        m->scalers = tab;
+        for (i=0; i<sd->extraNs; i++)
+            if ((tab[m->numScalers + i] = sd->hostExtra[sd->nHostExtra++] = (CLFlt *) SafeCalloc ((size_t)m->numChars, sizeof(CLFlt))) == NULL)
+                return (ERROR);
+        }
+    return (NO_ERROR);
+}
+
+static int SeamSyncHost (int division, int chain)
+{
+    ModelInfo    *m  = &modelSettings[division];
+    SeamDivision *sd = &seamDiv[division];
+    Tree         *t;
+    TreeNode     *p;
+    int           i, rc = MB200_SUCCESS;
+
+    if (sd->instance < 0 || m->condLikes == NULL || m->tiProbs == NULL || m->scalers == NULL)
+        return (ERROR);
+    if (sd->syncedStamp == sd->evalStamp && sd->syncedChain == chain && sd->syncedState == state[chain])
+        return (NO_ERROR);                      /* the host arrays mirror this state already */
+    if (SeamHostBuffersFor (m, sd) == ERROR)
+        return (ERROR);
+    t = GetTree (m->brlens, chain, state[chain]);
+    for (i=0; i<t->nNodes && rc == MB200_SUCCESS; i++)
+        {
+        p = t->allDownPass[i];
+        if (p->left != NULL && p->right != NULL)
+            rc = seamBackend.get_partials (sd->instance, m->condLikeIndex[chain][p->index], m->condLikes[m->condLikeIndex[chain][p->index]]);
+        if (rc == MB200_SUCCESS && p->anc != NULL && m->tiProbsIndex[chain][p->index] >= 0)
+            rc = seamBackend.get_transition_matrix (sd->instance, m->tiProbsIndex[chain][p->index], m->tiProbs[m->tiProbsIndex[chain][p->index]]);
+        }
+    if (rc == MB200_SUCCESS)
+        rc = seamBackend.get_scalers (sd->instance, m->siteScalerIndex[chain], m->scalers[m->siteScalerIndex[chain]]);
+    if (rc != MB200_SUCCESS)
+        {
+        MrBayesPrint ("%s   B200 engine: cannot read the buffers of division %d back (%s)\n", spacer, division+1, mb200_error_string (rc));
+        return (ERROR);
+        }
+    sd->syncedStamp = sd->evalStamp; sd->syncedChain = chain; sd->syncedState = state[chain];
+    return (NO_ERROR);
+}
+
+int CondLikeUp_B200 (TreeNode *p, int division, int chain)
+{
+    SeamDivision *sd = &seamDiv[division];
+    if (sd->refCondLikeUp == NULL || SeamSyncHost (division, chain) == ERROR)
+        return (ERROR);
+    return sd->refCondLikeUp (p, division, chain);
+}
+
+int PrintAncStates_B200 (TreeNode *p, int division, int chain)
+{
+    SeamDivision *sd = &seamDiv[division];
+    if (sd->refPrintAncStates == NULL || SeamSyncHost (division, chain) == ERROR)
+        return (ERROR);
+    return sd->refPrintAncStates (p, division, chain);
+}
+
+int PrintSiteRates_B200 (TreeNode *p, int division, int chain)
+{
+    SeamDivision *sd = &seamDiv[division];
+    if (sd->refPrintSiteRates == NULL || SeamSyncHost (division, chain) == ERROR)
+        return (ERROR);
+    return sd->refPrintSiteRates (p, division, chain);
+}
+
+/* what SetLikeFunctions would do for a covered division that reports ancestral states or site rates; call it after
+   SetLikeFunctions (it runs for every mcmc command) -- idempotent */
+int MB200InstallReaders (int division)
+{
+    ModelInfo    *m;
+    SeamDivision *sd;
+
+    SeamInit ();
+    if (division < 0 || division >= numCurrentDivisions || division >= SEAM_MAX_DIVISIONS)
+        return (ERROR);
+    m  = &modelSettings[division];
+    sd = &seamDiv[division];
+    if (SeamReadersWanted (m) == NO || MB200SeamDivisionSupported (m) == NO)
+        return (ERROR);
+    if (m->CondLikeUp != &CondLikeUp_B200 && m->CondLikeUp != NULL)
+        { sd->refCondLikeUp = m->CondLikeUp; m->CondLikeUp = &CondLikeUp_B200; }
+    if (m->PrintAncStates != &PrintAncStates_B200 && m->PrintAncStates != NULL)
+        { sd->refPrintAncStates = m->PrintAncStates; m->PrintAncStates = &PrintAncStates_B200; }
+    if (m->PrintSiteRates != &PrintSiteRates_B200 && m->PrintSiteRates != NULL)
+        { sd->refPrintSiteRates = m->PrintSiteRates; m->PrintSiteRates = &PrintSiteRates_B200; }
+    sd->readers = YES;
+    sd->syncedStamp = -1;
     return (NO_ERROR);
 }
 

@@ -50,6 +50,16 @@ int       CondLikeRoot_B200   (TreeNode *p, int division, int chain);
 int       CondLikeScaler_B200 (TreeNode *p, int division, int chain);
 int       Likelihood_B200     (TreeNode *p, int division, int chain, MrBFlt *lnL, int whichSitePats);
 int       MB200InstallLikeFunctions (int division);
+/* Host readers of conditional-likelihood buffers: CondLikeUp_* (src/likelihood.c:4574-4925),
+ * PrintAncStates_* (src/mcmc.c:10713, 10902), PrintSiteRates_Gen (src/mcmc.c:12212) run on the HOST arrays m->condLikes /
+ * m->tiProbs / m->scalers at sample time (src/mcmc.c:13029, 13141, 13151).  MB200InstallReaders wraps the three function
+ * pointers of a division: before the reference's own reader runs, the cold chain's current buffers are copied from the
+ * device into those arrays (once per evaluation state).  Returns ERROR when the division needs no readers or the backend
+ * has no read-back. */
+int       CondLikeUp_B200     (TreeNode *p, int division, int chain);
+int       PrintAncStates_B200 (TreeNode *p, int division, int chain);
+int       PrintSiteRates_B200 (TreeNode *p, int division, int chain);
+int       MB200InstallReaders (int division);
 long long MB200SeamUpdateCount (int division);   /* node*pattern*rate CL updates issued  */
 long long MB200SeamRescaleRetries (void);        /* MB200_RESCALE=dynamic: evaluations repeated after an underflow */
 int       MB200SeamInstance (int division);      /* engine instance of a division, or -1 */
@@ -72,6 +82,11 @@ typedef struct
     int (*set_pattern_states)  (int instance, const int *state_counts, const int *matrix_offsets,
                                 const int *freq_offsets, int matrix_length, int dummy_patterns,
                                 int uncompressed_sites);
+    /* optional read-back (host readers of conditional-likelihood buffers, MB200InstallReaders); NULL: divisions
+       that report ancestral states / site rates stay on the reference's kernels */
+    int (*get_partials)          (int instance, int buffer, float *out);
+    int (*get_transition_matrix) (int instance, int matrix, float *out);
+    int (*get_scalers)           (int instance, int scaler, float *out);
     } MB200SeamBackend;
 
 void      MB200SeamSetBackend (const MB200SeamBackend *backend);   /* NULL = the engine  */

@@ -292,6 +292,12 @@ static int rec_cijk (int inst, int eigen, const double *block)
     return MB200_SUCCESS;
 }
 
+static int rec_noread (int inst, int index, float *out)
+{
+    (void) inst; (void) index; (void) out;
+    return MB200_ERROR_UNSUPPORTED;
+}
+
 static int rec_eval (int inst, const mb200_evaluation *e, int n, double *lnL, int *status)
 {
     int i;
@@ -414,16 +420,21 @@ static struct
     int (*cijk) (int, int, const double *);
     int (*eval) (int, const mb200_evaluation *, int, double *, int *);
     int (*pstates) (int, const int *, const int *, const int *, int, int, int);
+    int (*getp) (int, int, float *);
+    int (*getm) (int, int, float *);
+    int (*gets) (int, int, float *);
     } hOrc;
 
 static int orc_create (const mb200_instance_config *c, int *inst)
 {
     int rc = hOrc.create (c, inst);
+    int fma = 0;
 #   if defined (HAVE_FMA3) || defined (FMA_ENABLED)
-    if (rc == MB200_SUCCESS) hOrc.arith (*inst, 1);     /* ORC_ARITH_FMA: this binary's reference objects use the FMA kernels */
-#   else
-    if (rc == MB200_SUCCESS) hOrc.arith (*inst, 0);
+    fma = 1;                                            /* ORC_ARITH_FMA: this binary's reference objects use the FMA kernels ... */
 #   endif
+    if (c->flags & MB200_CONFIG_SCALAR_KERNELS)
+        fma = 0;                                        /* ... except where the reference itself falls back to its scalar kernels */
+    if (rc == MB200_SUCCESS) hOrc.arith (*inst, fma);
     return rc;
 }
 
@@ -453,6 +464,9 @@ static void LoadOracle (void)
     hOrc.cijk     = (int (*) (int, int, const double *)) dlsym (hOrc.lib, "orc_set_cijk");
     hOrc.eval     = (int (*) (int, const mb200_evaluation *, int, double *, int *)) dlsym (hOrc.lib, "orc_evaluate");
     hOrc.pstates  = (int (*) (int, const int *, const int *, const int *, int, int, int)) dlsym (hOrc.lib, "orc_set_pattern_states");
+    hOrc.getp     = (int (*) (int, int, float *)) dlsym (hOrc.lib, "orc_get_partials");
+    hOrc.getm     = (int (*) (int, int, float *)) dlsym (hOrc.lib, "orc_get_transition_matrix");
+    hOrc.gets     = (int (*) (int, int, float *)) dlsym (hOrc.lib, "orc_get_scalers");
     if (!hOrc.create || !hOrc.finalize || !hOrc.arith || !hOrc.tips || !hOrc.weights || !hOrc.cijk || !hOrc.eval || !hOrc.pstates)
         { fprintf (stderr, "oracle mode: %s lacks part of the orc_ API\n", path); exit (2); }
 }
@@ -488,7 +502,13 @@ static void Setup (void)
         }
     if (hMode == MODE_DUMP || hMode == MODE_SHADOW)
         {
-        MB200SeamBackend be = { rec_create, rec_finalize, rec_tips, rec_weights, rec_cijk, rec_eval, NULL, NULL, rec_pstates };
+        MB200SeamBackend be = { rec_create, rec_finalize, rec_tips, rec_weights, rec_cijk, rec_eval, NULL, NULL, rec_pstates, NULL, NULL, NULL };
+        if (hMode == MODE_SHADOW)
+            {
+            /* the reference drives and its own readers see its own host arrays (the wrappers are not installed): a nominal
+               read-back lets divisions that report ancestral states / site rates be shadowed like any other */
+            be.get_partials = rec_noread; be.get_transition_matrix = rec_noread; be.get_scalers = rec_noread;
+            }
         MB200SeamSetBackend (&be);
         }
     if (hMode == MODE_ORACLE)
@@ -500,6 +520,7 @@ static void Setup (void)
         be.set_cijk = hOrc.cijk;               be.evaluate = hOrc.eval;
         be.evaluate_begin = NULL;              be.evaluate_end = NULL;
         be.set_pattern_states = hOrc.pstates;
+        be.get_partials = hOrc.getp; be.get_transition_matrix = hOrc.getm; be.get_scalers = hOrc.gets;
         MB200SeamSetBackend (&be);
         }
     if (ENGINE_DRIVES (hMode) && hBatch && &MB200RC_patched != NULL)
@@ -628,6 +649,14 @@ int MB200RC_Begin (void)
 {
     if (hMode < 0)
         Setup ();
+    if (ENGINE_DRIVES (hMode))
+        {
+        int d;
+        for (d=0; d<numCurrentDivisions; d++)
+            if ((modelSettings[d].printAncStates == YES || modelSettings[d].printSiteRates == YES) &&
+                modelSettings[d].PrintSiteRates != &PrintSiteRates_B200)
+                MB200InstallReaders (d);
+        }
     hBatchActive = (hBatch && ENGINE_DRIVES (hMode) && !hViaFn) ? MB200BatchBegin () : NO;
     if (hBatchActive == YES)
         hBatchedGens++;
@@ -727,6 +756,8 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
     if (ENGINE_DRIVES (hMode))
         {
         const int fresh = (MB200SeamInstance (d) < 0);
+        if ((m->printAncStates == YES || m->printSiteRates == YES) && m->PrintSiteRates != &PrintSiteRates_B200)
+            MB200InstallReaders (d);            /* what SetLikeFunctions would do (it runs again for every mcmc command) */
         t0 = Now ();
         if (hViaFn)
             {

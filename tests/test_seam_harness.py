@@ -138,11 +138,42 @@ def test_dynamic_rescaling_follows_the_always_rescale_run(tmp_path, env, min_ret
     assert worst < 1e-6, worst          # printed lnL of every chain, every generation (3 decimals of ~3e4: resolves 3e-8)
 
 
+# Host readers of conditional-likelihood buffers: ancestral states at a constrained node and site rates are
+# computed by the reference's own CondLikeUp_* / PrintAncStates_* / PrintSiteRates_* on its host arrays at sample time; the
+# seam wraps the three function pointers and copies the cold chain's buffers back first (MB200InstallReaders).  The
+# reference's own numbers cannot serve as the yardstick here: with these reports on it switches to its scalar kernels
+# (src/mcmc.c:17971-17992), which in this snapshot return lnL -1559.354 for two DIFFERENT starting trees of primates where
+# its SIMD kernels, the oracle and the engine agree on -8019.475 / -7576.147 / -7942.846 for such states (shadow mode
+# against the oracle shows it evaluation by evaluation; the covarion models use the same scalar path).  So: the run must be
+# driven entirely by the engine side, batched and serial must sample the same, and what the readers print must be
+# probabilities and rates.
+@needs_harness
+@needs_batched
+def test_host_readers_of_cl_buffers_run_on_synced_buffers(tmp_path):
+    ngen = 100
+    ser = run_harness(tmp_path, "primates_readers", ngen, "oracle", binary=BIN_BATCHED, extra_env={"MB200_BATCH": "0"}, tag=".s")
+    bat = run_harness(tmp_path, "primates_readers", ngen, "oracle", binary=BIN_BATCHED, extra_env={"MB200_BATCH": "1"}, tag=".b")
+    assert ser["unsupported_calls"] == 0 and bat["unsupported_calls"] == 0 and bat["batched_generations"] == ngen
+    assert ser["samples"] and ser["samples"] == bat["samples"]
+    lines = [l for l in ser["samples"][".p"].splitlines() if l and not l.startswith("[")]
+    head, rows = lines[0].split("\t"), [l.split("\t") for l in lines[1:]]
+    anc = [i for i, h in enumerate(head) if h.startswith("p(")]
+    rate = [i for i, h in enumerate(head) if h.startswith("r(") and h[2:-1].isdigit()]
+    lnl = head.index("lnLike")
+    assert len(anc) % 4 == 0 and len(anc) >= 4 * 800 and len(rate) >= 800 and len(rows) >= 5
+    for r in rows:
+        assert -9000.0 < float(r[lnl]) < -5000.0            # what primates allows; the reference's scalar path says -1559
+        for i in range(0, len(anc), 4):
+            p4 = [float(r[j]) for j in anc[i:i + 4]]
+            assert all(0.0 <= x <= 1.0 for x in p4) and abs(sum(p4) - 1.0) < 1e-5
+        assert all(0.0 < float(r[j]) < 100.0 for j in rate)
+
+
 # ---------------------------------------------------------------------------------------- GPU
 @needs_harness
 @needs_batched
 @pytest.mark.gpu
-@pytest.mark.parametrize("stem,ngen", [("primates_gtr_g4", 2000), ("cynmix_full", 200)])
+@pytest.mark.parametrize("stem,ngen", [("primates_gtr_g4", 2000), ("cynmix_full", 200), ("primates_readers", 200)])
 def test_chain_batched_generations_on_the_engine(tmp_path, engine_lib, stem, ngen):
     """The engine driving the chain: all local chains of a generation in ONE launch per division == one launch per chain
     (bit-identical lnL streams, hence identical samples), and both stay within the north-star tolerance of the
