@@ -776,12 +776,15 @@ def bench_engine(args):
 
     # ---- reduce over ranks: MAX time, SUM work ----
     vals = torch.tensor([ms_value, wall_value * 1e3, wall_e2e * 1e3], dtype=torch.float64, device=dev)
-    sums = torch.tensor([updates, float(launches), updates_e2e], dtype=torch.float64, device=dev)
+    # accepted swaps: every process of a sharded run takes every decision (global count on each rank); whole runs per GPU count their own
+    sums = torch.tensor([updates, float(launches), updates_e2e, float(swaps_acc) if w["scaling"] == "weak" else 0.0], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     ms_value, ms_wall_value, ms_e2e = (float(x) for x in vals.tolist())
-    all_updates, all_launches, all_updates_e2e = (float(x) for x in sums.tolist())
+    all_updates, all_launches, all_updates_e2e, swaps_sum = (float(x) for x in sums.tolist())
+    if w["scaling"] == "weak":
+        swaps_acc = swaps_sum
     decision_hash = mc.decision_hash()
 
     roof = kernel_roofline(torch, job, flush, peaks, local) if rank == 0 else None

@@ -107,13 +107,13 @@ def _lnl_columns(rep_stdout):
     return [[float(x) for x in re.findall(r"-\d+\.\d+", l)] for l in rep_stdout.splitlines() if re.match(r"^\s+\d+ -- ", l)]
 
 
-def _run_printing(tmp_path, stem, ngen, env, tag):
+def _run_printing(tmp_path, stem, ngen, env, tag, mode="oracle"):
     nex = tmp_path / f"r{tag}.nex"
     text = (CMD / f"{stem}.nex").read_text().replace("NGEN", str(ngen)).replace("OUTPREFIX", str(tmp_path / f"o{tag}")) \
                                           .replace("printfreq=100000", "printfreq=1")
     nex.write_text(text)
     report = tmp_path / f"r{tag}.json"
-    e = dict(os.environ, MB200_MODE="oracle", MB200_BATCH="1", MB200_REPORT=str(report))
+    e = dict(os.environ, MB200_MODE=mode, MB200_BATCH="1", MB200_REPORT=str(report))
     e.update(env)
     p = subprocess.run([str(BIN_BATCHED), str(nex)], cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
@@ -169,6 +169,25 @@ def test_host_readers_of_cl_buffers_run_on_synced_buffers(tmp_path):
         assert all(0.0 < float(r[j]) < 100.0 for j in rate)
 
 
+# Covarion divisions are opt-in (MB200_COVARION=1): the reference evaluates them with its scalar kernels, whose lnL in this
+# snapshot is not a likelihood of the data (-1558 on primates; see the readers test above), so there is no reference value
+# to compare with.  What can be checked: the seam takes the division, batched == per-chain, lnL is in the data's range.
+@needs_harness
+@needs_batched
+def test_covarion_division_is_opt_in(tmp_path):
+    ngen = 100
+    off = run_harness(tmp_path, "primates_covarion", 20, "oracle", binary=BIN_BATCHED, tag=".off")
+    assert off["unsupported_calls"] == off["calls"] > 0                 # default: left to the reference
+    env = {"MB200_COVARION": "1"}
+    ser = run_harness(tmp_path, "primates_covarion", ngen, "oracle", binary=BIN_BATCHED, extra_env=dict(env, MB200_BATCH="0"), tag=".s")
+    bat = run_harness(tmp_path, "primates_covarion", ngen, "oracle", binary=BIN_BATCHED, extra_env=dict(env, MB200_BATCH="1"), tag=".b")
+    assert ser["unsupported_calls"] == 0 and bat["unsupported_calls"] == 0 and bat["batched_generations"] == ngen
+    assert ser["samples"] and ser["samples"] == bat["samples"]
+    lines = [l for l in ser["samples"][".p"].splitlines() if l and not l.startswith("[")]
+    lnl = lines[0].split("\t").index("lnLike")
+    assert all(-9500.0 < float(l.split("\t")[lnl]) < -5000.0 for l in lines[1:])
+
+
 # ---------------------------------------------------------------------------------------- GPU
 @needs_harness
 @needs_batched
@@ -183,6 +202,23 @@ def test_chain_batched_generations_on_the_engine(tmp_path, engine_lib, stem, nge
     assert bat["batched_generations"] == ngen and bat["unsupported_calls"] == 0 and one["batched_generations"] == 0, (one, bat)
     assert bat["calls"] == one["calls"] and bat["aborts"] == one["aborts"]
     assert bat["samples"] and bat["samples"] == one["samples"], "chain-batched launches sample differently from per-chain launches"
+
+
+@needs_harness
+@needs_batched
+@pytest.mark.gpu
+def test_covarion_on_the_engine_follows_the_oracle_run(tmp_path, engine_lib):
+    """Engine (generic-state kernel, 8 states, per-category eigensystems) vs the CPU oracle as the seam's backend on the
+    same command: the two runs print the same lnL, generation by generation, within the north-star tolerance for as long
+    as they make the same decisions (at least the first 30 generations)."""
+    env = {"MB200_COVARION": "1"}
+    ro, lo = _run_printing(tmp_path, "primates_covarion", 60, env, ".co", mode="oracle")
+    rg, lg = _run_printing(tmp_path, "primates_covarion", 60, env, ".cg", mode="gpu")
+    assert rg["unsupported_calls"] == 0 and rg["batched_generations"] == 60 and ro["calls"] == rg["calls"]
+    assert len(lo) >= 60 and len(lg) >= 60
+    for g in range(30):
+        for a, b in zip(lo[g], lg[g]):
+            assert abs(a - b) <= 1e-6 * abs(a) + 2e-3, (g, lo[g], lg[g])      # 3 decimals are printed
 
 
 SHADOW_CASES = [
