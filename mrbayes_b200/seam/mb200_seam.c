@@ -28,6 +28,7 @@
  * No reference source text is copied: only the public structs and function
  * prototypes of the reference headers are used.
  */
+#include <time.h>
 #include "bayes.h"
 #include "likelihood.h"
 #include "mbbeagle.h"
@@ -155,6 +156,30 @@ static void SeamInit (void)
 }
 
 /* dynamic rescaling: evaluations repeated with every node rescaled after an underflow (all divisions) */
+/* host time spent on eigensystems (UpDateCijk: rate matrix, GetEigens, CalcCijk) and on shipping them to the engine */
+static double    seamSecCijk = 0.0, seamSecCijkUpload = 0.0;
+static long long seamCijkUpdates = 0;
+static double SeamNow (void)
+{
+    struct timespec ts;
+    clock_gettime (CLOCK_MONOTONIC, &ts);
+    return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+static int SeamUpDateCijk (int d, int chain)
+{
+    double t0 = SeamNow ();
+    int    rc = UpDateCijk (d, chain);
+    seamSecCijk += SeamNow () - t0;
+    seamCijkUpdates++;
+    return rc;
+}
+void MB200SeamCijkTimes (double *secHost, double *secUpload, long long *updates)
+{
+    if (secHost)   *secHost = seamSecCijk;
+    if (secUpload) *secUpload = seamSecCijkUpload;
+    if (updates)   *updates = seamCijkUpdates;
+}
+
 long long MB200SeamRescaleRetries (void)
 {
     long long n = 0;
@@ -1277,8 +1302,10 @@ static int SeamSyncCijk (ModelInfo *m, SeamDivision *sd, int d, int chain)
         return (ERROR);
     if (m->upDateCijk == YES || (seamCijkSeen[d][idx >> 3] & (1 << (idx & 7))) == 0)
         {
+        double t0 = SeamNow ();
         if (seamBackend.set_cijk (sd->instance, idx, m->cijks[idx]) != MB200_SUCCESS)
             return (ERROR);
+        seamSecCijkUpload += SeamNow () - t0;
         seamCijkSeen[d][idx >> 3] |= (unsigned char)(1 << (idx & 7));
         }
     return (NO_ERROR);
@@ -1339,7 +1366,7 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
            UpDateCijk when flagged (src/likelihood.c:7864), which is a no-op for these models */
         if (m->upDateCijk == YES)
             {
-            if (UpDateCijk (d, chain) == ERROR)
+            if (SeamUpDateCijk (d, chain) == ERROR)
                 {
                 (*lnL) = MRBFLT_NEG_MAX;
                 return (YES);
@@ -1359,7 +1386,7 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
 
     if (m->upDateCijk == YES)
         {
-        if (UpDateCijk (d, chain) == ERROR)
+        if (SeamUpDateCijk (d, chain) == ERROR)
             {
             (*lnL) = MRBFLT_NEG_MAX;    /* effectively abort the move */
             return (YES);

@@ -61,6 +61,7 @@ int       PrintAncStates_B200 (TreeNode *p, int division, int chain);
 int       PrintSiteRates_B200 (TreeNode *p, int division, int chain);
 int       MB200InstallReaders (int division);
 long long MB200SeamUpdateCount (int division);   /* node*pattern*rate CL updates issued  */
+void      MB200SeamCijkTimes (double *secHost, double *secUpload, long long *updates);   /* eigensystem work on the host */
 long long MB200SeamRescaleRetries (void);        /* MB200_RESCALE=dynamic: evaluations repeated after an underflow */
 int       MB200SeamInstance (int division);      /* engine instance of a division, or -1 */
 
