@@ -27,6 +27,8 @@
  *                                src/utils.c:9734)
  *   mb200_set_eigen_decomposition  beagleSetEigenDecomposition
  *                                (src/likelihood.c:10652)
+ *   mb200_set_rate_matrices      GetEigens + CalcCijk inside UpDateCijk
+ *                                (src/likelihood.c:10626-10760, src/utils.c:11201)
  *   mb200_update_transition_matrices  TiProbs_Gen (src/likelihood.c:9424) /
  *                                TreeTiProbs_Beagle (src/mbbeagle.c:1368)
  *   mb200_update_partials        CondLikeDown_* / CondLikeRoot_* /
@@ -243,6 +245,15 @@ int mb200_set_cijk (int instance, int eigen, const double *block);
  * the device */
 int mb200_set_eigen_decomposition (int instance, int eigen, const double *eigvecs,
                                    const double *inverse_eigvecs, const double *eigvals);
+/* The eigensolver itself on the device: replaces the host half of UpDateCijk (GetEigens src/utils.c:11201 +
+ * CalcCijk src/utils.c:9734, called at src/likelihood.c:10626-10760).  rate_matrices = the slot's Q matrices
+ * as SetNucQMatrix / SetProteinQMatrix fill them (row-major S x S, one per eigen part: category_count of them
+ * for instances created with omega categories, else one), already scaled the way UpDateCijk scales them;
+ * state_freqs = the stationary frequencies (all > 0) the matrices are reversible with respect to
+ * (pi_i q_ij == pi_j q_ji; the caller checks, the solver symmetrises).  Asynchronous: the call returns after
+ * queueing the copy and two kernels on the instance's stream; a failure to converge is reported by the next
+ * mb200_evaluate / _end as MB200_ERROR_GENERAL.  S <= 64, not for variable-state instances. */
+int mb200_set_rate_matrices (int instance, int eigen, const double *rate_matrices, const double *state_freqs);
 
 /* ---- node-granular verbs (the function-pointer / BEAGLE-verb level) ---------------- */
 int mb200_update_transition_matrices (int instance, const mb200_matrix_update *updates,

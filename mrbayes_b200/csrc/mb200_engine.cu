@@ -8,6 +8,7 @@
 #include "mb200_kernels.cuh"
 #include "mb200_kernels_tc.cuh"
 #include "mb200_kernels_tcp.cuh"
+#include "mb200_kernels_eigen.cuh"
 #include "mb200_kernels_std.cuh"
 
 #include <cuda_runtime.h>
@@ -68,6 +69,12 @@ struct Instance
     int           tcpStages = 0;         // pipelined tensor-core kernel: operand-ring stages that fit (0: kernel not usable)
     size_t        tcpSmem = 0;
     double       *dFactor = nullptr;    // large state counts: rank-one factors (U, W) of every eigensystem's c_ijk slices
+    // device eigensolver (mb200_set_rate_matrices): per slot [parts x S x S rate matrices | S frequencies]
+    double       *dEigIn = nullptr, *hEigIn = nullptr;     // device copy and its pinned staging
+    double       *dEigVec = nullptr;     // [slot][part][V | V^-1]; == dFactor where the P(t) kernel wants the factors anyway
+    int          *hEigStatus = nullptr;  // mapped: non-zero = the Jacobi iteration did not converge
+    size_t        eigInStride = 0;
+    std::vector<cudaEvent_t> evEigIn;    // per slot: the staging area has been read
     uint64_t     *dInvMask = nullptr;
     double       *dTilePartial = nullptr;
     int          *dTileAbort = nullptr;
@@ -933,6 +940,13 @@ int runEnd (Instance *I, double *lnL, int *status)
             if (status) status[e] = MB200_EVAL_OK;
             }
         }
+    if (I->hEigStatus && *(volatile int *) I->hEigStatus != 0)
+        {
+        // an eigensystem this launch (or an earlier one) read did not converge: nothing computed from it can be used
+        *(volatile int *) I->hEigStatus = 0;
+        fprintf (stderr, "mb200: device eigensolver did not converge\n");
+        return MB200_ERROR_GENERAL;
+        }
     return MB200_SUCCESS;
 }
 
@@ -955,6 +969,10 @@ void destroy (Instance *I)
     cudaFree (I->dTilePartial); cudaFree (I->dTileAbort); cudaFree (I->dTicket); cudaFree (I->dDbg);
     cudaFree (I->dStdTab); cudaFree (I->dStdClasses); cudaFree (I->dTilePartial2);
     cudaFree (I->dTcCounter); cudaFree (I->dTcFlags); cudaFree (I->dTcError);
+    cudaFree (I->dEigIn); if (I->dEigVec != I->dFactor) cudaFree (I->dEigVec);
+    if (I->hEigIn) cudaFreeHost (I->hEigIn);
+    if (I->hEigStatus) cudaFreeHost (I->hEigStatus);
+    for (cudaEvent_t e : I->evEigIn) cudaEventDestroy (e);
     if (I->hostStage) cudaFreeHost (I->hostStage);
     for (cudaEvent_t e : I->evA) cudaEventDestroy (e);
     for (cudaEvent_t e : I->evB) cudaEventDestroy (e);
@@ -1311,6 +1329,51 @@ int mb200_set_eigen_decomposition (int instance, int eigen, const double *V, con
     cudaError_t e = cudaStreamSynchronize (I->stream);
     cudaFree (tmp);
     CK (e);
+    return MB200_SUCCESS;
+}
+
+// Rate matrices in, eigensystems out, all on the instance's stream: nothing here waits for the device.
+int mb200_set_rate_matrices (int instance, int eigen, const double *Q, const double *pi)
+{
+    Instance *I = get (instance);
+    if (!I) return MB200_ERROR_BAD_INSTANCE;
+    if (eigen < 0 || eigen >= I->cfg.eigen_count || !Q || !pi) return MB200_ERROR_OUT_OF_RANGE;
+    const int S = I->cfg.state_count, parts = I->cijkParts;
+    if (I->std || S < 2 || S > MB200_EIG_NMAX) return MB200_ERROR_UNSUPPORTED;
+    for (int s = 0; s < S; s++)
+        if (!(pi[s] > 0.0)) return MB200_ERROR_OUT_OF_RANGE;           // sqrt(pi) scales the similarity transform
+    int rc = use (I); if (rc) return rc;
+    const size_t n2 = (size_t)S * S;
+    if (!I->dEigIn)
+        {
+        I->eigInStride = (size_t)parts * n2 + S;
+        const size_t bytes = (size_t)I->cfg.eigen_count * I->eigInStride * sizeof(double);
+        CK (cudaMalloc ((void **)&I->dEigIn, bytes));
+        CK (cudaHostAlloc ((void **)&I->hEigIn, bytes, cudaHostAllocDefault));
+        CK (cudaHostAlloc ((void **)&I->hEigStatus, sizeof(int), cudaHostAllocMapped));
+        *I->hEigStatus = 0;
+        if (I->dFactor) I->dEigVec = I->dFactor;
+        else CK (cudaMalloc ((void **)&I->dEigVec, (size_t)I->cfg.eigen_count * parts * 2 * n2 * sizeof(double)));
+        I->evEigIn.resize (I->cfg.eigen_count);
+        for (auto &e : I->evEigIn) CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+        CK (cudaFuncSetAttribute (eigen_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) eigen_smem_bytes ()));
+        }
+    else
+        CK (cudaEventSynchronize (I->evEigIn[eigen]));                 // the slot's previous matrices have left the staging area
+    double *h = I->hEigIn + (size_t)eigen * I->eigInStride, *d = I->dEigIn + (size_t)eigen * I->eigInStride;
+    memcpy (h, Q, (size_t)parts * n2 * sizeof(double));
+    memcpy (h + (size_t)parts * n2, pi, (size_t)S * sizeof(double));
+    CK (cudaMemcpyAsync (d, h, I->eigInStride * sizeof(double), cudaMemcpyHostToDevice, I->stream));
+    CK (cudaEventRecord (I->evEigIn[eigen], I->stream));
+    int *dStatus = nullptr;
+    CK (cudaHostGetDevicePointer ((void **)&dStatus, I->hEigStatus, 0));
+    double *vec = I->dEigVec + (size_t)eigen * parts * 2 * n2, *block = I->dEigen + (size_t)eigen * I->eigenStride;
+    eigen_jacobi_kernel<<<parts, MB200_EIG_THREADS, eigen_smem_bytes (), I->stream>>> (d, d + (size_t)parts * n2, S, vec, block, dStatus);
+    const size_t n3 = n2 * S;
+    int blocks = (int)((n3 + 255) / 256); if (blocks > 512) blocks = 512;
+    cijk_parts_kernel<<<dim3 (blocks, parts), 256, 0, I->stream>>> (block, vec, S);
+    CK (cudaGetLastError ());
+    I->launches += 2; I->launchKind[MB200_KERNEL_SETUP] += 2;
     return MB200_SUCCESS;
 }
 

@@ -44,6 +44,8 @@ extern int *chainId;
 extern int  numLocalChains;
 /* defined in src/likelihood.c:70, not declared in likelihood.h */
 int UpDateCijk (int whichPart, int whichChain);
+int SetNucQMatrix (MrBFlt **a, int n, int whichChain, int division, MrBFlt rateMult, MrBFlt *rA, MrBFlt *rS);   /* src/likelihood.c:8166 */
+int SetProteinQMatrix (MrBFlt **a, int n, int whichChain, int division, MrBFlt rateMult);                        /* src/likelihood.c:8765 */
 
 #define SEAM_MAX_DIVISIONS 512
 
@@ -121,8 +123,9 @@ static int be_pstates (int i, const int *n, const int *t, const int *b, int ml, 
 static int be_getp (int i, int b, float *o)                            { return mb200_get_partials (i, b, o); }
 static int be_getm (int i, int m, float *o)                            { return mb200_get_transition_matrix (i, m, o); }
 static int be_gets (int i, int s, float *o)                            { return mb200_get_scalers (i, s, o); }
+static int be_rates (int i, int e, const double *q, const double *f)   { return mb200_set_rate_matrices (i, e, q, f); }
 
-static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates, be_getp, be_getm, be_gets };
+static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates, be_getp, be_getm, be_gets, be_rates };
 static int seamDeferred = NO;   /* YES: TreeLikelihood_Beagle only launches; SeamCollect fetches the result */
 static int seamBatchWanted = NO;    /* MB200BatchEnable: instances are created with per-chain scratch buffers */
 static int seamBatchQueue = NO;     /* YES while MB200BatchQueueLogLike assembles: evaluations are queued, not launched */
@@ -134,7 +137,7 @@ void MB200SeamSetBackend (const MB200SeamBackend *backend)
 {
     if (backend == NULL)
         {
-        MB200SeamBackend def = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates, be_getp, be_getm, be_gets };
+        MB200SeamBackend def = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates, be_getp, be_getm, be_gets, be_rates };
         seamBackend = def;
         }
     else
@@ -1292,6 +1295,120 @@ void LaunchBEAGLELogLikeForDivision (int chain, int d, ModelInfo *m, Tree *tree,
     TreeLikelihood_Beagle (tree, d, chain, lnL, chainId[chain] % chainParams.numChains);
 }
 
+/* ---- eigensystems on the device (opt-in MB200_EIGEN=device) --------------------------------------
+ * What UpDateCijk (src/likelihood.c:10476) does, minus GetEigens and CalcCijk: flip the cijk space, build the rate
+ * matrix (or one per omega category, rescaled together so that the mean rate is one, :10676-10716) with the
+ * reference's own SetNucQMatrix / SetProteinQMatrix, and hand matrices + stationary frequencies to the backend,
+ * which diagonalises them on its stream while the host goes on to the next chain.  Taken only for time-reversible
+ * matrices (checked here, entry by entry); anything else -- and every backend without the entry point -- keeps the
+ * host path.  The host block m->cijks[idx] is NOT written on this path: nothing on the host reads it while the
+ * division is on the engine (the function-pointer forms keep the host path, the reference's own driver calls
+ * UpDateCijk for them). */
+static MrBFlt **seamQ[SEAM_MAX_DIVISIONS][MB200_MAX_CATEGORIES];
+static double  *seamQFlat[SEAM_MAX_DIVISIONS];
+static long long seamDeviceEigens = 0;
+
+long long MB200SeamDeviceEigens (void) { return seamDeviceEigens; }
+
+static int SeamDeviceEigenWanted (ModelInfo *m)
+{
+    static int wanted = -1;
+    if (wanted < 0)
+        {
+        const char *e = getenv ("MB200_EIGEN");
+        wanted = (e != NULL && strcmp (e, "device") == 0) ? YES : NO;
+        }
+    if (wanted == NO || seamBackend.set_rate_matrices == NULL)
+        return NO;
+    if (m->cijkLength <= 0 || m->switchRates != NULL || m->numModelStates > MB200_MAX_STATES)
+        return NO;
+    if (m->dataType == DNA || m->dataType == RNA)
+        {
+        if (m->nCijkParts > 1 && !(m->nucModelId == NUCMODEL_CODON && m->numOmegaCats == m->nCijkParts))
+            return NO;
+        return YES;
+        }
+    if (m->dataType == PROTEIN && m->nCijkParts == 1)
+        return YES;
+    return NO;
+}
+
+/* YES: the slot m->cijkIndex[chain] (after the flip) is being computed by the backend; NO: nothing was touched */
+static int SeamDeviceEigen (ModelInfo *m, SeamDivision *sd, int d, int chain)
+{
+    const int   n = m->numModelStates, parts = (m->nCijkParts > 1) ? m->nCijkParts : 1;
+    const int   codon = ((m->dataType == DNA || m->dataType == RNA) && m->nucModelId == NUCMODEL_CODON) ? YES : NO;
+    int         i, j, k;
+    MrBFlt      rA = 0.0, rS = 0.0, posScaler = 0.0, *omega = NULL, *omegaFreq = NULL, *bs, big = 0.0;
+    double      t0 = SeamNow ();
+
+    if (parts > MB200_MAX_CATEGORIES)
+        return (NO);
+    if (seamQFlat[d] == NULL)
+        {
+        for (k=0; k<parts; k++)
+            if ((seamQ[d][k] = AllocateSquareDoubleMatrix (n)) == NULL)
+                return (NO);
+        if ((seamQFlat[d] = (double *) SafeMalloc ((size_t) parts * n * n * sizeof(double))) == NULL)
+            return (NO);
+        }
+    if (codon == YES)
+        {
+        omega = GetParamVals (m->omega, chain, state[chain]);
+        if (m->numOmegaCats > 1)
+            omegaFreq = GetParamSubVals (m->omega, chain, state[chain]);
+        }
+    for (k=0; k<parts; k++)
+        {
+        if (m->dataType == PROTEIN)
+            {
+            if (SetProteinQMatrix (seamQ[d][k], n, chain, d, 1.0) == ERROR)
+                return (NO);
+            }
+        else if (SetNucQMatrix (seamQ[d][k], n, chain, d, (codon == YES) ? omega[k] : 1.0, &rA, &rS) == ERROR)
+            return (NO);
+        if (codon == YES && m->numOmegaCats > 1)
+            posScaler += omegaFreq[k] * (rS + rA);
+        }
+    if (codon == YES && m->numOmegaCats > 1)
+        posScaler = 1.0 / posScaler;
+    else
+        posScaler = 1.0;
+    bs = GetParamSubVals (m->stateFreq, chain, state[chain]);
+    for (k=0; k<parts; k++)
+        for (i=0; i<n; i++)
+            for (j=0; j<n; j++)
+                {
+                const double q = seamQ[d][k][i][j] * posScaler;
+                seamQFlat[d][((size_t) k * n + i) * n + j] = q;
+                if (fabs (q) > big)
+                    big = fabs (q);
+                }
+    /* detailed balance, entry by entry: pi_i q_ij == pi_j q_ji */
+    for (i=0; i<n; i++)
+        if (!(bs[i] > 0.0))
+            return (NO);
+    for (k=0; k<parts; k++)
+        for (i=0; i<n; i++)
+            for (j=i+1; j<n; j++)
+                {
+                const double a = bs[i] * seamQFlat[d][((size_t) k * n + i) * n + j], b = bs[j] * seamQFlat[d][((size_t) k * n + j) * n + i];
+                if (fabs (a - b) > 1e-12 * big)
+                    return (NO);
+                }
+    FlipCijkSpace (m, chain);
+    if (seamBackend.set_rate_matrices (sd->instance, m->cijkIndex[chain], seamQFlat[d], bs) != MB200_SUCCESS)
+        {
+        FlipCijkSpace (m, chain);       /* back; the host path flips again */
+        return (NO);
+        }
+    seamCijkSeen[d][m->cijkIndex[chain] >> 3] |= (unsigned char)(1 << (m->cijkIndex[chain] & 7));
+    seamSecCijk += SeamNow () - t0;
+    seamCijkUpdates++;
+    seamDeviceEigens++;
+    return (YES);
+}
+
 /* the engine's copy of the chain's eigensystem follows the host's: upload after UpDateCijk, and the
    first time a slot is read that the device has never seen */
 static int SeamSyncCijk (ModelInfo *m, SeamDivision *sd, int d, int chain)
@@ -1319,6 +1436,7 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
     ModelInfo  *m;
     Tree       *tree;
     SeamDivision *sd;
+    int         deviceEigen;
 
     SeamInit ();
     m = &modelSettings[d];
@@ -1384,16 +1502,19 @@ int MB200LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
         m->cijkScratchIndex < 0 || m->cijkScratchIndex > 2 * MAX_CHAINS)
         return (NO);
 
+    deviceEigen = NO;
     if (m->upDateCijk == YES)
         {
-        if (SeamUpDateCijk (d, chain) == ERROR)
+        if (SeamDeviceEigenWanted (m) == YES && SeamDeviceEigen (m, sd, d, chain) == YES)
+            deviceEigen = YES;
+        else if (SeamUpDateCijk (d, chain) == ERROR)
             {
             (*lnL) = MRBFLT_NEG_MAX;    /* effectively abort the move */
             return (YES);
             }
         m->upDateAll = YES;
         }
-    if (SeamSyncCijk (m, sd, d, chain) == ERROR)
+    if (deviceEigen == NO && SeamSyncCijk (m, sd, d, chain) == ERROR)
         {
         (*lnL) = MRBFLT_NEG_MAX;
         abortMove = YES;

@@ -62,6 +62,7 @@ int       PrintSiteRates_B200 (TreeNode *p, int division, int chain);
 int       MB200InstallReaders (int division);
 long long MB200SeamUpdateCount (int division);   /* node*pattern*rate CL updates issued  */
 void      MB200SeamCijkTimes (double *secHost, double *secUpload, long long *updates);   /* eigensystem work on the host */
+long long MB200SeamDeviceEigens (void);          /* MB200_EIGEN=device: eigensystems computed by the backend */
 long long MB200SeamRescaleRetries (void);        /* MB200_RESCALE=dynamic: evaluations repeated after an underflow */
 int       MB200SeamInstance (int division);      /* engine instance of a division, or -1 */
 
@@ -88,6 +89,9 @@ typedef struct
     int (*get_partials)          (int instance, int buffer, float *out);
     int (*get_transition_matrix) (int instance, int matrix, float *out);
     int (*get_scalers)           (int instance, int scaler, float *out);
+    /* optional: eigensystems computed by the backend from the rate matrices (MB200_EIGEN=device); NULL: the host's
+       UpDateCijk computes them and set_cijk ships the block */
+    int (*set_rate_matrices)     (int instance, int eigen, const double *rate_matrices, const double *state_freqs);
     } MB200SeamBackend;
 
 void      MB200SeamSetBackend (const MB200SeamBackend *backend);   /* NULL = the engine  */

@@ -400,11 +400,11 @@ static void Report (void)
     fprintf (f, "{\"mb200_harness\": \"%s\", \"calls\": %lld, \"node_updates\": %lld, \"cl_updates\": %lld, "
                 "\"sec_cpu\": %.6f, \"sec_gpu\": %.6f, \"aborts\": %lld, \"unsupported_calls\": %lld, "
                 "\"compared\": %lld, \"failed\": %lld, \"max_rel\": %.3e, \"mean_rel\": %.3e, \"tol\": %.1e, \"dumped\": %ld, "
-                "\"via\": \"%s\", \"lnl_hash\": \"%016llx\", \"batched_generations\": %lld, \"flushes\": %lld, \"rescale_retries\": %lld, \"sec_queue\": %.6f, \"sec_flush\": %.6f, \"sec_finish\": %.6f, \"sec_init\": %.6f, \"sec_cijk_host\": %.6f, \"sec_cijk_upload\": %.6f, \"cijk_updates\": %lld}\n",
+                "\"via\": \"%s\", \"lnl_hash\": \"%016llx\", \"batched_generations\": %lld, \"flushes\": %lld, \"rescale_retries\": %lld, \"sec_queue\": %.6f, \"sec_flush\": %.6f, \"sec_finish\": %.6f, \"sec_init\": %.6f, \"sec_cijk_host\": %.6f, \"sec_cijk_upload\": %.6f, \"cijk_updates\": %lld, \"device_eigens\": %lld}\n",
              names[hMode], hCalls, hNodeUpdates, hUpdates, hSecCpu, hSecGpu, hAborts, hUnsupported,
              hCompared, hFailed, (hMaxRel == hMaxRel && hMaxRel < 1e300) ? hMaxRel : 9.999e99,
              (hCompared && hSumRel == hSumRel && hSumRel < 1e300) ? hSumRel / hCompared : (hCompared ? 9.999e99 : 0.0), hTol, hDumped,
-             hViaFn ? "fnptr" : "seam", hLnlHash, hBatchedGens, hFlushes, MB200SeamRescaleRetries (), hSecQueue, hSecFlush, hSecFinish, hSecInit, cjH, cjU, cjN);
+             hViaFn ? "fnptr" : "seam", hLnlHash, hBatchedGens, hFlushes, MB200SeamRescaleRetries (), hSecQueue, hSecFlush, hSecFinish, hSecInit, cjH, cjU, cjN, MB200SeamDeviceEigens ());
     if (f != stderr) fclose (f);
     if (hDump) { fclose (hDump); hDump = NULL; }
     if (hMode == MODE_SHADOW || ENGINE_DRIVES (hMode))
@@ -517,6 +517,7 @@ static void Setup (void)
     if (hMode == MODE_ORACLE)
         {
         MB200SeamBackend be;
+        memset (&be, 0, sizeof(be));       /* optional entry points the oracle has no counterpart of stay NULL */
         LoadOracle ();
         be.create_instance = orc_create;       be.finalize_instance = hOrc.finalize;
         be.set_tip_states = hOrc.tips;         be.set_pattern_weights = hOrc.weights;

@@ -221,6 +221,25 @@ def test_covarion_on_the_engine_follows_the_oracle_run(tmp_path, engine_lib):
             assert abs(a - b) <= 1e-6 * abs(a) + 2e-3, (g, lo[g], lg[g])      # 3 decimals are printed
 
 
+@needs_harness
+@needs_batched
+@pytest.mark.gpu
+@pytest.mark.parametrize("stem,ngen,min_eigens", [("replicase_m0", 150, 2), ("replicase_ny98", 100, 2), ("primates_gtr_g4", 150, 4),
+                                                  ("ovomucoids_wag_g4", 40, 1)])
+def test_device_eigensystems_follow_the_host_run(tmp_path, engine_lib, stem, ngen, min_eigens):
+    """MB200_EIGEN=device: the rate matrices go to the engine, which diagonalises them on its stream, instead of
+    the host's GetEigens + CalcCijk and a block upload.  P(t) then agrees to the rounding of double sums, so the run prints
+    the same lnL as the host-eigensystem run, generation by generation, within the north-star tolerance."""
+    rh, lh = _run_printing(tmp_path, stem, ngen, {}, ".eh", mode="gpu")
+    rd, ld = _run_printing(tmp_path, stem, ngen, {"MB200_EIGEN": "device"}, ".ed", mode="gpu")
+    assert rh["device_eigens"] == 0 and rd["device_eigens"] >= min_eigens, (rh["device_eigens"], rd["device_eigens"])
+    assert rd["unsupported_calls"] == 0 and rd["calls"] == rh["calls"] and rd["aborts"] == rh["aborts"]
+    assert len(lh) >= ngen and len(ld) >= ngen
+    for g in range(ngen):
+        for a, b in zip(lh[g], ld[g]):
+            assert abs(a - b) <= 1e-6 * abs(a) + 2e-3, (g, lh[g], ld[g])      # 3 decimals are printed
+
+
 SHADOW_CASES = [
     # stem, generations, expected unsupported calls (None = any), min evaluations
     ("primates_gtr_g4", 2000, 0, 16000),
