@@ -251,9 +251,12 @@ int mb200_set_eigen_decomposition (int instance, int eigen, const double *eigvec
  * for instances created with omega categories, else one), already scaled the way UpDateCijk scales them;
  * state_freqs = the stationary frequencies (all > 0) the matrices are reversible with respect to
  * (pi_i q_ij == pi_j q_ji; the caller checks, the solver symmetrises).  Asynchronous: the call returns after
- * queueing the copy and two kernels on the instance's stream; a failure to converge is reported by the next
- * mb200_evaluate / _end as MB200_ERROR_GENERAL.  S <= 64, not for variable-state instances. */
-int mb200_set_rate_matrices (int instance, int eigen, const double *rate_matrices, const double *state_freqs);
+ * queueing the copy and three kernels on the instance's stream; a failure to converge is reported by the next
+ * mb200_evaluate / _end as MB200_ERROR_GENERAL.  S <= 64, not for variable-state instances.
+ * like_eigen: a slot whose matrices these are a small change of (the chain's current state when a move proposes
+ * new kappa / omega / frequencies), or MB200_NONE; when that slot was solved by this call too, its eigenvectors
+ * start the iteration (fewer sweeps).  A hint only: the result does not depend on it beyond rounding. */
+int mb200_set_rate_matrices (int instance, int eigen, int like_eigen, const double *rate_matrices, const double *state_freqs);
 
 /* ---- node-granular verbs (the function-pointer / BEAGLE-verb level) ---------------- */
 int mb200_update_transition_matrices (int instance, const mb200_matrix_update *updates,

@@ -116,7 +116,7 @@ class Library:
             "set_pattern_states": [I, P(I), P(I), P(I), I, I, I],
             "set_cijk": [I, I, P(D)],
             "set_eigen_decomposition": [I, I, P(D), P(D), P(D)],
-            "set_rate_matrices": [I, I, P(D), P(D)],
+            "set_rate_matrices": [I, I, I, P(D), P(D)],
             "evaluate": [I, P(Evaluation), I, P(D), P(I)],
             "get_partials": [I, I, P(C.c_float)],
             "set_partials": [I, I, P(C.c_float)],
@@ -308,12 +308,13 @@ class Instance:
         lam = np.ascontiguousarray(lam, np.float64)
         self._call("set_eigen_decomposition", eigen, _ptr(V, C.c_double), _ptr(Vi, C.c_double), _ptr(lam, C.c_double))
 
-    def set_rate_matrices(self, eigen: int, Q, pi):
-        """Device eigensolver: Q = [parts, S, S] reversible rate matrices, pi = their stationary frequencies."""
+    def set_rate_matrices(self, eigen: int, Q, pi, like: int = NONE):
+        """Device eigensolver: Q = [parts, S, S] reversible rate matrices, pi = their stationary frequencies;
+        like = a slot holding the eigensystem of nearby matrices (warm start) or NONE."""
         q = np.ascontiguousarray(Q, np.float64)
         f = np.ascontiguousarray(pi, np.float64)
         assert q.size == self.cijk_parts * self.S * self.S and f.size == self.S
-        self._call("set_rate_matrices", eigen, _ptr(q, C.c_double), _ptr(f, C.c_double))
+        self._call("set_rate_matrices", eigen, int(like), _ptr(q, C.c_double), _ptr(f, C.c_double))
 
     def set_arith(self, arith: int):
         self._call("set_arith", arith)

@@ -72,6 +72,10 @@ struct Instance
     // device eigensolver (mb200_set_rate_matrices): per slot [parts x S x S rate matrices | S frequencies]
     double       *dEigIn = nullptr, *hEigIn = nullptr;     // device copy and its pinned staging
     double       *dEigVec = nullptr;     // [slot][part][V | V^-1]; == dFactor where the P(t) kernel wants the factors anyway
+    double       *dEigU = nullptr;       // [slot][part][N x N] orthogonal eigenvectors of the symmetrised matrix (warm starts)
+    double2      *dEigLog = nullptr;     // [part] rotation log of the solve in flight (stream-ordered reuse)
+    int          *dEigRounds = nullptr;  // [part]
+    std::vector<int> eigWarmChain;       // per slot: -1 = no device eigenvectors, else warm starts since the last cold one
     int          *hEigStatus = nullptr;  // mapped: non-zero = the Jacobi iteration did not converge
     size_t        eigInStride = 0;
     std::vector<cudaEvent_t> evEigIn;    // per slot: the staging area has been read
@@ -970,6 +974,7 @@ void destroy (Instance *I)
     cudaFree (I->dStdTab); cudaFree (I->dStdClasses); cudaFree (I->dTilePartial2);
     cudaFree (I->dTcCounter); cudaFree (I->dTcFlags); cudaFree (I->dTcError);
     cudaFree (I->dEigIn); if (I->dEigVec != I->dFactor) cudaFree (I->dEigVec);
+    cudaFree (I->dEigU); cudaFree (I->dEigLog); cudaFree (I->dEigRounds);
     if (I->hEigIn) cudaFreeHost (I->hEigIn);
     if (I->hEigStatus) cudaFreeHost (I->hEigStatus);
     for (cudaEvent_t e : I->evEigIn) cudaEventDestroy (e);
@@ -1289,6 +1294,7 @@ int mb200_set_cijk (int instance, int eigen, const double *block)
     if (!I) return MB200_ERROR_BAD_INSTANCE;
     if (eigen < 0 || eigen >= I->cfg.eigen_count || !block) return MB200_ERROR_OUT_OF_RANGE;
     int rc = use (I); if (rc) return rc;
+    if (!I->eigWarmChain.empty ()) I->eigWarmChain[eigen] = -1;        // this slot's eigenvectors no longer come from the device solver
     CK (cudaMemcpyAsync (I->dEigen + (size_t)eigen * I->eigenStride, block, I->eigenStride * sizeof(double),
                          cudaMemcpyHostToDevice, I->stream));
     if (I->dFactor)
@@ -1310,6 +1316,7 @@ int mb200_set_eigen_decomposition (int instance, int eigen, const double *V, con
     if (eigen < 0 || eigen >= I->cfg.eigen_count || !V || !Vinv || !lambda) return MB200_ERROR_OUT_OF_RANGE;
     if (I->cijkParts != 1) return MB200_ERROR_UNSUPPORTED;        // multi-part slots are uploaded whole (mb200_set_cijk)
     int rc = use (I); if (rc) return rc;
+    if (!I->eigWarmChain.empty ()) I->eigWarmChain[eigen] = -1;
     const int S = I->cfg.state_count;
     const size_t n2 = (size_t)S * S;
     double *tmp = nullptr;
@@ -1333,17 +1340,19 @@ int mb200_set_eigen_decomposition (int instance, int eigen, const double *V, con
 }
 
 // Rate matrices in, eigensystems out, all on the instance's stream: nothing here waits for the device.
-int mb200_set_rate_matrices (int instance, int eigen, const double *Q, const double *pi)
+int mb200_set_rate_matrices (int instance, int eigen, int like_eigen, const double *Q, const double *pi)
 {
     Instance *I = get (instance);
     if (!I) return MB200_ERROR_BAD_INSTANCE;
-    if (eigen < 0 || eigen >= I->cfg.eigen_count || !Q || !pi) return MB200_ERROR_OUT_OF_RANGE;
+    if (eigen < 0 || eigen >= I->cfg.eigen_count || like_eigen >= I->cfg.eigen_count || !Q || !pi) return MB200_ERROR_OUT_OF_RANGE;
     const int S = I->cfg.state_count, parts = I->cijkParts;
     if (I->std || S < 2 || S > MB200_EIG_NMAX) return MB200_ERROR_UNSUPPORTED;
     for (int s = 0; s < S; s++)
         if (!(pi[s] > 0.0)) return MB200_ERROR_OUT_OF_RANGE;           // sqrt(pi) scales the similarity transform
     int rc = use (I); if (rc) return rc;
     const size_t n2 = (size_t)S * S;
+    const int    N = (S + 1) & ~1;
+    const size_t uLen = (size_t)parts * N * N;
     if (!I->dEigIn)
         {
         I->eigInStride = (size_t)parts * n2 + S;
@@ -1354,9 +1363,13 @@ int mb200_set_rate_matrices (int instance, int eigen, const double *Q, const dou
         *I->hEigStatus = 0;
         if (I->dFactor) I->dEigVec = I->dFactor;
         else CK (cudaMalloc ((void **)&I->dEigVec, (size_t)I->cfg.eigen_count * parts * 2 * n2 * sizeof(double)));
+        CK (cudaMalloc ((void **)&I->dEigU, (size_t)I->cfg.eigen_count * uLen * sizeof(double)));
+        CK (cudaMalloc ((void **)&I->dEigLog, (size_t)parts * MB200_EIG_LOG_DOUBLES * sizeof(double)));
+        CK (cudaMalloc ((void **)&I->dEigRounds, (size_t)parts * sizeof(int)));
+        I->eigWarmChain.assign (I->cfg.eigen_count, -1);
         I->evEigIn.resize (I->cfg.eigen_count);
         for (auto &e : I->evEigIn) CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
-        CK (cudaFuncSetAttribute (eigen_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) eigen_smem_bytes ()));
+        CK (cudaFuncSetAttribute (eigen_rotations_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) eigen_smem_bytes ()));
         }
     else
         CK (cudaEventSynchronize (I->evEigIn[eigen]));                 // the slot's previous matrices have left the staging area
@@ -1367,13 +1380,25 @@ int mb200_set_rate_matrices (int instance, int eigen, const double *Q, const dou
     CK (cudaEventRecord (I->evEigIn[eigen], I->stream));
     int *dStatus = nullptr;
     CK (cudaHostGetDevicePointer ((void **)&dStatus, I->hEigStatus, 0));
+    // warm start from the eigenvectors of a nearby matrix, unless that would extend an already long chain of warm starts
+    static const bool noWarm = getenv ("MB200_EIGEN_COLD") != nullptr;
+    const double *U0 = nullptr;
+    int chain = 0;
+    if (!noWarm && like_eigen >= 0 && like_eigen != eigen && I->eigWarmChain[like_eigen] >= 0 && I->eigWarmChain[like_eigen] < MB200_EIG_WARM_CHAIN)
+        {
+        U0 = I->dEigU + (size_t)like_eigen * uLen;
+        chain = I->eigWarmChain[like_eigen] + 1;
+        }
+    I->eigWarmChain[eigen] = chain;
+    const double *dPi = d + (size_t)parts * n2;
     double *vec = I->dEigVec + (size_t)eigen * parts * 2 * n2, *block = I->dEigen + (size_t)eigen * I->eigenStride;
-    eigen_jacobi_kernel<<<parts, MB200_EIG_THREADS, eigen_smem_bytes (), I->stream>>> (d, d + (size_t)parts * n2, S, vec, block, dStatus);
+    eigen_rotations_kernel<<<parts, MB200_EIG_THREADS, eigen_smem_bytes (), I->stream>>> (d, dPi, S, U0, I->dEigLog, I->dEigRounds, block, dStatus);
+    eigen_vectors_kernel<<<dim3 ((N + 7) / 8, parts), 256, 0, I->stream>>> (dPi, S, U0, I->dEigLog, I->dEigRounds, I->dEigU + (size_t)eigen * uLen, vec);
     const size_t n3 = n2 * S;
     int blocks = (int)((n3 + 255) / 256); if (blocks > 512) blocks = 512;
     cijk_parts_kernel<<<dim3 (blocks, parts), 256, 0, I->stream>>> (block, vec, S);
     CK (cudaGetLastError ());
-    I->launches += 2; I->launchKind[MB200_KERNEL_SETUP] += 2;
+    I->launches += 3; I->launchKind[MB200_KERNEL_SETUP] += 3;
     return MB200_SUCCESS;
 }
 

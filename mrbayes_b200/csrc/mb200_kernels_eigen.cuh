@@ -2,7 +2,7 @@
 //
 // What it replaces: the host side of UpDateCijk (src/likelihood.c:10476-10760): GetEigens (src/utils.c:11201, a general
 // real-matrix solver: balance, Hessenberg reduction, QR iterations, inverse by LU) followed by CalcCijk (src/utils.c:9734).
-// For a 61-state codon model that is 2.1 ms of host time per kappa / omega / pi move (5.3 ms with three omega categories),
+// For a 61-state codon model that is 1-2 ms of host time per kappa / omega / pi move (3-5 ms with three omega categories),
 // an order of magnitude more than the likelihood evaluation the move is followed by on this engine.
 //
 // Every rate matrix MrBayes builds for the divisions the seam accepts is time reversible: pi_i q_ij = pi_j q_ji.  With
@@ -12,19 +12,30 @@
 // reference's to the rounding of the double-precision sums (the float-rounded P(t) differ in the last place at most).
 //
 // Solver: cyclic Jacobi with a round-robin ("chess tournament") ordering: a round holds N/2 disjoint index pairs, all
-// rotated at once.  One CTA per matrix, 1024 threads; the matrix and the accumulated rotations live in shared memory.
-// A thread owns the 2 x 2 block (rows of pair P) x (columns of pair Q) and applies the row rotation of P and the
-// column rotation of Q to it in registers: A <- J^T A J in ONE pass, two barriers per round.  Jacobi is backward stable
-// and converges quadratically; 6-9 sweeps of N-1 rounds for N = 62.
+// rotated at once.  Two kernels:
+//   eigen_rotations_kernel  one CTA per matrix, the matrix in shared memory.  A thread owns the 2 x 2 block (rows of
+//                           pair P) x (columns of pair Q) and applies the row rotation of P and the column rotation of Q
+//                           to it in registers: A <- J^T A J in ONE pass, two barriers per round.  It does not carry the
+//                           eigenvectors along (that would double the shared-memory traffic that bounds a round); it logs
+//                           every rotation (c, s) instead.
+//   eigen_vectors_kernel    U = U0 J_1 J_2 ... : every ROW of U is independent of the others, so one warp per row replays
+//                           the log with warp-level synchronisation only (~30 us for 9 sweeps at N = 62).
+// Warm start: a proposal changes a rate matrix a little, so the eigenvectors U0 of the chain's current matrix nearly
+// diagonalise the proposed one: A0 = U0^T A U0 starts the sweeps with small off-diagonal entries and Jacobi's quadratic
+// convergence needs 3-5 sweeps instead of 8-9.  U0 is orthogonal to rounding (a product of plane rotations); the engine
+// restarts from the identity after MB200_EIG_WARM_CHAIN warm starts in a row so that rounding cannot accumulate.
 #pragma once
 #include <cuda_runtime.h>
 
 #define MB200_EIG_THREADS   1024
 #define MB200_EIG_NMAX      64
 #define MB200_EIG_LD        (MB200_EIG_NMAX + 1)
-#define MB200_EIG_SWEEPS    40
+#define MB200_EIG_SWEEPS    24
+#define MB200_EIG_WARM_CHAIN 32
+#define MB200_EIG_LOG_DOUBLES ((size_t) MB200_EIG_SWEEPS * (MB200_EIG_NMAX - 1) * (MB200_EIG_NMAX / 2) * 2)   // per matrix
 
-static inline size_t eigen_smem_bytes () { return (size_t)2 * MB200_EIG_NMAX * MB200_EIG_LD * sizeof(double); }
+// A | U0 | T (the two products of the warm start)
+static inline size_t eigen_smem_bytes () { return (size_t)3 * MB200_EIG_NMAX * MB200_EIG_LD * sizeof(double); }
 
 // pair k of round r among N (even) indices: index N-1 stays, the others walk round a circle
 __device__ __forceinline__ void eig_pair (int N, int r, int k, int &p, int &q)
@@ -34,22 +45,21 @@ __device__ __forceinline__ void eig_pair (int N, int r, int k, int &p, int &q)
     else        { p = (r + k) % M; q = (r - k + M) % M; }
 }
 
-// grid = eigen parts; Q: parts x S x S (row major), pi: S;  out: factor = [V (S x S) | V^-1 (S x S)] per part,
-// block = the slot's c_ijk block (lambda, imaginary parts = 0 written here; the c_ijk themselves by cijk_parts_kernel)
+// grid = eigen parts; Q: parts x S x S (row major), pi: S; U0: parts x N x N eigenvectors to start from, or nullptr.
+// out: rotation log (c, s per round and pair), number of rounds, eigenvalues into the slot's c_ijk block
 __global__ void __launch_bounds__(MB200_EIG_THREADS)
-eigen_jacobi_kernel (const double *__restrict__ Q, const double *__restrict__ pi, int S,
-                     double *__restrict__ factor, double *__restrict__ block, int *status)
+eigen_rotations_kernel (const double *__restrict__ Q, const double *__restrict__ pi, int S, const double *__restrict__ U0,
+                        double2 *__restrict__ rotLog, int *__restrict__ nRounds, double *__restrict__ block, int *status)
 {
     extern __shared__ __align__(16) double eigS[];
     __shared__ double sD[MB200_EIG_NMAX], sC[MB200_EIG_NMAX / 2], sSn[MB200_EIG_NMAX / 2];
-    __shared__ int    sP[MB200_EIG_NMAX / 2], sQ[MB200_EIG_NMAX / 2];
     __shared__ double sScale;
     __shared__ int    sFlag;
     double (*A)[MB200_EIG_LD] = reinterpret_cast<double (*)[MB200_EIG_LD]>(eigS);
-    double (*U)[MB200_EIG_LD] = reinterpret_cast<double (*)[MB200_EIG_LD]>(eigS + (size_t)MB200_EIG_NMAX * MB200_EIG_LD);
     const int tid = threadIdx.x, part = blockIdx.x;
     const int N = (S + 1) & ~1, H = N >> 1;
     const double *q = Q + (size_t)part * S * S;
+    double2 *rlog = rotLog + (size_t)part * (MB200_EIG_LOG_DOUBLES / 2);
 
     if (tid < N)
         sD[tid] = (tid < S) ? sqrt (pi[tid]) : 1.0;
@@ -61,7 +71,40 @@ eigen_jacobi_kernel (const double *__restrict__ Q, const double *__restrict__ pi
         if (i < S && j < S)
             a = 0.5 * (sD[i] * q[i*S + j] / sD[j] + sD[j] * q[j*S + i] / sD[i]);   // symmetric up to rounding; take the mean
         A[i][j] = a;
-        U[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    if (U0 != nullptr)
+        {
+        // A <- U0^T A U0, 2 x 2 outputs per thread
+        double (*Us)[MB200_EIG_LD] = reinterpret_cast<double (*)[MB200_EIG_LD]>(eigS + (size_t)MB200_EIG_NMAX * MB200_EIG_LD);
+        double (*T)[MB200_EIG_LD]  = reinterpret_cast<double (*)[MB200_EIG_LD]>(eigS + (size_t)2 * MB200_EIG_NMAX * MB200_EIG_LD);
+        const double *u0 = U0 + (size_t)part * N * N;
+        for (int e = tid; e < N * N; e += MB200_EIG_THREADS)
+            Us[e / N][e % N] = u0[e];
+        __syncthreads ();
+        const int i2 = (tid / H) * 2, j2 = (tid % H) * 2;
+        if (tid < H * H)
+            {
+            double t00 = 0.0, t01 = 0.0, t10 = 0.0, t11 = 0.0;       // T = A U0
+            for (int k = 0; k < N; k++)
+                {
+                const double a0 = A[i2][k], a1 = A[i2 + 1][k], b0 = Us[k][j2], b1 = Us[k][j2 + 1];
+                t00 = fma (a0, b0, t00); t01 = fma (a0, b1, t01); t10 = fma (a1, b0, t10); t11 = fma (a1, b1, t11);
+                }
+            T[i2][j2] = t00; T[i2][j2 + 1] = t01; T[i2 + 1][j2] = t10; T[i2 + 1][j2 + 1] = t11;
+            }
+        __syncthreads ();
+        if (tid < H * H && i2 <= j2)
+            {
+            double t00 = 0.0, t01 = 0.0, t10 = 0.0, t11 = 0.0;       // A = U0^T T, upper blocks, mirrored
+            for (int k = 0; k < N; k++)
+                {
+                const double a0 = Us[k][i2], a1 = Us[k][i2 + 1], b0 = T[k][j2], b1 = T[k][j2 + 1];
+                t00 = fma (a0, b0, t00); t01 = fma (a0, b1, t01); t10 = fma (a1, b0, t10); t11 = fma (a1, b1, t11);
+                }
+            if (i2 == j2) { t01 = 0.5 * (t01 + t10); t10 = t01; }
+            A[i2][j2] = t00; A[i2][j2 + 1] = t01; A[i2 + 1][j2] = t10; A[i2 + 1][j2 + 1] = t11;
+            A[j2][i2] = t00; A[j2 + 1][i2] = t01; A[j2][i2 + 1] = t10; A[j2 + 1][i2 + 1] = t11;
+            }
         }
     __syncthreads ();
     if (tid == 0)
@@ -74,82 +117,131 @@ eigen_jacobi_kernel (const double *__restrict__ Q, const double *__restrict__ pi
     __syncthreads ();
     const double tolCount = 1e-14 * sScale, tolSkip = 1e-19 * sScale;
 
-    int sweep = 0;
-    for (; sweep < MB200_EIG_SWEEPS; sweep++)
+    // a thread's block does not change from round to round: (row pair, column pair); the indices of pair k in round r
+    // are r + k and r - k on the circle of M = N - 1 indices (pair 0: the fixed index M and r), no table needed
+    const int  M = N - 1;
+    const int  bP = tid / H, bQ = tid % H;
+    const bool hasA = tid < H * H;
+
+    int  rounds = 0;
+    bool converged = false;
+    for (int sweep = 0; sweep < MB200_EIG_SWEEPS; sweep++)
         {
         if (tid == 0) sFlag = 0;
         __syncthreads ();
-        for (int r = 0; r < N - 1; r++)
+        for (int r = 0; r < M; r++, rounds++)
             {
             if (tid < H)
                 {
-                int p, qq;
-                eig_pair (N, r, tid, p, qq);
+                int p = r + tid, qq = r - tid;
+                if (p >= M) p -= M;
+                if (qq < 0) qq += M;
+                if (tid == 0) p = M;
                 const double g = A[p][qq];
                 double c = 1.0, s = 0.0;
                 if (fabs (g) > tolSkip)
                     {
-                    const double theta = 0.5 * (A[qq][qq] - A[p][p]) / g;
-                    double t;
-                    if (fabs (theta) > 1e100) t = 0.5 / theta;
-                    else
-                        {
-                        t = 1.0 / (fabs (theta) + sqrt (theta * theta + 1.0));
-                        if (theta < 0.0) t = -t;
-                        }
-                    c = 1.0 / sqrt (t * t + 1.0);
+                    // tan of the rotation angle, smaller root:  t = 2 g sgn(h) / (|h| + sqrt (h^2 + 4 g^2)),  h = a_qq - a_pp.
+                    // t may be a few ulps off (the rotation then leaves a_pq ~ 1e-16 |a_pq| behind, which the block update
+                    // computes rather than assumes); c and s must satisfy c^2 + s^2 = 1: s = t c with c = rsqrt (1 + t^2)
+                    const double h = A[qq][qq] - A[p][p];
+                    const double w = fma (h, h, 4.0 * g * g);
+                    const double den = fma (w, rsqrt (w), fabs (h));
+                    const double t = copysign (2.0 * g, (h < 0.0) ? -g : g) * __drcp_rn (den);
+                    c = rsqrt (fma (t, t, 1.0));
                     s = t * c;
                     if (fabs (g) > tolCount) sFlag = 1;
                     }
-                sP[tid] = p; sQ[tid] = qq; sC[tid] = c; sSn[tid] = s;
+                sC[tid] = c; sSn[tid] = s;
+                rlog[(size_t)rounds * H + tid] = make_double2 (c, s);
                 }
             __syncthreads ();
-            // A <- J^T A J : one 2 x 2 block per thread, rows of pair P, columns of pair Qp
-            for (int b = tid; b < H * H; b += MB200_EIG_THREADS)
+            // A <- J^T A J : one 2 x 2 block per thread, rows of pair bP, columns of pair bQ
+            if (hasA)
                 {
-                const int P = b / H, Qp = b % H;
-                const int r0 = sP[P], r1 = sQ[P], c0 = sP[Qp], c1 = sQ[Qp];
-                const double cr = sC[P], sr = sSn[P], cc = sC[Qp], sc = sSn[Qp];
+                int r0 = r + bP, r1 = r - bP, c0 = r + bQ, c1 = r - bQ;
+                if (r0 >= M) r0 -= M;
+                if (r1 < 0)  r1 += M;
+                if (c0 >= M) c0 -= M;
+                if (c1 < 0)  c1 += M;
+                if (bP == 0) r0 = M;
+                if (bQ == 0) c0 = M;
+                const double cr = sC[bP], sr = sSn[bP], cc = sC[bQ], sc = sSn[bQ];
                 const double x00 = A[r0][c0], x01 = A[r0][c1], x10 = A[r1][c0], x11 = A[r1][c1];
                 const double y00 = cr * x00 - sr * x10, y01 = cr * x01 - sr * x11;       // rows:   r0' = c r0 - s r1
                 const double y10 = sr * x00 + cr * x10, y11 = sr * x01 + cr * x11;       //         r1' = s r0 + c r1
-                double z00 = cc * y00 - sc * y01, z01 = sc * y00 + cc * y01;             // columns likewise
-                double z10 = cc * y10 - sc * y11, z11 = sc * y10 + cc * y11;
-                if (P == Qp) { z01 = 0.0; z10 = 0.0; }                                   // the annihilated pair, exactly
+                const double z00 = cc * y00 - sc * y01, z01 = sc * y00 + cc * y01;       // columns likewise
+                const double z10 = cc * y10 - sc * y11, z11 = sc * y10 + cc * y11;
                 A[r0][c0] = z00; A[r0][c1] = z01; A[r1][c0] = z10; A[r1][c1] = z11;
-                }
-            // U <- U J
-            for (int b = tid; b < N * H; b += MB200_EIG_THREADS)
-                {
-                const int i = b / H, Qp = b % H;
-                const int c0 = sP[Qp], c1 = sQ[Qp];
-                const double cc = sC[Qp], sc = sSn[Qp];
-                const double u0 = U[i][c0], u1 = U[i][c1];
-                U[i][c0] = cc * u0 - sc * u1;
-                U[i][c1] = sc * u0 + cc * u1;
                 }
             __syncthreads ();
             }
         const int any = sFlag;
         __syncthreads ();
-        if (!any) break;
+        if (!any) { converged = true; break; }
         }
-    if (sweep >= MB200_EIG_SWEEPS && tid == 0 && status != nullptr)
-        { *status = 1; __threadfence_system (); }
-
-    // the padded index (odd S) never rotates: eigenpairs 0 .. S-1 are the matrix's
-    double *V = factor + (size_t)part * 2 * S * S, *W = V + (size_t)S * S;
-    for (int e = tid; e < S * S; e += MB200_EIG_THREADS)
+    if (tid == 0)
         {
-        const int a = e / S, b = e % S;
-        V[e] = U[a][b] / sD[a];          // V[i = a][k = b]
-        W[e] = U[b][a] * sD[b];          // V^-1[k = a][j = b]
+        nRounds[part] = rounds;
+        if (!converged && status != nullptr)
+            { *status = 1; __threadfence_system (); }
         }
+    // the padded index (odd S) never rotates: eigenvalues 0 .. S-1 are the matrix's
     double *lam = block + (size_t)part * (2*(size_t)S + (size_t)S*S*S);
     if (tid < S)
         {
         lam[tid] = A[tid][tid];
         lam[S + tid] = 0.0;
+        }
+}
+
+// grid = (ceil (N / 8), eigen parts), block = 256: one warp per row of U.  U = U0 (or I) times every logged rotation;
+// writes U (for the next warm start) and the factors V = D^-1 U, V^-1 = U^T D
+__global__ void __launch_bounds__(256)
+eigen_vectors_kernel (const double *__restrict__ pi, int S, const double *__restrict__ U0, const double2 *__restrict__ rotLog,
+                      const int *__restrict__ nRounds, double *__restrict__ Uout, double *__restrict__ factor)
+{
+    __shared__ double sRow[8][MB200_EIG_NMAX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, part = blockIdx.y;
+    const int N = (S + 1) & ~1, H = N >> 1;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= N)
+        return;
+    const double2 *rlog = rotLog + (size_t)part * (MB200_EIG_LOG_DOUBLES / 2);
+    double *row = sRow[warp];
+    for (int k = lane; k < N; k += 32)
+        row[k] = (U0 != nullptr) ? U0[((size_t)part * N + i) * N + k] : ((k == i) ? 1.0 : 0.0);
+    __syncwarp ();
+    const int R = nRounds[part];
+    double2 cs = (lane < H && R > 0) ? rlog[lane] : make_double2 (1.0, 0.0);
+    for (int r = 0, rin = 0; r < R; r++)
+        {
+        const double2 cur = cs;
+        if (lane < H && r + 1 < R)
+            cs = rlog[(size_t)(r + 1) * H + lane];                 // next round's rotation, requested before this one's math
+        if (lane < H)
+            {
+            int p, q;
+            eig_pair (N, rin, lane, p, q);
+            const double a0 = row[p], a1 = row[q];
+            row[p] = cur.x * a0 - cur.y * a1;
+            row[q] = cur.y * a0 + cur.x * a1;
+            }
+        __syncwarp ();
+        if (++rin == N - 1) rin = 0;
+        }
+    double *uo = Uout + ((size_t)part * N + i) * N;
+    for (int k = lane; k < N; k += 32)
+        uo[k] = row[k];
+    if (i < S)
+        {
+        const double d = sqrt (pi[i]);
+        double *V = factor + (size_t)part * 2 * S * S, *W = V + (size_t)S * S;
+        for (int k = lane; k < S; k += 32)
+            {
+            V[(size_t)i * S + k] = row[k] / d;        // V[i][k]
+            W[(size_t)k * S + i] = row[k] * d;        // V^-1[k][j = i]
+            }
         }
 }
 

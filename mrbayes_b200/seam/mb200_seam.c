@@ -123,7 +123,7 @@ static int be_pstates (int i, const int *n, const int *t, const int *b, int ml, 
 static int be_getp (int i, int b, float *o)                            { return mb200_get_partials (i, b, o); }
 static int be_getm (int i, int m, float *o)                            { return mb200_get_transition_matrix (i, m, o); }
 static int be_gets (int i, int s, float *o)                            { return mb200_get_scalers (i, s, o); }
-static int be_rates (int i, int e, const double *q, const double *f)   { return mb200_set_rate_matrices (i, e, q, f); }
+static int be_rates (int i, int e, int l, const double *q, const double *f) { return mb200_set_rate_matrices (i, e, l, q, f); }
 
 static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates, be_getp, be_getm, be_gets, be_rates };
 static int seamDeferred = NO;   /* YES: TreeLikelihood_Beagle only launches; SeamCollect fetches the result */
@@ -1397,7 +1397,8 @@ static int SeamDeviceEigen (ModelInfo *m, SeamDivision *sd, int d, int chain)
                     return (NO);
                 }
     FlipCijkSpace (m, chain);
-    if (seamBackend.set_rate_matrices (sd->instance, m->cijkIndex[chain], seamQFlat[d], bs) != MB200_SUCCESS)
+    /* after the flip the scratch entry is the slot of the chain's pre-proposal state: a nearby eigensystem */
+    if (seamBackend.set_rate_matrices (sd->instance, m->cijkIndex[chain], m->cijkScratchIndex, seamQFlat[d], bs) != MB200_SUCCESS)
         {
         FlipCijkSpace (m, chain);       /* back; the host path flips again */
         return (NO);

@@ -91,7 +91,7 @@ typedef struct
     int (*get_scalers)           (int instance, int scaler, float *out);
     /* optional: eigensystems computed by the backend from the rate matrices (MB200_EIGEN=device); NULL: the host's
        UpDateCijk computes them and set_cijk ships the block */
-    int (*set_rate_matrices)     (int instance, int eigen, const double *rate_matrices, const double *state_freqs);
+    int (*set_rate_matrices)     (int instance, int eigen, int like_eigen, const double *rate_matrices, const double *state_freqs);
     } MB200SeamBackend;
 
 void      MB200SeamSetBackend (const MB200SeamBackend *backend);   /* NULL = the engine  */

@@ -114,7 +114,42 @@ def test_rejects_what_it_cannot_diagonalise(engine_lib):
     Q, pi = reversible_q(np.random.default_rng(3), 4)
     bad = pi.copy(); bad[2] = 0.0
     with make(engine_lib, 4, 1, 1) as dev:
-        rc = engine_lib.fn("set_rate_matrices")(dev.handle, 0, abi._ptr(np.ascontiguousarray(Q), abi.C.c_double), abi._ptr(bad, abi.C.c_double))
+        rc = engine_lib.fn("set_rate_matrices")(dev.handle, 0, -1, abi._ptr(np.ascontiguousarray(Q), abi.C.c_double), abi._ptr(bad, abi.C.c_double))
         assert rc != 0
-        rc = engine_lib.fn("set_rate_matrices")(dev.handle, 9, abi._ptr(np.ascontiguousarray(Q), abi.C.c_double), abi._ptr(pi, abi.C.c_double))
+        rc = engine_lib.fn("set_rate_matrices")(dev.handle, 9, -1, abi._ptr(np.ascontiguousarray(Q), abi.C.c_double), abi._ptr(pi, abi.C.c_double))
         assert rc != 0
+        rc = engine_lib.fn("set_rate_matrices")(dev.handle, 0, 9, abi._ptr(np.ascontiguousarray(Q), abi.C.c_double), abi._ptr(pi, abi.C.c_double))
+        assert rc != 0
+
+
+@pytest.mark.parametrize("S,parts", [(4, 1), (20, 1), (61, 1), (61, 3)])
+def test_warm_started_chain_of_proposals(engine_lib, S, parts):
+    """What a run does: every proposal's matrices are a small change of the chain's current ones and start from their
+    eigenvectors (like = the other slot); accepted or not, the slots ping-pong.  80 links, i.e. more than two of the
+    engine's forced cold restarts; every link against the matrix exponential."""
+    rng = np.random.default_rng(S + parts)
+    K = parts if parts > 1 else 2
+    rates = np.ones(K) if parts > 1 else np.array([0.5, 1.5])
+    Q, pi = reversible_q(rng, S, sparse=(S > 20))
+    R = Q / pi[None, :]; np.fill_diagonal(R, 0.0)          # exchangeabilities
+    mats = np.zeros(1, abi.MAT_DTYPE)
+    cur = 0
+    with make(engine_lib, S, K, parts) as dev:
+        for link in range(80):
+            # a multiplier move on a block of exchangeabilities and a Dirichlet-like nudge of the frequencies
+            i, j = rng.integers(0, S, 2)
+            if i != j and R[i, j] > 0:
+                f = np.exp(0.4 * (rng.random() - 0.5)); R[i, j] *= f; R[j, i] *= f
+            pi = pi * np.exp(0.1 * (rng.random(S) - 0.5)); pi /= pi.sum()
+            Qn = R * pi[None, :]; np.fill_diagonal(Qn, 0.0); np.fill_diagonal(Qn, -Qn.sum(1)); Qn /= -(pi * np.diag(Qn)).sum()
+            Qs = np.stack([Qn * (0.5 + 0.7 * p) for p in range(parts)])
+            new = 1 - cur if rng.random() < 0.7 else cur ^ 1
+            dev.set_rate_matrices(new, Qs, pi, like=cur)
+            mats[0] = (0, new, 0.37)
+            dev.update_transition_matrices(mats, rates, pi)
+            P = np.asarray(dev.get_transition_matrix(0), np.float64).reshape(K, S, S)
+            for k in range(K):
+                want = expm(Qs[k if parts > 1 else 0] * (0.37 * rates[k]))
+                assert np.abs(P[k] - want).max() < 2e-7, (link, k, np.abs(P[k] - want).max())
+            if rng.random() < 0.5:
+                cur = new                                    # accepted
