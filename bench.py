@@ -151,7 +151,7 @@ class Job:
     """One analysis' share on this process: partitions (Problems with the local chains), engine instances,
     the pre-generated proposal cycle, the coordinator."""
 
-    def __init__(self, name, rank, world, lib, device, cycle_len, seed=20260924):
+    def __init__(self, name, rank, world, lib, device, cycle_len, seed=20260924, flags=0):
         from mrbayes_b200 import mc3, workloads
         w = WORKLOADS[name]
         self.name, self.rank, self.world, self.w = name, rank, world, w
@@ -180,7 +180,7 @@ class Job:
             self.parts = cynmix_partitions(self.n_local, trees)
         else:
             self.parts = [synthetic_partition(name, self.n_local, trees, seed)]
-        self.insts = [p.create(lib, device=device, max_evaluations=self.n_local) for p in self.parts]
+        self.insts = [p.create(lib, device=device, max_evaluations=self.n_local, flags=flags) for p in self.parts]
         self.cycle_len = cycle_len
         self.seed = seed
         self.mc = None
@@ -644,7 +644,10 @@ def many_analyses(torch, lib, hl, device, flush, R=32, gens=1024):
     """Throughput regime (informational): R independent 8-chain primates analyses in flight on one GPU,
     one instance / stream / launch per analysis and generation."""
     from mrbayes_b200 import abi
-    jobs = [Job("primates", 0, 1, lib, device, 128, seed=20260924 + 1000 * (r + 1)) for r in range(R)]
+    # MB200_CONFIG_THROUGHPUT (one CTA per evaluation walks its pattern tiles, P(t) built once) was measured here: 86 us per
+    # generation against 75 us for one CTA per tile -- 256 CTAs leave half the SMs' warp slots empty; MB200_BENCH_THROUGHPUT=1 for the A/B
+    tflag = abi.CONFIG_THROUGHPUT if os.environ.get("MB200_BENCH_THROUGHPUT") else 0
+    jobs = [Job("primates", 0, 1, lib, device, 128, seed=20260924 + 1000 * (r + 1), flags=tflag) for r in range(R)]
     for j in jobs:
         j.batches = [[j.insts[0].pack(j.steps[0][i]) for i in range(j.cycle_len)]]
         j.host_arrays = [[abi.make_eval_array(j.steps[0][i]) for i in range(j.cycle_len)]]
@@ -697,7 +700,7 @@ def bench_engine(args):
     G = args.generations_per_step if args.generations_per_step > 0 else w["gens"]
     K, W = args.steps, max(args.warmup, 3)
     cycle_len = 128 if name in ("primates", "cynmix") else 16
-    job = Job(name, rank, world, lib, local, cycle_len)
+    job = Job(name, rank, world, lib, local, cycle_len, flags=(abi.CONFIG_THROUGHPUT if os.environ.get("MB200_BENCH_THROUGHPUT") else 0))
 
     # ---- coordinator: its own NCCL communicator, id shipped through the launcher's process group ----
     nccl_id = None
