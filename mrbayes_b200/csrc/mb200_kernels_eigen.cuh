@@ -29,7 +29,7 @@
 
 #define MB200_EIG_THREADS   1024
 #define MB200_EIG_NMAX      64
-#define MB200_EIG_LD        (MB200_EIG_NMAX + 1)
+#define MB200_EIG_LD        MB200_EIG_NMAX        // even: the round's pairs (r + k, r - k) and the diagonal fall on distinct banks
 #define MB200_EIG_SWEEPS    24
 #define MB200_EIG_WARM_CHAIN 32
 #define MB200_EIG_LOG_DOUBLES ((size_t) MB200_EIG_SWEEPS * (MB200_EIG_NMAX - 1) * (MB200_EIG_NMAX / 2) * 2)   // per matrix
@@ -196,40 +196,81 @@ eigen_rotations_kernel (const double *__restrict__ Q, const double *__restrict__
 }
 
 // grid = (ceil (N / 8), eigen parts), block = 256: one warp per row of U.  U = U0 (or I) times every logged rotation;
-// writes U (for the next warm start) and the factors V = D^-1 U, V^-1 = U^T D
+// the log passes through shared memory in chunks of 32 rounds (every warp of the CTA replays the same rotations), the
+// next chunk's loads are in flight while the current one is applied.  Writes U (for the next warm start) and the
+// factors V = D^-1 U, V^-1 = U^T D
+#define MB200_EIG_CHUNK 32
 __global__ void __launch_bounds__(256)
 eigen_vectors_kernel (const double *__restrict__ pi, int S, const double *__restrict__ U0, const double2 *__restrict__ rotLog,
                       const int *__restrict__ nRounds, double *__restrict__ Uout, double *__restrict__ factor)
 {
-    __shared__ double sRow[8][MB200_EIG_NMAX];
+    __shared__ double  sRow[8][MB200_EIG_NMAX];
+    __shared__ double2 sLog[2][MB200_EIG_CHUNK * (MB200_EIG_NMAX / 2)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, part = blockIdx.y;
-    const int N = (S + 1) & ~1, H = N >> 1;
+    const int N = (S + 1) & ~1, H = N >> 1, M = N - 1;
     const int i = blockIdx.x * 8 + warp;
-    if (i >= N)
-        return;
+    const bool live = i < N;
     const double2 *rlog = rotLog + (size_t)part * (MB200_EIG_LOG_DOUBLES / 2);
     double *row = sRow[warp];
-    for (int k = lane; k < N; k += 32)
-        row[k] = (U0 != nullptr) ? U0[((size_t)part * N + i) * N + k] : ((k == i) ? 1.0 : 0.0);
-    __syncwarp ();
+    if (live)
+        for (int k = lane; k < N; k += 32)
+            row[k] = (U0 != nullptr) ? U0[((size_t)part * N + i) * N + k] : ((k == i) ? 1.0 : 0.0);
     const int R = nRounds[part];
-    double2 cs = (lane < H && R > 0) ? rlog[lane] : make_double2 (1.0, 0.0);
-    for (int r = 0, rin = 0; r < R; r++)
+    const int per = MB200_EIG_CHUNK * H;                         // log entries per chunk
+    constexpr int LPT = MB200_EIG_CHUNK * (MB200_EIG_NMAX / 2) / 256;   // entries per thread and chunk (4)
+    double2 nx[LPT];
+    auto fetch = [&] (int chunk)
         {
-        const double2 cur = cs;
-        if (lane < H && r + 1 < R)
-            cs = rlog[(size_t)(r + 1) * H + lane];                 // next round's rotation, requested before this one's math
-        if (lane < H)
+        #pragma unroll
+        for (int j = 0; j < LPT; j++)
             {
-            int p, q;
-            eig_pair (N, rin, lane, p, q);
-            const double a0 = row[p], a1 = row[q];
-            row[p] = cur.x * a0 - cur.y * a1;
-            row[q] = cur.y * a0 + cur.x * a1;
+            const int eIdx = j * 256 + threadIdx.x;
+            const size_t g = (size_t)chunk * per + eIdx;
+            nx[j] = (eIdx < per && g < (size_t)R * H) ? rlog[g] : make_double2 (1.0, 0.0);
             }
-        __syncwarp ();
-        if (++rin == N - 1) rin = 0;
+        };
+    auto stash = [&] (int buf)
+        {
+        #pragma unroll
+        for (int j = 0; j < LPT; j++)
+            {
+            const int eIdx = j * 256 + threadIdx.x;
+            if (eIdx < per) sLog[buf][eIdx] = nx[j];
+            }
+        };
+    const int nChunk = (R + MB200_EIG_CHUNK - 1) / MB200_EIG_CHUNK;
+    if (nChunk > 0) { fetch (0); stash (0); }
+    __syncthreads ();
+    int rin = 0;
+    for (int ck = 0; ck < nChunk; ck++)
+        {
+        const int buf = ck & 1;
+        if (ck + 1 < nChunk) fetch (ck + 1);                     // in flight while this chunk is applied
+        const int r1 = min (MB200_EIG_CHUNK, R - ck * MB200_EIG_CHUNK);
+        if (live)
+            for (int r = 0; r < r1; r++)
+                {
+                if (lane < H)
+                    {
+                    int p = rin + lane, q = rin - lane;
+                    if (p >= M) p -= M;
+                    if (q < 0)  q += M;
+                    if (lane == 0) p = M;
+                    const double2 cs = sLog[buf][r * H + lane];
+                    const double a0 = row[p], a1 = row[q];
+                    row[p] = cs.x * a0 - cs.y * a1;
+                    row[q] = cs.y * a0 + cs.x * a1;
+                    }
+                __syncwarp ();
+                if (++rin == M) rin = 0;
+                }
+        else
+            { rin = (rin + r1) % M; }
+        if (ck + 1 < nChunk) stash (buf ^ 1);
+        __syncthreads ();
         }
+    if (!live)
+        return;
     double *uo = Uout + ((size_t)part * N + i) * N;
     for (int k = lane; k < N; k += 32)
         uo[k] = row[k];
