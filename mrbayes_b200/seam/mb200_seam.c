@@ -1295,7 +1295,7 @@ void LaunchBEAGLELogLikeForDivision (int chain, int d, ModelInfo *m, Tree *tree,
     TreeLikelihood_Beagle (tree, d, chain, lnL, chainId[chain] % chainParams.numChains);
 }
 
-/* ---- eigensystems on the device (opt-in MB200_EIGEN=device) --------------------------------------
+/* ---- eigensystems on the device (MB200_EIGEN=device|host, default: device for more than 32 states) ----
  * What UpDateCijk (src/likelihood.c:10476) does, minus GetEigens and CalcCijk: flip the cijk space, build the rate
  * matrix (or one per omega category, rescaled together so that the mean rate is one, :10676-10716) with the
  * reference's own SetNucQMatrix / SetProteinQMatrix, and hand matrices + stationary frequencies to the backend,
@@ -1312,13 +1312,18 @@ long long MB200SeamDeviceEigens (void) { return seamDeviceEigens; }
 
 static int SeamDeviceEigenWanted (ModelInfo *m)
 {
-    static int wanted = -1;
-    if (wanted < 0)
+    /* MB200_EIGEN = device: whenever possible; host: never; unset: where it pays -- more than 32 states (codon models:
+       the host's GetEigens + CalcCijk cost 1-5 ms per move there, the device 0.3-0.5 ms off the host's critical path;
+       for 4 and 20 states the two are on a par) */
+    static int mode = -1;
+    if (mode < 0)
         {
         const char *e = getenv ("MB200_EIGEN");
-        wanted = (e != NULL && strcmp (e, "device") == 0) ? YES : NO;
+        mode = (e == NULL) ? 2 : (strcmp (e, "device") == 0) ? 1 : 0;
         }
-    if (wanted == NO || seamBackend.set_rate_matrices == NULL)
+    if (mode == 0 || seamBackend.set_rate_matrices == NULL)
+        return NO;
+    if (mode == 2 && m->numModelStates <= 32)
         return NO;
     if (m->cijkLength <= 0 || m->switchRates != NULL || m->numModelStates > MB200_MAX_STATES)
         return NO;

@@ -18,7 +18,7 @@ run mb_b200_batched gpu cynmix_full 2000 MB200_BATCH=0
 run mb_b200_batched gpu cynmix_full 2000 MB200_BATCH=1
 run mb_b200_batched gpu cynmix_full 2000 MB200_BATCH=1 MB200_RESCALE=dynamic
 run mb_b200 cpu replicase_ny98 1000
-run mb_b200_batched gpu replicase_ny98 1000 MB200_BATCH=1
+run mb_b200_batched gpu replicase_ny98 1000 MB200_BATCH=1 MB200_EIGEN=host
 run mb_b200_batched gpu replicase_ny98 1000 MB200_BATCH=1 MB200_EIGEN=device
-run mb_b200_batched gpu replicase_m0 2000 MB200_BATCH=1
+run mb_b200_batched gpu replicase_m0 2000 MB200_BATCH=1 MB200_EIGEN=host
 run mb_b200_batched gpu replicase_m0 2000 MB200_BATCH=1 MB200_EIGEN=device

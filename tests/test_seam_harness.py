@@ -227,10 +227,10 @@ def test_covarion_on_the_engine_follows_the_oracle_run(tmp_path, engine_lib):
 @pytest.mark.parametrize("stem,ngen,min_eigens", [("replicase_m0", 150, 2), ("replicase_ny98", 100, 2), ("primates_gtr_g4", 150, 4),
                                                   ("ovomucoids_wag_g4", 40, 1)])
 def test_device_eigensystems_follow_the_host_run(tmp_path, engine_lib, stem, ngen, min_eigens):
-    """MB200_EIGEN=device: the rate matrices go to the engine, which diagonalises them on its stream, instead of
+    """MB200_EIGEN=device (the default for more than 32 states): the rate matrices go to the engine, which diagonalises them on its stream, instead of
     the host's GetEigens + CalcCijk and a block upload.  P(t) then agrees to the rounding of double sums, so the run prints
     the same lnL as the host-eigensystem run, generation by generation, within the north-star tolerance."""
-    rh, lh = _run_printing(tmp_path, stem, ngen, {}, ".eh", mode="gpu")
+    rh, lh = _run_printing(tmp_path, stem, ngen, {"MB200_EIGEN": "host"}, ".eh", mode="gpu")
     rd, ld = _run_printing(tmp_path, stem, ngen, {"MB200_EIGEN": "device"}, ".ed", mode="gpu")
     assert rh["device_eigens"] == 0 and rd["device_eigens"] >= min_eigens, (rh["device_eigens"], rd["device_eigens"])
     assert rd["unsupported_calls"] == 0 and rd["calls"] == rh["calls"] and rd["aborts"] == rh["aborts"]
@@ -270,8 +270,10 @@ def test_shadow_run_matches_reference_per_evaluation(tmp_path, engine_lib, stem,
 @pytest.mark.gpu
 @pytest.mark.parametrize("stem,ngen", [("primates_gtr_g4", 1000), ("cynmix_full", 100), ("replicase_m0", 60)])
 def test_engine_drives_the_chain_identically_through_both_entry_levels(tmp_path, engine_lib, stem, ngen):
-    a = run_harness(tmp_path, stem, ngen, "gpu", "seam", {"MB200_MULTIPART": "0"})
-    b = run_harness(tmp_path, stem, ngen, "gpu", "fnptr")
+    # eigensystems from the host in both runs: the function-pointer forms are driven by the reference's own loop, which calls
+    # UpDateCijk itself, and "bit for bit" needs the same eigensystem on both sides (codon divisions default to the device solver)
+    a = run_harness(tmp_path, stem, ngen, "gpu", "seam", {"MB200_MULTIPART": "0", "MB200_EIGEN": "host"})
+    b = run_harness(tmp_path, stem, ngen, "gpu", "fnptr", {"MB200_EIGEN": "host"})
     assert a["calls"] == b["calls"] and a["calls"] > 0
     assert a["unsupported_calls"] == 0 and b["unsupported_calls"] == 0
     assert a["lnl_hash"] == b["lnl_hash"], (a, b)       # the same lnL, bit for bit, at every evaluation
