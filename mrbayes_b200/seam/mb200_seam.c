@@ -488,7 +488,7 @@ void MB200SeamDivisionConfig (ModelInfo *m, int division, mb200_instance_config 
     cfg->flags           = (SeamCategoryEigens (m) == YES) ? MB200_CONFIG_CIJK_PARTS (m->nCijkParts) : 0;
     if (m->dataType == STANDARD)
         cfg->flags      |= MB200_CONFIG_VARIABLE_STATES;
-    if (SeamReadersWanted (m) == YES && getenv ("MB200_DEBUG_NOSCALAR") == NULL)
+    if (SeamReadersWanted (m) == YES)
         cfg->flags      |= MB200_CONFIG_SCALAR_KERNELS;     /* the reference's scalar kernel family (src/mcmc.c:17971-17992) */
     cfg->matrix_count    = m->numTiProbs;
     cfg->scaler_count    = m->numScalers;
@@ -1077,7 +1077,7 @@ static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL
     else if (m->numModelStates == 4 && (m->dataType == DNA || m->dataType == RNA))
         {
         sd->ev.flags |= MB200_FLAG_NUC4_PINVAR_QUIRK;   /* Likelihood_NUC4_* family */
-        if (SeamReadersWanted (m) == YES && getenv ("MB200_DEBUG_NOSHORT") == NULL)
+        if (SeamReadersWanted (m) == YES)
             sd->ev.flags |= MB200_FLAG_TIP_SHORTCUTS;   /* scalar CondLikeDown_NUC4: preLike shortcuts (src/likelihood.c:816-832) */
         if (sd->guard == YES)
             sd->ev.flags |= MB200_FLAG_RANGE_GUARD;     /* sparsely rescaled evaluation (dynamic scheme) */
@@ -1131,23 +1131,6 @@ static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL
             }
         }
 
-    if (getenv ("MB200_SEAM_DEBUG") != NULL)
-        {
-        int i;
-        fprintf (stderr, "seam eval: div %d chain %d nMat %d nOp %d root %d wrow %d flags %d pinv %d %.17g dst %d src %d stamp %llx\n rates",
-                 division, chain, sd->ev.matrix_update_count, sd->ev.operation_count, sd->ev.root_buffer, sd->ev.weights_row, sd->ev.flags,
-                 sd->ev.has_p_invar, sd->ev.p_invar, sd->ev.site_scaler_dst, sd->ev.site_scaler_src, sd->tipStamp);
-        for (i=0; i<m->numRateCats; i++) fprintf (stderr, " %.17g", sd->ev.category_rates[i]);
-        fprintf (stderr, "\n w");
-        for (i=0; i<m->numRateCats; i++) fprintf (stderr, " %.17g", sd->ev.category_weights[i]);
-        fprintf (stderr, "\n f");
-        for (i=0; i<m->numModelStates; i++) fprintf (stderr, " %.17g", sd->ev.state_freqs[i]);
-        fprintf (stderr, "\n");
-        for (i=0; i<sd->ev.matrix_update_count; i++) fprintf (stderr, " m%d e%d %.17g", sd->mats[i].matrix, sd->mats[i].eigen, sd->mats[i].length);
-        fprintf (stderr, "\n");
-        for (i=0; i<sd->ev.operation_count; i++) fprintf (stderr, " [%d<-%d.%d %d.%d %d.%d w%d r%d]", sd->ops[i].dest, sd->ops[i].child1, sd->ops[i].matrix1, sd->ops[i].child2, sd->ops[i].matrix2, sd->ops[i].child3, sd->ops[i].matrix3, sd->ops[i].scale_write, sd->ops[i].scale_remove);
-        fprintf (stderr, "\n");
-        }
     if (seamBatchQueue == YES)
         {
         /* chain-batched generation: the evaluation waits in the division's queue until MB200BatchFlush
