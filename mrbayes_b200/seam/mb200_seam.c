@@ -90,6 +90,8 @@ typedef struct
     int                  syncedChain, syncedState, readers;
     CLFlt              **hostExtra;         /* the appended host buffers (freed by the seam) */
     int                  nHostExtra;
+    int                  stdHostP;          /* STANDARD division whose P(t) the reference's TiProbs_Std builds on the host */
+    int                  hostPFailed;       /* ... and one of this evaluation's matrices could not be built or shipped */
     /* dynamic rescaling (MB200_RESCALE=dynamic): per chain, the rescale frequency and the run of clean evaluations */
     int                 *dynFreq, *dynRun;
     int                 *extraFlip, *nExtraFlip, *queuedState;  /* [chain][capOps] nodes the retry flipped beyond the move's own;
@@ -123,9 +125,10 @@ static int be_pstates (int i, const int *n, const int *t, const int *b, int ml, 
 static int be_getp (int i, int b, float *o)                            { return mb200_get_partials (i, b, o); }
 static int be_getm (int i, int m, float *o)                            { return mb200_get_transition_matrix (i, m, o); }
 static int be_gets (int i, int s, float *o)                            { return mb200_get_scalers (i, s, o); }
+static int be_setm (int i, int m, const float *in)                     { return mb200_set_transition_matrix (i, m, in); }
 static int be_rates (int i, int e, int l, const double *q, const double *f) { return mb200_set_rate_matrices (i, e, l, q, f); }
 
-static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates, be_getp, be_getm, be_gets, be_rates };
+static MB200SeamBackend seamBackend = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates, be_getp, be_getm, be_gets, be_setm, be_rates };
 static int seamDeferred = NO;   /* YES: TreeLikelihood_Beagle only launches; SeamCollect fetches the result */
 static int seamBatchWanted = NO;    /* MB200BatchEnable: instances are created with per-chain scratch buffers */
 static int seamBatchQueue = NO;     /* YES while MB200BatchQueueLogLike assembles: evaluations are queued, not launched */
@@ -137,7 +140,7 @@ void MB200SeamSetBackend (const MB200SeamBackend *backend)
 {
     if (backend == NULL)
         {
-        MB200SeamBackend def = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates, be_getp, be_getm, be_gets, be_rates };
+        MB200SeamBackend def = { be_create, be_finalize, be_tips, be_weights, be_cijk, be_eval, be_begin, be_end, be_pstates, be_getp, be_getm, be_gets, be_setm, be_rates };
         seamBackend = def;
         }
     else
@@ -319,6 +322,25 @@ static int SeamCategories (ModelInfo *m)
  * eigensystem per multistate character, TiProbs_Std's second half src/likelihood.c:10410-10470) and
  * state counts whose frequency table does not fit mb200_evaluation.state_freqs stay on the
  * reference's own kernels. */
+/* Who builds P(t) of a STANDARD division?  The engine, when every matrix is the equal-frequency Mk matrix of an unordered
+ * character (two values per state count and category: TiProbs_Std's first loop, src/likelihood.c:10143-10173).  Ordered
+ * characters (closed forms for 3 .. 6 states, :10175-10405) and unequal state frequencies (binary closed form, one
+ * eigensystem per multistate character, :10410-10470) keep the reference's own TiProbs_Std: the seam calls it for every
+ * dirty branch -- it writes the host array of the branch's slot -- and ships the buffer (set_transition_matrix); pruning,
+ * rescaling and the root stay on the engine, which reads every entry of a caller-supplied matrix. */
+static int SeamStdHostMatrices (ModelInfo *m)
+{
+    int c;
+    if (m->dataType != STANDARD || m->stateFreq == NULL || m->cType == NULL)
+        return NO;
+    if (m->stateFreq->paramId != SYMPI_EQUAL)
+        return YES;
+    for (c=0; c<m->numChars; c++)
+        if (m->cType[c] != UNORD)
+            return YES;
+    return NO;
+}
+
 static int SeamStdDivision (ModelInfo *m)
 {
     int c, freqLen = 0;
@@ -327,19 +349,21 @@ static int SeamStdDivision (ModelInfo *m)
         return NO;
     if (getenv ("MB200_NO_STD") != NULL)
         return NO;                              /* A/B switch: leave these divisions on the reference's kernels */
-    if (m->stateFreq == NULL || m->stateFreq->paramId != SYMPI_EQUAL || m->numBetaCats != 1)
+    if (m->stateFreq == NULL || m->numBetaCats != 1)
         return NO;
     if (m->pInvar != NULL || m->switchRates != NULL || m->numOmegaCats != 1 || m->nStates == NULL ||
         m->tiIndex == NULL || m->bsIndex == NULL || m->cType == NULL)
         return NO;
     for (c=0; c<m->numChars; c++)
         {
-        if (m->cType[c] != UNORD || m->nStates[c] < 2 || m->nStates[c] > MB200_MAX_STATES)
+        if ((m->cType[c] != UNORD && m->cType[c] != ORD) || m->nStates[c] < 2 || m->nStates[c] > MB200_MAX_STATES)
             return NO;
         if (m->bsIndex[c] + m->nStates[c] > freqLen)
             freqLen = m->bsIndex[c] + m->nStates[c];
         }
     if (freqLen > MB200_MAX_STATES)
+        return NO;
+    if (SeamStdHostMatrices (m) == YES && seamBackend.set_transition_matrix == NULL)
         return NO;
     return YES;
 }
@@ -777,6 +801,8 @@ int InitBeagleInstance (ModelInfo *m, int division)
     sd->extraTi = cfg.matrix_count - m->numTiProbs;
     sd->extraNs = cfg.scaler_count - m->numScalers;
     sd->extraEig = cfg.eigen_count - (numLocalChains + 1);
+    sd->stdHostP = SeamStdHostMatrices (m);
+    sd->hostPFailed = NO;
     if (seamBatchWanted == YES && numLocalChains > 1 && SeamBuildScratchSets (m, sd) == ERROR)
         {
         MrBayesPrint ("%s   B200 engine: cannot build the per-chain scratch sets of division %d\n", spacer, division+1);
@@ -828,11 +854,23 @@ static MrBFlt SeamBranchLength (ModelInfo *m, TreeNode *p, int chain)
     return p->length;
 }
 
+static int SeamHostBuffersFor (ModelInfo *m, SeamDivision *sd);
+
 static void SeamQueueMatrix (SeamDivision *sd, ModelInfo *m, TreeNode *p, int chain)
 {
     mb200_matrix_update *u;
 
     FlipTiProbsSpace (m, chain, p->index);
+    if (sd->stdHostP == YES)
+        {
+        /* the reference's TiProbs_Std fills the slot's host array; the engine gets a copy.  (A chain-batched run gave the
+           chains slots beyond the reference's own table: SeamHostBuffersFor appends host arrays for them.) */
+        const int division = (int)(m - modelSettings), idx = m->tiProbsIndex[chain][p->index];
+        if (SeamHostBuffersFor (m, sd) == ERROR || TiProbs_Std (p, division, chain) == ERROR ||
+            seamBackend.set_transition_matrix (sd->instance, idx, m->tiProbs[idx]) != MB200_SUCCESS)
+            sd->hostPFailed = YES;
+        return;
+        }
     u = &sd->mats[sd->ev.matrix_update_count++];
     u->matrix = m->tiProbsIndex[chain][p->index];
     u->eigen  = (sd->inlineEigen == YES) ? MB200_EIGEN_INLINE : (m->dataType == STANDARD) ? MB200_NONE : m->cijkIndex[chain];
@@ -1056,6 +1094,13 @@ static int SeamRootAndLaunch (int division, int chain, int rootNode, MrBFlt *lnL
     m  = &modelSettings[division];
     sd = &seamDiv[division];
 
+    if (sd->hostPFailed == YES)
+        {
+        sd->hostPFailed = NO;
+        (*lnL) = MRBFLT_NEG_MAX;
+        abortMove = YES;
+        return (ERROR);
+        }
     sd->evalStamp++;
     sd->ev.root_buffer = m->condLikeIndex[chain][rootNode];
     sd->ev.weights_row = whichSitePats;
@@ -1830,6 +1875,14 @@ int TiProbs_B200 (TreeNode *p, int division, int chain)
     if (sd->instance < 0)
         return (ERROR);
     SeamOpenRecord (sd, m, chain);
+    if (sd->stdHostP == YES)
+        {
+        const int idx = m->tiProbsIndex[chain][p->index];
+        if (TiProbs_Std (p, division, chain) == ERROR ||
+            seamBackend.set_transition_matrix (sd->instance, idx, m->tiProbs[idx]) != MB200_SUCCESS)
+            return (ERROR);
+        return (NO_ERROR);
+        }
     if (sd->ev.matrix_update_count >= sd->capMats)
         return (ERROR);
     /* the caller has flipped the branch's slot already (src/likelihood.c:7899) */

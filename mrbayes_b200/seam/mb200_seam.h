@@ -89,6 +89,10 @@ typedef struct
     int (*get_partials)          (int instance, int buffer, float *out);
     int (*get_transition_matrix) (int instance, int matrix, float *out);
     int (*get_scalers)           (int instance, int scaler, float *out);
+    /* optional: a transition-matrix buffer filled by the caller (STANDARD-data divisions whose matrices the reference's own
+       TiProbs_Std builds on the host: ordered characters, unequal state frequencies); NULL: those divisions stay on the
+       reference's kernels */
+    int (*set_transition_matrix) (int instance, int matrix, const float *in);
     /* optional: eigensystems computed by the backend from the rate matrices (MB200_EIGEN=device); NULL: the host's
        UpDateCijk computes them and set_cijk ships the block */
     int (*set_rate_matrices)     (int instance, int eigen, int like_eigen, const double *rate_matrices, const double *state_freqs);

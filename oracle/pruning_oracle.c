@@ -744,6 +744,18 @@ int orc_get_transition_matrix (int instance, int matrix, float *out)
     return MB200_SUCCESS;
 }
 
+/* a transition-matrix buffer filled by the caller (host layout = device layout here) */
+int orc_set_transition_matrix (int instance, int matrix, const float *in)
+{
+    size_t n;
+    OrcInst *o = Get (instance);
+    if (!o) return MB200_ERROR_BAD_INSTANCE;
+    if (matrix < 0 || matrix >= o->cfg.matrix_count || !in) return MB200_ERROR_OUT_OF_RANGE;
+    n = o->std ? (size_t)o->matLen : (size_t)o->cfg.category_count * o->cfg.state_count * o->cfg.state_count;
+    memcpy (o->matrices + (size_t)matrix * n, in, n * sizeof(float));
+    return MB200_SUCCESS;
+}
+
 int orc_get_scalers (int instance, int scaler, float *out)
 {
     OrcInst *o = Get (instance);

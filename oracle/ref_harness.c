@@ -147,8 +147,9 @@ static struct
     int (*cijk) (int, int, const double *);
     int (*eval) (int, const mb200_evaluation *, int, double *, int *);
     int (*pstates) (int, const int *, const int *, const int *, int, int, int);
+    int (*setm) (int, int, const float *);
     } hSh = { mb200_create_instance, mb200_finalize_instance, mb200_set_tip_states, mb200_set_pattern_weights, mb200_set_cijk,
-              mb200_evaluate, mb200_set_pattern_states };
+              mb200_evaluate, mb200_set_pattern_states, mb200_set_transition_matrix };
 
 /* ---- recording backend ------------------------------------------------------------- */
 static int rec_create (const mb200_instance_config *c, int *inst)
@@ -292,6 +293,13 @@ static int rec_cijk (int inst, int eigen, const double *block)
     return MB200_SUCCESS;
 }
 
+/* host-built transition matrices (STANDARD divisions with ordered characters / unequal frequencies): shadow runs pass them
+   on; the golden record format has no such record, so dump runs leave those divisions to the reference */
+static int rec_setm (int inst, int matrix, const float *in)
+{
+    return hSh.setm (inst, matrix, in);
+}
+
 static int rec_noread (int inst, int index, float *out)
 {
     (void) inst; (void) index; (void) out;
@@ -426,6 +434,7 @@ static struct
     int (*getp) (int, int, float *);
     int (*getm) (int, int, float *);
     int (*gets) (int, int, float *);
+    int (*setm) (int, int, const float *);
     } hOrc;
 
 static int orc_create (const mb200_instance_config *c, int *inst)
@@ -470,6 +479,7 @@ static void LoadOracle (void)
     hOrc.getp     = (int (*) (int, int, float *)) dlsym (hOrc.lib, "orc_get_partials");
     hOrc.getm     = (int (*) (int, int, float *)) dlsym (hOrc.lib, "orc_get_transition_matrix");
     hOrc.gets     = (int (*) (int, int, float *)) dlsym (hOrc.lib, "orc_get_scalers");
+    hOrc.setm     = (int (*) (int, int, const float *)) dlsym (hOrc.lib, "orc_set_transition_matrix");
     if (!hOrc.create || !hOrc.finalize || !hOrc.arith || !hOrc.tips || !hOrc.weights || !hOrc.cijk || !hOrc.eval || !hOrc.pstates)
         { fprintf (stderr, "oracle mode: %s lacks part of the orc_ API\n", path); exit (2); }
 }
@@ -502,6 +512,7 @@ static void Setup (void)
         LoadOracle ();
         hSh.create = orc_create;   hSh.finalize = hOrc.finalize; hSh.tips = hOrc.tips; hSh.weights = hOrc.weights;
         hSh.cijk = hOrc.cijk;      hSh.eval = hOrc.eval;         hSh.pstates = hOrc.pstates;
+        hSh.setm = hOrc.setm;
         }
     if (hMode == MODE_DUMP || hMode == MODE_SHADOW)
         {
@@ -511,6 +522,7 @@ static void Setup (void)
             /* the reference drives and its own readers see its own host arrays (the wrappers are not installed): a nominal
                read-back lets divisions that report ancestral states / site rates be shadowed like any other */
             be.get_partials = rec_noread; be.get_transition_matrix = rec_noread; be.get_scalers = rec_noread;
+            be.set_transition_matrix = rec_setm;
             }
         MB200SeamSetBackend (&be);
         }
@@ -525,6 +537,7 @@ static void Setup (void)
         be.evaluate_begin = NULL;              be.evaluate_end = NULL;
         be.set_pattern_states = hOrc.pstates;
         be.get_partials = hOrc.getp; be.get_transition_matrix = hOrc.getm; be.get_scalers = hOrc.gets;
+        be.set_transition_matrix = hOrc.setm;
         MB200SeamSetBackend (&be);
         }
     if (ENGINE_DRIVES (hMode) && hBatch && &MB200RC_patched != NULL)

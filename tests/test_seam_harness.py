@@ -87,7 +87,8 @@ needs_batched = pytest.mark.skipif(not BIN_BATCHED.exists(), reason="oracle/_ref
 
 @needs_harness
 @needs_batched
-@pytest.mark.parametrize("stem,ngen", [("primates_gtr_g4", 400), ("primates_hky_g4", 200), ("primates_gtr_ig4", 200), ("cynmix_full", 60)])
+@pytest.mark.parametrize("stem,ngen", [("primates_gtr_g4", 400), ("primates_hky_g4", 200), ("primates_gtr_ig4", 200), ("cynmix_full", 60),
+                                       ("cynmix_ordered", 60)])      # ordered characters: P(t) from the reference's TiProbs_Std on the host
 def test_chain_batched_generations_reproduce_the_serial_reference(tmp_path, stem, ngen):
     ref = run_harness(tmp_path, stem, ngen, "cpu", tag=".ref")                                  # the unmodified reference
     ser = run_harness(tmp_path, stem, ngen, "cpu", binary=BIN_BATCHED, tag=".patched")          # patched loop, serial path
@@ -192,7 +193,7 @@ def test_covarion_division_is_opt_in(tmp_path):
 @needs_harness
 @needs_batched
 @pytest.mark.gpu
-@pytest.mark.parametrize("stem,ngen", [("primates_gtr_g4", 2000), ("cynmix_full", 200), ("primates_readers", 200)])
+@pytest.mark.parametrize("stem,ngen", [("primates_gtr_g4", 2000), ("cynmix_full", 200), ("primates_readers", 200), ("cynmix_ordered", 100)])
 def test_chain_batched_generations_on_the_engine(tmp_path, engine_lib, stem, ngen):
     """The engine driving the chain: all local chains of a generation in ONE launch per division == one launch per chain
     (bit-identical lnL streams, hence identical samples), and both stay within the north-star tolerance of the
@@ -250,6 +251,7 @@ SHADOW_CASES = [
     ("replicase_m0", 200, 0, 200),
     ("replicase_ny98", 100, 0, 100),
     ("cynmix_full", 300, 0, 1500),
+    ("cynmix_ordered", 200, 0, 1000),     # ordered morphology: host-built matrices (set_transition_matrix), engine pruning
 ]
 
 
