@@ -404,13 +404,12 @@ int MB200SeamDivisionSupported (ModelInfo *m)
         return NO;
     if (m->gibbsGamma == YES || m->correlation != NULL)
         return NO;
-    if (m->switchRates != NULL && getenv ("MB200_COVARION") == NULL)
-        return NO;                              /* covarion (TiProbs_GenCov with hidden states, on/off frequencies): opt-in.  The
-                                                   reference evaluates these models with its SCALAR kernels, which in this snapshot
-                                                   return lnL -1558.16 on primates (and the same -1559.354 for two different trees
-                                                   with the nucleotide scalar kernels, tests/test_seam_harness.py); the engine, the
-                                                   oracle and an independent float64 recomputation agree on -8553.72.  There is no
-                                                   reference value to be in parity with, so the default leaves the division alone. */
+    if (m->switchRates != NULL && getenv ("MB200_NO_COVARION") != NULL)
+        return NO;                              /* covarion (TiProbs_GenCov with hidden states, on/off frequencies): A/B switch.
+                                                   Parity is pinned on a build of the reference WITHOUT SIMD switches
+                                                   (oracle/_ref/mb_b200_scalar): the reference evaluates these models with its scalar
+                                                   kernel family, which reads SIMD-laid-out buffers in an SSE-enabled build (lnL
+                                                   -1558.16 on primates there, -9051.351 in the scalar build and on the engine) */
     if (m->numModelStates < 2 || m->numModelStates > MB200_MAX_STATES)
         return NO;
     if (m->numRateCats < 1 || m->numRateCats > MB200_MAX_CATEGORIES)

@@ -170,18 +170,64 @@ def test_host_readers_of_cl_buffers_run_on_synced_buffers(tmp_path):
         assert all(0.0 < float(r[j]) < 100.0 for j in rate)
 
 
-# Covarion divisions are opt-in (MB200_COVARION=1): the reference evaluates them with its scalar kernels, whose lnL in this
-# snapshot is not a likelihood of the data (-1558 on primates; see the readers test above), so there is no reference value
-# to compare with.  What can be checked: the seam takes the division, batched == per-chain, lnL is in the data's range.
+# The reference's SCALAR kernel family (CondLikeDown_Gen / _NUC4, Likelihood_Gen, ...) serves covarion and doublet divisions and
+# every division whose conditional likelihoods are read on the host (report ancstates / siterates).  In an SSE-enabled build of
+# the reference those kernels read SIMD-laid-out buffers: primates starts at lnL -1558.16 with covarion=yes and at the SAME
+# -1559.354 for two different trees with ancstates=yes.  A build without any SIMD switch (oracle/Makefile: mb_ref_scalar,
+# mb_b200_scalar) gives -9051.351 / -7576.147, -7942.846 -- the values of the seam + oracle and of the engine.  Parity of
+# these paths is therefore pinned on the scalar build: every evaluation of a shadow run compared.
+BIN_SCALAR = ROOT / "oracle" / "_ref" / "mb_b200_scalar"
+needs_scalar = pytest.mark.skipif(not BIN_SCALAR.exists(), reason="oracle/_ref/mb_b200_scalar not built")
+SCALAR_CASES = [("primates_covarion", 200, 400), ("primates_readers", 200, 400), ("kim_mixed", 60, 600)]
+
+
+@needs_scalar
+@pytest.mark.parametrize("stem,ngen,min_calls", SCALAR_CASES)
+def test_scalar_kernel_family_matches_the_no_simd_reference(tmp_path, stem, ngen, min_calls):
+    rep = run_harness(tmp_path, stem, ngen, "shadow", binary=BIN_SCALAR, extra_env={"MB200_SHADOW_BACKEND": "oracle"}, tag=".sc")
+    assert rep["calls"] >= min_calls and rep["unsupported_calls"] == 0, rep
+    assert rep["failed"] == 0 and rep["compared"] == rep["calls"], rep
+    assert rep["max_rel"] < 1e-6, rep
+
+
+def _sample_rows(rep):
+    lines = [l for l in rep["samples"][".p"].splitlines() if l and not l.startswith("[")]
+    return lines[0].split("\t"), [[float(x) for x in l.split("\t")] for l in lines[1:]]
+
+
+def _rows_agree(ra, rb, rel=2e-6):
+    """How many leading sample rows agree in every column (7 significant digits are printed)."""
+    n = 0
+    for x, y in zip(ra, rb):
+        if len(x) != len(y) or any(abs(u - v) > rel * max(abs(u), abs(v)) + 1e-9 for u, v in zip(x, y)):
+            break
+        n += 1
+    return n
+
+
+@needs_scalar
+@pytest.mark.parametrize("stem", ["primates_covarion", "primates_readers"])
+def test_scalar_build_runs_sample_what_the_reference_samples(tmp_path, stem):
+    """The no-SIMD reference driving itself vs the seam + CPU oracle driving the same binary: the sampled parameters -- for
+    primates_readers including ~3 300 ancestral-state probabilities and ~900 site rates per sample, read by the reference's own
+    CondLikeUp / PrintAncStates / PrintSiteRates from the buffers the seam synced -- agree to the printed precision."""
+    ngen = 200
+    ref = run_harness(tmp_path, stem, ngen, "cpu", binary=BIN_SCALAR, tag=".scr")
+    orc = run_harness(tmp_path, stem, ngen, "oracle", binary=BIN_SCALAR, tag=".sco")
+    assert orc["unsupported_calls"] == 0 and orc["calls"] == ref["calls"]
+    (ha, ra), (hb, rb) = _sample_rows(ref), _sample_rows(orc)
+    assert ha == hb and len(ra) == len(rb) >= 10
+    assert _rows_agree(ra, rb) == len(ra), (_rows_agree(ra, rb), len(ra))
+
+
 @needs_harness
 @needs_batched
-def test_covarion_division_is_opt_in(tmp_path):
+def test_covarion_division_batched_equals_per_chain(tmp_path):
     ngen = 100
-    off = run_harness(tmp_path, "primates_covarion", 20, "oracle", binary=BIN_BATCHED, tag=".off")
-    assert off["unsupported_calls"] == off["calls"] > 0                 # default: left to the reference
-    env = {"MB200_COVARION": "1"}
-    ser = run_harness(tmp_path, "primates_covarion", ngen, "oracle", binary=BIN_BATCHED, extra_env=dict(env, MB200_BATCH="0"), tag=".s")
-    bat = run_harness(tmp_path, "primates_covarion", ngen, "oracle", binary=BIN_BATCHED, extra_env=dict(env, MB200_BATCH="1"), tag=".b")
+    off = run_harness(tmp_path, "primates_covarion", 20, "oracle", binary=BIN_BATCHED, extra_env={"MB200_NO_COVARION": "1"}, tag=".off")
+    assert off["unsupported_calls"] == off["calls"] > 0                 # A/B switch: left to the reference
+    ser = run_harness(tmp_path, "primates_covarion", ngen, "oracle", binary=BIN_BATCHED, extra_env={"MB200_BATCH": "0"}, tag=".s")
+    bat = run_harness(tmp_path, "primates_covarion", ngen, "oracle", binary=BIN_BATCHED, extra_env={"MB200_BATCH": "1"}, tag=".b")
     assert ser["unsupported_calls"] == 0 and bat["unsupported_calls"] == 0 and bat["batched_generations"] == ngen
     assert ser["samples"] and ser["samples"] == bat["samples"]
     lines = [l for l in ser["samples"][".p"].splitlines() if l and not l.startswith("[")]
@@ -205,6 +251,33 @@ def test_chain_batched_generations_on_the_engine(tmp_path, engine_lib, stem, nge
     assert bat["samples"] and bat["samples"] == one["samples"], "chain-batched launches sample differently from per-chain launches"
 
 
+@needs_scalar
+@pytest.mark.gpu
+@pytest.mark.parametrize("stem,ngen,min_calls", SCALAR_CASES)
+def test_engine_matches_the_no_simd_reference_on_its_scalar_kernel_family(tmp_path, engine_lib, stem, ngen, min_calls):
+    """Covarion (8 hidden-state model states), host readers, and kim.nex's seven partitions (doublet 16 states on the generic
+    kernel, 4-state, 20-state tensor-core, morphology) against the reference built without SIMD switches: every evaluation."""
+    rep = run_harness(tmp_path, stem, ngen, "shadow", binary=BIN_SCALAR, tag=".scg")
+    assert rep["calls"] >= min_calls and rep["unsupported_calls"] == 0, rep
+    assert rep["failed"] == 0 and rep["compared"] == rep["calls"], rep
+    assert rep["max_rel"] < 1e-6, rep
+
+
+@needs_scalar
+@pytest.mark.gpu
+@pytest.mark.parametrize("stem", ["primates_covarion", "primates_readers"])
+def test_engine_driven_scalar_build_samples_like_the_reference(tmp_path, engine_lib, stem):
+    """The engine drives the no-SIMD reference binary; its samples (incl. ancestral states / site rates through the wrapped host
+    readers) follow the reference's own for as long as the two runs take the same decisions (at least the first five samples)."""
+    ngen = 200
+    ref = run_harness(tmp_path, stem, ngen, "cpu", binary=BIN_SCALAR, tag=".sgr")
+    eng = run_harness(tmp_path, stem, ngen, "gpu", binary=BIN_SCALAR, tag=".sge")
+    assert eng["unsupported_calls"] == 0
+    (ha, ra), (hb, rb) = _sample_rows(ref), _sample_rows(eng)
+    assert ha == hb and len(ra) >= 10
+    assert _rows_agree(ra, rb, rel=1e-5) >= 5, _rows_agree(ra, rb, rel=1e-5)
+
+
 @needs_harness
 @needs_batched
 @pytest.mark.gpu
@@ -212,7 +285,7 @@ def test_covarion_on_the_engine_follows_the_oracle_run(tmp_path, engine_lib):
     """Engine (generic-state kernel, 8 states, per-category eigensystems) vs the CPU oracle as the seam's backend on the
     same command: the two runs print the same lnL, generation by generation, within the north-star tolerance for as long
     as they make the same decisions (at least the first 30 generations)."""
-    env = {"MB200_COVARION": "1"}
+    env = {}
     ro, lo = _run_printing(tmp_path, "primates_covarion", 60, env, ".co", mode="oracle")
     rg, lg = _run_printing(tmp_path, "primates_covarion", 60, env, ".cg", mode="gpu")
     assert rg["unsupported_calls"] == 0 and rg["batched_generations"] == 60 and ro["calls"] == rg["calls"]
