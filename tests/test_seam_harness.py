@@ -178,7 +178,7 @@ def test_host_readers_of_cl_buffers_run_on_synced_buffers(tmp_path):
 # these paths is therefore pinned on the scalar build: every evaluation of a shadow run compared.
 BIN_SCALAR = ROOT / "oracle" / "_ref" / "mb_b200_scalar"
 needs_scalar = pytest.mark.skipif(not BIN_SCALAR.exists(), reason="oracle/_ref/mb_b200_scalar not built")
-SCALAR_CASES = [("primates_covarion", 200, 400), ("primates_readers", 200, 400), ("kim_mixed", 60, 600)]
+SCALAR_CASES = [("primates_covarion", 200, 400), ("primates_readers", 200, 400), ("kim_mixed", 60, 600), ("ovomucoids_covarion", 30, 60)]
 
 
 @needs_scalar
