@@ -171,6 +171,7 @@ struct DevCtx                       // instance geometry + buffer bases, passed 
     int S, Sp, K, C;
     int tipCount, partialsCount, matrixCount, scalerCount, eigenCount, weightRows;
     int tilePatterns;               // patterns per CTA in the evaluation kernels
+    int genKB;                      // generic kernel: rate categories whose P matrices share a pass
     int numTiles;
     int hostSum;                    // 1: every tile writes its partial lnL to the (mapped) result buffer,
                                     //    the host adds them up in tile order (small launches only)

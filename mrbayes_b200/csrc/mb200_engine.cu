@@ -1058,8 +1058,13 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
 
     // tile geometry of the generic kernel: keep P + child tile + product under ~96 KB
     int TP = 32;
-    auto smemFor = [&] (int tp) { return sizeof(float) * ((size_t)S*S + (size_t)tp*(Sp+1) + (size_t)K*tp*S + 3*(size_t)tp); };
+    // rate categories per pass: all of them when their P matrices fit in 48 KB, else one at a time
+    const int KB = ((size_t)K * S * (S + 1) * sizeof(float) <= 48*1024) ? K : 1;
+    auto smemFor = [&] (int tp) { return sizeof(float) * ((size_t)KB*S*(S+1) + (size_t)KB*tp*(Sp+1) + (size_t)K*tp*S + 3*(size_t)tp); };
     while (TP > 1 && smemFor (TP) > 96*1024) TP >>= 1;
+    // small divisions: a CTA walks its tile's nodes one (child, category) step at a time, each step a global round trip and
+    // two barriers whatever the tile holds -- fewer patterns per tile put more SMs on the evaluation
+    while (TP > 4 && (C + TP - 1) / TP < I->numSMs) TP >>= 1;
     I->smemGen = smemFor (TP);
     I->std = (cfg->flags & MB200_CONFIG_VARIABLE_STATES) != 0;
     if (I->std && (S > MB200_STD_MAX_STATES || I->cijkParts != 1)) { delete I; return MB200_ERROR_UNSUPPORTED; }
@@ -1169,6 +1174,7 @@ int mb200_create_instance (const mb200_instance_config *cfg, int *instance)
     x.tipCount = cfg->tip_count; x.partialsCount = cfg->partials_count; x.matrixCount = cfg->matrix_count;
     x.scalerCount = cfg->scaler_count; x.eigenCount = cfg->eigen_count; x.weightRows = cfg->weight_rows;
     x.tilePatterns = I->tcS ? 128 : nuc4 ? nuc4PatternsPerBlock (K, false) : TP;
+    x.genKB = KB;
     x.numTiles = I->maxTiles;
     x.tip8 = I->dTip8; x.tip64 = I->dTip64; x.tipPartAmbig = I->dTipPartAmbig; x.partials = I->dPartials; x.matrices = I->dMatrices;
     x.scalers = I->dScalers; x.eigen = I->dEigen; x.weights = I->dWeights; x.invMask = I->dInvMask;

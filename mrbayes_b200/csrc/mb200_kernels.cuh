@@ -1206,10 +1206,11 @@ eval_gen_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__
 {
     extern __shared__ __align__(16) float smem[];
     const int S = ctx.S, Sp = ctx.Sp, K = ctx.K, C = ctx.C, TP = ctx.tilePatterns;
-    const int ldc = Sp + 1;
-    float *sPm   = smem;                          // [S][S]
-    float *sCh   = sPm + S*S;                     // [TP][ldc]
-    float *sProd = sCh + TP*ldc;                  // [K][TP][S]
+    const int KB = ctx.genKB;                     // rate categories per pass (all of them when their P matrices fit)
+    const int ldc = Sp + 1, ldp = S + 1;          // odd leading dimensions: thread = (pattern, state i) reads row i of P conflict-free
+    float *sPm   = smem;                          // [KB][S][ldp]
+    float *sCh   = sPm + (size_t)KB*S*ldp;        // [KB][TP][ldc]
+    float *sProd = sCh + (size_t)KB*TP*ldc;       // [K][TP][S]
     float *sMax  = sProd + (size_t)K*TP*S;        // [TP]
     float *sSite = sMax + TP;                     // [TP]
     int   *sFull = reinterpret_cast<int *>(sSite + TP);   // [TP] tip shortcut: pattern is missing
@@ -1233,48 +1234,55 @@ eval_gen_kernel (DevCtx ctx, const DevEval *__restrict__ evals, const double *__
             {
             const int child = (ch == 0) ? op.c1 : (ch == 1) ? op.c2 : op.c3;
             const int mat   = (ch == 0) ? op.m1 : (ch == 1) ? op.m2 : op.m3;
-            for (int k = 0; k < K; k++)
+            const bool isTip = child < ctx.tipCount;
+            const bool shortcut = isTip && (ev->flags & MB200_SHORTCUT_FLAG) && !ctx.tipPartAmbig[child];
+            // one pass = one global round trip and two barriers: KB categories' P matrices and child rows at a time
+            for (int k0 = 0; k0 < K; k0 += KB)
                 {
+                const int kb = min (KB, K - k0);
                 __syncthreads ();
-                const float *P = ctx.matrices + ((size_t)mat * K + k) * S * S;
-                for (int idx = threadIdx.x; idx < S*S; idx += NT)
-                    sPm[idx] = P[idx];
-                const bool isTip = child < ctx.tipCount;
-                const bool shortcut = isTip && (ev->flags & MB200_SHORTCUT_FLAG) && !ctx.tipPartAmbig[child];
+                const float *P = ctx.matrices + ((size_t)mat * K + k0) * S * S;
+                for (int idx = threadIdx.x; idx < kb*S*S; idx += NT)
+                    sPm[(idx / S) * ldp + idx % S] = P[idx];            // row (kk, i) of the pass at (kk*S + i) * ldp
                 if (isTip)
                     {
                     for (int idx = threadIdx.x; idx < np*S; idx += NT)
                         {
                         const int p = idx / S, j = idx % S;
                         const uint64_t m = ctx.tip64[(size_t)child * C + c0 + p];
-                        sCh[p*ldc + j] = ((m >> j) & 1) ? 1.0f : 0.0f;
+                        sCh[p*ldc + j] = ((m >> j) & 1) ? 1.0f : 0.0f;  // the same for every category
                         if (j == 0)
                             sFull[p] = (shortcut && m == fullMask) ? 1 : 0;
                         }
                     }
                 else
                     {
-                    const float *src = ctx.partials + (size_t)(child - ctx.tipCount) * bufStride
-                                     + ((size_t)k * C + c0) * Sp;
-                    for (int idx = threadIdx.x; idx < np*Sp; idx += NT)
+                    for (int kk = 0; kk < kb; kk++)
                         {
-                        const int p = idx / Sp, j = idx % Sp;
-                        if (j < S)
-                            sCh[p*ldc + j] = src[idx];
+                        const float *src = ctx.partials + (size_t)(child - ctx.tipCount) * bufStride
+                                         + ((size_t)(k0 + kk) * C + c0) * Sp;
+                        float *dstc = sCh + (size_t)kk * TP * ldc;
+                        for (int idx = threadIdx.x; idx < np*Sp; idx += NT)
+                            {
+                            const int p = idx / Sp, j = idx % Sp;
+                            if (j < S)
+                                dstc[p*ldc + j] = src[idx];
+                            }
                         }
                     }
                 __syncthreads ();
-                for (int idx = threadIdx.x; idx < np*S; idx += NT)
+                for (int idx = threadIdx.x; idx < kb*np*S; idx += NT)
                     {
-                    const int p = idx / S, i = idx % S;
-                    const float *prow = sPm + i*S;
-                    const float *crow = sCh + p*ldc;
+                    const int kk = idx / (np*S), r = idx % (np*S);
+                    const int p = r / S, i = r % S;
+                    const float *prow = sPm + ((size_t)kk*S + i)*ldp;
+                    const float *crow = sCh + (isTip ? 0 : (size_t)kk*TP*ldc) + p*ldc;
                     float acc = 0.0f;
                     for (int j = 0; j < S; j++)
                         acc = fmaf (prow[j], crow[j], acc);
                     if (isTip && sFull[p])
                         acc = 1.0f;                 // preLike shortcut (src/likelihood.c:257-258)
-                    float *dst = sProd + ((size_t)k*TP + p)*S + i;
+                    float *dst = sProd + ((size_t)(k0 + kk)*TP + p)*S + i;
                     *dst = (ch == 0) ? acc : (*dst) * acc;
                     }
                 }
