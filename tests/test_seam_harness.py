@@ -190,6 +190,47 @@ def test_scalar_kernel_family_matches_the_no_simd_reference(tmp_path, stem, ngen
     assert rep["max_rel"] < 1e-6, rep
 
 
+# A sweep over the model space the seam accepts, each as a shadow run in the no-SIMD build (every evaluation compared with the
+# reference's own): substitution-model jumping (nst=mixed), closed-form models with readers, lognormal / k-mixture rate
+# variation, JC, amino-acid model jumping and protein GTR, codon M3 (three omega categories) and codon GTR; autocorrelated gamma
+# is outside the path and must be declined, not mis-evaluated.
+MODEL_SWEEP = [
+    ("primates.nex", "lset nst=mixed rates=gamma;", True),
+    ("primates.nex", "lset nst=2 rates=propinv; report ancstates=yes;", True),
+    ("primates.nex", "lset nst=6 rates=lnorm;", True),
+    ("primates.nex", "lset nst=6 rates=kmixture;", True),
+    ("primates.nex", "lset nst=1 rates=equal;", True),
+    ("avian_ovomucoids.nex", "prset aamodelpr=mixed; lset rates=gamma;", True),
+    ("avian_ovomucoids.nex", "prset aamodelpr=fixed(gtr); lset rates=equal;", True),
+    ("replicase.nex", "lset nucmodel=codon omegavar=m3;", True),
+    ("replicase.nex", "lset nucmodel=codon nst=6 rates=equal;", True),
+    ("primates.nex", "lset nst=6 rates=adgamma;", False),
+]
+
+
+def _run_sweep_case(tmp_path, data, cmds, ngen, env):
+    nex = tmp_path / "sweep.nex"
+    nex.write_text(f"set autoclose=yes nowarn=yes seed=99 swapseed=99;\nexecute oracle/_ref/data/{data};\n{cmds}\n"
+                   f"mcmc nruns=1 nchains=2 ngen={ngen} printfreq=100000 samplefreq=50 diagnfreq=100000 filename={tmp_path}/o;\nquit;\n")
+    report = tmp_path / "sweep.json"
+    e = dict(os.environ, MB200_MODE="shadow", MB200_REPORT=str(report))
+    e.update(env)
+    p = subprocess.run([str(BIN_SCALAR), str(nex)], cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return json.loads(report.read_text().strip().splitlines()[-1])
+
+
+@needs_scalar
+@pytest.mark.parametrize("data,cmds,supported", MODEL_SWEEP)
+def test_model_sweep_against_the_no_simd_reference(tmp_path, data, cmds, supported):
+    rep = _run_sweep_case(tmp_path, data, cmds, 100, {"MB200_SHADOW_BACKEND": "oracle"})
+    assert rep["calls"] >= 150, rep
+    if supported:
+        assert rep["unsupported_calls"] == 0 and rep["compared"] == rep["calls"] and rep["failed"] == 0 and rep["max_rel"] < 1e-6, rep
+    else:
+        assert rep["unsupported_calls"] == rep["calls"] and rep["compared"] == 0, rep
+
+
 def _sample_rows(rep):
     lines = [l for l in rep["samples"][".p"].splitlines() if l and not l.startswith("[")]
     return lines[0].split("\t"), [[float(x) for x in l.split("\t")] for l in lines[1:]]
@@ -261,6 +302,15 @@ def test_engine_matches_the_no_simd_reference_on_its_scalar_kernel_family(tmp_pa
     assert rep["calls"] >= min_calls and rep["unsupported_calls"] == 0, rep
     assert rep["failed"] == 0 and rep["compared"] == rep["calls"], rep
     assert rep["max_rel"] < 1e-6, rep
+
+
+@needs_scalar
+@pytest.mark.gpu
+@pytest.mark.parametrize("data,cmds,supported", [c for c in MODEL_SWEEP if c[2]])
+def test_model_sweep_on_the_engine(tmp_path, engine_lib, data, cmds, supported):
+    rep = _run_sweep_case(tmp_path, data, cmds, 150, {})
+    assert rep["calls"] >= 250 and rep["unsupported_calls"] == 0, rep
+    assert rep["compared"] == rep["calls"] and rep["failed"] == 0 and rep["max_rel"] < 1e-6, rep
 
 
 @needs_scalar
