@@ -193,7 +193,8 @@ def test_scalar_kernel_family_matches_the_no_simd_reference(tmp_path, stem, ngen
 # A sweep over the model space the seam accepts, each as a shadow run in the no-SIMD build (every evaluation compared with the
 # reference's own): substitution-model jumping (nst=mixed), closed-form models with readers, lognormal / k-mixture rate
 # variation, JC, amino-acid model jumping and protein GTR, codon M3 (three omega categories) and codon GTR; autocorrelated gamma
-# is outside the path and must be declined, not mis-evaluated.
+# is outside the path and must be declined, not mis-evaluated; rooted clock trees with and without relaxed-clock branch rates,
+# eight gamma categories, two differently modelled partitions of one alignment.
 MODEL_SWEEP = [
     ("primates.nex", "lset nst=mixed rates=gamma;", True),
     ("primates.nex", "lset nst=2 rates=propinv; report ancstates=yes;", True),
@@ -204,6 +205,13 @@ MODEL_SWEEP = [
     ("avian_ovomucoids.nex", "prset aamodelpr=fixed(gtr); lset rates=equal;", True),
     ("replicase.nex", "lset nucmodel=codon omegavar=m3;", True),
     ("replicase.nex", "lset nucmodel=codon nst=6 rates=equal;", True),
+    # rooted (clock) trees, relaxed-clock branch rates (the effective branch length is length x rate, SeamBranchLength)
+    ("primates.nex", "lset nst=6 rates=gamma; prset brlenspr=clock:uniform;", True),
+    ("primates.nex", "lset nst=6 rates=invgamma; prset brlenspr=clock:birthdeath clockvarpr=igr;", True),
+    ("primates.nex", "lset nst=6 rates=gamma; prset brlenspr=clock:uniform clockvarpr=tk02;", True),
+    ("primates.nex", "lset nst=6 rates=gamma ngammacat=8;", True),
+    ("primates.nex", "charset a=1-400; charset b=401-898; partition p=2:a,b; set partition=p; lset applyto=(1) nst=2 rates=gamma; "
+                     "lset applyto=(2) nst=6 rates=propinv; unlink shape=(all) revmat=(all); prset applyto=(all) ratepr=variable;", True),
     ("primates.nex", "lset nst=6 rates=adgamma;", False),
 ]
 
