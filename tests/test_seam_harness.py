@@ -99,6 +99,46 @@ def test_chain_batched_generations_reproduce_the_serial_reference(tmp_path, stem
     assert bat["samples"] == ref["samples"], "chain-batched generations sample differently from the serial reference"
 
 
+# The same identity over the model space: two runs x three chains, every sampled tree and parameter of the chain-batched loop
+# (seam + bit-exact CPU oracle) equal to the unmodified reference's -- model jumping, rooted clock trees with relaxed-clock
+# rates, amino-acid model jumping, codon models with one and three omega categories (host eigensystems), two partitions.
+BATCHED_SWEEP = [
+    ("primates.nex", "lset nst=mixed rates=gamma;", 200),
+    ("primates.nex", "lset nst=6 rates=invgamma; prset brlenspr=clock:birthdeath clockvarpr=igr;", 200),
+    ("avian_ovomucoids.nex", "prset aamodelpr=mixed; lset rates=gamma;", 60),
+    ("replicase.nex", "lset nucmodel=codon omegavar=m3;", 100),
+    ("primates.nex", "charset a=1-400; charset b=401-898; partition p=2:a,b; set partition=p; lset applyto=(1) nst=2 rates=gamma; "
+                     "lset applyto=(2) nst=6 rates=propinv; unlink shape=(all) revmat=(all); prset applyto=(all) ratepr=variable;", 200),
+]
+
+
+def _run_inline(tmp_path, binary, mode, data, cmds, ngen, tag, env=None):
+    d = tmp_path / tag
+    d.mkdir()
+    nex = d / "r.nex"
+    nex.write_text(f"set autoclose=yes nowarn=yes seed=99 swapseed=99;\nexecute oracle/_ref/data/{data};\n{cmds}\n"
+                   f"mcmc nruns=2 nchains=3 ngen={ngen} printfreq=100000 samplefreq=25 diagnfreq=100000 filename={d}/o;\nquit;\n")
+    report = d / "r.json"
+    e = dict(os.environ, MB200_MODE=mode, MB200_BATCH="1", MB200_REPORT=str(report))
+    e.update(env or {})
+    p = subprocess.run([str(binary), str(nex)], cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    rep = json.loads(report.read_text().strip().splitlines()[-1])
+    rep["samples"] = {f.name: "\n".join(l for l in f.read_text().splitlines() if "ID:" not in l)
+                      for f in sorted(d.glob("o*")) if f.suffix in (".p", ".t")}
+    return rep
+
+
+@needs_harness
+@needs_batched
+@pytest.mark.parametrize("data,cmds,ngen", BATCHED_SWEEP)
+def test_chain_batched_generations_over_the_model_space(tmp_path, data, cmds, ngen):
+    ref = _run_inline(tmp_path, BIN, "cpu", data, cmds, ngen, "ref")
+    bat = _run_inline(tmp_path, BIN_BATCHED, "oracle", data, cmds, ngen, "bat")
+    assert bat["batched_generations"] == ngen and bat["unsupported_calls"] == 0 and bat["calls"] == ref["calls"], bat
+    assert len(ref["samples"]) == 4 and bat["samples"] == ref["samples"]
+
+
 # Dynamic rescaling (opt-in MB200_RESCALE=dynamic): nodes are rescaled every few levels instead of at every
 # node; an evaluation that trips the float-range guard is repeated at once with every node rescaled.  lnL then differs from
 # the always-rescale arithmetic by rounding only -- a run follows the reference run's decisions and stays within the
