@@ -252,6 +252,11 @@ MODEL_SWEEP = [
     ("primates.nex", "lset nst=6 rates=gamma ngammacat=8;", True),
     ("primates.nex", "charset a=1-400; charset b=401-898; partition p=2:a,b; set partition=p; lset applyto=(1) nst=2 rates=gamma; "
                      "lset applyto=(2) nst=6 rates=propinv; unlink shape=(all) revmat=(all); prset applyto=(all) ratepr=variable;", True),
+    # hymfossil.nex: 114 taxa (45 fossils: mostly missing data), 7-state morphology with ordered characters and coding=variable,
+    # 2 765 DNA patterns, rooted clock tree with independent-gamma branch rates
+    ("hymfossil_nomcmc.nex", "ctype ordered: 20 23 27 30 35 36 41 42 44 46 48 59 65 75 78 79 89 99 112 117 134 146 157; "
+                             "lset applyto=(1) coding=variable rates=gamma; lset applyto=(2) nst=6 rates=invgamma; unlink shape=(all); "
+                             "prset applyto=(all) ratepr=variable; prset brlenspr=clock:uniform clockvarpr=igr;", True),
     ("primates.nex", "lset nst=6 rates=adgamma;", False),
 ]
 
