@@ -14,3 +14,5 @@ run mb_b200_scalar cpu primates_covarion 5000
 run mb_b200_scalar gpu primates_covarion 5000
 run mb_b200_scalar cpu ovomucoids_covarion 300
 run mb_b200_scalar gpu ovomucoids_covarion 300
+run mb_b200_scalar cpu hymfossil_te 2000
+run mb_b200_scalar gpu hymfossil_te 2000
