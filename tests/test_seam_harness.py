@@ -257,6 +257,8 @@ MODEL_SWEEP = [
     ("hymfossil_nomcmc.nex", "ctype ordered: 20 23 27 30 35 36 41 42 44 46 48 59 65 75 78 79 89 99 112 117 134 146 157; "
                              "lset applyto=(1) coding=variable rates=gamma; lset applyto=(2) nst=6 rates=invgamma; unlink shape=(all); "
                              "prset applyto=(all) ratepr=variable; prset brlenspr=clock:uniform clockvarpr=igr;", True),
+    # finch.nex: 30 loci with UNLINKED topologies (gene trees under a species tree): every division has its own tree
+    ("finch.nex", "lset nst=2 rates=gamma;", True),
     ("primates.nex", "lset nst=6 rates=adgamma;", False),
 ]
 
