@@ -109,6 +109,9 @@ BATCHED_SWEEP = [
     ("replicase.nex", "lset nucmodel=codon omegavar=m3;", 100),
     ("primates.nex", "charset a=1-400; charset b=401-898; partition p=2:a,b; set partition=p; lset applyto=(1) nst=2 rates=gamma; "
                      "lset applyto=(2) nst=6 rates=propinv; unlink shape=(all) revmat=(all); prset applyto=(all) ratepr=variable;", 200),
+    ("finch.nex", "lset nst=2 rates=gamma;", 200),          # 30 unlinked gene trees under a species tree
+    ("hymfossil_nomcmc.nex", "lset applyto=(1) coding=variable rates=gamma; lset applyto=(2) nst=6 rates=invgamma; unlink shape=(all); "
+                             "prset applyto=(all) ratepr=variable; prset brlenspr=clock:uniform clockvarpr=igr;", 40),
 ]
 
 
@@ -136,7 +139,7 @@ def test_chain_batched_generations_over_the_model_space(tmp_path, data, cmds, ng
     ref = _run_inline(tmp_path, BIN, "cpu", data, cmds, ngen, "ref")
     bat = _run_inline(tmp_path, BIN_BATCHED, "oracle", data, cmds, ngen, "bat")
     assert bat["batched_generations"] == ngen and bat["unsupported_calls"] == 0 and bat["calls"] == ref["calls"], bat
-    assert len(ref["samples"]) == 4 and bat["samples"] == ref["samples"]
+    assert len(ref["samples"]) >= 4 and bat["samples"] == ref["samples"]
 
 
 # Dynamic rescaling (opt-in MB200_RESCALE=dynamic): nodes are rescaled every few levels instead of at every
