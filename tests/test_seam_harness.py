@@ -142,6 +142,30 @@ def test_chain_batched_generations_over_the_model_space(tmp_path, data, cmds, ng
     assert len(ref["samples"]) >= 4 and bat["samples"] == ref["samples"]
 
 
+@needs_harness
+@needs_batched
+@pytest.mark.parametrize("mc", ["nruns=2 nchains=8 ngen=100", "nruns=3 nchains=2 ngen=150 swapfreq=3 nswaps=2 temp=0.3"])
+def test_chain_batched_generations_with_other_chain_layouts(tmp_path, mc):
+    """16 local chains in one call per generation; three runs with two swap attempts every third generation at a hotter ladder."""
+    def run(binary, mode, tag):
+        d = tmp_path / tag
+        d.mkdir()
+        nex = d / "r.nex"
+        nex.write_text(f"set autoclose=yes nowarn=yes seed=99 swapseed=99;\nexecute oracle/_ref/data/primates.nex;\nlset nst=6 rates=gamma;\n"
+                       f"mcmc {mc} printfreq=100000 samplefreq=25 diagnfreq=100000 filename={d}/o;\nquit;\n")
+        report = d / "r.json"
+        e = dict(os.environ, MB200_MODE=mode, MB200_BATCH="1", MB200_REPORT=str(report))
+        p = subprocess.run([str(binary), str(nex)], cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        rep = json.loads(report.read_text().strip().splitlines()[-1])
+        rep["samples"] = {f.name: "\n".join(l for l in f.read_text().splitlines() if "ID:" not in l)
+                          for f in sorted(d.glob("o*")) if f.suffix in (".p", ".t")}
+        return rep
+    ref, bat = run(BIN, "cpu", "ref"), run(BIN_BATCHED, "oracle", "bat")
+    assert bat["batched_generations"] > 0 and bat["unsupported_calls"] == 0 and bat["calls"] == ref["calls"]
+    assert len(ref["samples"]) >= 4 and bat["samples"] == ref["samples"]
+
+
 # Dynamic rescaling (SURVEY 8f2, opt-in MB200_RESCALE=dynamic): nodes are rescaled every few levels instead of at every
 # node; an evaluation that trips the float-range guard is repeated at once with every node rescaled.  lnL then differs from
 # the always-rescale arithmetic by rounding only -- a run follows the reference run's decisions and stays within the
