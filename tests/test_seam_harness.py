@@ -446,6 +446,46 @@ def test_device_eigensystems_follow_the_host_run(tmp_path, engine_lib, stem, nge
             assert abs(a - b) <= 1e-6 * abs(a) + 2e-3, (g, lh[g], ld[g])      # 3 decimals are printed
 
 
+ENGINE_BATCH_SWEEP = [
+    ("replicase.nex", "lset nucmodel=codon omegavar=ny98;", "nruns=1 nchains=4 ngen=200", {}),                       # device eigensystems
+    ("replicase.nex", "lset nucmodel=codon omegavar=ny98;", "nruns=1 nchains=4 ngen=200", {"MB200_EIGEN": "host"}),
+    ("finch.nex", "lset nst=2 rates=gamma;", "nruns=2 nchains=3 ngen=300", {}),                                     # 30 unlinked gene trees
+    ("hymfossil_nomcmc.nex", "lset applyto=(1) coding=variable rates=gamma; lset applyto=(2) nst=6 rates=invgamma; unlink shape=(all); "
+                             "prset applyto=(all) ratepr=variable; prset brlenspr=clock:uniform clockvarpr=igr;", "nruns=1 nchains=4 ngen=300", {}),
+    ("kim.nex", "set partition=by_gene_and_struct; lset applyto=(1) nucmodel=doublet nst=6; lset applyto=(2,3,4) nst=6 rates=invgamma; "
+                "prset applyto=(5,6) aamodelpr=fixed(wag); lset applyto=(5,6) rates=gamma; lset applyto=(7) rates=gamma; "
+                "unlink revmat=(all) pinvar=(all) shape=(all) statefreq=(all); prset applyto=(all) ratepr=variable;", "nruns=1 nchains=4 ngen=200", {}),
+    ("primates.nex", "lset nst=6 rates=gamma covarion=yes;", "nruns=2 nchains=4 ngen=300", {}),
+]
+
+
+@needs_harness
+@needs_batched
+@pytest.mark.gpu
+@pytest.mark.parametrize("data,cmds,mc,env", ENGINE_BATCH_SWEEP)
+def test_chain_batched_launches_equal_per_chain_launches_over_data_sets(tmp_path, engine_lib, data, cmds, mc, env):
+    """All local chains of a generation in one launch per division == one launch per chain: identical samples, whatever the
+    kernel family (4-state, tensor-core 20 / 61 states, generic 8 / 16 states, morphology) and the tree layout."""
+    def run(batch):
+        d = tmp_path / ("b" + batch)
+        d.mkdir()
+        nex = d / "r.nex"
+        nex.write_text(f"set autoclose=yes nowarn=yes seed=99 swapseed=99;\nexecute oracle/_ref/data/{data};\n{cmds}\n"
+                       f"mcmc {mc} printfreq=100000 samplefreq=25 diagnfreq=100000 filename={d}/o;\nquit;\n")
+        report = d / "r.json"
+        e = dict(os.environ, MB200_MODE="gpu", MB200_BATCH=batch, MB200_REPORT=str(report))
+        e.update(env)
+        p = subprocess.run([str(BIN_BATCHED), str(nex)], cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        rep = json.loads(report.read_text().strip().splitlines()[-1])
+        rep["samples"] = {f.name: "\n".join(l for l in f.read_text().splitlines() if "ID:" not in l)
+                          for f in sorted(d.glob("o*")) if f.suffix in (".p", ".t")}
+        return rep
+    one, bat = run("0"), run("1")
+    assert one["unsupported_calls"] == 0 and bat["unsupported_calls"] == 0 and one["batched_generations"] == 0 and bat["batched_generations"] > 0
+    assert bat["calls"] == one["calls"] and len(one["samples"]) >= 2 and bat["samples"] == one["samples"]
+
+
 SHADOW_CASES = [
     # stem, generations, expected unsupported calls (None = any), min evaluations
     ("primates_gtr_g4", 2000, 0, 16000),
