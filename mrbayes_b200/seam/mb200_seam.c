@@ -86,6 +86,7 @@ typedef struct
     LikeUpFxn            refCondLikeUp;
     PrintAncStFxn        refPrintAncStates;
     PrintSiteRateFxn     refPrintSiteRates;
+    int                  omegaReaders;      /* PosSelProbs / SiteOmegas wrapped (report possel / siteomega) */
     long long            evalStamp, syncedStamp;
     int                  syncedChain, syncedState, readers;
     CLFlt              **hostExtra;         /* the appended host buffers (freed by the seam) */
@@ -418,8 +419,10 @@ int MB200SeamDivisionSupported (ModelInfo *m)
         return NO;
     if (m->nParsIntsPerSite != 1)
         return NO;
-    if (m->printPosSel == YES || m->printSiteOmegas == YES)
-        return NO;                              /* PosSelProbs / SiteOmegas read the CL buffers on the host (src/mcmc.c:5761-5772) */
+    if ((m->printPosSel == YES || m->printSiteOmegas == YES) &&
+        (seamBackend.get_partials == NULL || SeamOmegaCategories (m) == NO || getenv ("MB200_NO_READERS") != NULL))
+        return NO;                              /* PosSelProbs / SiteOmegas read the root's conditional likelihoods on the host
+                                                   (src/mcmc.c:5761-5772, 12627, 12664): MB200InstallReaders wraps them too */
     if (SeamReadersWanted (m) == YES &&
         (seamBackend.get_partials == NULL || seamBackend.get_transition_matrix == NULL || seamBackend.get_scalers == NULL ||
          m->numOmegaCats != 1 || getenv ("MB200_NO_READERS") != NULL))
@@ -2106,6 +2109,41 @@ int PrintSiteRates_B200 (TreeNode *p, int division, int chain)
     return sd->refPrintSiteRates (p, division, chain);
 }
 
+/* report possel=yes / siteomega=yes (codon models with omega categories): PosSelProbs and SiteOmegas (src/mcmc.c:10108, 10267)
+   read the conditional likelihoods of ONE node, the root's left child, in the scalar layout [k][c][s] -- the layout
+   mb200_get_partials delivers.  The SIMD builds install PosSelProbs_SSE / SiteOmegas_SSE, which expect the vector layout of
+   their own kernels; the wrappers therefore call the scalar functions on the synced buffer, whatever the build. */
+int PosSelProbs (TreeNode *p, int division, int chain);
+int SiteOmegas (TreeNode *p, int division, int chain);
+
+static int SeamSyncRootPartials (TreeNode *p, int division, int chain)
+{
+    ModelInfo    *m  = &modelSettings[division];
+    SeamDivision *sd = &seamDiv[division];
+    int           idx;
+
+    if (sd->instance < 0 || m->condLikes == NULL || SeamHostBuffersFor (m, sd) == ERROR)
+        return (ERROR);
+    idx = m->condLikeIndex[chain][p->index];
+    if (seamBackend.get_partials (sd->instance, idx, m->condLikes[idx]) != MB200_SUCCESS)
+        return (ERROR);
+    return (NO_ERROR);
+}
+
+int PosSelProbs_B200 (TreeNode *p, int division, int chain)
+{
+    if (SeamSyncRootPartials (p, division, chain) == ERROR)
+        return (ERROR);
+    return PosSelProbs (p, division, chain);
+}
+
+int SiteOmegas_B200 (TreeNode *p, int division, int chain)
+{
+    if (SeamSyncRootPartials (p, division, chain) == ERROR)
+        return (ERROR);
+    return SiteOmegas (p, division, chain);
+}
+
 /* what SetLikeFunctions would do for a covered division that reports ancestral states or site rates; call it after
    SetLikeFunctions (it runs for every mcmc command) -- idempotent */
 int MB200InstallReaders (int division)
@@ -2118,8 +2156,16 @@ int MB200InstallReaders (int division)
         return (ERROR);
     m  = &modelSettings[division];
     sd = &seamDiv[division];
-    if (SeamReadersWanted (m) == NO || MB200SeamDivisionSupported (m) == NO)
+    if (MB200SeamDivisionSupported (m) == NO)
         return (ERROR);
+    if (m->printPosSel == YES || m->printSiteOmegas == YES)
+        {
+        m->PosSelProbs = &PosSelProbs_B200;
+        m->SiteOmegas  = &SiteOmegas_B200;
+        sd->omegaReaders = YES;
+        }
+    if (SeamReadersWanted (m) == NO)
+        return (sd->omegaReaders == YES) ? NO_ERROR : ERROR;
     if (m->CondLikeUp != &CondLikeUp_B200 && m->CondLikeUp != NULL)
         { sd->refCondLikeUp = m->CondLikeUp; m->CondLikeUp = &CondLikeUp_B200; }
     if (m->PrintAncStates != &PrintAncStates_B200 && m->PrintAncStates != NULL)

@@ -60,6 +60,8 @@ int       CondLikeUp_B200     (TreeNode *p, int division, int chain);
 int       PrintAncStates_B200 (TreeNode *p, int division, int chain);
 int       PrintSiteRates_B200 (TreeNode *p, int division, int chain);
 int       MB200InstallReaders (int division);
+int       PosSelProbs_B200 (TreeNode *p, int division, int chain);     /* report possel=yes   */
+int       SiteOmegas_B200 (TreeNode *p, int division, int chain);      /* report siteomega=yes */
 long long MB200SeamUpdateCount (int division);   /* node*pattern*rate CL updates issued  */
 void      MB200SeamCijkTimes (double *secHost, double *secUpload, long long *updates);   /* eigensystem work on the host */
 long long MB200SeamDeviceEigens (void);          /* MB200_EIGEN=device: eigensystems computed by the backend */

@@ -670,8 +670,10 @@ int MB200RC_Begin (void)
         {
         int d;
         for (d=0; d<numCurrentDivisions; d++)
-            if ((modelSettings[d].printAncStates == YES || modelSettings[d].printSiteRates == YES) &&
-                modelSettings[d].PrintSiteRates != &PrintSiteRates_B200)
+            if (((modelSettings[d].printAncStates == YES || modelSettings[d].printSiteRates == YES) &&
+                 modelSettings[d].PrintSiteRates != &PrintSiteRates_B200) ||
+                ((modelSettings[d].printPosSel == YES || modelSettings[d].printSiteOmegas == YES) &&
+                 modelSettings[d].PosSelProbs != &PosSelProbs_B200))
                 MB200InstallReaders (d);
         }
     hBatchActive = (hBatch && ENGINE_DRIVES (hMode) && !hViaFn) ? MB200BatchBegin () : NO;
@@ -773,7 +775,8 @@ void __wrap_LaunchLogLikeForDivision (int chain, int d, MrBFlt *lnL)
     if (ENGINE_DRIVES (hMode))
         {
         const int fresh = (MB200SeamInstance (d) < 0);
-        if ((m->printAncStates == YES || m->printSiteRates == YES) && m->PrintSiteRates != &PrintSiteRates_B200)
+        if (((m->printAncStates == YES || m->printSiteRates == YES) && m->PrintSiteRates != &PrintSiteRates_B200) ||
+            ((m->printPosSel == YES || m->printSiteOmegas == YES) && m->PosSelProbs != &PosSelProbs_B200))
             MB200InstallReaders (d);            /* what SetLikeFunctions would do (it runs again for every mcmc command) */
         t0 = Now ();
         if (hViaFn)

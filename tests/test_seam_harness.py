@@ -329,12 +329,12 @@ def _rows_agree(ra, rb, rel=2e-6):
 
 
 @needs_scalar
-@pytest.mark.parametrize("stem", ["primates_covarion", "primates_readers"])
+@pytest.mark.parametrize("stem", ["primates_covarion", "primates_readers", "replicase_possel"])
 def test_scalar_build_runs_sample_what_the_reference_samples(tmp_path, stem):
     """The no-SIMD reference driving itself vs the seam + CPU oracle driving the same binary: the sampled parameters -- for
     primates_readers including ~3 300 ancestral-state probabilities and ~900 site rates per sample, read by the reference's own
     CondLikeUp / PrintAncStates / PrintSiteRates from the buffers the seam synced -- agree to the printed precision."""
-    ngen = 200
+    ngen = 100 if stem == "replicase_possel" else 200      # (possel: ~240 selection probabilities + ~240 site omegas per sample)
     ref = run_harness(tmp_path, stem, ngen, "cpu", binary=BIN_SCALAR, tag=".scr")
     orc = run_harness(tmp_path, stem, ngen, "oracle", binary=BIN_SCALAR, tag=".sco")
     assert orc["unsupported_calls"] == 0 and orc["calls"] == ref["calls"]
@@ -397,7 +397,7 @@ def test_model_sweep_on_the_engine(tmp_path, engine_lib, data, cmds, supported):
 
 @needs_scalar
 @pytest.mark.gpu
-@pytest.mark.parametrize("stem", ["primates_covarion", "primates_readers"])
+@pytest.mark.parametrize("stem", ["primates_covarion", "primates_readers", "replicase_possel"])
 def test_engine_driven_scalar_build_samples_like_the_reference(tmp_path, engine_lib, stem):
     """The engine drives the no-SIMD reference binary; its samples (incl. ancestral states / site rates through the wrapped host
     readers) follow the reference's own for as long as the two runs take the same decisions (at least the first five samples)."""
