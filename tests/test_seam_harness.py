@@ -313,6 +313,42 @@ def test_model_sweep_against_the_no_simd_reference(tmp_path, data, cmds, support
         assert rep["unsupported_calls"] == rep["calls"] and rep["compared"] == 0, rep
 
 
+FNPTR_SWEEP = [
+    ("primates.nex", "lset nst=6 rates=gamma covarion=yes;"),
+    ("primates.nex", "lset nst=2 rates=propinv; report ancstates=yes;"),
+    ("kim.nex", "set partition=by_gene_and_struct; lset applyto=(1) nucmodel=doublet nst=6; lset applyto=(2,3,4) nst=6 rates=invgamma; "
+                "prset applyto=(5,6) aamodelpr=fixed(wag); lset applyto=(5,6) rates=gamma; lset applyto=(7) rates=gamma;"),
+    ("hymfossil_nomcmc.nex", "ctype ordered: 20 23 27 30 35 36; lset applyto=(1) coding=variable rates=gamma; lset applyto=(2) nst=6 rates=invgamma; "
+                             "prset brlenspr=clock:uniform clockvarpr=igr;"),
+    ("finch.nex", "lset nst=2 rates=gamma;"),
+]
+
+
+@needs_scalar
+@pytest.mark.parametrize("data,cmds", FNPTR_SWEEP)
+def test_function_pointer_forms_drive_like_the_seam_loop_over_models(tmp_path, data, cmds):
+    """The node-granular forms installed in ModelInfo (the reference's own LaunchLogLikeForDivision loop records the evaluation
+    through them) and the seam's replacement loop sample the same trees and parameters: hidden-state models, host readers,
+    seven mixed partitions, host-built ordered-character matrices, unlinked gene trees."""
+    def run(via):
+        d = tmp_path / via
+        d.mkdir()
+        nex = d / "r.nex"
+        nex.write_text(f"set autoclose=yes nowarn=yes seed=99 swapseed=99;\nexecute oracle/_ref/data/{data};\n{cmds}\n"
+                       f"mcmc nruns=1 nchains=2 ngen=100 printfreq=100000 samplefreq=25 diagnfreq=100000 filename={d}/o;\nquit;\n")
+        report = d / "r.json"
+        e = dict(os.environ, MB200_MODE="oracle", MB200_VIA=via, MB200_MULTIPART="0", MB200_EIGEN="host", MB200_REPORT=str(report))
+        p = subprocess.run([str(BIN_SCALAR), str(nex)], cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        rep = json.loads(report.read_text().strip().splitlines()[-1])
+        rep["samples"] = {f.name: "\n".join(l for l in f.read_text().splitlines() if "ID:" not in l)
+                          for f in sorted(d.glob("o*")) if f.suffix in (".p", ".t")}
+        return rep
+    a, b = run("seam"), run("fnptr")
+    assert a["unsupported_calls"] == 0 and b["unsupported_calls"] == 0 and a["calls"] == b["calls"] > 0
+    assert len(a["samples"]) >= 2 and a["samples"] == b["samples"]
+
+
 def _sample_rows(rep):
     lines = [l for l in rep["samples"][".p"].splitlines() if l and not l.startswith("[")]
     return lines[0].split("\t"), [[float(x) for x in l.split("\t")] for l in lines[1:]]
