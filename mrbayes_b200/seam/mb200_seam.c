@@ -1336,6 +1336,7 @@ void LaunchBEAGLELogLikeForDivision (int chain, int d, ModelInfo *m, Tree *tree,
  * UpDateCijk for them). */
 static MrBFlt **seamQ[SEAM_MAX_DIVISIONS][MB200_MAX_CATEGORIES];
 static double  *seamQFlat[SEAM_MAX_DIVISIONS];
+static int      seamQDim[SEAM_MAX_DIVISIONS], seamQParts[SEAM_MAX_DIVISIONS];   /* what the two above were allocated for */
 static long long seamDeviceEigens = 0;
 
 long long MB200SeamDeviceEigens (void) { return seamDeviceEigens; }
@@ -1379,6 +1380,14 @@ static int SeamDeviceEigen (ModelInfo *m, SeamDivision *sd, int d, int chain)
 
     if (parts > MB200_MAX_CATEGORIES)
         return (NO);
+    if (seamQFlat[d] != NULL && (seamQDim[d] != n || seamQParts[d] != parts))
+        {
+        /* another mcmc command changed the division's model: the work matrices no longer fit */
+        for (k=0; k<seamQParts[d]; k++)
+            { FreeSquareDoubleMatrix (seamQ[d][k]); seamQ[d][k] = NULL; }
+        free (seamQFlat[d]);
+        seamQFlat[d] = NULL;
+        }
     if (seamQFlat[d] == NULL)
         {
         for (k=0; k<parts; k++)
@@ -1386,6 +1395,7 @@ static int SeamDeviceEigen (ModelInfo *m, SeamDivision *sd, int d, int chain)
                 return (NO);
         if ((seamQFlat[d] = (double *) SafeMalloc ((size_t) parts * n * n * sizeof(double))) == NULL)
             return (NO);
+        seamQDim[d] = n; seamQParts[d] = parts;
         }
     if (codon == YES)
         {
