@@ -313,6 +313,38 @@ def test_model_sweep_against_the_no_simd_reference(tmp_path, data, cmds, support
         assert rep["unsupported_calls"] == rep["calls"] and rep["compared"] == 0, rep
 
 
+def _run_session(tmp_path, binary, mode, tag, env=None):
+    """Three mcmc commands in ONE session, the model changed in between: codon M0 (61 states) -> GTR + 6 gamma categories on the
+    nucleotides (3 chains) -> codon NY98 (three eigensystems per slot).  Instances, scratch sets and work matrices must follow."""
+    d = tmp_path / tag
+    d.mkdir()
+    nex = d / "r.nex"
+    nex.write_text("set autoclose=yes nowarn=yes seed=99 swapseed=99;\nexecute oracle/_ref/data/replicase.nex;\nlset nucmodel=codon;\n"
+                   f"mcmc nruns=1 nchains=2 ngen=40 printfreq=100000 samplefreq=20 diagnfreq=100000 filename={d}/a;\n"
+                   "lset nucmodel=4by4 nst=6 rates=gamma ngammacat=6;\n"
+                   f"mcmc nruns=1 nchains=3 ngen=60 printfreq=100000 samplefreq=20 diagnfreq=100000 filename={d}/b;\n"
+                   "lset nucmodel=codon omegavar=ny98;\n"
+                   f"mcmc nruns=1 nchains=2 ngen=40 printfreq=100000 samplefreq=20 diagnfreq=100000 filename={d}/c;\nquit;\n")
+    report = d / "r.json"
+    e = dict(os.environ, MB200_MODE=mode, MB200_BATCH="1", MB200_REPORT=str(report))
+    e.update(env or {})
+    p = subprocess.run([str(binary), str(nex)], cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    rep = json.loads(report.read_text().strip().splitlines()[-1])
+    rep["samples"] = {f.name: "\n".join(l for l in f.read_text().splitlines() if "ID:" not in l)
+                      for f in sorted(d.glob("[abc].*")) if f.suffix in (".p", ".t")}
+    return rep
+
+
+@needs_harness
+@needs_batched
+def test_model_changes_between_mcmc_commands(tmp_path):
+    ref = _run_session(tmp_path, BIN, "cpu", "ref")
+    bat = _run_session(tmp_path, BIN_BATCHED, "oracle", "bat")
+    assert bat["unsupported_calls"] == 0 and bat["calls"] == ref["calls"] and bat["batched_generations"] == 140
+    assert len(ref["samples"]) == 6 and bat["samples"] == ref["samples"]
+
+
 FNPTR_SWEEP = [
     ("primates.nex", "lset nst=6 rates=gamma covarion=yes;"),
     ("primates.nex", "lset nst=2 rates=propinv; report ancstates=yes;"),
@@ -480,6 +512,18 @@ def test_device_eigensystems_follow_the_host_run(tmp_path, engine_lib, stem, nge
     for g in range(ngen):
         for a, b in zip(lh[g], ld[g]):
             assert abs(a - b) <= 1e-6 * abs(a) + 2e-3, (g, lh[g], ld[g])      # 3 decimals are printed
+
+
+@needs_harness
+@needs_batched
+@pytest.mark.gpu
+def test_model_changes_between_mcmc_commands_on_the_engine(tmp_path, engine_lib):
+    """The same session on the engine (device eigensystems for the two codon runs: 1 and then 3 rate matrices per slot): batched
+    launches == per-chain launches, nothing handed back to the reference."""
+    one = _run_session(tmp_path, BIN_BATCHED, "gpu", "one", {"MB200_BATCH": "0"})
+    bat = _run_session(tmp_path, BIN_BATCHED, "gpu", "bat", {"MB200_BATCH": "1"})
+    assert one["unsupported_calls"] == 0 and bat["unsupported_calls"] == 0 and bat["batched_generations"] == 140
+    assert bat["device_eigens"] > 0 and len(one["samples"]) == 6 and bat["samples"] == one["samples"]
 
 
 ENGINE_BATCH_SWEEP = [
