@@ -16,3 +16,8 @@ run mb_b200_scalar cpu ovomucoids_covarion 300
 run mb_b200_scalar gpu ovomucoids_covarion 300
 run mb_b200_scalar cpu hymfossil_te 2000
 run mb_b200_scalar gpu hymfossil_te 2000
+# chain-batched generations in the same build
+run mb_b200_scalar_batched gpu kim_mixed 2000 MB200_BATCH=1
+run mb_b200_scalar_batched gpu primates_covarion 5000 MB200_BATCH=1
+run mb_b200_scalar_batched gpu ovomucoids_covarion 300 MB200_BATCH=1
+run mb_b200_scalar_batched gpu hymfossil_te 2000 MB200_BATCH=1

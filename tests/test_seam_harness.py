@@ -345,6 +345,24 @@ def test_model_changes_between_mcmc_commands(tmp_path):
     assert len(ref["samples"]) == 6 and bat["samples"] == ref["samples"]
 
 
+BIN_SCALAR_BATCHED = ROOT / "oracle" / "_ref" / "mb_b200_scalar_batched"
+
+
+@pytest.mark.skipif(not BIN_SCALAR_BATCHED.exists(), reason="oracle/_ref/mb_b200_scalar_batched not built")
+@pytest.mark.parametrize("stem,ngen", [("primates_covarion", 200), ("primates_readers", 200), ("kim_mixed", 100), ("replicase_possel", 60)])
+def test_chain_batched_scalar_family_follows_the_no_simd_reference(tmp_path, stem, ngen):
+    """Chain-batched generations in the no-SIMD build (seam + CPU oracle) vs the reference driving itself: hidden-state models,
+    host readers (ancestral states / site rates; selection probabilities / site omegas), kim.nex's seven partitions -- every sampled
+    value agrees to the printed precision over the whole run, i.e. the two runs took the same decisions throughout."""
+    ref = run_harness(tmp_path, stem, ngen, "cpu", binary=BIN_SCALAR, tag=".sbr")
+    bat = run_harness(tmp_path, stem, ngen, "oracle", binary=BIN_SCALAR_BATCHED, extra_env={"MB200_BATCH": "1"}, tag=".sbb")
+    assert bat["unsupported_calls"] == 0 and bat["calls"] == ref["calls"] and bat["batched_generations"] == ngen
+    (ha, ra), (hb, rb) = _sample_rows(ref), _sample_rows(bat)
+    assert ha == hb and len(ra) == len(rb) >= 4
+    assert _rows_agree(ra, rb) == len(ra), (_rows_agree(ra, rb), len(ra))
+    assert ref["samples"][".t"] == bat["samples"][".t"]            # the sampled trees: identical text
+
+
 FNPTR_SWEEP = [
     ("primates.nex", "lset nst=6 rates=gamma covarion=yes;"),
     ("primates.nex", "lset nst=2 rates=propinv; report ancstates=yes;"),
