@@ -102,6 +102,10 @@ struct Instance
     std::vector<Batch *> batches;      // resident batches (mb200_pack_evaluations)
     void         *hostStage = nullptr; // pinned staging for set/get calls
     size_t        hostStageBytes = 0;
+    float        *hMatRing = nullptr;  // pinned ring for caller-supplied transition matrices (mb200_set_transition_matrix without a sync)
+    size_t        matRingStride = 0;
+    int           matRingNext = 0;
+    std::vector<cudaEvent_t> evMatRing;
     std::vector<int> slotOf;           // scratch: matrix index -> shared-memory slot in the current evaluation
     std::vector<int> touched;          // scratch: matrices whose slotOf entry is set
     std::vector<int> dirtyOf;          // scratch: matrix index -> index in the evaluation's update list
@@ -979,6 +983,8 @@ void destroy (Instance *I)
     if (I->hEigStatus) cudaFreeHost (I->hEigStatus);
     for (cudaEvent_t e : I->evEigIn) cudaEventDestroy (e);
     if (I->hostStage) cudaFreeHost (I->hostStage);
+    if (I->hMatRing) cudaFreeHost (I->hMatRing);
+    for (cudaEvent_t e : I->evMatRing) cudaEventDestroy (e);
     for (cudaEvent_t e : I->evA) cudaEventDestroy (e);
     for (cudaEvent_t e : I->evB) cudaEventDestroy (e);
     if (I->stream) cudaStreamDestroy (I->stream);
@@ -1592,6 +1598,26 @@ int mb200_set_transition_matrix (int instance, int matrix, const float *in)
     if (I->std && !I->stdReady) return MB200_ERROR_UNSUPPORTED;
     const size_t n = I->std ? (size_t) I->sx.matLen : (size_t)I->cfg.category_count * I->cfg.state_count * I->cfg.state_count;
     if (I->std) I->stdUniformMk = false;        // a caller-supplied matrix need not have the Mk form: read every entry from now on
+    const int MAT_RING = 64;
+    if (!I->tcS && n * sizeof(float) <= 64*1024)
+        {
+        // small matrices (host-built P(t) of a STANDARD division, one call per dirty branch): stage through a pinned ring and let
+        // the copy ride the instance's stream -- the evaluation that reads the matrix is queued behind it; no host wait
+        if (!I->hMatRing)
+            {
+            I->matRingStride = n;
+            CK (cudaHostAlloc ((void **)&I->hMatRing, (size_t)MAT_RING * n * sizeof(float), cudaHostAllocDefault));
+            I->evMatRing.resize (MAT_RING);
+            for (auto &e : I->evMatRing) CK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+            }
+        const int slot = I->matRingNext++ % MAT_RING;
+        CK (cudaEventSynchronize (I->evMatRing[slot]));           // the slot's previous copy has left the ring
+        float *h = I->hMatRing + (size_t)slot * I->matRingStride;
+        memcpy (h, in, n * sizeof(float));
+        CK (cudaMemcpyAsync (I->dMatrices + (size_t)matrix * n, h, n * sizeof(float), cudaMemcpyHostToDevice, I->stream));
+        CK (cudaEventRecord (I->evMatRing[slot], I->stream));
+        return MB200_SUCCESS;
+        }
     CK (cudaMemcpyAsync (I->dMatrices + (size_t)matrix * n, in, n * sizeof(float), cudaMemcpyHostToDevice, I->stream));
     if (I->tcS)
         {
