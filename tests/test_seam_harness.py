@@ -277,6 +277,8 @@ MODEL_SWEEP = [
     ("primates.nex", "lset nst=6 rates=invgamma; prset brlenspr=clock:birthdeath clockvarpr=igr;", True),
     ("primates.nex", "lset nst=6 rates=gamma; prset brlenspr=clock:uniform clockvarpr=tk02;", True),
     ("primates.nex", "lset nst=6 rates=gamma ngammacat=8;", True),
+    ("primates.nex", "lset nst=6 rates=gamma ngammacat=10;", True),          # more than 8 categories: 4 states on the generic kernel
+    ("primates.nex", "lset nst=6 rates=invgamma ngammacat=19;", True),       # the most MrBayes accepts
     ("primates.nex", "charset a=1-400; charset b=401-898; partition p=2:a,b; set partition=p; lset applyto=(1) nst=2 rates=gamma; "
                      "lset applyto=(2) nst=6 rates=propinv; unlink shape=(all) revmat=(all); prset applyto=(all) ratepr=variable;", True),
     # hymfossil.nex: 114 taxa (45 fossils: mostly missing data), 7-state morphology with ordered characters and coding=variable,
